@@ -1,0 +1,84 @@
+/*
+ * dftpav_oracle.h — CPU oracle for the Dftpav MINCO / L-BFGS hot path.
+ *
+ * TEST INFRASTRUCTURE ONLY.  Nothing under oracle/ is part of the product: only tests/,
+ * __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs may load it, and
+ * there only as the checker / the CPU arm.  The product path (dftpav_b200/csrc, the C-ABI of
+ * include/dftpav_b200.h) never calls into this library and has no CPU fallback.
+ *
+ * PARITY STATUS: "parity unpinned" by the reference's own tests — the reference ships no golden
+ * vectors, KATs or fixtures for this path and its implementation
+ * cannot be built here (needs Eigen3, ROS1, protobuf: all absent).  What pins this restatement
+ * instead (tests/test_oracle_*.py):
+ *   - the L-BFGS + Lewis-Overton restatement is compared against the UNMODIFIED reference header
+ *     include/geo_utils2d/lbfgs.hpp compiled in place against a minimal test-only Eigen shim
+ *     (oracle/_ref, built by oracle/Makefile) — iterates are bit-identical;
+ *   - central finite differences of every cost term, MINCO identities (boundary PVA, waypoint
+ *     interpolation, C4 continuity, jerk energy vs quadrature), banded LU vs dense solve;
+ *   - an independent numpy restatement (tests/np_restatement.py).
+ *
+ * Input structs are those of include/dftpav_b200.h (the oracle exports the same batch format so
+ * tests and the baseline timer are backend-agnostic).
+ */
+#ifndef DFTPAV_ORACLE_H
+#define DFTPAV_ORACLE_H
+
+#include "../include/dftpav_b200.h"
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* One cost+gradient evaluation (costFunctionCallback, OPT.cpp:206-350) of problem `p` at x.
+ * x and g have n(p) entries.  If coeffs != NULL it receives the rows*2 MINCO coefficients
+ * (row-major pairs), if piece_dT != NULL the S per-piece durations.  terms[5] (optional) receives
+ * {jerk, time, corridor, dynamic-obstacle, feasibility} cost parts.  Returns 0 or a DFTPAV_ERR_*. */
+int oracle_eval(const dftpav_params* prm, const dftpav_batch* batch, int p, const double* x,
+                double* f, double* g, double* coeffs, double* piece_dT, double* terms);
+
+/* Per-problem sizes: n, coefficient rows, samples. */
+int oracle_problem_dims(const dftpav_params* prm, const dftpav_batch* batch, int p, int* n,
+                        int* rows, int* samples);
+
+/* Full OptimizeTrajectory (OPT.cpp:7-202) for problems [p0, p1) using `threads` OpenMP threads
+ * (each problem is solved by one thread, exactly like the single-threaded reference).
+ * `out` arrays are indexed like the C-ABI's (absolute problem index, strides from
+ * dftpav_batch_dims).  trace (optional): [B][trace_cap][3] = (fx, step, ls) per L-BFGS iteration. */
+int oracle_optimize(const dftpav_params* prm, const dftpav_batch* batch, int p0, int p1,
+                    int threads, const dftpav_result* out, double* trace, int trace_cap);
+
+/* Generic L-BFGS restatement (LBFGS.hpp:276-390, 440-751) on a C callback; used to pin the
+ * restatement against the reference header (oracle/_ref).  trace: [trace_cap][3]. */
+typedef double (*oracle_fg_t)(void* user, const double* x, double* g, int n);
+int oracle_lbfgs(int n, double* x, double* f, oracle_fg_t fg, void* user, const dftpav_params* prm,
+                 int* iters, int* evals, double* trace, int trace_cap);
+
+/* MINCO building blocks exposed for identity tests (MINCO.hpp:855-1095). */
+/* Fills the dense 6N x 6N coefficient matrix (row-major) and the banded LU factor
+ * (band storage ptr[(i-j+6)*6N + j], 13*6N doubles). */
+int oracle_minco_matrix(int N, double* dense, double* lu_band);
+/* generate(): inner points P (2 x (N-1) col-major), dT, head/tail 2x3 col-major -> c (6N x 2 row-major). */
+int oracle_minco_generate(int N, const double* P, double dT, const double* head, const double* tail,
+                          double* c);
+
+/* Synthetic-test analytic functions for oracle_lbfgs / the reference header: id 0 = Rosenbrock
+ * chain, 1 = ill-conditioned quadratic, 2 = nonsmooth |x| mix.  Same code is compiled into
+ * oracle/_ref so both sides evaluate bit-identical f,g. */
+double oracle_testfunc(int id, const double* x, double* g, int n);
+
+double oracle_testfunc_fg(void* user /* int* id */, const double* x, double* g, int n);
+
+/* Problem handles: expose one problem's cost function as an oracle_fg_t so that an external optimizer
+ * loop (the reference lbfgs.hpp in oracle/_ref) can drive it. */
+void* oracle_problem_create(const dftpav_params* prm, const dftpav_batch* batch, int p);
+void oracle_problem_free(void* h);
+int oracle_problem_n(void* h);
+void oracle_problem_initial_x(void* h, double* x);
+double oracle_problem_fg(void* h, const double* x, double* g, int n);
+
+int oracle_num_threads(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

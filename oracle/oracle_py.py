@@ -1,0 +1,169 @@
+"""ctypes loader for the CPU oracle (oracle/libdftpav_oracle.so) and the reference-header build
+(oracle/_ref/libref_lbfgs.so).
+
+TEST INFRASTRUCTURE ONLY — import from tests/, __graft_entry__.smoke() and bench.py's CPU legs, never from the
+product package ``dftpav_b200``.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+from dftpav_b200 import capi
+from dftpav_b200.batch import TrajBatch
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ORACLE_SO = os.path.join(HERE, "libdftpav_oracle.so")
+REF_SO = os.path.join(HERE, "_ref", "libref_lbfgs.so")
+
+FG_T = C.CFUNCTYPE(C.c_double, C.c_void_p, capi.c_double_p, capi.c_double_p, C.c_int)
+
+_lib = None
+_ref = None
+
+
+def build(force: bool = False) -> None:
+    """Compiles the oracle (and oracle/_ref when /root/reference is present) with oracle/Makefile."""
+    if force or not os.path.exists(ORACLE_SO) or os.path.getmtime(ORACLE_SO) < os.path.getmtime(
+            os.path.join(HERE, "dftpav_oracle.cpp")):
+        subprocess.check_call(["make", "-C", HERE, "libdftpav_oracle.so"])
+    if os.path.exists("/root/reference/src/Plan/traj_planner/include/geo_utils2d/lbfgs.hpp") and (
+            force or not os.path.exists(REF_SO)):
+        subprocess.check_call(["make", "-C", HERE, "ref"])
+
+
+def lib() -> C.CDLL:
+    global _lib
+    if _lib is None:
+        if not os.path.exists(ORACLE_SO):
+            build()
+        L = C.CDLL(ORACLE_SO)
+        P, Bt = C.POINTER(capi.Params), C.POINTER(capi.Batch)
+        dp, ip = capi.c_double_p, capi.c_int32_p
+        L.oracle_eval.argtypes = [P, Bt, C.c_int, dp, dp, dp, dp, dp, dp]
+        L.oracle_problem_dims.argtypes = [P, Bt, C.c_int, C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_int)]
+        L.oracle_optimize.argtypes = [P, Bt, C.c_int, C.c_int, C.c_int, C.POINTER(capi.Result), dp, C.c_int]
+        L.oracle_lbfgs.argtypes = [C.c_int, dp, dp, C.c_void_p, C.c_void_p, P, C.POINTER(C.c_int), C.POINTER(C.c_int),
+                                   dp, C.c_int]
+        L.oracle_minco_matrix.argtypes = [C.c_int, dp, dp]
+        L.oracle_minco_generate.argtypes = [C.c_int, dp, C.c_double, dp, dp, dp]
+        L.oracle_testfunc.argtypes = [C.c_int, dp, dp, C.c_int]
+        L.oracle_testfunc.restype = C.c_double
+        L.oracle_problem_create.argtypes = [P, Bt, C.c_int]
+        L.oracle_problem_create.restype = C.c_void_p
+        L.oracle_problem_free.argtypes = [C.c_void_p]
+        L.oracle_problem_free.restype = None
+        L.oracle_problem_n.argtypes = [C.c_void_p]
+        L.oracle_problem_initial_x.argtypes = [C.c_void_p, dp]
+        L.oracle_problem_initial_x.restype = None
+        L.oracle_problem_fg.restype = C.c_double
+        L.oracle_num_threads.argtypes = []
+        _lib = L
+    return _lib
+
+
+def ref_lib():
+    """The reference lbfgs.hpp compiled in place (None if it could not be built and no prebuilt copy travelled)."""
+    global _ref
+    if _ref is None:
+        if not os.path.exists(REF_SO):
+            try:
+                build()
+            except Exception:
+                return None
+        if not os.path.exists(REF_SO):
+            return None
+        R = C.CDLL(REF_SO)
+        dp = capi.c_double_p
+        R.ref_lbfgs.argtypes = [C.c_int, dp, dp, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_double, C.c_double,
+                                C.c_double, C.c_int, C.c_int, C.POINTER(C.c_int), dp, C.c_int]
+        _ref = R
+    return _ref
+
+
+def _dp(a: np.ndarray):
+    return a.ctypes.data_as(capi.c_double_p)
+
+
+def _ip(a: np.ndarray):
+    return a.ctypes.data_as(capi.c_int32_p)
+
+
+def problem_dims(prm: capi.Params, batch: TrajBatch, p: int):
+    n, r, s = C.c_int(), C.c_int(), C.c_int()
+    cb = batch.as_c()
+    rc = lib().oracle_problem_dims(C.byref(prm), C.byref(cb), p, C.byref(n), C.byref(r), C.byref(s))
+    assert rc == 0, rc
+    return n.value, r.value, s.value
+
+
+def evaluate(prm: capi.Params, batch: TrajBatch, p: int, x: np.ndarray, want_terms: bool = False):
+    """One costFunctionCallback: returns (f, g, coeffs[rows,2], piece_dT[S]) (+ terms[5])."""
+    n, rows, _ = problem_dims(prm, batch, p)
+    x = np.ascontiguousarray(x[:n], dtype=np.float64)
+    g = np.zeros(n)
+    f = C.c_double()
+    S = int(batch.seg_ptr[p + 1] - batch.seg_ptr[p])
+    coeffs = np.zeros((rows, 2))
+    dT = np.zeros(S)
+    terms = np.zeros(5)
+    cb = batch.as_c()
+    rc = lib().oracle_eval(C.byref(prm), C.byref(cb), p, _dp(x), C.cast(C.byref(f), capi.c_double_p), _dp(g),
+                           _dp(coeffs), _dp(dT), _dp(terms))
+    if rc != 0:
+        raise RuntimeError(f"oracle_eval rc={rc}")
+    if want_terms:
+        return f.value, g, coeffs, dT, terms
+    return f.value, g, coeffs, dT
+
+
+def initial_x(prm: capi.Params, batch: TrajBatch, p: int) -> np.ndarray:
+    cb = batch.as_c()
+    h = lib().oracle_problem_create(C.byref(prm), C.byref(cb), p)
+    if not h:
+        raise RuntimeError("oracle_problem_create failed (bad input)")
+    n = lib().oracle_problem_n(h)
+    x = np.zeros(n)
+    lib().oracle_problem_initial_x(h, _dp(x))
+    lib().oracle_problem_free(h)
+    return x
+
+
+class Solution:
+    """Outputs of a batch solve, same layout as dftpav_result."""
+
+    def __init__(self, B, n_stride, row_stride, G):
+        self.x = np.zeros((B, n_stride))
+        self.cost = np.zeros(B)
+        self.status = np.zeros(B, dtype=np.int32)
+        self.success = np.zeros(B, dtype=np.int32)
+        self.iters = np.zeros(B, dtype=np.int32)
+        self.evals = np.zeros(B, dtype=np.int32)
+        self.coeffs = np.zeros((B, row_stride, 2))
+        self.piece_dT = np.zeros(G)
+
+    def as_c(self) -> capi.Result:
+        r = capi.Result()
+        r.x, r.cost, r.coeffs, r.piece_dT = _dp(self.x), _dp(self.cost), _dp(self.coeffs), _dp(self.piece_dT)
+        r.status, r.success, r.iters, r.evals = _ip(self.status), _ip(self.success), _ip(self.iters), _ip(self.evals)
+        return r
+
+
+def optimize(prm: capi.Params, batch: TrajBatch, p0: int = 0, p1: int | None = None, threads: int = 0,
+             trace_cap: int = 0):
+    """Full OptimizeTrajectory for problems [p0,p1) on `threads` host threads (0 = all)."""
+    if p1 is None:
+        p1 = batch.B
+    sol = Solution(batch.B, batch.n_stride(), batch.row_stride(), batch.G)
+    trace = np.zeros((batch.B, trace_cap, 3)) if trace_cap else None
+    cb = batch.as_c()
+    res = sol.as_c()
+    rc = lib().oracle_optimize(C.byref(prm), C.byref(cb), p0, p1, threads, C.byref(res),
+                               _dp(trace) if trace is not None else None, trace_cap)
+    if rc != 0:
+        raise RuntimeError(f"oracle_optimize rc={rc}")
+    sol.trace = trace
+    return sol
