@@ -1,0 +1,846 @@
+// dftpav_api.cu — host side of the C-ABI declared in include/dftpav_b200.h.
+//
+// Host responsibilities (everything else runs in the kernels of dftpav_kernels.cu):
+//   * validation of the reference's preconditions (traj_optimizer.cpp:26-48),
+//   * grouping the batch by problem shape (S, N_0..N_{S-1}); one persistent-kernel launch per shape,
+//   * MinJerkOpt::reset (poly_traj_utils.hpp:880-951): the time-normalised MINCO matrix depends only on the piece
+//     count N, so it is filled and LU-factorised (BandedSystem::factorizeLU, poly_traj_utils.hpp:776-800) ONCE per
+//     distinct N on the host and shipped as a packed table that each CTA stages into shared memory with TMA,
+//   * device memory, H2D/D2H copies, CUDA-event timings.
+// There is no CPU implementation of the solve behind this ABI: without an sm_100 device every call fails.
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <map>
+#include <string>
+#include <vector>
+
+#include "../../include/dftpav_b200.h"
+#include "dftpav_device.cuh"
+
+namespace dftpav {
+cudaError_t launch_solve(bool has_obs, int grid, int block, size_t smem, cudaStream_t st, const ShapeDev& sh,
+                         const ParamsDev& P, const BatchDev& bd, const GroupDev& grp, const OutDev& out,
+                         const HistDev& hist, int* counter);
+cudaError_t launch_eval(bool has_obs, int grid, int block, size_t smem, cudaStream_t st, const ShapeDev& sh,
+                        const ParamsDev& P, const BatchDev& bd, const GroupDev& grp, const double* x, double* f,
+                        double* g, double* coeffs, double* dT);
+cudaError_t launch_layout(int grid, int block, cudaStream_t st, const ShapeDev& sh, const int* prob_id, int count,
+                          const long long* samp_base, const long long* plane_ptr, int uniform_H, const double* raw,
+                          double* soa);
+cudaError_t launch_prepare(int grid, int block, cudaStream_t st, const ShapeDev& sh, const ParamsDev& P,
+                           const int* prob_id, int count, const int* seg_base, const int* singul, const double* ini_raw,
+                           const double* fin_raw, const double* init_T, const long long* inner_base,
+                           const double* inner_pts, double* ini, double* fin, double* x0, int n_stride);
+int ws_doubles_host(int rows, int npad);
+}  // namespace dftpav
+
+using namespace dftpav;
+
+namespace {
+
+// ---------------------------------------------------------------------------------------------
+// MinJerkOpt::reset on the host: banded matrix fill + LU (poly_traj_utils.hpp:776-800, 897-948)
+// ---------------------------------------------------------------------------------------------
+struct BandLU {
+  int n;
+  std::vector<double> d;  // band storage d[(i-j+6)*n + j], lower = upper = 6
+  explicit BandLU(int N) : n(6 * N), d((size_t)13 * 6 * N, 0.0) {
+    auto A = [&](int i, int j) -> double& { return d[(size_t)(i - j + 6) * n + j]; };
+    A(0, 0) = 1.0;
+    A(1, 1) = 1.0;
+    A(2, 2) = 2.0;
+    for (int i = 0; i < N - 1; i++) {
+      const int r = 6 * i;
+      A(r + 3, r + 3) = 6.0, A(r + 3, r + 4) = 24.0, A(r + 3, r + 5) = 60.0, A(r + 3, r + 9) = -6.0;
+      A(r + 4, r + 4) = 24.0, A(r + 4, r + 5) = 120.0, A(r + 4, r + 10) = -24.0;
+      for (int k = 0; k < 6; k++) A(r + 5, r + k) = 1.0;
+      for (int k = 0; k < 6; k++) A(r + 6, r + k) = 1.0;
+      A(r + 6, r + 6) = -1.0;
+      A(r + 7, r + 1) = 1.0, A(r + 7, r + 2) = 2.0, A(r + 7, r + 3) = 3.0, A(r + 7, r + 4) = 4.0, A(r + 7, r + 5) = 5.0;
+      A(r + 7, r + 7) = -1.0;
+      A(r + 8, r + 2) = 2.0, A(r + 8, r + 3) = 6.0, A(r + 8, r + 4) = 12.0, A(r + 8, r + 5) = 20.0;
+      A(r + 8, r + 8) = -2.0;
+    }
+    const int m = n;
+    for (int k = 0; k < 6; k++) A(m - 3, m - 6 + k) = 1.0;
+    A(m - 2, m - 5) = 1.0, A(m - 2, m - 4) = 2.0, A(m - 2, m - 3) = 3.0, A(m - 2, m - 2) = 4.0, A(m - 2, m - 1) = 5.0;
+    A(m - 1, m - 4) = 2.0, A(m - 1, m - 3) = 6.0, A(m - 1, m - 2) = 12.0, A(m - 1, m - 1) = 20.0;
+    // factorizeLU: no pivoting, exact zeros skipped
+    for (int k = 0; k <= n - 2; k++) {
+      const int iM = std::min(k + 6, n - 1);
+      double cVl = A(k, k);
+      for (int i = k + 1; i <= iM; i++)
+        if (A(i, k) != 0.0) A(i, k) /= cVl;
+      const int jM = std::min(k + 6, n - 1);
+      for (int j = k + 1; j <= jM; j++) {
+        cVl = A(k, j);
+        if (cVl != 0.0)
+          for (int i = k + 1; i <= iM; i++)
+            if (A(i, k) != 0.0) A(i, j) -= A(i, k) * cVl;
+      }
+    }
+  }
+  // packed column table: C[j][0..12] = band rows 0..12 of column j, C[j][13] = 1/U(j,j)
+  void pack(double* C) const {
+    for (int j = 0; j < n; j++) {
+      double* Cj = C + (size_t)j * kLuLd;
+      for (int r = 0; r < 13; r++) {
+        const int i = j + r - 6;  // matrix row of band row r
+        Cj[r] = (i >= 0 && i < n) ? d[(size_t)r * n + j] : 0.0;
+      }
+      Cj[13] = 1.0 / Cj[6];
+      Cj[14] = 0.0;
+      Cj[15] = 0.0;
+    }
+  }
+};
+
+struct DevBuf {
+  void* p = nullptr;
+  size_t cap = 0;
+  cudaError_t ensure(size_t bytes) {
+    if (bytes <= cap) return cudaSuccess;
+    if (p) cudaFree(p);
+    p = nullptr;
+    cap = 0;
+    cudaError_t e = cudaMalloc(&p, bytes ? bytes : 1);
+    if (e == cudaSuccess) cap = bytes;
+    return e;
+  }
+  void release() {
+    if (p) cudaFree(p);
+    p = nullptr;
+    cap = 0;
+  }
+  template <class T>
+  T* as() const { return reinterpret_cast<T*>(p); }
+};
+
+struct Group {
+  ShapeDev sh;
+  std::vector<int> probs;
+  DevBuf d_prob_id, d_planes, d_lu;
+  int warps = 0, grid = 0;
+  size_t smem = 0;
+};
+
+inline int samples_of(int N, int K, int Kd) { return (N - 2) * (K + 1) + 2 * (Kd + 1); }
+
+}  // namespace
+
+struct dftpav_handle {
+  dftpav_params prm;
+  ParamsDev pd;
+  int device = 0;
+  int num_sms = 0;
+  size_t smem_optin = 0;
+  cudaStream_t own_stream = nullptr, stream = nullptr;
+  cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
+  std::string err;
+  bool uploaded = false, solved = false, has_obs = false;
+  dftpav_dims dims{};
+  dftpav_stats stats{};
+  std::vector<Group*> groups;
+  // host copies needed later
+  std::vector<int> h_seg_ptr, h_piece_num, h_n, h_evalbytes;
+  // device buffers
+  DevBuf seg_base, t_now, obs_ptr, obs_idx, singul, ini_raw, fin_raw, ini, fin, init_T, inner_base, inner_pts, samp_base,
+      plane_ptr, planes_raw, obs_start, obs_dur, obs_piece_ptr, obs_piece_dur, obs_coeffs, x0, xin, fout, gout;
+  DevBuf o_x, o_cost, o_status, o_success, o_iters, o_evals, o_coeffs, o_dT, counter;
+  DevBuf hist_s, hist_y, hist_ys, hist_alpha;
+  int hist_ld = 0, hist_slots = 0;
+  int upload_launches = 0;
+  BatchDev bd{};
+};
+
+namespace {
+
+int fail(dftpav_handle* h, int code, const std::string& msg) {
+  if (h) h->err = msg;
+  return code;
+}
+
+#define CU_TRY(h, call)                                                                                  \
+  do {                                                                                                   \
+    cudaError_t e__ = (call);                                                                            \
+    if (e__ != cudaSuccess)                                                                              \
+      return fail(h, DFTPAV_ERR_CUDA, std::string(#call) + ": " + cudaGetErrorString(e__));              \
+  } while (0)
+
+// Validation shared by dftpav_batch_dims / upload.  Returns 0 or an error; fills dims and (optionally) bad index.
+int validate(const dftpav_params* prm, const dftpav_batch* b, dftpav_dims* dims, std::string* why) {
+  auto bad = [&](int code, const std::string& s) {
+    if (why) *why = s;
+    return code;
+  };
+  if (!prm || !b) return bad(DFTPAV_ERR_INVALID_ARG, "null params or batch");
+  if (prm->abi_version != DFTPAV_ABI_VERSION) return bad(DFTPAV_ERR_INVALID_ARG, "abi_version mismatch");
+  if (b->B < 0) return bad(DFTPAV_ERR_INVALID_ARG, "B < 0");
+  if (b->B > 0 && (!b->seg_ptr || !b->piece_num || !b->singul || !b->ini_state || !b->fin_state || !b->init_T ||
+                   !b->inner_pts || !b->planes))
+    return bad(DFTPAV_ERR_INVALID_ARG, "null array in batch");
+  if (prm->traj_resolution < 1 || prm->des_traj_resolution < 1) return bad(DFTPAV_ERR_INVALID_ARG, "resolution < 1");
+  if (prm->lbfgs_past < 0 || prm->lbfgs_past > 8) return bad(DFTPAV_ERR_UNSUPPORTED, "lbfgs_past must be in [0,8]");
+  if (prm->lbfgs_mem_size < 1) return bad(DFTPAV_ERR_INVALID_ARG, "lbfgs_mem_size < 1");
+  if (!b->plane_cnt && b->uniform_H < 0) return bad(DFTPAV_ERR_INVALID_ARG, "uniform_H < 0");
+  int n_stride = 0, row_stride = 0;
+  long long samples = 0;
+  for (int p = 0; p < b->B; p++) {
+    const int g0 = b->seg_ptr[p], g1 = b->seg_ptr[p + 1];
+    const int S = g1 - g0;
+    if (S < 1) return bad(DFTPAV_ERR_INVALID_ARG, "problem " + std::to_string(p) + ": no segments");
+    if (S > kMaxSeg) return bad(DFTPAV_ERR_UNSUPPORTED, "problem " + std::to_string(p) + ": more than 4 gear segments");
+    int n = 0, rows = 0;
+    for (int g = g0; g < g1; g++) {
+      const int N = b->piece_num[g];
+      if (N < 2)  // traj_optimizer.cpp:38-41 "There is only a piece?"
+        return bad(DFTPAV_ERR_BAD_INPUT, "problem " + std::to_string(p) + ": segment with fewer than 2 pieces");
+      if (N > kMaxPieces) return bad(DFTPAV_ERR_UNSUPPORTED, "problem " + std::to_string(p) + ": more than 64 pieces");
+      if (!(b->init_T[g] >= prm->mini_T))  // traj_optimizer.cpp:30-33
+        return bad(DFTPAV_ERR_BAD_INPUT, "problem " + std::to_string(p) + ": initTs < mini_T");
+      n += 2 * (N - 1);
+      rows += 6 * N;
+      samples += samples_of(N, prm->traj_resolution, prm->des_traj_resolution);
+    }
+    n += S + 3 * (S - 1);
+    n_stride = std::max(n_stride, n);
+    row_stride = std::max(row_stride, rows);
+  }
+  if (dims) {
+    dims->B = b->B;
+    dims->n_stride = n_stride;
+    dims->row_stride = row_stride;
+    dims->seg_total = b->B ? b->seg_ptr[b->B] : 0;
+    dims->sample_total = samples;
+  }
+  return DFTPAV_OK;
+}
+
+void fill_params_dev(const dftpav_params& p, ParamsDev& d) {
+  d.wei_obs = p.wei_obs;
+  d.wei_surround = p.wei_surround;
+  d.wei_feas = p.wei_feas;
+  d.wei_time = p.wei_time;
+  d.surround_clearance = p.surround_clearance;
+  d.d_min = p.surround_clearance + std::log(8.0) / p.lse_alpha;  // traj_optimizer.cpp:1336
+  d.max_vel[0] = p.max_forward_vel, d.max_vel[1] = p.max_backward_vel;
+  d.max_cur[0] = p.max_forward_cur, d.max_cur[1] = p.max_backward_cur;
+  d.max_acc[0] = p.max_forward_acc, d.max_acc[1] = p.max_backward_acc;
+  d.non_sinv = p.non_sinv;
+  d.mini_T = p.mini_T;
+  d.help_eps = p.help_eps;
+  d.min_speed = p.min_speed;
+  d.smooth_eps = p.smooth_eps;
+  d.cur_weight_scale = p.cur_weight_scale;
+  d.lse_alpha = p.lse_alpha;
+  // vehicle box inflated by 2*half_margin (traj_optimizer.cpp:1749-1768), vertices clockwise from front-left
+  const double width = p.veh_width + 2 * p.half_margin, length = p.veh_length + 2 * p.half_margin;
+  d.cull_dist = length * p.obs_cull_factor;
+  d.cost_limit = p.cost_limit;
+  d.le[0][0] = p.veh_d_cr + length / 2.0, d.le[0][1] = width / 2.0;
+  d.le[1][0] = p.veh_d_cr + length / 2.0, d.le[1][1] = -width / 2.0;
+  d.le[2][0] = p.veh_d_cr - length / 2.0, d.le[2][1] = -width / 2.0;
+  d.le[3][0] = p.veh_d_cr - length / 2.0, d.le[3][1] = width / 2.0;
+  d.gear_opt = p.gear_opt;
+  d.mem_size = p.lbfgs_mem_size;
+  d.past = p.lbfgs_past;
+  d.max_iterations = p.lbfgs_max_iterations;
+  d.max_linesearch = p.lbfgs_max_linesearch;
+  d.delta = p.lbfgs_delta;
+  d.g_epsilon = p.lbfgs_g_epsilon;
+  d.min_step = p.lbfgs_min_step;
+  d.max_step = p.lbfgs_max_step;
+  d.f_dec_coeff = p.lbfgs_f_dec_coeff;
+  d.s_curv_coeff = p.lbfgs_s_curv_coeff;
+  d.cautious_factor = p.lbfgs_cautious_factor;
+  d.machine_prec = p.lbfgs_machine_prec;
+}
+
+void free_groups(dftpav_handle* h) {
+  for (Group* g : h->groups) {
+    g->d_prob_id.release();
+    g->d_planes.release();
+    g->d_lu.release();
+    delete g;
+  }
+  h->groups.clear();
+}
+
+// host twin of prepare_states_kernel's clamp (traj_optimizer.cpp:55-76)
+void clamp_state(double* st, double max_vel, double max_acc) {
+  for (int c = 2; c <= 4; c += 2) {
+    const double lim = (c == 2) ? max_vel : max_acc;
+    const double vx = st[c], vy = st[c + 1];
+    const double z = vx * vx + vy * vy;
+    if (std::sqrt(z) >= lim) {
+      double nx = vx, ny = vy;
+      if (z > 0.0) {
+        const double sz = std::sqrt(z);
+        nx = vx / sz;
+        ny = vy / sz;
+      }
+      st[c] = nx * (lim - 1.0e-2);
+      st[c + 1] = ny * (lim - 1.0e-2);
+    }
+  }
+}
+
+}  // namespace
+
+extern "C" {
+
+const char* dftpav_version(void) { return "dftpav_b200 0.1 (sm_100a, abi 1)"; }
+
+void dftpav_default_params(dftpav_params* p) {
+  if (!p) return;
+  std::memset(p, 0, sizeof(*p));
+  p->abi_version = DFTPAV_ABI_VERSION;
+  p->traj_resolution = 16;
+  p->des_traj_resolution = 32;
+  p->gear_opt = 1;
+  p->wei_obs = 1000.0;
+  p->wei_surround = 5000.0;
+  p->wei_feas = 2500.0;
+  p->wei_time = 500.0;
+  p->surround_clearance = 0.4;
+  p->half_margin = 0.15;
+  p->veh_width = 1.90;
+  p->veh_length = 4.88;
+  p->veh_d_cr = 1.015;
+  p->max_forward_vel = 5.0;
+  p->max_backward_vel = 2.0;
+  p->max_forward_cur = 1.0;
+  p->max_backward_cur = 1.0;
+  p->max_forward_acc = 8.0;
+  p->max_backward_acc = 4.0;
+  p->non_sinv = 0.24;
+  p->mini_T = 0.1;
+  p->help_eps = 0.0;
+  p->min_speed = 1.0e-4;
+  p->smooth_eps = 1.0e-4;
+  p->cur_weight_scale = 10.0;
+  p->lse_alpha = 100.0;
+  p->obs_cull_factor = 1.5;
+  p->cost_limit = 50000.0;
+  p->lbfgs_mem_size = 256;
+  p->lbfgs_past = 3;
+  p->lbfgs_max_iterations = 12000;
+  p->lbfgs_max_linesearch = 64;
+  p->lbfgs_delta = 1.0e-4;
+  p->lbfgs_g_epsilon = 1.0e-16;
+  p->lbfgs_min_step = 1.0e-32;
+  p->lbfgs_max_step = 1.0e20;
+  p->lbfgs_f_dec_coeff = 1.0e-4;
+  p->lbfgs_s_curv_coeff = 0.9;
+  p->lbfgs_cautious_factor = 1.0e-6;
+  p->lbfgs_machine_prec = 1.0e-16;
+}
+
+int dftpav_batch_dims(const dftpav_params* prm, const dftpav_batch* batch, dftpav_dims* dims) {
+  return validate(prm, batch, dims, nullptr);
+}
+
+int dftpav_initial_x(const dftpav_params* prm, const dftpav_batch* b, double* x0) {
+  dftpav_dims dims;
+  int rc = validate(prm, b, &dims, nullptr);
+  if (rc) return rc;
+  if (!x0) return DFTPAV_ERR_INVALID_ARG;
+  long long inner = 0;
+  for (int p = 0; p < b->B; p++) {
+    double* x = x0 + (size_t)p * dims.n_stride;
+    std::fill(x, x + dims.n_stride, 0.0);
+    const int g0 = b->seg_ptr[p], g1 = b->seg_ptr[p + 1], S = g1 - g0;
+    int off = 0;
+    for (int g = g0; g < g1; g++) {
+      const int np = 2 * (b->piece_num[g] - 1);
+      std::memcpy(x + off, b->inner_pts + inner, sizeof(double) * np);
+      off += np;
+      inner += np;
+    }
+    for (int s = 0; s < S; s++) {  // RealT2VirtualT, traj_optimizer.cpp:361-369
+      const double RT = b->init_T[g0 + s], mini_T = prm->mini_T;
+      x[off + s] = RT > 1.0 + mini_T ? (std::sqrt(2.0 * RT - 1.0 - 2 * mini_T) - 1.0)
+                                     : (1.0 - std::sqrt(2.0 / (RT - mini_T) - 1.0));
+    }
+    off += S;
+    for (int s = 0; s < S - 1; s++) {
+      double st[6];
+      std::memcpy(st, b->fin_state + 6 * (g0 + s), sizeof(st));
+      const bool fwd = b->singul[g0 + s] > 0;
+      clamp_state(st, fwd ? prm->max_forward_vel : prm->max_backward_vel, fwd ? prm->max_forward_acc : prm->max_backward_acc);
+      x[off + 2 * s] = st[0];
+      x[off + 2 * s + 1] = st[1];
+      x[off + 2 * (S - 1) + s] = std::atan2(st[3], st[2]);
+    }
+  }
+  return DFTPAV_OK;
+}
+
+int dftpav_create(const dftpav_params* prm, int device, dftpav_handle** out) {
+  if (!prm || !out) return DFTPAV_ERR_INVALID_ARG;
+  *out = nullptr;
+  if (prm->abi_version != DFTPAV_ABI_VERSION) return DFTPAV_ERR_INVALID_ARG;
+  int count = 0;
+  if (cudaGetDeviceCount(&count) != cudaSuccess || count == 0) return DFTPAV_ERR_NO_DEVICE;
+  if (device < 0) {
+    if (cudaGetDevice(&device) != cudaSuccess) return DFTPAV_ERR_NO_DEVICE;
+  }
+  if (device >= count) return DFTPAV_ERR_NO_DEVICE;
+  cudaDeviceProp prop;
+  if (cudaGetDeviceProperties(&prop, device) != cudaSuccess) return DFTPAV_ERR_NO_DEVICE;
+  if (prop.major != 10) return DFTPAV_ERR_NO_DEVICE;  // kernels are built for sm_100a only
+  dftpav_handle* h = new dftpav_handle();
+  h->prm = *prm;
+  fill_params_dev(*prm, h->pd);
+  h->device = device;
+  h->num_sms = prop.multiProcessorCount;
+  h->smem_optin = prop.sharedMemPerBlockOptin;
+  if (cudaSetDevice(device) != cudaSuccess || cudaStreamCreateWithFlags(&h->own_stream, cudaStreamNonBlocking) != cudaSuccess) {
+    delete h;
+    return DFTPAV_ERR_CUDA;
+  }
+  h->stream = h->own_stream;
+  for (auto& e : h->ev) cudaEventCreate(&e);
+  *out = h;
+  return DFTPAV_OK;
+}
+
+int dftpav_destroy(dftpav_handle* h) {
+  if (!h) return DFTPAV_ERR_INVALID_ARG;
+  cudaSetDevice(h->device);
+  cudaStreamSynchronize(h->stream);
+  free_groups(h);
+  DevBuf* bufs[] = {&h->seg_base, &h->t_now, &h->obs_ptr, &h->obs_idx, &h->singul, &h->ini_raw, &h->fin_raw, &h->ini,
+                    &h->fin, &h->init_T, &h->inner_base, &h->inner_pts, &h->samp_base, &h->plane_ptr, &h->planes_raw,
+                    &h->obs_start, &h->obs_dur, &h->obs_piece_ptr, &h->obs_piece_dur, &h->obs_coeffs, &h->x0, &h->xin,
+                    &h->fout, &h->gout, &h->o_x, &h->o_cost, &h->o_status, &h->o_success, &h->o_iters, &h->o_evals,
+                    &h->o_coeffs, &h->o_dT, &h->counter, &h->hist_s, &h->hist_y, &h->hist_ys, &h->hist_alpha};
+  for (DevBuf* b : bufs) b->release();
+  for (auto& e : h->ev)
+    if (e) cudaEventDestroy(e);
+  if (h->own_stream) cudaStreamDestroy(h->own_stream);
+  delete h;
+  return DFTPAV_OK;
+}
+
+int dftpav_set_stream(dftpav_handle* h, void* cuda_stream) {
+  if (!h) return DFTPAV_ERR_INVALID_ARG;
+  h->stream = cuda_stream ? reinterpret_cast<cudaStream_t>(cuda_stream) : h->own_stream;
+  return DFTPAV_OK;
+}
+
+int dftpav_get_dims(const dftpav_handle* h, dftpav_dims* dims) {
+  if (!h || !dims) return DFTPAV_ERR_INVALID_ARG;
+  if (!h->uploaded) return DFTPAV_ERR_STATE;
+  *dims = h->dims;
+  return DFTPAV_OK;
+}
+
+int dftpav_upload_batch(dftpav_handle* h, const dftpav_batch* b) {
+  if (!h) return DFTPAV_ERR_INVALID_ARG;
+  std::string why;
+  dftpav_dims dims;
+  int rc = validate(&h->prm, b, &dims, &why);
+  if (rc) return fail(h, rc, why);
+  CU_TRY(h, cudaSetDevice(h->device));
+  cudaStream_t st = h->stream;
+  h->uploaded = false;
+  h->solved = false;
+  free_groups(h);
+  h->dims = dims;
+  std::memset(&h->stats, 0, sizeof(h->stats));
+  CU_TRY(h, cudaEventRecord(h->ev[0], st));
+  const int B = b->B, G = dims.seg_total;
+  const int K = h->prm.traj_resolution, Kd = h->prm.des_traj_resolution;
+  const long long Q = dims.sample_total;
+  long long h2d = 0;
+
+  // ---- per-problem prefixes and shape groups
+  std::vector<int> seg_base(B);
+  std::vector<long long> samp_base(B), inner_base(B);
+  std::map<std::vector<int>, Group*> by_shape;
+  long long samp = 0, inner = 0;
+  h->h_seg_ptr.assign(b->seg_ptr, b->seg_ptr + B + 1);
+  h->h_piece_num.assign(b->piece_num, b->piece_num + G);
+  h->h_n.resize(B);
+  for (int p = 0; p < B; p++) {
+    const int g0 = b->seg_ptr[p], g1 = b->seg_ptr[p + 1];
+    seg_base[p] = g0;
+    samp_base[p] = samp;
+    inner_base[p] = inner;
+    std::vector<int> key(b->piece_num + g0, b->piece_num + g1);
+    int n = 0;
+    for (int g = g0; g < g1; g++) {
+      samp += samples_of(b->piece_num[g], K, Kd);
+      inner += 2LL * (b->piece_num[g] - 1);
+      n += 2 * (b->piece_num[g] - 1);
+    }
+    n += (g1 - g0) + 3 * (g1 - g0 - 1);
+    h->h_n[p] = n;
+    Group*& grp = by_shape[key];
+    if (!grp) {
+      grp = new Group();
+      h->groups.push_back(grp);
+    }
+    grp->probs.push_back(p);
+  }
+  // plane prefix (only for ragged corridors)
+  std::vector<long long> plane_ptr;
+  long long total_planes;
+  if (b->plane_cnt) {
+    plane_ptr.resize(Q + 1);
+    plane_ptr[0] = 0;
+    for (long long q = 0; q < Q; q++) {
+      if (b->plane_cnt[q] < 0) return fail(h, DFTPAV_ERR_INVALID_ARG, "negative plane_cnt");
+      plane_ptr[q + 1] = plane_ptr[q] + b->plane_cnt[q];
+    }
+    total_planes = plane_ptr[Q];
+  } else {
+    total_planes = Q * b->uniform_H;
+  }
+  // algorithmic bytes per evaluation of each problem
+  h->h_evalbytes.resize(B);
+  for (int p = 0; p < B; p++) {
+    const int g0 = b->seg_ptr[p], g1 = b->seg_ptr[p + 1];
+    long long q0 = samp_base[p], q1 = (p + 1 < B) ? samp_base[p + 1] : Q;
+    long long planes = b->plane_cnt ? plane_ptr[q1] - plane_ptr[q0] : (q1 - q0) * b->uniform_H;
+    long long obs = 0;
+    if (b->obs_ptr)
+      for (int k = b->obs_ptr[p]; k < b->obs_ptr[p + 1]; k++) {
+        const int u = b->obs_idx[k];
+        obs += b->obs_piece_ptr[u + 1] - b->obs_piece_ptr[u];
+      }
+    h->h_evalbytes[p] = (int)(16LL * h->h_n[p] + 32LL * planes + 96LL * (g1 - g0) + 104LL * obs);
+  }
+
+  // ---- raw uploads
+  auto up = [&](DevBuf& buf, const void* src, size_t bytes) -> cudaError_t {
+    cudaError_t e = buf.ensure(bytes);
+    if (e != cudaSuccess) return e;
+    if (bytes) e = cudaMemcpyAsync(buf.p, src, bytes, cudaMemcpyHostToDevice, st);
+    h2d += (long long)bytes;
+    return e;
+  };
+  CU_TRY(h, up(h->seg_base, seg_base.data(), sizeof(int) * B));
+  CU_TRY(h, up(h->samp_base, samp_base.data(), sizeof(long long) * B));
+  CU_TRY(h, up(h->inner_base, inner_base.data(), sizeof(long long) * B));
+  CU_TRY(h, up(h->singul, b->singul, sizeof(int) * G));
+  CU_TRY(h, up(h->ini_raw, b->ini_state, sizeof(double) * 6 * G));
+  CU_TRY(h, up(h->fin_raw, b->fin_state, sizeof(double) * 6 * G));
+  CU_TRY(h, up(h->init_T, b->init_T, sizeof(double) * G));
+  CU_TRY(h, up(h->inner_pts, b->inner_pts, sizeof(double) * inner));
+  CU_TRY(h, up(h->planes_raw, b->planes, sizeof(double) * 4 * total_planes));
+  if (b->plane_cnt) CU_TRY(h, up(h->plane_ptr, plane_ptr.data(), sizeof(long long) * (Q + 1)));
+  std::vector<double> tnow(B, 0.0);
+  if (b->t_now) std::copy(b->t_now, b->t_now + B, tnow.begin());
+  CU_TRY(h, up(h->t_now, tnow.data(), sizeof(double) * B));
+  h->has_obs = (b->obs_ptr != nullptr) && B > 0 && b->obs_ptr[B] > 0;
+  if (h->has_obs) {
+    const int U = b->n_obs_pool;
+    if (U <= 0 || !b->obs_idx || !b->obs_start_time || !b->obs_duration || !b->obs_piece_ptr || !b->obs_piece_dur ||
+        !b->obs_coeffs)
+      return fail(h, DFTPAV_ERR_INVALID_ARG, "obstacle arrays missing");
+    const int NP = b->obs_piece_ptr[U];
+    CU_TRY(h, up(h->obs_ptr, b->obs_ptr, sizeof(int) * (B + 1)));
+    CU_TRY(h, up(h->obs_idx, b->obs_idx, sizeof(int) * b->obs_ptr[B]));
+    CU_TRY(h, up(h->obs_start, b->obs_start_time, sizeof(double) * U));
+    CU_TRY(h, up(h->obs_dur, b->obs_duration, sizeof(double) * U));
+    CU_TRY(h, up(h->obs_piece_ptr, b->obs_piece_ptr, sizeof(int) * (U + 1)));
+    CU_TRY(h, up(h->obs_piece_dur, b->obs_piece_dur, sizeof(double) * NP));
+    CU_TRY(h, up(h->obs_coeffs, b->obs_coeffs, sizeof(double) * 12 * NP));
+  }
+  CU_TRY(h, h->ini.ensure(sizeof(double) * 6 * G));
+  CU_TRY(h, h->fin.ensure(sizeof(double) * 6 * G));
+  CU_TRY(h, h->x0.ensure(sizeof(double) * (size_t)B * dims.n_stride));
+  // outputs
+  CU_TRY(h, h->o_x.ensure(sizeof(double) * (size_t)B * dims.n_stride));
+  CU_TRY(h, h->o_cost.ensure(sizeof(double) * B));
+  CU_TRY(h, h->o_status.ensure(sizeof(int) * B));
+  CU_TRY(h, h->o_success.ensure(sizeof(int) * B));
+  CU_TRY(h, h->o_iters.ensure(sizeof(int) * B));
+  CU_TRY(h, h->o_evals.ensure(sizeof(int) * B));
+  CU_TRY(h, h->o_coeffs.ensure(sizeof(double) * (size_t)B * dims.row_stride * 2));
+  CU_TRY(h, h->o_dT.ensure(sizeof(double) * G));
+  CU_TRY(h, h->counter.ensure(sizeof(int) * 64));
+
+  // ---- per-group tables, layout + state kernels
+  int max_slots = 0, max_npad = 0;
+  int launches = 0;
+  for (Group* grp : h->groups) {
+    ShapeDev& sh = grp->sh;
+    std::memset(&sh, 0, sizeof(sh));
+    const int p0 = grp->probs[0];
+    const int g0 = b->seg_ptr[p0], g1 = b->seg_ptr[p0 + 1];
+    sh.S = g1 - g0;
+    sh.K = K;
+    sh.Kd = Kd;
+    const int td = (Kd + kTile - 1) / kTile, tk = (K + kTile - 1) / kTile;
+    std::map<int, int> lu_of_N;
+    int rows = 0, var = 0, sampoff = 0, luoff = 0, pieces = 0;
+    for (int s = 0; s < sh.S; s++) {
+      const int N = b->piece_num[g0 + s];
+      sh.N[s] = N;
+      sh.row0[s] = rows;
+      sh.var0[s] = var;
+      sh.samp0[s] = sampoff;
+      sh.ntile[s] = 2 * td + (N - 2) * tk;
+      rows += 6 * N;
+      var += 2 * (N - 1);
+      pieces += N;
+      int store = sh.ntile[s] * kTile + N;
+      store = (store + kTile - 1) / kTile * kTile;
+      sampoff += store;
+      auto it = lu_of_N.find(N);
+      if (it == lu_of_N.end()) {
+        lu_of_N[N] = luoff;
+        sh.lu_off[s] = luoff;
+        luoff += 6 * N * kLuLd;
+      } else {
+        sh.lu_off[s] = it->second;
+      }
+    }
+    sh.rows = rows;
+    sh.pieces = pieces;
+    sh.n = var + sh.S + 3 * (sh.S - 1);
+    sh.npad = (sh.n + 3) / 4 * 4;
+    sh.Mpad = sampoff;
+    sh.lu_doubles = luoff;
+    sh.ws_doubles = ws_doubles_host(sh.rows, sh.npad);
+    // padded plane count of the group
+    int Hmax = 0;
+    if (b->plane_cnt) {
+      for (int p : grp->probs) {
+        long long q0 = samp_base[p], q1 = (p + 1 < B) ? samp_base[p + 1] : Q;
+        for (long long q = q0; q < q1; q++) Hmax = std::max(Hmax, (int)b->plane_cnt[q]);
+      }
+    } else {
+      Hmax = b->uniform_H;
+    }
+    sh.H = Hmax;
+    // LU block
+    std::vector<double> lu((size_t)luoff, 0.0);
+    for (auto& kv : lu_of_N) BandLU(kv.first).pack(lu.data() + kv.second);
+    CU_TRY(h, up(grp->d_lu, lu.data(), sizeof(double) * lu.size()));
+    CU_TRY(h, up(grp->d_prob_id, grp->probs.data(), sizeof(int) * grp->probs.size()));
+    const int count = (int)grp->probs.size();
+    const size_t plane_bytes = sizeof(double) * (size_t)count * std::max(1, sh.H) * 4 * sh.Mpad;
+    CU_TRY(h, grp->d_planes.ensure(plane_bytes));
+    // launch configuration
+    const size_t ws_bytes = sizeof(double) * sh.ws_doubles, lu_bytes = sizeof(double) * sh.lu_doubles;
+    const size_t cap = h->smem_optin > 2048 ? h->smem_optin - 1024 : 0;
+    if (lu_bytes + ws_bytes > cap) return fail(h, DFTPAV_ERR_UNSUPPORTED, "problem shape does not fit in shared memory");
+    int W = (int)std::min<size_t>(16, (cap - lu_bytes) / ws_bytes);
+    const int want = (count + h->num_sms - 1) / h->num_sms;
+    W = std::max(1, std::min(W, want));
+    grp->warps = W;
+    grp->smem = lu_bytes + ws_bytes * W;
+    grp->grid = std::min((count + W - 1) / W, h->num_sms);
+    max_slots = std::max(max_slots, grp->grid * W);
+    max_npad = std::max(max_npad, sh.npad);
+    // kernels
+    const long long total = (long long)count * sh.Mpad;
+    const int lgrid = (int)std::min<long long>((total + 255) / 256, 65535LL * 4);
+    CU_TRY(h, launch_layout(std::max(1, lgrid), 256, st, sh, grp->d_prob_id.as<int>(), count, h->samp_base.as<long long>(),
+                            b->plane_cnt ? h->plane_ptr.as<long long>() : nullptr, b->uniform_H,
+                            h->planes_raw.as<double>(), grp->d_planes.as<double>()));
+    CU_TRY(h, launch_prepare((count + 127) / 128, 128, st, sh, h->pd, grp->d_prob_id.as<int>(), count,
+                             h->seg_base.as<int>(), h->singul.as<int>(), h->ini_raw.as<double>(),
+                             h->fin_raw.as<double>(), h->init_T.as<double>(), h->inner_base.as<long long>(),
+                             h->inner_pts.as<double>(), h->ini.as<double>(), h->fin.as<double>(), h->x0.as<double>(),
+                             dims.n_stride));
+    launches += 2;
+  }
+  // L-BFGS history ring per resident warp
+  h->hist_ld = max_npad;
+  h->hist_slots = max_slots;
+  const size_t hbytes = sizeof(double) * (size_t)max_slots * h->prm.lbfgs_mem_size * max_npad;
+  CU_TRY(h, h->hist_s.ensure(hbytes));
+  CU_TRY(h, h->hist_y.ensure(hbytes));
+  CU_TRY(h, h->hist_ys.ensure(sizeof(double) * (size_t)max_slots * h->prm.lbfgs_mem_size));
+  CU_TRY(h, h->hist_alpha.ensure(sizeof(double) * (size_t)max_slots * h->prm.lbfgs_mem_size));
+
+  BatchDev& bd = h->bd;
+  bd.seg_base = h->seg_base.as<int>();
+  bd.t_now = h->t_now.as<double>();
+  bd.obs_ptr = h->has_obs ? h->obs_ptr.as<int>() : nullptr;
+  bd.obs_idx = h->obs_idx.as<int>();
+  bd.singul = h->singul.as<int>();
+  bd.ini = h->ini.as<double>();
+  bd.fin = h->fin.as<double>();
+  bd.obs_start = h->obs_start.as<double>();
+  bd.obs_dur = h->obs_dur.as<double>();
+  bd.obs_piece_ptr = h->obs_piece_ptr.as<int>();
+  bd.obs_piece_dur = h->obs_piece_dur.as<double>();
+  bd.obs_coeffs = h->obs_coeffs.as<double>();
+  bd.x0 = h->x0.as<double>();
+  bd.n_stride = dims.n_stride;
+  bd.row_stride = dims.row_stride;
+
+  CU_TRY(h, cudaEventRecord(h->ev[1], st));
+  CU_TRY(h, cudaStreamSynchronize(st));  // host staging vectors above go out of scope
+  float ms = 0.f;
+  cudaEventElapsedTime(&ms, h->ev[0], h->ev[1]);
+  h->stats.upload_ms = ms;
+  h->stats.h2d_bytes = h2d;
+  h->upload_launches = launches;
+  h->stats.kernel_launches = launches;
+  h->stats.n_shapes = (int)h->groups.size();
+  h->uploaded = true;
+  return DFTPAV_OK;
+}
+
+int dftpav_eval(dftpav_handle* h, const double* x, double* f, double* g) {
+  if (!h || !x || !f || !g) return DFTPAV_ERR_INVALID_ARG;
+  if (!h->uploaded) return fail(h, DFTPAV_ERR_STATE, "dftpav_eval before dftpav_upload_batch");
+  CU_TRY(h, cudaSetDevice(h->device));
+  cudaStream_t st = h->stream;
+  const int B = h->dims.B, ns = h->dims.n_stride;
+  const size_t xb = sizeof(double) * (size_t)B * ns;
+  CU_TRY(h, h->xin.ensure(xb));
+  CU_TRY(h, h->gout.ensure(xb));
+  CU_TRY(h, h->fout.ensure(sizeof(double) * B));
+  CU_TRY(h, cudaMemcpyAsync(h->xin.p, x, xb, cudaMemcpyHostToDevice, st));
+  CU_TRY(h, cudaEventRecord(h->ev[0], st));
+  int launches = 0;
+  for (Group* grp : h->groups) {
+    GroupDev gd;
+    gd.prob_id = grp->d_prob_id.as<int>();
+    gd.count = (int)grp->probs.size();
+    gd.planes = grp->d_planes.as<double>();
+    gd.lu = grp->d_lu.as<double>();
+    CU_TRY(h, launch_eval(h->has_obs, grp->grid, 32 * grp->warps, grp->smem, st, grp->sh, h->pd, h->bd, gd,
+                          h->xin.as<double>(), h->fout.as<double>(), h->gout.as<double>(), h->o_coeffs.as<double>(),
+                          h->o_dT.as<double>()));
+    launches++;
+  }
+  CU_TRY(h, cudaEventRecord(h->ev[1], st));
+  CU_TRY(h, cudaMemcpyAsync(f, h->fout.p, sizeof(double) * B, cudaMemcpyDeviceToHost, st));
+  CU_TRY(h, cudaMemcpyAsync(g, h->gout.p, xb, cudaMemcpyDeviceToHost, st));
+  CU_TRY(h, cudaStreamSynchronize(st));
+  float ms = 0.f;
+  cudaEventElapsedTime(&ms, h->ev[0], h->ev[1]);
+  h->stats.solve_ms = ms;
+  h->stats.kernel_launches = launches;
+  h->stats.total_evals = B;
+  h->stats.total_iters = 0;
+  long long ab = 0;
+  for (int p = 0; p < B; p++) ab += h->h_evalbytes[p];
+  h->stats.algorithmic_bytes = ab;
+  return DFTPAV_OK;
+}
+
+int dftpav_optimize(dftpav_handle* h) {
+  if (!h) return DFTPAV_ERR_INVALID_ARG;
+  if (!h->uploaded) return fail(h, DFTPAV_ERR_STATE, "dftpav_optimize before dftpav_upload_batch");
+  CU_TRY(h, cudaSetDevice(h->device));
+  cudaStream_t st = h->stream;
+  CU_TRY(h, cudaMemsetAsync(h->counter.p, 0, sizeof(int) * 64, st));
+  CU_TRY(h, cudaEventRecord(h->ev[0], st));
+  OutDev out;
+  out.x = h->o_x.as<double>();
+  out.cost = h->o_cost.as<double>();
+  out.status = h->o_status.as<int>();
+  out.success = h->o_success.as<int>();
+  out.iters = h->o_iters.as<int>();
+  out.evals = h->o_evals.as<int>();
+  out.coeffs = h->o_coeffs.as<double>();
+  out.piece_dT = h->o_dT.as<double>();
+  HistDev hist;
+  hist.s = h->hist_s.as<double>();
+  hist.y = h->hist_y.as<double>();
+  hist.ys = h->hist_ys.as<double>();
+  hist.alpha = h->hist_alpha.as<double>();
+  hist.ld = h->hist_ld;
+  hist.mem = h->prm.lbfgs_mem_size;
+  int launches = 0, gi = 0;
+  for (Group* grp : h->groups) {
+    if (gi >= 64) return fail(h, DFTPAV_ERR_UNSUPPORTED, "more than 64 distinct shapes in one batch");
+    GroupDev gd;
+    gd.prob_id = grp->d_prob_id.as<int>();
+    gd.count = (int)grp->probs.size();
+    gd.planes = grp->d_planes.as<double>();
+    gd.lu = grp->d_lu.as<double>();
+    CU_TRY(h, launch_solve(h->has_obs, grp->grid, 32 * grp->warps, grp->smem, st, grp->sh, h->pd, h->bd, gd, out, hist,
+                           h->counter.as<int>() + gi));
+    launches++;
+    gi++;
+  }
+  CU_TRY(h, cudaEventRecord(h->ev[1], st));
+  CU_TRY(h, cudaStreamSynchronize(st));
+  float ms = 0.f;
+  cudaEventElapsedTime(&ms, h->ev[0], h->ev[1]);
+  h->stats.solve_ms = ms;
+  h->stats.kernel_launches = h->upload_launches + launches;
+  h->solved = true;
+  return DFTPAV_OK;
+}
+
+int dftpav_download(dftpav_handle* h, const dftpav_result* out) {
+  if (!h || !out) return DFTPAV_ERR_INVALID_ARG;
+  if (!h->solved) return fail(h, DFTPAV_ERR_STATE, "dftpav_download before dftpav_optimize");
+  CU_TRY(h, cudaSetDevice(h->device));
+  cudaStream_t st = h->stream;
+  const int B = h->dims.B, ns = h->dims.n_stride, rs = h->dims.row_stride, G = h->dims.seg_total;
+  long long d2h = 0;
+  CU_TRY(h, cudaEventRecord(h->ev[2], st));
+  auto down = [&](void* dst, const DevBuf& src, size_t bytes) -> cudaError_t {
+    if (!dst || !bytes) return cudaSuccess;
+    d2h += (long long)bytes;
+    return cudaMemcpyAsync(dst, src.p, bytes, cudaMemcpyDeviceToHost, st);
+  };
+  std::vector<int> iters(B), evals(B);
+  CU_TRY(h, down(out->x, h->o_x, sizeof(double) * (size_t)B * ns));
+  CU_TRY(h, down(out->cost, h->o_cost, sizeof(double) * B));
+  CU_TRY(h, down(out->status, h->o_status, sizeof(int) * B));
+  CU_TRY(h, down(out->success, h->o_success, sizeof(int) * B));
+  CU_TRY(h, down(out->coeffs, h->o_coeffs, sizeof(double) * (size_t)B * rs * 2));
+  CU_TRY(h, down(out->piece_dT, h->o_dT, sizeof(double) * G));
+  CU_TRY(h, down(iters.data(), h->o_iters, sizeof(int) * B));
+  CU_TRY(h, down(evals.data(), h->o_evals, sizeof(int) * B));
+  CU_TRY(h, cudaEventRecord(h->ev[3], st));
+  CU_TRY(h, cudaStreamSynchronize(st));
+  if (out->iters) std::copy(iters.begin(), iters.end(), out->iters);
+  if (out->evals) std::copy(evals.begin(), evals.end(), out->evals);
+  float ms = 0.f;
+  cudaEventElapsedTime(&ms, h->ev[2], h->ev[3]);
+  h->stats.download_ms = ms;
+  h->stats.d2h_bytes = d2h;
+  long long ti = 0, te = 0, ab = 0;
+  const long long m = h->prm.lbfgs_mem_size;
+  for (int p = 0; p < B; p++) {
+    ti += iters[p];
+    te += evals[p];
+    const long long n = h->h_n[p];
+    ab += (long long)evals[p] * h->h_evalbytes[p];
+    // B_iter(k) = 32 n min(k-1, m) + 112 n, k = 1..iters  
+    const long long k = iters[p];
+    const long long kk = std::min(k, m + 1);  // iterations with k-1 <= m
+    ab += 32 * n * (kk * (kk - 1) / 2 + (k - kk) * m) + 112 * n * k;
+  }
+  h->stats.total_iters = ti;
+  h->stats.total_evals = te;
+  h->stats.algorithmic_bytes = ab;
+  return DFTPAV_OK;
+}
+
+int dftpav_solve(dftpav_handle* h, const dftpav_batch* batch, const dftpav_result* out) {
+  int rc = dftpav_upload_batch(h, batch);
+  if (rc) return rc;
+  rc = dftpav_optimize(h);
+  if (rc) return rc;
+  return dftpav_download(h, out);
+}
+
+int dftpav_last_stats(const dftpav_handle* h, dftpav_stats* stats) {
+  if (!h || !stats) return DFTPAV_ERR_INVALID_ARG;
+  *stats = h->stats;
+  return DFTPAV_OK;
+}
+
+const char* dftpav_last_error(const dftpav_handle* h) { return h ? h->err.c_str() : "null handle"; }
+
+}  // extern "C"

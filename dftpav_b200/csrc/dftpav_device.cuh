@@ -1,0 +1,105 @@
+// dftpav_device.cuh — shared host/device structures of the batched MINCO / L-BFGS solver (sm_100a).
+//
+// Mapping of the hot path onto the GPU:
+//   * one warp owns one trajectory problem for its whole L-BFGS solve (no inter-warp communication);
+//   * MINCO forward solve / adjoint solve: banded substitutions with the constant LU factor staged in
+//     shared memory once per CTA by a TMA bulk copy (cp.async.bulk), two lanes per gear segment (x / y column);
+//   * constraint-sample sweep: lane <-> sample, 16-sample tiles, plane data read coalesced from a tiled SoA
+//     layout, fixed-order (deterministic) tile reduction of the 6x2 coefficient gradient in shared memory;
+//   * L-BFGS two-loop recursion + Lewis-Overton line search: warp-shuffle dot products, (s,y) history ring in
+//     global memory (L2-resident), no host synchronisation until the batch is done.
+#pragma once
+#include <cstdint>
+
+namespace dftpav {
+
+constexpr int kMaxSeg = 4;        // max gear segments per problem (compiled-in limit)
+constexpr int kMaxPieces = 64;    // max pieces per segment
+constexpr int kTile = 16;         // samples per tile (half warp)
+constexpr int kLuLd = 16;         // doubles per packed LU column (13 band entries + 1/diag + pad)
+constexpr int kStageLd = 17;      // leading dimension of the tile-reduction staging rows
+
+// Problem "shape": everything that fixes control flow and shared-memory layout.  All problems of one kernel
+// launch share one shape (the host groups the batch by shape).
+struct ShapeDev {
+  int S;                 // gear segments
+  int n;                 // decision variables
+  int rows;              // sum 6*N_i
+  int pieces;            // sum N_i
+  int H;                 // padded planes per sample (group-wide max)
+  int Mpad;              // padded sample-storage length of a problem (multiple of 16)
+  int K, Kd;             // traj_resolution, des_traj_resolution
+  int N[kMaxSeg];        // pieces per segment
+  int row0[kMaxSeg];     // first coefficient row of the segment
+  int var0[kMaxSeg];     // offset of the segment's inner points in x
+  int lu_off[kMaxSeg];   // offset (doubles) of the segment's packed LU table in the LU block
+  int samp0[kMaxSeg];    // sample-storage offset of the segment
+  int ntile[kMaxSeg];    // regular 16-sample tiles of the segment
+  int lu_doubles;        // size of the LU block (all distinct N of this shape)
+  int npad;              // n rounded up to a multiple of 4
+  int ws_doubles;        // per-warp workspace size in doubles
+};
+
+// Scalar parameters reaching the arithmetic (mirror of dftpav_params, device side).
+struct ParamsDev {
+  double wei_obs, wei_surround, wei_feas, wei_time;
+  double surround_clearance, d_min;      // d_min = clearance + log(8)/alpha  (OPT.cpp:1336)
+  double max_vel[2], max_cur[2], max_acc[2];  // [0] forward, [1] backward
+  double non_sinv, mini_T, help_eps, min_speed, smooth_eps, cur_weight_scale, lse_alpha, cull_dist, cost_limit;
+  double le[4][2];                        // ego / obstacle box vertices (OPT.cpp:1765-1768), clockwise
+  int gear_opt;
+  int mem_size, past, max_iterations, max_linesearch;
+  double delta, g_epsilon, min_step, max_step, f_dec_coeff, s_curv_coeff, cautious_factor, machine_prec;
+};
+
+// Device views of the uploaded batch.
+struct BatchDev {
+  // per problem (global problem id)
+  const int* seg_base;          // [B] index of the problem's first segment
+  const double* t_now;          // [B]
+  const int* obs_ptr;           // [B+1] or nullptr
+  const int* obs_idx;
+  // per segment
+  const int* singul;            // [G]
+  const double* ini;            // [G][6] clamped
+  const double* fin;            // [G][6] clamped
+  // obstacle pool
+  const double* obs_start;
+  const double* obs_dur;
+  const int* obs_piece_ptr;
+  const double* obs_piece_dur;
+  const double* obs_coeffs;     // [pieces][12], 2x6 column-major, highest power first
+  // decision vectors
+  const double* x0;             // [B][n_stride]
+  int n_stride, row_stride;
+};
+
+// One launch = one shape group.
+struct GroupDev {
+  const int* prob_id;           // [count] global problem ids of this group
+  int count;
+  const double* planes;         // tiled SoA: [count][H][4][Mpad]
+  const double* lu;             // packed LU block of this shape
+};
+
+struct OutDev {
+  double* x;        // [B][n_stride]
+  double* cost;     // [B]
+  int* status;      // [B]
+  int* success;     // [B]
+  int* iters;       // [B]
+  int* evals;       // [B]
+  double* coeffs;   // [B][row_stride][2]
+  double* piece_dT; // [G]
+};
+
+struct HistDev {
+  double* s;        // [slots][mem][npad_max]
+  double* y;
+  double* ys;       // [slots][mem]
+  double* alpha;    // [slots][mem]
+  int ld;           // npad_max
+  int mem;
+};
+
+}  // namespace dftpav

@@ -1,0 +1,1442 @@
+// dftpav_kernels.cu — sm_100a kernels of the batched MINCO / L-BFGS trajectory optimizer.
+//
+// Reference path restated here (file:line of ZJU-FAST-Lab/Dftpav):
+//   costFunctionCallback            src/Plan/traj_planner/src/traj_optimizer.cpp:206-350      -> eval_cost_grad()
+//   addPVAGradCost2CT               traj_optimizer.cpp:422-779                                -> sweep_segment()/sample_eval()
+//   dynamicObsGradCostP/log_sum_exp traj_optimizer.cpp:1311-1707                              -> dyn_obstacles()
+//   MinJerkOpt::generate/calGrads   include/plan_utils/poly_traj_utils.hpp:953-1066           -> minco_* ()
+//   BandedSystem::solve/solveAdj    poly_traj_utils.hpp:805-852                               -> banded_solve()/banded_solve_adj()
+//   lbfgs_optimize / lewisoverton   include/geo_utils2d/lbfgs.hpp:276-390, 440-751            -> lbfgs_solve()
+// All arithmetic is IEEE fp64; no fast-math.  One warp per trajectory; nothing here touches tensor cores
+// (there is no dense contraction on this path).
+#include <cuda_runtime.h>
+#include <math_constants.h>
+
+#include "dftpav_device.cuh"
+#include "../../include/dftpav_b200.h"
+
+namespace dftpav {
+
+#define FULL 0xffffffffu
+
+// ------------------------------------------------------------------------------------------------
+// small helpers
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ double warp_sum(double v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(FULL, v, o);
+  return v;
+}
+__device__ __forceinline__ double warp_max(double v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v = fmax(v, __shfl_xor_sync(FULL, v, o));
+  return v;
+}
+__device__ __forceinline__ double warp_dot(const double* a, const double* b, int n, int lane) {
+  double s = 0.0;
+  for (int i = lane; i < n; i += 32) s += a[i] * b[i];
+  return warp_sum(s);
+}
+__device__ __forceinline__ double warp_maxabs(const double* a, int n, int lane) {
+  double m = 0.0;
+  for (int i = lane; i < n; i += 32) m = fmax(m, fabs(a[i]));
+  return warp_max(m);
+}
+
+// positiveSmoothedL1 (traj_optimizer.cpp:783-806)
+__device__ __forceinline__ void smoothed_l1(double pe, double x, double& f, double& df) {
+  const double half = 0.5 * pe;
+  const double f3c = 1.0 / (pe * pe);
+  const double f4c = -0.5 * f3c / pe;
+  const double d2c = 3.0 * f3c;
+  const double d3c = 4.0 * f4c;
+  if (x < pe) {
+    f = (f4c * x + f3c) * x * x * x;
+    df = (d3c * x + d2c) * x * x;
+  } else {
+    f = x - half;
+    df = 1.0;
+  }
+}
+
+struct V2 {
+  double x, y;
+};
+struct M2 {
+  double a, b, c, d;  // row-major [[a,b],[c,d]]
+};
+__device__ __forceinline__ V2 mk(double x, double y) { return V2{x, y}; }
+__device__ __forceinline__ V2 operator+(V2 a, V2 b) { return V2{a.x + b.x, a.y + b.y}; }
+__device__ __forceinline__ V2 operator-(V2 a, V2 b) { return V2{a.x - b.x, a.y - b.y}; }
+__device__ __forceinline__ V2 operator-(V2 a) { return V2{-a.x, -a.y}; }
+__device__ __forceinline__ V2 operator*(double s, V2 a) { return V2{s * a.x, s * a.y}; }
+__device__ __forceinline__ V2 operator/(V2 a, double s) { return V2{a.x / s, a.y / s}; }
+__device__ __forceinline__ double dot(V2 a, V2 b) { return a.x * b.x + a.y * b.y; }
+__device__ __forceinline__ double norm(V2 a) { return sqrt(a.x * a.x + a.y * a.y); }
+__device__ __forceinline__ M2 operator*(double s, M2 m) { return M2{s * m.a, s * m.b, s * m.c, s * m.d}; }
+__device__ __forceinline__ M2 operator-(M2 p, M2 q) { return M2{p.a - q.a, p.b - q.b, p.c - q.c, p.d - q.d}; }
+__device__ __forceinline__ M2 operator*(M2 p, M2 q) {
+  return M2{p.a * q.a + p.b * q.c, p.a * q.b + p.b * q.d, p.c * q.a + p.d * q.c, p.c * q.b + p.d * q.d};
+}
+__device__ __forceinline__ V2 operator*(M2 m, V2 v) { return V2{m.a * v.x + m.b * v.y, m.c * v.x + m.d * v.y}; }
+__device__ __forceinline__ M2 transpose(M2 m) { return M2{m.a, m.c, m.b, m.d}; }
+__device__ __forceinline__ V2 rowmul(V2 r, M2 m) { return V2{r.x * m.a + r.y * m.c, r.x * m.b + r.y * m.d}; }
+__device__ __forceinline__ M2 outer(V2 u, V2 v) { return M2{u.x * v.x, u.x * v.y, u.y * v.x, u.y * v.y}; }
+__device__ __forceinline__ M2 l_Bl(V2 l) { return M2{l.x, -l.y, l.y, l.x}; }
+// B_h * M for B_h = [[0,-1],[1,0]]
+__device__ __forceinline__ M2 Bh_mul(M2 m) { return M2{-m.c, -m.d, m.a, m.b}; }
+// M * B_h
+__device__ __forceinline__ M2 mul_Bh(M2 m) { return M2{m.b, -m.a, m.d, -m.c}; }
+// M * B_h^T
+__device__ __forceinline__ M2 mul_BhT(M2 m) { return M2{-m.b, m.a, -m.d, m.c}; }
+
+// ------------------------------------------------------------------------------------------------
+// per-warp workspace in shared memory
+// ------------------------------------------------------------------------------------------------
+struct SegScratch {   // 24 doubles per segment
+  double head[6];
+  double tail[6];
+  double T, dT;
+  double gdT;         // dJ/d(dT) accumulated (MinJerkOpt::gdT)
+  double jerk;        // smoothness cost of the segment
+  double pen[3];      // corridor / dynamic / feasibility penalty of the segment
+  double trajtime;    // quirk Q5: T of the previous segment (0 for the first)
+  double pad[4];
+};
+
+struct WarpWS {
+  double* c;      // [2*rows]  MINCO coefficients, row-major pairs
+  double* bt;     // [2*rows]  solved rhs before 1/dT^k scaling (b of MinJerkOpt after A.solve)
+  double* gd;     // [2*rows]  gdC, then the adjoint solution in place
+  double* x;      // [npad] current point
+  double* xp;     // [npad]
+  double* g;      // [npad]
+  double* gp;     // [npad]
+  double* d;      // [npad]
+  double* stage;  // [2][12][kStageLd]
+  SegScratch* seg;  // [kMaxSeg]
+};
+
+__host__ __device__ inline int ws_doubles_for(int rows, int npad) {
+  return 6 * rows + 5 * npad + 2 * 12 * kStageLd + kMaxSeg * (int)(sizeof(SegScratch) / sizeof(double));
+}
+
+__device__ __forceinline__ WarpWS carve_ws(double* base, const ShapeDev& sh) {
+  WarpWS w;
+  w.c = base;
+  w.bt = w.c + 2 * sh.rows;
+  w.gd = w.bt + 2 * sh.rows;
+  w.x = w.gd + 2 * sh.rows;
+  w.xp = w.x + sh.npad;
+  w.g = w.xp + sh.npad;
+  w.gp = w.g + sh.npad;
+  w.d = w.gp + sh.npad;
+  w.stage = w.d + sh.npad;
+  w.seg = reinterpret_cast<SegScratch*>(w.stage + 2 * 12 * kStageLd);
+  return w;
+}
+
+// ------------------------------------------------------------------------------------------------
+// banded substitutions (poly_traj_utils.hpp:805-852) on the packed LU table
+//   packed column j: C[j][0..5] = U(j-6..j-1, j), C[j][6] = U(j,j), C[j][7..12] = L(j+1..j+6, j), C[j][13] = 1/U(j,j)
+// Each calling lane owns one right-hand-side column `col` of the row-major n x 2 array b.
+// The 1/U(j,j) product replaces the reference's division (<= 1 ulp per row).
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void banded_solve(const double* __restrict__ C, double* b, int n, int col) {
+  // forward, update form (poly_traj_utils.hpp:808-815)
+  double w0 = b[col], w1 = b[2 + col], w2 = b[4 + col], w3 = b[6 + col], w4 = b[8 + col], w5 = b[10 + col];
+  double w6 = (6 < n) ? b[12 + col] : 0.0;
+#pragma unroll 6
+  for (int j = 0; j < n; j++) {
+    const double y = w0;
+    const double* Cj = C + j * kLuLd;
+    b[2 * j + col] = y;
+    w0 = w1 - Cj[7] * y;
+    w1 = w2 - Cj[8] * y;
+    w2 = w3 - Cj[9] * y;
+    w3 = w4 - Cj[10] * y;
+    w4 = w5 - Cj[11] * y;
+    w5 = w6 - Cj[12] * y;
+    w6 = (j + 7 < n) ? b[2 * (j + 7) + col] : 0.0;
+  }
+  // backward, update form (poly_traj_utils.hpp:816-824)
+  double v0 = b[2 * (n - 1) + col], v1 = b[2 * (n - 2) + col], v2 = b[2 * (n - 3) + col], v3 = b[2 * (n - 4) + col];
+  double v4 = b[2 * (n - 5) + col], v5 = b[2 * (n - 6) + col];
+  double v6 = (n - 7 >= 0) ? b[2 * (n - 7) + col] : 0.0;
+#pragma unroll 6
+  for (int j = n - 1; j >= 0; j--) {
+    const double* Cj = C + j * kLuLd;
+    const double xj = v0 * Cj[13];
+    b[2 * j + col] = xj;
+    v0 = v1 - Cj[5] * xj;
+    v1 = v2 - Cj[4] * xj;
+    v2 = v3 - Cj[3] * xj;
+    v3 = v4 - Cj[2] * xj;
+    v4 = v5 - Cj[1] * xj;
+    v5 = v6 - Cj[0] * xj;
+    v6 = (j - 7 >= 0) ? b[2 * (j - 7) + col] : 0.0;
+  }
+}
+
+__device__ __forceinline__ void banded_solve_adj(const double* __restrict__ C, double* b, int n, int col) {
+  // U^T z = b, ascending, gather form: row i receives U(i-6,i) z_{i-6} ... U(i-1,i) z_{i-1} in that order, then / U(i,i)
+  double z1 = 0.0, z2 = 0.0, z3 = 0.0, z4 = 0.0, z5 = 0.0, z6 = 0.0;
+#pragma unroll 6
+  for (int i = 0; i < n; i++) {
+    const double* Ci = C + i * kLuLd;
+    double t = b[2 * i + col];
+    t -= Ci[0] * z6;
+    t -= Ci[1] * z5;
+    t -= Ci[2] * z4;
+    t -= Ci[3] * z3;
+    t -= Ci[4] * z2;
+    t -= Ci[5] * z1;
+    const double zi = t * Ci[13];
+    b[2 * i + col] = zi;
+    z6 = z5;
+    z5 = z4;
+    z4 = z3;
+    z3 = z2;
+    z2 = z1;
+    z1 = zi;
+  }
+  // L^T w = z, descending, gather form: row i receives L(i+6,i) w_{i+6} ... L(i+1,i) w_{i+1} in that order
+  double q1 = 0.0, q2 = 0.0, q3 = 0.0, q4 = 0.0, q5 = 0.0, q6 = 0.0;
+#pragma unroll 6
+  for (int i = n - 1; i >= 0; i--) {
+    const double* Ci = C + i * kLuLd;
+    double t = b[2 * i + col];
+    t -= Ci[12] * q6;
+    t -= Ci[11] * q5;
+    t -= Ci[10] * q4;
+    t -= Ci[9] * q3;
+    t -= Ci[8] * q2;
+    t -= Ci[7] * q1;
+    b[2 * i + col] = t;
+    q6 = q5;
+    q5 = q4;
+    q4 = q3;
+    q3 = q2;
+    q2 = q1;
+    q1 = t;
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// obstacle trajectory evaluation (Piece/Trajectory, poly_traj_utils.hpp:77-112,179-211,510-603)
+// ------------------------------------------------------------------------------------------------
+struct ObsView {
+  int P;
+  const double* dur;
+  const double* cf;  // [P][12]
+  double start_time, duration;
+};
+__device__ __forceinline__ int obs_locate(const ObsView& o, double& t) {
+  int idx;
+  double d = 0.0;
+  for (idx = 0; idx < o.P && t > (d = o.dur[idx]); idx++) t -= d;
+  if (idx == o.P) {
+    idx--;
+    t += o.dur[idx];
+  }
+  return idx;
+}
+__device__ __forceinline__ V2 piece_pos(const double* cm, double t) {
+  V2 pos = mk(0.0, 0.0);
+  double tn = 1.0;
+#pragma unroll
+  for (int i = 5; i >= 0; i--) {
+    pos = pos + tn * mk(cm[2 * i], cm[2 * i + 1]);
+    tn *= t;
+  }
+  return pos;
+}
+__device__ __forceinline__ V2 piece_vel(const double* cm, double t) {
+  V2 ds = mk(0.0, 0.0);
+  double tn = 1.0;
+  int n = 1;
+#pragma unroll
+  for (int i = 4; i >= 0; i--) {
+    ds = ds + (n * tn) * mk(cm[2 * i], cm[2 * i + 1]);
+    tn *= t;
+    n++;
+  }
+  return ds;
+}
+__device__ __forceinline__ V2 piece_acc(const double* cm, double t) {
+  V2 dd = mk(0.0, 0.0);
+  double tn = 1.0;
+  int m = 1, n = 2;
+#pragma unroll
+  for (int i = 3; i >= 0; i--) {
+    dd = dd + ((m * n) * tn) * mk(cm[2 * i], cm[2 * i + 1]);
+    tn *= t;
+    m++;
+    n++;
+  }
+  return dd;
+}
+
+// log_sum_exp (traj_optimizer.cpp:1686-1707); v is overwritten with the exponentials (quirk Q7)
+template <int NV>
+__device__ __forceinline__ double lse(double alpha, double* v, double& exp_sum) {
+  double d0 = v[0];
+  if (alpha > 0) {
+#pragma unroll
+    for (int j = 1; j < NV; j++) d0 = fmax(d0, v[j]);
+  } else {
+#pragma unroll
+    for (int j = 1; j < NV; j++) d0 = fmin(d0, v[j]);
+  }
+  exp_sum = 0.0;
+#pragma unroll
+  for (int j = 0; j < NV; j++) {
+    v[j] = exp(alpha * (v[j] - d0));
+    exp_sum += v[j];
+  }
+  return log(exp_sum) / alpha + d0;
+}
+
+// Accumulators of one sample: G0 = d/d sigma, G1 = d/d sigma', G2 = d/d sigma'' (already weighted), plus the
+// sample's contributions to gdT and to the three penalty sums.
+struct SampleAcc {
+  V2 G0, G1, G2;
+  double gdT;
+  double pen0, pen1, pen2;
+};
+
+// dynamicObsGradCostP (traj_optimizer.cpp:1311-1684) for one sample; `t` = time of the sample inside the segment.
+__device__ __noinline__ void dyn_obstacles(const ParamsDev& P, const BatchDev& bd, int prob, SampleAcc& acc, double omg,
+                                           double step, double t, double gama, int pieceid, int trajres, V2 sigma,
+                                           V2 dsigma, V2 ddsigma, M2 ego_R, int singul_, int trajid, int Nseg,
+                                           double trajtime) {
+  const int o0 = bd.obs_ptr[prob], o1 = bd.obs_ptr[prob + 1];
+  if (o1 <= o0) return;
+  const double alpha = P.lse_alpha, d_min = P.d_min, wei_surround = P.wei_surround;
+  const double temp0 = norm(dsigma);
+  const double temp0_reci = (temp0 != 0.0) ? 1.0 / temp0 : 0.0;
+  const double temp3 = temp0_reci * temp0_reci;
+  const double t_now = bd.t_now[prob];
+  V2 vle[5];
+#pragma unroll
+  for (int k = 0; k < 4; k++) vle[k] = mk(P.le[k][0], P.le[k][1]);
+  vle[4] = vle[0];
+
+  for (int oi = o0; oi < o1; oi++) {
+    const int u = bd.obs_idx[oi];
+    ObsView ob;
+    ob.P = bd.obs_piece_ptr[u + 1] - bd.obs_piece_ptr[u];
+    ob.dur = bd.obs_piece_dur + bd.obs_piece_ptr[u];
+    ob.cf = bd.obs_coeffs + 12L * bd.obs_piece_ptr[u];
+    ob.start_time = bd.obs_start[u];
+    ob.duration = bd.obs_dur[u];
+    const double offsettime = t_now - ob.start_time + trajtime;
+    const double pt_time = offsettime + t;
+    V2 sp, sv, sa;
+    if (pt_time < ob.duration) {
+      double tt = pt_time;
+      const int i = obs_locate(ob, tt);
+      sp = piece_pos(ob.cf + 12 * i, tt);
+      sv = piece_vel(ob.cf + 12 * i, tt);
+      sa = piece_acc(ob.cf + 12 * i, tt);
+    } else {
+      double tt = ob.duration;
+      const int i = obs_locate(ob, tt);
+      sa = piece_acc(ob.cf + 12 * i, tt);
+      const double exceed = pt_time - ob.duration;
+      const V2 vd = piece_vel(ob.cf + 12 * i, tt);
+      sv = vd + exceed * sa;
+      V2 h = 0.5 * sa;
+      h = mk(h.x * exceed, h.y * exceed);
+      h = mk(h.x * exceed, h.y * exceed);
+      sp = piece_pos(ob.cf + 12 * i, tt) + exceed * vd + h;
+    }
+    if (norm(sp - sigma) > P.cull_dist) continue;  // traj_optimizer.cpp:1393
+
+    // getR / getRdot at pt_time (quirk Q6: evaluated on the clamped last piece past the duration)
+    double tr = pt_time;
+    const int ir = obs_locate(ob, tr);
+    const V2 rv = piece_vel(ob.cf + 12 * ir, tr);
+    const V2 ra = piece_acc(ob.cf + 12 * ir, tr);
+    const double rn = norm(rv);
+    M2 sur_R = M2{rv.x / rn, -rv.y / rn, rv.y / rn, rv.x / rn};
+    M2 Rud;
+    {
+      const double p3 = rn * rn * rn;  // pow(|v|,3)
+      const double va = dot(rv, ra);
+      M2 ta = M2{ra.x / rn, -ra.y / rn, ra.y / rn, ra.x / rn};
+      M2 tv = M2{rv.x / p3 * va, -rv.y / p3 * va, rv.y / p3 * va, rv.x / p3 * va};
+      Rud = ta - tv;
+    }
+
+    double sum_exp_U[4], d_test[8], sum_exp_E[4];
+    V2 ego_normal[4], sur_normal[4];
+    double dUoe[4][4], dEeo[4][4];
+    M2 F_dle[4], F_le[4];
+#pragma unroll
+    for (int e = 0; e < 4; e++) {
+      const V2 le = vle[e];
+      const V2 delta_le = vle[e + 1] - vle[e];
+      const double dn_inv = 1.0 / norm(delta_le);
+      F_dle[e] = (temp0_reci * ((double)singul_ * transpose(l_Bl(delta_le)))) - (temp3 * outer(dsigma, ego_R * delta_le));
+      F_le[e] = (temp0_reci * ((double)singul_ * transpose(l_Bl(le)))) - (temp3 * outer(dsigma, ego_R * le));
+      const V2 H_tilde = dn_inv * (Bh_mul(ego_R) * delta_le);
+      ego_normal[e] = H_tilde;
+      const double d_U_e_tilde = dot(H_tilde, (sp - sigma) - ego_R * le);
+      const V2 hr = rowmul(H_tilde, sur_R);
+#pragma unroll
+      for (int o = 0; o < 4; o++) dUoe[e][o] = dot(hr, vle[o]);
+      double es;
+      d_test[e] = lse<4>(-alpha, dUoe[e], es) + d_U_e_tilde;
+      sum_exp_U[e] = es;
+    }
+#pragma unroll
+    for (int o = 0; o < 4; o++) {
+      const V2 lo = vle[o];
+      const V2 delta_lo = vle[o + 1] - vle[o];
+      const double dn_inv = 1.0 / norm(delta_lo);
+      const V2 H_tilde = dn_inv * (Bh_mul(sur_R) * delta_lo);
+      sur_normal[o] = H_tilde;
+      const double d_E_o_tilde = dot(H_tilde, (sigma - sp) - sur_R * lo);
+      const V2 hr = rowmul(H_tilde, ego_R);
+#pragma unroll
+      for (int e = 0; e < 4; e++) dEeo[o][e] = dot(hr, vle[e]);
+      double es;
+      d_test[4 + o] = lse<4>(-alpha, dEeo[o], es) + d_E_o_tilde;
+      sum_exp_E[o] = es;
+    }
+    double exp_sum_d;
+    const double costp = d_min - lse<8>(alpha, d_test, exp_sum_d);
+    if (costp <= 0.0) continue;
+    double pena, penaD;
+    smoothed_l1(P.smooth_eps, costp, pena, penaD);
+    acc.pen1 += omg * step * wei_surround * pena;
+
+    V2 pG_sigma = mk(0.0, 0.0);
+#pragma unroll
+    for (int e = 0; e < 4; e++) pG_sigma = pG_sigma - (d_test[e] / exp_sum_d) * (-ego_normal[e]);
+#pragma unroll
+    for (int o = 0; o < 4; o++) pG_sigma = pG_sigma - (d_test[o + 4] / exp_sum_d) * sur_normal[o];
+
+    V2 pG_dsigma = mk(0.0, 0.0);
+#pragma unroll
+    for (int e = 0; e < 4; e++) {
+      const V2 le = vle[e];
+      const V2 delta_le = vle[e + 1] - vle[e];
+      const double dnrm = norm(delta_le);
+      const V2 a1 = mul_Bh(F_dle[e]) * ((-sp + sigma) + ego_R * le);
+      const V2 a2 = (mul_Bh(F_le[e]) * ego_R) * delta_le;
+      V2 pdU = (a1 - a2) / dnrm;
+      const M2 FdBt = mul_BhT(F_dle[e]);
+#pragma unroll
+      for (int o = 0; o < 4; o++) {
+        const V2 pd = (FdBt * (sur_R * vle[o])) / dnrm;
+        pdU = pdU + (dUoe[e][o] / sum_exp_U[e]) * pd;
+      }
+      pG_dsigma = pG_dsigma - (d_test[e] / exp_sum_d) * pdU;
+    }
+#pragma unroll
+    for (int o = 0; o < 4; o++) {
+      const V2 delta_lo = vle[o + 1] - vle[o];
+      const double dnrm = norm(delta_lo);
+      V2 pdE = mk(0.0, 0.0);
+#pragma unroll
+      for (int e = 0; e < 4; e++) {
+        const V2 pd = ((mul_Bh(F_le[e]) * sur_R) * delta_lo) / dnrm;
+        pdE = pdE + (dEeo[o][e] / sum_exp_E[o]) * pd;
+      }
+      pG_dsigma = pG_dsigma - (d_test[o + 4] / exp_sum_d) * pdE;
+    }
+    const double pG_tbar = dot(pG_sigma, dsigma) + dot(pG_dsigma, ddsigma);
+
+    double pG_that = 0.0;
+#pragma unroll
+    for (int e = 0; e < 4; e++) {
+      double pdU = dot(ego_normal[e], sv);
+      const V2 nr = rowmul(ego_normal[e], Rud);
+#pragma unroll
+      for (int o = 0; o < 4; o++) pdU += dUoe[e][o] / sum_exp_U[e] * dot(nr, vle[o]);
+      pG_that -= d_test[e] / exp_sum_d * pdU;
+    }
+#pragma unroll
+    for (int o = 0; o < 4; o++) {
+      const V2 lo = vle[o];
+      const V2 delta_lo = vle[o + 1] - vle[o];
+      const double dnrm = norm(delta_lo);
+      const V2 r1 = (Bh_mul(Rud) * delta_lo) / dnrm;
+      const V2 r2 = (Bh_mul(sur_R) * delta_lo) / dnrm;
+      double pdE = dot(r1, (sigma - sp) - sur_R * lo) + dot(r2, -sv - Rud * lo);
+#pragma unroll
+      for (int e = 0; e < 4; e++) {
+        const V2 row = rowmul(rowmul(ego_R * vle[e], M2{0.0, -1.0, 1.0, 0.0}), Rud);
+        pdE += dEeo[o][e] / sum_exp_E[o] * (dot(row, delta_lo) / dnrm);
+      }
+      pG_that -= d_test[o + 4] / exp_sum_d * pdE;
+    }
+
+    const double wc = omg * step * wei_surround * penaD;
+    acc.G0 = acc.G0 + wc * pG_sigma;
+    acc.G1 = acc.G1 + wc * pG_dsigma;
+    acc.gdT += omg * wei_surround * (pena / trajres + penaD * (gama * pG_tbar) * step);
+    acc.gdT += omg * step * wei_surround * pG_that * penaD * pieceid;
+    acc.gdT += omg * step * wei_surround * gama * pG_that * penaD;
+    for (int idx = 0; idx < trajid; idx++) acc.gdT += omg * step * wei_surround * pG_that * penaD * Nseg;  // quirk Q5
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// constraint-sample sweep of one gear segment (addPVAGradCost2CT, traj_optimizer.cpp:422-779)
+// ------------------------------------------------------------------------------------------------
+template <bool HAS_OBS>
+__device__ __forceinline__ void sweep_segment(const ShapeDev& sh, const ParamsDev& P, const BatchDev& bd, int prob,
+                                              const double* __restrict__ planes, WarpWS& ws, int s, int singul_,
+                                              int lane) {
+  const int N = sh.N[s];
+  const int K = sh.K, Kd = sh.Kd;
+  const int td = (Kd + kTile - 1) / kTile, tk = (K + kTile - 1) / kTile;
+  const int ntile = sh.ntile[s];
+  const int npass_reg = (ntile + 1) >> 1;
+  const int npass_end = (N + 31) >> 5;
+  const int half = lane >> 4, r = lane & 15;
+  const double dT = ws.seg[s].dT;
+  const double trajtime = ws.seg[s].trajtime;
+  const int sidx = singul_ > 0 ? 0 : 1;
+  const double max_vel = P.max_vel[sidx], max_cur = P.max_cur[sidx], max_acc = P.max_acc[sidx];
+  const double* cseg = ws.c + 2 * sh.row0[s];
+  double* gdseg = ws.gd + 2 * sh.row0[s];
+  const int Mpad = sh.Mpad;
+  const int H = sh.H;
+  const double* pl = planes + sh.samp0[s];
+
+  double acc_gdT = 0.0, acc_p0 = 0.0, acc_p1 = 0.0, acc_p2 = 0.0;
+
+  for (int pass = 0; pass < npass_reg + npass_end; pass++) {
+    const bool endpass = pass >= npass_reg;
+    int piece, j, Kp, store;
+    bool valid;
+    if (!endpass) {
+      const int t = 2 * pass + half;
+      int j0;
+      if (t < td) {
+        piece = 0;
+        j0 = kTile * t;
+      } else if (t < td + (N - 2) * tk) {
+        const int u = t - td;
+        piece = 1 + u / tk;
+        j0 = kTile * (u % tk);
+      } else {
+        const int u = t - td - (N - 2) * tk;
+        piece = N - 1;
+        j0 = kTile * u;
+      }
+      Kp = (piece == 0 || piece == N - 1) ? Kd : K;
+      j = j0 + r;
+      valid = (t < ntile) && (j < Kp);
+      store = t * kTile + r;
+    } else {
+      piece = (pass - npass_reg) * 32 + lane;
+      valid = piece < N;
+      if (!valid) piece = N - 1;
+      Kp = (piece == 0 || piece == N - 1) ? Kd : K;
+      j = Kp;
+      store = ntile * kTile + piece;
+    }
+
+    double out[12];
+#pragma unroll
+    for (int q = 0; q < 12; q++) out[q] = 0.0;
+
+    if (valid) {
+      const double* c = cseg + 12 * piece;
+      const double step = dT / Kp;
+      const double s1 = j * step;  // reference accumulates s1 += step (quirk Q3); differs by O(j) ulp
+      const double s2 = s1 * s1, s3 = s2 * s1, s4 = s2 * s2, s5 = s4 * s1;
+      const double b0[6] = {1.0, s1, s2, s3, s4, s5};
+      const double b1[6] = {0.0, 1.0, 2.0 * s1, 3.0 * s2, 4.0 * s3, 5.0 * s4};
+      const double b2[6] = {0.0, 0.0, 2.0, 6.0 * s1, 12.0 * s2, 20.0 * s3};
+      const double b3[6] = {0.0, 0.0, 0.0, 6.0, 24.0 * s1, 60.0 * s2};
+      const double alpha = 1.0 / Kp * j;
+      V2 sigma = mk(0.0, 0.0), dsigma = mk(0.0, 0.0), ddsigma = mk(0.0, 0.0), dddsigma = mk(0.0, 0.0);
+#pragma unroll
+      for (int k = 0; k < 6; k++) {
+        const double cx = c[2 * k], cy = c[2 * k + 1];
+        sigma.x += cx * b0[k];
+        sigma.y += cy * b0[k];
+        dsigma.x += cx * b1[k];
+        dsigma.y += cy * b1[k];
+        ddsigma.x += cx * b2[k];
+        ddsigma.y += cy * b2[k];
+        dddsigma.x += cx * b3[k];
+        dddsigma.y += cy * b3[k];
+      }
+      const double omg = (j == 0 || j == Kp) ? 0.5 : 1.0;
+      double z_h0 = norm(dsigma);
+      const bool skip = (z_h0 < P.min_speed) || (j == 0 && piece == 0) || (piece == N - 1 && j == Kp);
+      if (!skip) {
+        const double z_h1 = dot(ddsigma, dsigma);
+        const double z_h2 = dot(dddsigma, dsigma);
+        const double z_h3 = ddsigma.y * dsigma.x - ddsigma.x * dsigma.y;
+        const double vel2_reci = 1.0 / (z_h0 * z_h0);
+        const double vel2_reci_e = 1.0 / (z_h0 * z_h0 + P.help_eps);
+        const double vel3_2_reci_e = vel2_reci_e * sqrt(vel2_reci_e);
+        z_h0 = 1.0 / z_h0;
+        const double z_h4 = z_h1 * vel2_reci;
+        const double violaVel = 1.0 / vel2_reci - max_vel * max_vel;
+        const double acc2 = z_h1 * z_h1 * vel2_reci;
+        const double cur = z_h3 * vel3_2_reci_e;
+        const double violaAcc = acc2 - max_acc * max_acc;
+        const double violaCurL = cur - max_cur;
+        const double violaCurR = -cur - max_cur;
+        const double sg = (double)singul_;
+        const M2 rot = M2{dsigma.x, -dsigma.y, dsigma.y, dsigma.x};
+        const M2 ego_R = M2{sg * rot.a * z_h0, sg * rot.b * z_h0, sg * rot.c * z_h0, sg * rot.d * z_h0};
+        M2 R_dot;
+        {
+          const double f2 = vel2_reci * z_h0 * z_h1;
+          R_dot = M2{sg * (ddsigma.x * z_h0 - rot.a * f2), sg * (-ddsigma.y * z_h0 - rot.b * f2),
+                     sg * (ddsigma.y * z_h0 - rot.c * f2), sg * (ddsigma.x * z_h0 - rot.d * f2)};
+        }
+        SampleAcc acc;
+        acc.G0 = mk(0.0, 0.0);
+        acc.G1 = mk(0.0, 0.0);
+        acc.G2 = mk(0.0, 0.0);
+        acc.gdT = 0.0;
+        acc.pen0 = acc.pen1 = acc.pen2 = 0.0;
+
+        // ---- static corridor (traj_optimizer.cpp:592-622).  Quirk Q1: the vertex list has 5 entries, vertex 0 twice;
+        //      the duplicate is folded into a weight of 2 on vertex 0.
+        const double wobs = omg * step * P.wei_obs;
+        for (int v = 0; v < 4; v++) {
+          const V2 le = mk(P.le[v][0], P.le[v][1]);
+          const double mult = (v == 0) ? 2.0 : 1.0;
+          const V2 q = ego_R * le;
+          const V2 bpt = sigma + q;
+          const V2 rl = R_dot * le;
+          for (int h = 0; h < H; h++) {
+            const double* ph = pl + (size_t)(4 * h) * Mpad + store;
+            const V2 nrm = mk(ph[0], ph[Mpad]);
+            const V2 pnt = mk(ph[2 * Mpad], ph[3 * Mpad]);
+            const double violaPos = dot(nrm, bpt - pnt);
+            if (violaPos > 0.0) {
+              double pena, penaD;
+              smoothed_l1(P.smooth_eps, violaPos, pena, penaD);
+              // n^T M,  M = singul*[l,Bl]/|v| - (R l) sigma'^T / |v|^2
+              const double nq = dot(nrm, q);
+              const V2 nM = mk(sg * z_h0 * (nrm.x * le.x + nrm.y * le.y) - vel2_reci * nq * dsigma.x,
+                               sg * z_h0 * (-nrm.x * le.y + nrm.y * le.x) - vel2_reci * nq * dsigma.y);
+              const double gradViolaPt = alpha * dot(nrm, dsigma + rl);
+              const double wc = mult * wobs * penaD;
+              acc.G0 = acc.G0 + wc * nrm;
+              acc.G1 = acc.G1 + wc * nM;
+              acc.gdT += mult * (omg * P.wei_obs * (penaD * gradViolaPt * step + pena / Kp));
+              acc.pen0 += mult * (wobs * pena);
+            }
+          }
+        }
+        // ---- moving obstacles (traj_optimizer.cpp:636-638)
+        if (HAS_OBS) {
+          dyn_obstacles(P, bd, prob, acc, omg, step, piece * dT + step * j, alpha, piece, Kp, sigma, dsigma, ddsigma,
+                        ego_R, singul_, s, N, trajtime);
+        }
+        // ---- velocity (642-653)
+        if (violaVel > 0.0) {
+          double pena, penaD;
+          smoothed_l1(P.smooth_eps, violaVel, pena, penaD);
+          const double wc = omg * step * P.wei_feas * penaD;
+          acc.G1 = acc.G1 + (2.0 * wc) * dsigma;
+          acc.gdT += omg * P.wei_feas * (penaD * (2.0 * alpha * z_h1) * step + pena / Kp);
+          acc.pen2 += omg * step * P.wei_feas * pena;
+        }
+        // ---- longitudinal acceleration (655-665)
+        if (violaAcc > 0.0) {
+          double pena, penaD;
+          smoothed_l1(P.smooth_eps, violaAcc, pena, penaD);
+          const double wc = omg * step * P.wei_feas * penaD;
+          const V2 w1 = z_h4 * ddsigma - (z_h4 * z_h4) * dsigma;
+          acc.G1 = acc.G1 + (2.0 * wc) * w1;
+          acc.G2 = acc.G2 + (2.0 * wc * z_h4) * dsigma;
+          const double gradViolaAt = 2.0 * alpha * (z_h4 * (dot(ddsigma, ddsigma) + z_h2) - z_h4 * z_h4 * z_h1);
+          acc.gdT += omg * P.wei_feas * (penaD * gradViolaAt * step + pena / Kp);
+          acc.pen2 += omg * step * P.wei_feas * pena;
+        }
+        // ---- curvature, both signs (684-705)
+        if (violaCurL > 0.0 || violaCurR > 0.0) {
+          const V2 aB = mk(ddsigma.y, -ddsigma.x);
+          const V2 Bv = mk(-dsigma.y, dsigma.x);
+          const double z_d3 = dddsigma.y * dsigma.x - dddsigma.x * dsigma.y;
+          const V2 w1 = vel3_2_reci_e * aB - (3.0 * vel3_2_reci_e * vel2_reci_e * z_h3) * dsigma;
+          const double gt = alpha * vel3_2_reci_e * (z_d3 - 3.0 * vel2_reci_e * z_h3 * z_h1);
+          const double wf = P.wei_feas * P.cur_weight_scale;
+          if (violaCurL > 0.0) {
+            double pena, penaD;
+            smoothed_l1(P.smooth_eps, violaCurL, pena, penaD);
+            const double wc = omg * step * wf * penaD;
+            acc.G1 = acc.G1 + wc * w1;
+            acc.G2 = acc.G2 + (wc * vel3_2_reci_e) * Bv;
+            acc.gdT += omg * wf * (penaD * gt * step + pena / Kp);
+            acc.pen2 += omg * step * wf * pena;
+          }
+          if (violaCurR > 0.0) {
+            double pena, penaD;
+            smoothed_l1(P.smooth_eps, violaCurR, pena, penaD);
+            const double wc = omg * step * wf * penaD;
+            acc.G1 = acc.G1 - wc * w1;
+            acc.G2 = acc.G2 - (wc * vel3_2_reci_e) * Bv;
+            acc.gdT += omg * wf * (penaD * (-gt) * step + pena / Kp);
+            acc.pen2 += omg * step * wf * pena;
+          }
+        }
+        acc_gdT += acc.gdT;
+        acc_p0 += acc.pen0;
+        acc_p1 += acc.pen1;
+        acc_p2 += acc.pen2;
+#pragma unroll
+        for (int k = 0; k < 6; k++) {
+          out[2 * k] = b0[k] * acc.G0.x + b1[k] * acc.G1.x + b2[k] * acc.G2.x;
+          out[2 * k + 1] = b0[k] * acc.G0.y + b1[k] * acc.G1.y + b2[k] * acc.G2.y;
+        }
+      }
+    }
+
+    if (endpass) {
+      // every lane owns a distinct piece: direct accumulation
+      if (valid) {
+#pragma unroll
+        for (int q = 0; q < 12; q++) gdseg[12 * piece + q] += out[q];
+      }
+      __syncwarp();
+    } else {
+      // fixed-order tile reduction: stage[half][q][r], then 12 lanes per half sum their row over r = 0..15
+      double* st = ws.stage + half * (12 * kStageLd);
+#pragma unroll
+      for (int q = 0; q < 12; q++) st[q * kStageLd + r] = out[q];
+      __syncwarp();
+      double sum = 0.0;
+      if (r < 12) {
+#pragma unroll
+        for (int i = 0; i < kTile; i++) sum += st[r * kStageLd + i];
+      }
+      // the two halves may hit the same piece (Kd > 16): add one after the other
+      const int tvalid = (2 * pass + half) < ntile;
+      if (half == 0 && r < 12 && tvalid) gdseg[12 * piece + r] += sum;
+      __syncwarp();
+      if (half == 1 && r < 12 && tvalid) gdseg[12 * piece + r] += sum;
+      __syncwarp();
+    }
+  }
+  // segment totals
+  acc_gdT = warp_sum(acc_gdT);
+  acc_p0 = warp_sum(acc_p0);
+  acc_p2 = warp_sum(acc_p2);
+  if (HAS_OBS) acc_p1 = warp_sum(acc_p1);
+  if (lane == 0) {
+    ws.seg[s].gdT += acc_gdT;
+    ws.seg[s].pen[0] = acc_p0;
+    ws.seg[s].pen[1] = acc_p1;
+    ws.seg[s].pen[2] = acc_p2;
+  }
+  __syncwarp();
+}
+
+// ------------------------------------------------------------------------------------------------
+// one cost + gradient evaluation (costFunctionCallback, traj_optimizer.cpp:206-350)
+// x, g: shared-memory vectors of the warp.  Leaves c / bt in the workspace (quirk Q8 relies on that).
+// ------------------------------------------------------------------------------------------------
+template <bool HAS_OBS>
+__device__ double eval_cost_grad(const ShapeDev& sh, const ParamsDev& P, const BatchDev& bd, int prob,
+                                 const double* __restrict__ planes, const double* __restrict__ lu, WarpWS& ws,
+                                 const double* x, double* g, int lane) {
+  const int S = sh.S;
+  const int seg0 = bd.seg_base[prob];
+  const int tv0 = sh.var0[S - 1] + 2 * (sh.N[S - 1] - 1);  // offset of tau
+  const int gb = tv0 + S;                                  // gear positions
+  const int ab = gb + 2 * (S - 1);                         // angles
+
+  // ---- per-segment scalars and boundary states (traj_optimizer.cpp:224-234, 269-282)
+  if (lane < S) {
+    const int s = lane;
+    const double VT = x[tv0 + s];
+    const double T = VT > 0.0 ? ((0.5 * VT + 1.0) * VT + 1.0) + P.mini_T : 1.0 / ((0.5 * VT - 1.0) * VT + 1.0) + P.mini_T;
+    SegScratch& sc = ws.seg[s];
+    sc.T = T;
+    sc.dT = T / sh.N[s];
+#pragma unroll
+    for (int k = 0; k < 6; k++) {
+      sc.head[k] = bd.ini[6 * (seg0 + s) + k];
+      sc.tail[k] = bd.fin[6 * (seg0 + s) + k];
+    }
+    if (s > 0) {
+      const double theta = x[ab + s - 1];
+      double sn, cs;
+      sincos(theta, &sn, &cs);
+      sc.head[0] = x[gb + 2 * (s - 1)];
+      sc.head[1] = x[gb + 2 * (s - 1) + 1];
+      sc.head[2] = -P.non_sinv * cs;
+      sc.head[3] = -P.non_sinv * sn;
+    }
+    if (s < S - 1) {
+      const double theta = x[ab + s];
+      double sn, cs;
+      sincos(theta, &sn, &cs);
+      sc.tail[0] = x[gb + 2 * s];
+      sc.tail[1] = x[gb + 2 * s + 1];
+      sc.tail[2] = P.non_sinv * cs;
+      sc.tail[3] = P.non_sinv * sn;
+    }
+  }
+  for (int i = lane; i < 2 * sh.rows; i += 32) ws.bt[i] = 0.0;
+  __syncwarp();
+  if (lane < S) {
+    // trajtimes (quirk Q5): T of the previous segment, not cumulative
+    ws.seg[lane].trajtime = lane == 0 ? 0.0 : ws.seg[lane - 1].T;
+  }
+  // ---- right-hand side (poly_traj_utils.hpp:968-977)
+  for (int s = 0; s < S; s++) {
+    const int N = sh.N[s];
+    const SegScratch& sc = ws.seg[s];
+    const double t1 = sc.dT, t2 = t1 * t1;
+    double* b = ws.bt + 2 * sh.row0[s];
+    if (lane < 2) {
+      b[0 + lane] = sc.head[0 + lane];
+      b[2 + lane] = sc.head[2 + lane] * t1;
+      b[4 + lane] = sc.head[4 + lane] * t2;
+      b[2 * (6 * N - 3) + lane] = sc.tail[0 + lane];
+      b[2 * (6 * N - 2) + lane] = sc.tail[2 + lane] * t1;
+      b[2 * (6 * N - 1) + lane] = sc.tail[4 + lane] * t2;
+    }
+    const double* Pin = x + sh.var0[s];
+    for (int i = lane; i < 2 * (N - 1); i += 32) b[2 * (6 * (i >> 1) + 5) + (i & 1)] = Pin[i];
+  }
+  __syncwarp();
+  // ---- banded solve, two lanes per segment
+  if (lane < 2 * S) {
+    const int s = lane >> 1;
+    banded_solve(lu + sh.lu_off[s], ws.bt + 2 * sh.row0[s], 6 * sh.N[s], lane & 1);
+  }
+  __syncwarp();
+  // ---- c = b~ / dT^k, jerk energy, gdC / gdT initialisation (poly_traj_utils.hpp:981-984, 998-1035)
+  for (int s = 0; s < S; s++) {
+    const int N = sh.N[s];
+    const double t1 = ws.seg[s].dT, t2 = t1 * t1, t3 = t2 * t1, t4 = t2 * t2, t5 = t4 * t1;
+    const double ti1 = 1.0 / t1, ti2 = 1.0 / t2, ti3 = 1.0 / t3, ti4 = 1.0 / t4, ti5 = 1.0 / t5;
+    const double* b = ws.bt + 2 * sh.row0[s];
+    double* c = ws.c + 2 * sh.row0[s];
+    double* gd = ws.gd + 2 * sh.row0[s];
+    double energy = 0.0, gdT = 0.0;
+    for (int i = lane; i < N; i += 32) {
+      const double* bi = b + 12 * i;
+      double* ci = c + 12 * i;
+      double* gi = gd + 12 * i;
+      const double c0x = bi[0], c0y = bi[1];
+      const double c1x = bi[2] * ti1, c1y = bi[3] * ti1;
+      const double c2x = bi[4] * ti2, c2y = bi[5] * ti2;
+      const double c3x = bi[6] * ti3, c3y = bi[7] * ti3;
+      const double c4x = bi[8] * ti4, c4y = bi[9] * ti4;
+      const double c5x = bi[10] * ti5, c5y = bi[11] * ti5;
+      ci[0] = c0x, ci[1] = c0y, ci[2] = c1x, ci[3] = c1y, ci[4] = c2x, ci[5] = c2y;
+      ci[6] = c3x, ci[7] = c3y, ci[8] = c4x, ci[9] = c4y, ci[10] = c5x, ci[11] = c5y;
+      const double d33 = c3x * c3x + c3y * c3y, d43 = c4x * c3x + c4y * c3y, d44 = c4x * c4x + c4y * c4y;
+      const double d53 = c5x * c3x + c5y * c3y, d54 = c5x * c4x + c5y * c4y, d55 = c5x * c5x + c5y * c5y;
+      energy += 36.0 * d33 * t1 + 144.0 * d43 * t2 + 192.0 * d44 * t3 + 240.0 * d53 * t3 + 720.0 * d54 * t4 +
+                720.0 * d55 * t5;
+      gdT += 36.0 * d33 + 288.0 * d43 * t1 + 576.0 * d44 * t2 + 720.0 * d53 * t2 + 2880.0 * d54 * t3 +
+             3600.0 * d55 * t4;
+      gi[0] = gi[1] = gi[2] = gi[3] = gi[4] = gi[5] = 0.0;
+      gi[6] = 72.0 * c3x * t1 + 144.0 * c4x * t2 + 240.0 * c5x * t3;
+      gi[7] = 72.0 * c3y * t1 + 144.0 * c4y * t2 + 240.0 * c5y * t3;
+      gi[8] = 144.0 * c3x * t2 + 384.0 * c4x * t3 + 720.0 * c5x * t4;
+      gi[9] = 144.0 * c3y * t2 + 384.0 * c4y * t3 + 720.0 * c5y * t4;
+      gi[10] = 240.0 * c3x * t3 + 720.0 * c4x * t4 + 1440.0 * c5x * t5;
+      gi[11] = 240.0 * c3y * t3 + 720.0 * c4y * t4 + 1440.0 * c5y * t5;
+    }
+    energy = warp_sum(energy);
+    gdT = warp_sum(gdT);
+    if (lane == 0) {
+      ws.seg[s].jerk = energy;
+      ws.seg[s].gdT = gdT;
+    }
+  }
+  __syncwarp();
+  // ---- constraint sweep
+  for (int s = 0; s < S; s++) sweep_segment<HAS_OBS>(sh, P, bd, prob, planes, ws, s, bd.singul[seg0 + s], lane);
+
+  // ---- MinJerkOpt::calGrads_PT (poly_traj_utils.hpp:1037-1066)
+  for (int s = 0; s < S; s++) {
+    const int N = sh.N[s];
+    const double t1 = ws.seg[s].dT, t2 = t1 * t1, t3 = t2 * t1, t4 = t2 * t2, t5 = t4 * t1;
+    double tInv[6] = {1.0, 1.0 / t1, 1.0 / t2, 1.0 / t3, 1.0 / t4, 1.0 / t5};
+    double gdtInv[6] = {0.0, -1.0 * tInv[2], -2.0 * tInv[3], -3.0 * tInv[4], -4.0 * tInv[5], -5.0 * tInv[5] * tInv[1]};
+    const double* b = ws.bt + 2 * sh.row0[s];
+    double* gd = ws.gd + 2 * sh.row0[s];
+    double part = 0.0;
+    for (int i = lane; i < N; i += 32) {
+      double sacc = 0.0;
+#pragma unroll
+      for (int k = 0; k < 6; k++) {
+        const int rr = 2 * (6 * i + k);
+        sacc += gdtInv[k] * (gd[rr] * b[rr] + gd[rr + 1] * b[rr + 1]);
+        gd[rr] *= tInv[k];      // adjScaledGrad, in place
+        gd[rr + 1] *= tInv[k];
+      }
+      part += sacc;
+    }
+    part = warp_sum(part);
+    if (lane == 0) ws.seg[s].pad[0] = part;  // added to gdT after the boundary terms, like the reference
+  }
+  __syncwarp();
+  if (lane < 2 * S) {
+    const int s = lane >> 1;
+    banded_solve_adj(lu + sh.lu_off[s], ws.gd + 2 * sh.row0[s], 6 * sh.N[s], lane & 1);
+  }
+  __syncwarp();
+  // gdP -> g
+  for (int s = 0; s < S; s++) {
+    const int N = sh.N[s];
+    const double* adj = ws.gd + 2 * sh.row0[s];
+    double* gP = g + sh.var0[s];
+    for (int i = lane; i < 2 * (N - 1); i += 32) gP[i] = adj[2 * (6 * (i >> 1) + 5) + (i & 1)];
+  }
+  // gdT, time gradient (traj_optimizer.cpp:325, 405-419)
+  if (lane < S) {
+    const int s = lane;
+    const int N = sh.N[s];
+    SegScratch& sc = ws.seg[s];
+    const double* adj = ws.gd + 2 * sh.row0[s];
+    const double t1 = sc.dT;
+    double gdT = sc.gdT;
+    gdT += sc.head[2] * adj[2] + sc.head[3] * adj[3];
+    gdT += (sc.head[4] * adj[4] + sc.head[5] * adj[5]) * 2.0 * t1;
+    gdT += sc.tail[2] * adj[2 * (6 * N - 2)] + sc.tail[3] * adj[2 * (6 * N - 2) + 1];
+    gdT += (sc.tail[4] * adj[2 * (6 * N - 1)] + sc.tail[5] * adj[2 * (6 * N - 1) + 1]) * 2.0 * t1;
+    gdT += sc.pad[0];
+    sc.gdT = gdT;
+    const double VT = x[tv0 + s];
+    double gdVT2Rt;
+    if (VT > 0.0) {
+      gdVT2Rt = VT + 1.0;
+    } else {
+      const double den = (0.5 * VT - 1.0) * VT + 1.0;
+      gdVT2Rt = (1.0 - VT) / (den * den);
+    }
+    g[tv0 + s] = (gdT / N + P.wei_time) * gdVT2Rt;
+  }
+  // gear position / angle gradients (traj_optimizer.cpp:308-319): gear j joins tail of segment j and head of segment j+1
+  if (lane < S - 1) {
+    const int j = lane;
+    double gx = 0.0, gy = 0.0, ga = 0.0;
+    if (P.gear_opt) {
+      const double theta = x[ab + j];
+      double sn, cs;
+      sincos(theta, &sn, &cs);
+      {  // segment j: gradFin
+        const int N = sh.N[j];
+        const double* adj = ws.gd + 2 * sh.row0[j];
+        const double t1 = ws.seg[j].dT;
+        const double f0x = adj[2 * (6 * N - 3)], f0y = adj[2 * (6 * N - 3) + 1];
+        const double f1x = adj[2 * (6 * N - 2)] * t1, f1y = adj[2 * (6 * N - 2) + 1] * t1;
+        gx += f0x;
+        gy += f0y;
+        ga += f1x * (-P.non_sinv * sn) + f1y * (P.non_sinv * cs);
+      }
+      {  // segment j+1: gradIni
+        const double* adj = ws.gd + 2 * sh.row0[j + 1];
+        const double t1 = ws.seg[j + 1].dT;
+        const double h0x = adj[0], h0y = adj[1];
+        const double h1x = adj[2] * t1, h1y = adj[3] * t1;
+        gx += h0x;
+        gy += h0y;
+        ga += h1x * (P.non_sinv * sn) + h1y * (-P.non_sinv * cs);
+      }
+    }
+    g[gb + 2 * j] = gx;
+    g[gb + 2 * j + 1] = gy;
+    g[ab + j] = ga;
+  }
+  __syncwarp();
+  // ---- total (traj_optimizer.cpp:293-294, 329, 344)
+  double sm = 0.0, tc = 0.0, pen = 0.0;
+  for (int s = 0; s < S; s++) {
+    sm += ws.seg[s].jerk;
+    pen += (ws.seg[s].pen[0] + ws.seg[s].pen[1]) + ws.seg[s].pen[2];
+    tc += ws.seg[s].T * P.wei_time;
+  }
+  return sm + tc + pen;
+}
+
+// ------------------------------------------------------------------------------------------------
+// TMA bulk copy of the LU block into shared memory (one elected thread, mbarrier completion)
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void tma_load_block(double* smem_dst, const double* gmem_src, unsigned bytes,
+                                               unsigned long long* mbar) {
+  const unsigned mbar_a = (unsigned)__cvta_generic_to_shared(mbar);
+  const unsigned dst_a = (unsigned)__cvta_generic_to_shared(smem_dst);
+  if (threadIdx.x == 0) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(mbar_a));
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(mbar_a), "r"(bytes) : "memory");
+    asm volatile(
+        "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst_a),
+        "l"(gmem_src), "r"(bytes), "r"(mbar_a)
+        : "memory");
+  }
+  // all threads wait for phase 0
+  unsigned done = 0;
+  while (!done) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], 0;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(done)
+        : "r"(mbar_a)
+        : "memory");
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// standalone evaluation kernel: f, g at caller-provided x (the parity hook dftpav_eval)
+// ------------------------------------------------------------------------------------------------
+template <bool HAS_OBS>
+__global__ void __launch_bounds__(512, 1)
+    eval_kernel(const __grid_constant__ ShapeDev sh, const __grid_constant__ ParamsDev P, const BatchDev bd,
+                const GroupDev grp, const double* __restrict__ xin, double* __restrict__ fout,
+                double* __restrict__ gout, double* __restrict__ coeffs_out, double* __restrict__ dT_out) {
+  extern __shared__ __align__(128) double smem[];
+  __shared__ __align__(8) unsigned long long mbar;
+  tma_load_block(smem, grp.lu, (unsigned)(sh.lu_doubles * sizeof(double)), &mbar);
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarp = blockDim.x >> 5;
+  WarpWS ws = carve_ws(smem + sh.lu_doubles + warp * sh.ws_doubles, sh);
+  for (int local = blockIdx.x * nwarp + warp; local < grp.count; local += gridDim.x * nwarp) {
+    const int prob = grp.prob_id[local];
+    const double* planes = grp.planes + (size_t)local * sh.H * 4 * sh.Mpad;
+    for (int i = lane; i < sh.n; i += 32) ws.x[i] = xin[(size_t)prob * bd.n_stride + i];
+    __syncwarp();
+    const double f = eval_cost_grad<HAS_OBS>(sh, P, bd, prob, planes, smem, ws, ws.x, ws.g, lane);
+    __syncwarp();
+    if (lane == 0) fout[prob] = f;
+    for (int i = lane; i < bd.n_stride; i += 32) gout[(size_t)prob * bd.n_stride + i] = i < sh.n ? ws.g[i] : 0.0;
+    if (coeffs_out)
+      for (int i = lane; i < 2 * sh.rows; i += 32) coeffs_out[(size_t)prob * bd.row_stride * 2 + i] = ws.c[i];
+    if (dT_out && lane < sh.S) dT_out[bd.seg_base[prob] + lane] = ws.seg[lane].dT;
+    __syncwarp();
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// the solver: persistent warps, each runs lbfgs_optimize (lbfgs.hpp:440-751) for one problem at a time
+// ------------------------------------------------------------------------------------------------
+template <bool HAS_OBS>
+__global__ void __launch_bounds__(512, 1)
+    solve_kernel(const __grid_constant__ ShapeDev sh, const __grid_constant__ ParamsDev P, const BatchDev bd,
+                 const GroupDev grp, const OutDev out, const HistDev hist, int* __restrict__ work_counter) {
+  extern __shared__ __align__(128) double smem[];
+  __shared__ __align__(8) unsigned long long mbar;
+  tma_load_block(smem, grp.lu, (unsigned)(sh.lu_doubles * sizeof(double)), &mbar);
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarp = blockDim.x >> 5;
+  WarpWS ws = carve_ws(smem + sh.lu_doubles + warp * sh.ws_doubles, sh);
+  const int slot = blockIdx.x * nwarp + warp;
+  const int n = sh.n;
+  const int m = P.mem_size;
+  double* lm_s = hist.s + (size_t)slot * hist.mem * hist.ld;
+  double* lm_y = hist.y + (size_t)slot * hist.mem * hist.ld;
+  double* lm_ys = hist.ys + (size_t)slot * hist.mem;
+  double* lm_alpha = hist.alpha + (size_t)slot * hist.mem;
+  const int ld = hist.ld;
+
+  while (true) {
+    int local = 0;
+    if (lane == 0) local = atomicAdd(work_counter, 1);
+    local = __shfl_sync(FULL, local, 0);
+    if (local >= grp.count) break;
+    const int prob = grp.prob_id[local];
+    const double* planes = grp.planes + (size_t)local * sh.H * 4 * sh.Mpad;
+
+    for (int i = lane; i < n; i += 32) ws.x[i] = bd.x0[(size_t)prob * bd.n_stride + i];
+    __syncwarp();
+    int evals = 0;
+    double fx = eval_cost_grad<HAS_OBS>(sh, P, bd, prob, planes, smem, ws, ws.x, ws.g, lane);
+    evals++;
+    double pf[8];  // past <= 8 supported (host checks)
+    pf[0] = fx;
+    for (int i = lane; i < n; i += 32) ws.d[i] = -ws.g[i];
+    __syncwarp();
+    double gnorm_inf = warp_maxabs(ws.g, n, lane);
+    double xnorm_inf = warp_maxabs(ws.x, n, lane);
+    int ret = 0, k = 0;
+    if (gnorm_inf / fmax(1.0, xnorm_inf) < P.g_epsilon) {
+      ret = DFTPAV_LBFGS_CONVERGENCE;
+    } else {
+      double step = 1.0 / sqrt(warp_dot(ws.d, ws.d, n, lane));
+      k = 1;
+      int end = 0, bound = 0;
+      while (true) {
+        for (int i = lane; i < n; i += 32) {
+          ws.xp[i] = ws.x[i];
+          ws.gp[i] = ws.g[i];
+        }
+        __syncwarp();
+        // ---------------- line_search_lewisoverton (lbfgs.hpp:276-390)
+        int ls;
+        {
+          int count = 0;
+          bool brackt = false, touched = false;
+          double mu = 0.0, nu = P.max_step;
+          const double stpmin = P.min_step, stpmax = P.max_step;
+          if (!(step > 0.0)) {
+            ls = DFTPAV_LBFGSERR_INVALIDPARAMETERS;
+          } else {
+            const double dginit = warp_dot(ws.gp, ws.d, n, lane);
+            if (0.0 < dginit) {
+              ls = DFTPAV_LBFGSERR_INCREASEGRADIENT;
+            } else {
+              const double finit = fx;
+              const double dgtest = P.f_dec_coeff * dginit;
+              const double dstest = P.s_curv_coeff * dginit;
+              while (true) {
+                for (int i = lane; i < n; i += 32) ws.x[i] = ws.xp[i] + step * ws.d[i];
+                __syncwarp();
+                fx = eval_cost_grad<HAS_OBS>(sh, P, bd, prob, planes, smem, ws, ws.x, ws.g, lane);
+                evals++;
+                ++count;
+                if (isinf(fx) || isnan(fx)) {
+                  ls = DFTPAV_LBFGSERR_INVALID_FUNCVAL;
+                  break;
+                }
+                if (P.past > 0 && fabs(finit - fx) / (fabs(finit) + 1.0) < P.delta / P.past) {
+                  ls = count;
+                  break;
+                }
+                if (fx > finit + step * dgtest) {
+                  nu = step;
+                  brackt = true;
+                } else {
+                  if (warp_dot(ws.g, ws.d, n, lane) < dstest) {
+                    mu = step;
+                  } else {
+                    ls = count;
+                    break;
+                  }
+                }
+                if (P.max_linesearch <= count) {
+                  ls = DFTPAV_LBFGSERR_MAXIMUMLINESEARCH;
+                  break;
+                }
+                if (brackt && (nu - mu) < P.machine_prec * nu) {
+                  ls = DFTPAV_LBFGSERR_WIDTHTOOSMALL;
+                  break;
+                }
+                if (brackt) {
+                  step = 0.5 * (mu + nu);
+                } else {
+                  step *= 2.0;
+                }
+                if (step < stpmin) {
+                  ls = DFTPAV_LBFGSERR_MINIMUMSTEP;
+                  break;
+                }
+                if (step > stpmax) {
+                  if (touched) {
+                    ls = DFTPAV_LBFGSERR_MAXIMUMSTEP;
+                    break;
+                  } else {
+                    touched = true;
+                    step = stpmax;
+                  }
+                }
+              }
+            }
+          }
+        }
+        if (ls < 0) {
+          for (int i = lane; i < n; i += 32) {
+            ws.x[i] = ws.xp[i];
+            ws.g[i] = ws.gp[i];
+          }
+          __syncwarp();
+          ret = ls;
+          break;
+        }
+        gnorm_inf = warp_maxabs(ws.g, n, lane);
+        xnorm_inf = warp_maxabs(ws.x, n, lane);
+        if (gnorm_inf / fmax(1.0, xnorm_inf) < P.g_epsilon) {
+          ret = DFTPAV_LBFGS_CONVERGENCE;
+          break;
+        }
+        if (0 < P.past) {
+          if (P.past <= k) {
+            const double rate = fabs(pf[k % P.past] - fx) / fmax(1.0, fabs(fx));
+            if (rate < P.delta) {
+              ret = DFTPAV_LBFGS_STOP;
+              break;
+            }
+          }
+          pf[k % P.past] = fx;
+        }
+        if (P.max_iterations != 0 && P.max_iterations <= k) {
+          ret = DFTPAV_LBFGSERR_MAXIMUMITERATION;
+          break;
+        }
+        ++k;
+        // ---------------- history update (lbfgs.hpp:676-687)
+        double* se = lm_s + (size_t)end * ld;
+        double* ye = lm_y + (size_t)end * ld;
+        double ys = 0.0, yy = 0.0, ss = 0.0, gg = 0.0;
+        for (int i = lane; i < n; i += 32) {
+          const double sv = ws.x[i] - ws.xp[i];
+          const double yv = ws.g[i] - ws.gp[i];
+          se[i] = sv;
+          ye[i] = yv;
+          ys += yv * sv;
+          yy += yv * yv;
+          ss += sv * sv;
+          gg += ws.gp[i] * ws.gp[i];
+          ws.d[i] = -ws.g[i];
+        }
+        ys = warp_sum(ys);
+        yy = warp_sum(yy);
+        ss = warp_sum(ss);
+        gg = warp_sum(gg);
+        if (lane == 0) lm_ys[end] = ys;
+        __syncwarp();
+        const double cau = ss * sqrt(gg) * P.cautious_factor;
+        if (ys > cau) {
+          // ---------------- two-loop recursion (lbfgs.hpp:716-739)
+          ++bound;
+          bound = m < bound ? m : bound;
+          end = (end + 1) % m;
+          int j = end;
+          for (int i = 0; i < bound; ++i) {
+            j = (j + m - 1) % m;
+            const double* sj = lm_s + (size_t)j * ld;
+            const double* yj = lm_y + (size_t)j * ld;
+            const double ysj = (i == 0) ? ys : lm_ys[j];
+            const double a = warp_dot(sj, ws.d, n, lane) / ysj;
+            if (lane == 0) lm_alpha[j] = a;
+            const double na = -a;
+            for (int q = lane; q < n; q += 32) ws.d[q] += na * yj[q];
+            __syncwarp();
+          }
+          const double sc = ys / yy;
+          for (int q = lane; q < n; q += 32) ws.d[q] *= sc;
+          __syncwarp();
+          for (int i = 0; i < bound; ++i) {
+            const double* sj = lm_s + (size_t)j * ld;
+            const double* yj = lm_y + (size_t)j * ld;
+            const double beta = warp_dot(yj, ws.d, n, lane) / lm_ys[j];
+            const double a = lm_alpha[j] - beta;
+            for (int q = lane; q < n; q += 32) ws.d[q] += a * sj[q];
+            __syncwarp();
+            j = (j + 1) % m;
+          }
+        }
+        step = 1.0;
+      }
+    }
+    // ---------------- results (traj_optimizer.cpp:176-201)
+    bool success = (ret == DFTPAV_LBFGS_CONVERGENCE || ret == DFTPAV_LBFGS_CANCELED || ret == DFTPAV_LBFGS_STOP ||
+                    ret == DFTPAV_LBFGSERR_MAXIMUMITERATION || ret == DFTPAV_LBFGSERR_MAXIMUMLINESEARCH);
+    if (fx >= P.cost_limit) success = false;
+    for (int i = lane; i < bd.n_stride; i += 32) out.x[(size_t)prob * bd.n_stride + i] = i < n ? ws.x[i] : 0.0;
+    for (int i = lane; i < 2 * bd.row_stride; i += 32)
+      out.coeffs[(size_t)prob * bd.row_stride * 2 + i] = i < 2 * sh.rows ? ws.c[i] : 0.0;
+    if (lane < sh.S) out.piece_dT[bd.seg_base[prob] + lane] = ws.seg[lane].dT;
+    if (lane == 0) {
+      out.cost[prob] = fx;
+      out.status[prob] = ret;
+      out.success[prob] = success ? 1 : 0;
+      out.iters[prob] = k;
+      out.evals[prob] = evals;
+    }
+    __syncwarp();
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// layout kernel: raw (n, p) planes [sample][h][4] -> tiled SoA [local][h][4][Mpad] with unit normals
+// (replaces the deep copy + colwise().normalize() of traj_optimizer.cpp:15, 49-52)
+// ------------------------------------------------------------------------------------------------
+__global__ void layout_planes_kernel(const ShapeDev sh, const int* __restrict__ prob_id, int count,
+                                     const long long* __restrict__ samp_base,   // [B] first raw sample of the problem
+                                     const long long* __restrict__ plane_ptr,   // [Q+1] or nullptr (uniform)
+                                     int uniform_H, const double* __restrict__ raw, double* __restrict__ soa) {
+  const int Mpad = sh.Mpad;
+  const long long total = (long long)count * Mpad;
+  for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total;
+       idx += (long long)gridDim.x * blockDim.x) {
+    const int local = (int)(idx / Mpad);
+    const int u = (int)(idx % Mpad);
+    const int prob = prob_id[local];
+    // which segment / piece / sample does storage slot u hold?
+    int s = 0;
+    while (s + 1 < sh.S && u >= sh.samp0[s + 1]) s++;
+    const int us = u - sh.samp0[s];
+    const int N = sh.N[s], K = sh.K, Kd = sh.Kd;
+    const int td = (Kd + kTile - 1) / kTile, tk = (K + kTile - 1) / kTile;
+    const int ntile = sh.ntile[s];
+    int piece = -1, j = 0;
+    if (us < ntile * kTile) {
+      const int t = us / kTile, r = us % kTile;
+      int j0;
+      if (t < td) {
+        piece = 0;
+        j0 = kTile * t;
+      } else if (t < td + (N - 2) * tk) {
+        const int uu = t - td;
+        piece = 1 + uu / tk;
+        j0 = kTile * (uu % tk);
+      } else {
+        piece = N - 1;
+        j0 = kTile * (t - td - (N - 2) * tk);
+      }
+      j = j0 + r;
+      const int Kp = (piece == 0 || piece == N - 1) ? Kd : K;
+      if (j >= Kp) piece = -1;
+    } else if (us < ntile * kTile + N) {
+      piece = us - ntile * kTile;
+      j = (piece == 0 || piece == N - 1) ? Kd : K;
+    }
+    double* dst = soa + (size_t)local * sh.H * 4 * Mpad + u;
+    int Hs = 0;
+    const double* src = nullptr;
+    if (piece >= 0) {
+      // pointid inside the segment (traj_optimizer.cpp:514): pieces before contribute K_i + 1 samples each
+      long long pid = 0;
+      for (int ss = 0; ss < s; ss++) pid += (long long)(sh.N[ss] - 2) * (K + 1) + 2 * (Kd + 1);
+      if (piece > 0) pid += (Kd + 1) + (long long)(piece - 1) * (K + 1);
+      pid += j;
+      const long long q = samp_base[prob] + pid;
+      if (plane_ptr) {
+        Hs = (int)(plane_ptr[q + 1] - plane_ptr[q]);
+        src = raw + 4 * plane_ptr[q];
+      } else {
+        Hs = uniform_H;
+        src = raw + 4 * q * uniform_H;
+      }
+    }
+    for (int h = 0; h < sh.H; h++) {
+      double nx = 0.0, ny = 0.0, px = 0.0, py = 0.0;
+      if (h < Hs) {
+        nx = src[4 * h], ny = src[4 * h + 1], px = src[4 * h + 2], py = src[4 * h + 3];
+        const double z = nx * nx + ny * ny;
+        if (z > 0.0) {
+          const double nz = sqrt(z);
+          nx /= nz;
+          ny /= nz;
+        }
+      }
+      dst[(size_t)(4 * h + 0) * Mpad] = nx;
+      dst[(size_t)(4 * h + 1) * Mpad] = ny;
+      dst[(size_t)(4 * h + 2) * Mpad] = px;
+      dst[(size_t)(4 * h + 3) * Mpad] = py;
+    }
+  }
+}
+
+// boundary-state clamps (traj_optimizer.cpp:55-76) and packing of x0 (traj_optimizer.cpp:96-115)
+__global__ void prepare_states_kernel(const ShapeDev sh, ParamsDev P, const int* __restrict__ prob_id, int count,
+                                      const int* __restrict__ seg_base, const int* __restrict__ singul,
+                                      const double* __restrict__ ini_raw, const double* __restrict__ fin_raw,
+                                      const double* __restrict__ init_T, const long long* __restrict__ inner_base,
+                                      const double* __restrict__ inner_pts, double* __restrict__ ini,
+                                      double* __restrict__ fin, double* __restrict__ x0, int n_stride) {
+  const int local = blockIdx.x * blockDim.x + threadIdx.x;
+  if (local >= count) return;
+  const int prob = prob_id[local];
+  const int g0 = seg_base[prob];
+  double* x = x0 + (size_t)prob * n_stride;
+  const int S = sh.S;
+  const int tv0 = sh.var0[S - 1] + 2 * (sh.N[S - 1] - 1);
+  const int gb = tv0 + S, ab = gb + 2 * (S - 1);
+  long long ib = inner_base[prob];
+  for (int s = 0; s < S; s++) {
+    const int g = g0 + s;
+    const int sidx = singul[g] > 0 ? 0 : 1;
+    const double max_vel = P.max_vel[sidx], max_acc = P.max_acc[sidx];
+    double st[2][6];
+    for (int k = 0; k < 6; k++) {
+      st[0][k] = ini_raw[6 * g + k];
+      st[1][k] = fin_raw[6 * g + k];
+    }
+    for (int w = 0; w < 2; w++) {
+      for (int c = 2; c <= 4; c += 2) {
+        const double lim = (c == 2) ? max_vel : max_acc;
+        const double vx = st[w][c], vy = st[w][c + 1];
+        const double z = vx * vx + vy * vy;
+        if (sqrt(z) >= lim) {
+          double nx = vx, ny = vy;
+          if (z > 0.0) {
+            const double sz = sqrt(z);
+            nx = vx / sz;
+            ny = vy / sz;
+          }
+          st[w][c] = nx * (lim - 1.0e-2);
+          st[w][c + 1] = ny * (lim - 1.0e-2);
+        }
+      }
+    }
+    for (int k = 0; k < 6; k++) {
+      ini[6 * g + k] = st[0][k];
+      fin[6 * g + k] = st[1][k];
+    }
+    const int np = 2 * (sh.N[s] - 1);
+    for (int i = 0; i < np; i++) x[sh.var0[s] + i] = inner_pts[ib + i];
+    ib += np;
+    const double RT = init_T[g], mini_T = P.mini_T;
+    x[tv0 + s] = RT > 1.0 + mini_T ? (sqrt(2.0 * RT - 1.0 - 2 * mini_T) - 1.0) : (1.0 - sqrt(2.0 / (RT - mini_T) - 1.0));
+    if (s < S - 1) {
+      x[gb + 2 * s] = st[1][0];
+      x[gb + 2 * s + 1] = st[1][1];
+      x[ab + s] = atan2(st[1][3], st[1][2]);
+    }
+  }
+  for (int i = sh.n; i < n_stride; i++) x[i] = 0.0;
+}
+
+// ------------------------------------------------------------------------------------------------
+// host-callable launchers (used by dftpav_api.cu)
+// ------------------------------------------------------------------------------------------------
+cudaError_t launch_solve(bool has_obs, int grid, int block, size_t smem, cudaStream_t st, const ShapeDev& sh,
+                         const ParamsDev& P, const BatchDev& bd, const GroupDev& grp, const OutDev& out,
+                         const HistDev& hist, int* counter) {
+  if (has_obs) {
+    cudaFuncSetAttribute(solve_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    solve_kernel<true><<<grid, block, smem, st>>>(sh, P, bd, grp, out, hist, counter);
+  } else {
+    cudaFuncSetAttribute(solve_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    solve_kernel<false><<<grid, block, smem, st>>>(sh, P, bd, grp, out, hist, counter);
+  }
+  return cudaGetLastError();
+}
+
+cudaError_t launch_eval(bool has_obs, int grid, int block, size_t smem, cudaStream_t st, const ShapeDev& sh,
+                        const ParamsDev& P, const BatchDev& bd, const GroupDev& grp, const double* x, double* f,
+                        double* g, double* coeffs, double* dT) {
+  if (has_obs) {
+    cudaFuncSetAttribute(eval_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    eval_kernel<true><<<grid, block, smem, st>>>(sh, P, bd, grp, x, f, g, coeffs, dT);
+  } else {
+    cudaFuncSetAttribute(eval_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    eval_kernel<false><<<grid, block, smem, st>>>(sh, P, bd, grp, x, f, g, coeffs, dT);
+  }
+  return cudaGetLastError();
+}
+
+cudaError_t launch_layout(int grid, int block, cudaStream_t st, const ShapeDev& sh, const int* prob_id, int count,
+                          const long long* samp_base, const long long* plane_ptr, int uniform_H, const double* raw,
+                          double* soa) {
+  layout_planes_kernel<<<grid, block, 0, st>>>(sh, prob_id, count, samp_base, plane_ptr, uniform_H, raw, soa);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_prepare(int grid, int block, cudaStream_t st, const ShapeDev& sh, const ParamsDev& P,
+                           const int* prob_id, int count, const int* seg_base, const int* singul, const double* ini_raw,
+                           const double* fin_raw, const double* init_T, const long long* inner_base,
+                           const double* inner_pts, double* ini, double* fin, double* x0, int n_stride) {
+  prepare_states_kernel<<<grid, block, 0, st>>>(sh, P, prob_id, count, seg_base, singul, ini_raw, fin_raw, init_T,
+                                                inner_base, inner_pts, ini, fin, x0, n_stride);
+  return cudaGetLastError();
+}
+
+int ws_doubles_host(int rows, int npad) { return ws_doubles_for(rows, npad); }
+
+}  // namespace dftpav

@@ -1,0 +1,155 @@
+"""Python host binding over the C-ABI (include/dftpav_b200.h) — thin, no arithmetic of its own.
+
+``BatchOptimizer`` mirrors the call sequence a planner makes against the reference
+``plan_manage::PolyTrajOptimizer`` (traj_optimizer.h:100-120):
+
+    reference                               this binding                     C-ABI
+    ---------------------------------------------------------------------------------------------
+    new PolyTrajOptimizer; setParam(cfg)    BatchOptimizer(params)           dftpav_create
+    setSurroundTrajs(&trajs)                (obstacles are part of the batch) dftpav_upload_batch
+    OptimizeTrajectory(ini, fin, P, T, ...) solve(batch) / optimize()        dftpav_optimize
+    getMinJerkOptPtr()->at(i).getTraj(s)    download() -> Solution.coeffs    dftpav_download
+
+The C++ adapter with the reference's exact signatures lives in dftpav_b200/host/poly_traj_optimizer.hpp.
+All failures raise; there is no CPU fallback.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Optional
+
+import numpy as np
+
+from . import capi
+from .batch import TrajBatch
+
+
+class DftpavError(RuntimeError):
+    def __init__(self, code: int, msg: str):
+        super().__init__(f"dftpav error {code}: {msg}")
+        self.code = code
+
+
+class Solution:
+    """Host copies of dftpav_result (same strides as dftpav_dims)."""
+
+    def __init__(self, B: int, n_stride: int, row_stride: int, G: int, pinned: bool = False):
+        def alloc(shape, dtype):
+            if pinned:
+                import torch
+
+                t = torch.empty(shape, dtype={np.float64: torch.float64, np.int32: torch.int32}[dtype]).pin_memory()
+                self._keep.append(t)
+                return t.numpy()
+            return np.zeros(shape, dtype=dtype)
+
+        self._keep = []
+        self.x = alloc((B, n_stride), np.float64)
+        self.cost = alloc((B,), np.float64)
+        self.status = alloc((B,), np.int32)
+        self.success = alloc((B,), np.int32)
+        self.iters = alloc((B,), np.int32)
+        self.evals = alloc((B,), np.int32)
+        self.coeffs = alloc((B, row_stride, 2), np.float64)
+        self.piece_dT = alloc((G,), np.float64)
+
+    def as_c(self) -> capi.Result:
+        r = capi.Result()
+        dp, ip = capi.c_double_p, capi.c_int32_p
+        r.x = self.x.ctypes.data_as(dp)
+        r.cost = self.cost.ctypes.data_as(dp)
+        r.status = self.status.ctypes.data_as(ip)
+        r.success = self.success.ctypes.data_as(ip)
+        r.iters = self.iters.ctypes.data_as(ip)
+        r.evals = self.evals.ctypes.data_as(ip)
+        r.coeffs = self.coeffs.ctypes.data_as(dp)
+        r.piece_dT = self.piece_dT.ctypes.data_as(dp)
+        return r
+
+    def nbytes(self) -> int:
+        return sum(a.nbytes for a in (self.x, self.cost, self.status, self.success, self.iters, self.evals, self.coeffs,
+                                      self.piece_dT))
+
+
+class BatchOptimizer:
+    def __init__(self, params: Optional[capi.Params] = None, device: int = -1):
+        self._lib = capi.load_library()
+        self.params = params if params is not None else capi.default_params()
+        self._h = C.c_void_p()
+        rc = self._lib.dftpav_create(C.byref(self.params), device, C.byref(self._h))
+        if rc != capi.OK:
+            raise DftpavError(rc, "dftpav_create failed (no sm_100 device? there is no CPU fallback)")
+        self._batch = None
+        self._dims = None
+
+    # -- plumbing ------------------------------------------------------------------------------
+    def _check(self, rc: int):
+        if rc != capi.OK:
+            raise DftpavError(rc, self._lib.dftpav_last_error(self._h).decode())
+
+    def close(self):
+        if self._h:
+            self._lib.dftpav_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def set_stream(self, cuda_stream_ptr: int):
+        self._check(self._lib.dftpav_set_stream(self._h, C.c_void_p(cuda_stream_ptr)))
+
+    def stats(self) -> capi.Stats:
+        s = capi.Stats()
+        self._check(self._lib.dftpav_last_stats(self._h, C.byref(s)))
+        return s
+
+    # -- the call sequence ---------------------------------------------------------------------
+    def upload(self, batch: TrajBatch) -> capi.Dims:
+        self._batch = batch
+        cb = batch.as_c()
+        self._check(self._lib.dftpav_upload_batch(self._h, C.byref(cb)))
+        d = capi.Dims()
+        self._check(self._lib.dftpav_get_dims(self._h, C.byref(d)))
+        self._dims = d
+        return d
+
+    def optimize(self):
+        self._check(self._lib.dftpav_optimize(self._h))
+
+    def new_solution(self, pinned: bool = False) -> Solution:
+        d = self._dims
+        return Solution(d.B, d.n_stride, d.row_stride, d.seg_total, pinned=pinned)
+
+    def download(self, sol: Optional[Solution] = None) -> Solution:
+        if sol is None:
+            sol = self.new_solution()
+        res = sol.as_c()
+        self._check(self._lib.dftpav_download(self._h, C.byref(res)))
+        return sol
+
+    def solve(self, batch: TrajBatch, sol: Optional[Solution] = None) -> Solution:
+        """upload + optimize + download: the end-to-end call (dftpav_solve)."""
+        self.upload(batch)
+        self.optimize()
+        return self.download(sol)
+
+    def evaluate(self, x: np.ndarray):
+        """One cost+gradient evaluation per problem at x [B, n_stride] (dftpav_eval)."""
+        d = self._dims
+        x = np.ascontiguousarray(x, dtype=np.float64).reshape(d.B, d.n_stride)
+        f = np.zeros(d.B)
+        g = np.zeros((d.B, d.n_stride))
+        dp = capi.c_double_p
+        self._check(self._lib.dftpav_eval(self._h, x.ctypes.data_as(dp), f.ctypes.data_as(dp), g.ctypes.data_as(dp)))
+        return f, g
+
+    def initial_x(self, batch: TrajBatch) -> np.ndarray:
+        d = capi.Dims()
+        cb = batch.as_c()
+        self._check(self._lib.dftpav_batch_dims(C.byref(self.params), C.byref(cb), C.byref(d)))
+        x0 = np.zeros((d.B, d.n_stride))
+        self._check(self._lib.dftpav_initial_x(C.byref(self.params), C.byref(cb), x0.ctypes.data_as(capi.c_double_p)))
+        return x0
