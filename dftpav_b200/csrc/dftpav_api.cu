@@ -36,6 +36,7 @@ cudaError_t launch_prepare(int grid, int block, cudaStream_t st, const ShapeDev&
                            const double* fin_raw, const double* init_T, const long long* inner_base,
                            const double* inner_pts, double* ini, double* fin, double* x0, int n_stride);
 int ws_doubles_host(int rows, int npad);
+cudaError_t set_phase_clock(unsigned long long* dev_ptr);
 }  // namespace dftpav
 
 using namespace dftpav;
@@ -186,6 +187,8 @@ int validate(const dftpav_params* prm, const dftpav_batch* b, dftpav_dims* dims,
   if (prm->traj_resolution < 1 || prm->des_traj_resolution < 1) return bad(DFTPAV_ERR_INVALID_ARG, "resolution < 1");
   if (prm->lbfgs_past < 0 || prm->lbfgs_past > 8) return bad(DFTPAV_ERR_UNSUPPORTED, "lbfgs_past must be in [0,8]");
   if (prm->lbfgs_mem_size < 1) return bad(DFTPAV_ERR_INVALID_ARG, "lbfgs_mem_size < 1");
+  if (prm->lbfgs_mem_size > 2 * 12 * kStageLd)  // alpha array lives in the sweep staging buffer
+    return bad(DFTPAV_ERR_UNSUPPORTED, "lbfgs_mem_size > 408");
   if (!b->plane_cnt && b->uniform_H < 0) return bad(DFTPAV_ERR_INVALID_ARG, "uniform_H < 0");
   int n_stride = 0, row_stride = 0;
   long long samples = 0;
@@ -596,9 +599,11 @@ int dftpav_upload_batch(dftpav_handle* h, const dftpav_batch* b) {
       sampoff += store;
       auto it = lu_of_N.find(N);
       if (it == lu_of_N.end()) {
-        lu_of_N[N] = luoff;
-        sh.lu_off[s] = luoff;
-        luoff += 6 * N * kLuLd;
+        // table layout per distinct N: [6 zero columns][6N packed columns][6 zero columns] so that the update-form
+        // substitutions may address columns j-6 .. j+6 without bounds checks
+        lu_of_N[N] = luoff + 6 * kLuLd;
+        sh.lu_off[s] = luoff + 6 * kLuLd;
+        luoff += (6 * N + 12) * kLuLd;
       } else {
         sh.lu_off[s] = it->second;
       }
@@ -838,6 +843,20 @@ int dftpav_solve(dftpav_handle* h, const dftpav_batch* batch, const dftpav_resul
 int dftpav_last_stats(const dftpav_handle* h, dftpav_stats* stats) {
   if (!h || !stats) return DFTPAV_ERR_INVALID_ARG;
   *stats = h->stats;
+  return DFTPAV_OK;
+}
+
+// Diagnostic (not part of the drop-in ABI): enables per-phase cycle counters of the evaluation and returns them.
+// phases: 0 rhs build, 1 banded solve, 2 coefficients + jerk, 3 sweep, 4 adjoint rhs, 5 adjoint solve, 6 gradient assembly
+int dftpav_debug_phase_clock(dftpav_handle* h, int enable, unsigned long long* cycles8) {
+  if (!h) return DFTPAV_ERR_INVALID_ARG;
+  static unsigned long long* d_clk = nullptr;
+  CU_TRY(h, cudaSetDevice(h->device));
+  CU_TRY(h, cudaStreamSynchronize(h->stream));
+  if (!d_clk) CU_TRY(h, cudaMalloc(&d_clk, 8 * sizeof(unsigned long long)));
+  if (cycles8) CU_TRY(h, cudaMemcpy(cycles8, d_clk, 8 * sizeof(unsigned long long), cudaMemcpyDeviceToHost));
+  CU_TRY(h, cudaMemset(d_clk, 0, 8 * sizeof(unsigned long long)));
+  CU_TRY(h, set_phase_clock(enable ? d_clk : nullptr));
   return DFTPAV_OK;
 }
 

@@ -32,13 +32,15 @@ __device__ __forceinline__ double warp_max(double v) {
   for (int o = 16; o > 0; o >>= 1) v = fmax(v, __shfl_xor_sync(FULL, v, o));
   return v;
 }
-__device__ __forceinline__ double warp_dot(const double* a, const double* b, int n, int lane) {
+__device__ __noinline__ double warp_dot(const double* a, const double* b, int n, int lane) {
   double s = 0.0;
+#pragma unroll 1
   for (int i = lane; i < n; i += 32) s += a[i] * b[i];
   return warp_sum(s);
 }
-__device__ __forceinline__ double warp_maxabs(const double* a, int n, int lane) {
+__device__ __noinline__ double warp_maxabs(const double* a, int n, int lane) {
   double m = 0.0;
+#pragma unroll 1
   for (int i = lane; i < n; i += 32) m = fmax(m, fabs(a[i]));
   return warp_max(m);
 }
@@ -113,12 +115,13 @@ struct WarpWS {
   double* g;      // [npad]
   double* gp;     // [npad]
   double* d;      // [npad]
-  double* stage;  // [2][12][kStageLd]
+  double* stage;  // [2][12][kStageLd]; doubles as the L-BFGS alpha array between evaluations
+  double* pf;     // [8] past cost values (lbfgs.hpp:508, 658)
   SegScratch* seg;  // [kMaxSeg]
 };
 
 __host__ __device__ inline int ws_doubles_for(int rows, int npad) {
-  return 6 * rows + 5 * npad + 2 * 12 * kStageLd + kMaxSeg * (int)(sizeof(SegScratch) / sizeof(double));
+  return 6 * rows + 5 * npad + 2 * 12 * kStageLd + 8 + kMaxSeg * (int)(sizeof(SegScratch) / sizeof(double));
 }
 
 __device__ __forceinline__ WarpWS carve_ws(double* base, const ShapeDev& sh) {
@@ -132,7 +135,8 @@ __device__ __forceinline__ WarpWS carve_ws(double* base, const ShapeDev& sh) {
   w.gp = w.g + sh.npad;
   w.d = w.gp + sh.npad;
   w.stage = w.d + sh.npad;
-  w.seg = reinterpret_cast<SegScratch*>(w.stage + 2 * 12 * kStageLd);
+  w.pf = w.stage + 2 * 12 * kStageLd;
+  w.seg = reinterpret_cast<SegScratch*>(w.pf + 8);
   return w;
 }
 
@@ -142,83 +146,116 @@ __device__ __forceinline__ WarpWS carve_ws(double* base, const ShapeDev& sh) {
 // Each calling lane owns one right-hand-side column `col` of the row-major n x 2 array b.
 // The 1/U(j,j) product replaces the reference's division (<= 1 ulp per row).
 // ------------------------------------------------------------------------------------------------
-__device__ __forceinline__ void banded_solve(const double* __restrict__ C, double* b, int n, int col) {
+// Shared-memory load the compiler may schedule freely (a pure function of its address for the compiler: no memory
+// clobber, not volatile).  ONLY for data that is not written between the producing barrier and the consuming loop
+// iteration: the read-only LU table, and right-hand-side rows that the running substitution pass has not reached
+// yet.  In the banded passes a plain C++ load sits behind the previous row's store in program order (the compiler
+// cannot prove the two shared arrays distinct after inlining) and the in-order issue then exposes the full LDS
+// latency on every row of the dependent chain.
+__device__ __forceinline__ double lds_pure(unsigned addr) {
+  double v;
+#ifdef DFTPAV_NO_PURE_LDS
+  asm volatile("ld.shared.f64 %0, [%1];" : "=d"(v) : "r"(addr) : "memory");
+#else
+  asm("ld.shared.f64 %0, [%1];" : "=d"(v) : "r"(addr));
+#endif
+  return v;
+}
+__device__ __forceinline__ unsigned smem_addr(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
+// Opaque zero created by a volatile asm with a memory clobber: the compiler keeps it behind every earlier store and
+// barrier.  Adding it to the base address of lds_pure loads pins those loads behind that point as well.
+__device__ __forceinline__ unsigned order_token() {
+  unsigned t;
+  asm volatile("mov.u32 %0, 0;" : "=r"(t)::"memory");
+  return t;
+}
+
+__device__ __forceinline__ void banded_solve(const double* C, double* b, int n, int col) {
+  const unsigned tok0 = order_token();
+  const unsigned Ca = smem_addr(C) + tok0;  // also keeps the table reads behind the TMA completion wait
+  unsigned ba = smem_addr(b) + 8u * col + tok0;
+  constexpr unsigned CS = kLuLd * 8u;  // bytes per packed column
   // forward, update form (poly_traj_utils.hpp:808-815)
   double w0 = b[col], w1 = b[2 + col], w2 = b[4 + col], w3 = b[6 + col], w4 = b[8 + col], w5 = b[10 + col];
   double w6 = (6 < n) ? b[12 + col] : 0.0;
 #pragma unroll 6
   for (int j = 0; j < n; j++) {
+    const unsigned cj = Ca + j * CS;
     const double y = w0;
-    const double* Cj = C + j * kLuLd;
     b[2 * j + col] = y;
-    w0 = w1 - Cj[7] * y;
-    w1 = w2 - Cj[8] * y;
-    w2 = w3 - Cj[9] * y;
-    w3 = w4 - Cj[10] * y;
-    w4 = w5 - Cj[11] * y;
-    w5 = w6 - Cj[12] * y;
-    w6 = (j + 7 < n) ? b[2 * (j + 7) + col] : 0.0;
+    w0 = w1 - lds_pure(cj + 7 * 8) * y;
+    w1 = w2 - lds_pure(cj + 8 * 8) * y;
+    w2 = w3 - lds_pure(cj + 9 * 8) * y;
+    w3 = w4 - lds_pure(cj + 10 * 8) * y;
+    w4 = w5 - lds_pure(cj + 11 * 8) * y;
+    w5 = w6 - lds_pure(cj + 12 * 8) * y;
+    w6 = (j + 7 < n) ? lds_pure(ba + 16u * (j + 7)) : 0.0;
   }
+  // (no __syncwarp here: only the two solving lanes of a segment execute this function)
+  ba = smem_addr(b) + 8u * col + order_token();
   // backward, update form (poly_traj_utils.hpp:816-824)
   double v0 = b[2 * (n - 1) + col], v1 = b[2 * (n - 2) + col], v2 = b[2 * (n - 3) + col], v3 = b[2 * (n - 4) + col];
   double v4 = b[2 * (n - 5) + col], v5 = b[2 * (n - 6) + col];
   double v6 = (n - 7 >= 0) ? b[2 * (n - 7) + col] : 0.0;
 #pragma unroll 6
   for (int j = n - 1; j >= 0; j--) {
-    const double* Cj = C + j * kLuLd;
-    const double xj = v0 * Cj[13];
+    const unsigned cj = Ca + j * CS;
+    const double xj = v0 * lds_pure(cj + 13 * 8);
     b[2 * j + col] = xj;
-    v0 = v1 - Cj[5] * xj;
-    v1 = v2 - Cj[4] * xj;
-    v2 = v3 - Cj[3] * xj;
-    v3 = v4 - Cj[2] * xj;
-    v4 = v5 - Cj[1] * xj;
-    v5 = v6 - Cj[0] * xj;
-    v6 = (j - 7 >= 0) ? b[2 * (j - 7) + col] : 0.0;
+    v0 = v1 - lds_pure(cj + 5 * 8) * xj;
+    v1 = v2 - lds_pure(cj + 4 * 8) * xj;
+    v2 = v3 - lds_pure(cj + 3 * 8) * xj;
+    v3 = v4 - lds_pure(cj + 2 * 8) * xj;
+    v4 = v5 - lds_pure(cj + 1 * 8) * xj;
+    v5 = v6 - lds_pure(cj + 0 * 8) * xj;
+    v6 = (j - 7 >= 0) ? lds_pure(ba + 16u * (j - 7)) : 0.0;
   }
 }
 
-__device__ __forceinline__ void banded_solve_adj(const double* __restrict__ C, double* b, int n, int col) {
-  // U^T z = b, ascending, gather form: row i receives U(i-6,i) z_{i-6} ... U(i-1,i) z_{i-1} in that order, then / U(i,i)
-  double z1 = 0.0, z2 = 0.0, z3 = 0.0, z4 = 0.0, z5 = 0.0, z6 = 0.0;
+__device__ __forceinline__ void banded_solve_adj(const double* C, double* b, int n, int col) {
+  // Update ("column") form, exactly the reference loops (poly_traj_utils.hpp:834-850): when row j is final its
+  // contribution is pushed into the six pending rows with six INDEPENDENT fused multiply-adds, so the dependent
+  // chain per row is one FMA (+ one multiply by 1/U(j,j)).  Row i still receives its terms in the reference order.
+  const unsigned tok0 = order_token();
+  const unsigned Ca = smem_addr(C) + tok0;
+  unsigned ba = smem_addr(b) + 8u * col + tok0;
+  constexpr unsigned CS = kLuLd * 8u;
+  // U^T z = b, ascending:  z_j = acc_j / U(j,j);  acc_{j+k} -= U(j, j+k) z_j,   U(j, j+k) = C[j+k][6-k]
+  // (columns beyond the matrix are the zero padding behind the table)
+  double a0 = b[col], a1 = b[2 + col], a2 = b[4 + col], a3 = b[6 + col], a4 = b[8 + col], a5 = b[10 + col];
+  double a6 = (6 < n) ? b[12 + col] : 0.0;
 #pragma unroll 6
-  for (int i = 0; i < n; i++) {
-    const double* Ci = C + i * kLuLd;
-    double t = b[2 * i + col];
-    t -= Ci[0] * z6;
-    t -= Ci[1] * z5;
-    t -= Ci[2] * z4;
-    t -= Ci[3] * z3;
-    t -= Ci[4] * z2;
-    t -= Ci[5] * z1;
-    const double zi = t * Ci[13];
-    b[2 * i + col] = zi;
-    z6 = z5;
-    z5 = z4;
-    z4 = z3;
-    z3 = z2;
-    z2 = z1;
-    z1 = zi;
+  for (int j = 0; j < n; j++) {
+    const unsigned cj = Ca + j * CS;
+    const double zj = a0 * lds_pure(cj + 13 * 8);
+    b[2 * j + col] = zj;
+    a0 = a1 - lds_pure(cj + 1 * CS + 5 * 8) * zj;
+    a1 = a2 - lds_pure(cj + 2 * CS + 4 * 8) * zj;
+    a2 = a3 - lds_pure(cj + 3 * CS + 3 * 8) * zj;
+    a3 = a4 - lds_pure(cj + 4 * CS + 2 * 8) * zj;
+    a4 = a5 - lds_pure(cj + 5 * CS + 1 * 8) * zj;
+    a5 = a6 - lds_pure(cj + 6 * CS + 0 * 8) * zj;
+    a6 = (j + 7 < n) ? lds_pure(ba + 16u * (j + 7)) : 0.0;
   }
-  // L^T w = z, descending, gather form: row i receives L(i+6,i) w_{i+6} ... L(i+1,i) w_{i+1} in that order
-  double q1 = 0.0, q2 = 0.0, q3 = 0.0, q4 = 0.0, q5 = 0.0, q6 = 0.0;
+  // (no __syncwarp here: only the two solving lanes of a segment execute this function)
+  ba = smem_addr(b) + 8u * col + order_token();
+  // L^T w = z, descending:  w_j = acc_j;  acc_{j-k} -= L(j, j-k) w_j,   L(j, j-k) = C[j-k][6+k]
+  // (columns in front of the matrix are the zero padding before the table)
+  double q0 = b[2 * (n - 1) + col], q1 = b[2 * (n - 2) + col], q2 = b[2 * (n - 3) + col], q3 = b[2 * (n - 4) + col];
+  double q4 = b[2 * (n - 5) + col], q5 = b[2 * (n - 6) + col];
+  double q6 = (n - 7 >= 0) ? b[2 * (n - 7) + col] : 0.0;
 #pragma unroll 6
-  for (int i = n - 1; i >= 0; i--) {
-    const double* Ci = C + i * kLuLd;
-    double t = b[2 * i + col];
-    t -= Ci[12] * q6;
-    t -= Ci[11] * q5;
-    t -= Ci[10] * q4;
-    t -= Ci[9] * q3;
-    t -= Ci[8] * q2;
-    t -= Ci[7] * q1;
-    b[2 * i + col] = t;
-    q6 = q5;
-    q5 = q4;
-    q4 = q3;
-    q3 = q2;
-    q2 = q1;
-    q1 = t;
+  for (int j = n - 1; j >= 0; j--) {
+    const unsigned cj = Ca + j * CS;
+    const double wj = q0;
+    b[2 * j + col] = wj;
+    q0 = q1 - lds_pure(cj - 1 * CS + 7 * 8) * wj;
+    q1 = q2 - lds_pure(cj - 2 * CS + 8 * 8) * wj;
+    q2 = q3 - lds_pure(cj - 3 * CS + 9 * 8) * wj;
+    q3 = q4 - lds_pure(cj - 4 * CS + 10 * 8) * wj;
+    q4 = q5 - lds_pure(cj - 5 * CS + 11 * 8) * wj;
+    q5 = q6 - lds_pure(cj - 6 * CS + 12 * 8) * wj;
+    q6 = (j - 7 >= 0) ? lds_pure(ba + 16u * (j - 7)) : 0.0;
   }
 }
 
@@ -295,6 +332,25 @@ __device__ __forceinline__ double lse(double alpha, double* v, double& exp_sum) 
     exp_sum += v[j];
   }
   return log(exp_sum) / alpha + d0;
+}
+
+constexpr int kPlaneChunk = 4;
+// Loads planes h0..h0+3 of storage slot `store` into registers; planes beyond H read as the null plane (n = p = 0).
+__device__ __forceinline__ void load_plane_chunk(double (&pn)[kPlaneChunk][4], const double* __restrict__ pl, int Mpad,
+                                                 int store, int h0, int H) {
+#pragma unroll
+  for (int hh = 0; hh < kPlaneChunk; hh++) {
+    const int h = h0 + hh;
+    if (h < H) {
+      const double* ph = pl + (size_t)(4 * h) * Mpad + store;
+      pn[hh][0] = __ldg(ph);
+      pn[hh][1] = __ldg(ph + Mpad);
+      pn[hh][2] = __ldg(ph + 2 * (size_t)Mpad);
+      pn[hh][3] = __ldg(ph + 3 * (size_t)Mpad);
+    } else {
+      pn[hh][0] = pn[hh][1] = pn[hh][2] = pn[hh][3] = 0.0;
+    }
+  }
 }
 
 // Accumulators of one sample: G0 = d/d sigma, G1 = d/d sigma', G2 = d/d sigma'' (already weighted), plus the
@@ -502,6 +558,7 @@ __device__ __forceinline__ void sweep_segment(const ShapeDev& sh, const ParamsDe
   const double trajtime = ws.seg[s].trajtime;
   const int sidx = singul_ > 0 ? 0 : 1;
   const double max_vel = P.max_vel[sidx], max_cur = P.max_cur[sidx], max_acc = P.max_acc[sidx];
+  const double sg = (double)singul_;
   const double* cseg = ws.c + 2 * sh.row0[s];
   double* gdseg = ws.gd + 2 * sh.row0[s];
   const int Mpad = sh.Mpad;
@@ -509,10 +566,20 @@ __device__ __forceinline__ void sweep_segment(const ShapeDev& sh, const ParamsDe
   const double* pl = planes + sh.samp0[s];
 
   double acc_gdT = 0.0, acc_p0 = 0.0, acc_p1 = 0.0, acc_p2 = 0.0;
+  const int npass = npass_reg + npass_end;
+  // storage slot of this lane in a given pass (regular tiles first, then the piece-endpoint samples)
+  auto slot_of = [&](int pass) -> int {
+    if (pass < npass_reg) return (2 * pass + half) * kTile + r;
+    const int pc = (pass - npass_reg) * 32 + lane;
+    return ntile * kTile + (pc < N ? pc : N - 1);
+  };
+  double pn[kPlaneChunk][4];
+  load_plane_chunk(pn, pl, Mpad, slot_of(0), 0, H);
 
-  for (int pass = 0; pass < npass_reg + npass_end; pass++) {
+  for (int pass = 0; pass < npass; pass++) {
     const bool endpass = pass >= npass_reg;
-    int piece, j, Kp, store;
+    int piece, j, Kp;
+    const int store = slot_of(pass);
     bool valid;
     if (!endpass) {
       const int t = 2 * pass + half;
@@ -532,31 +599,29 @@ __device__ __forceinline__ void sweep_segment(const ShapeDev& sh, const ParamsDe
       Kp = (piece == 0 || piece == N - 1) ? Kd : K;
       j = j0 + r;
       valid = (t < ntile) && (j < Kp);
-      store = t * kTile + r;
     } else {
       piece = (pass - npass_reg) * 32 + lane;
       valid = piece < N;
       if (!valid) piece = N - 1;
       Kp = (piece == 0 || piece == N - 1) ? Kd : K;
       j = Kp;
-      store = ntile * kTile + piece;
     }
 
-    double out[12];
-#pragma unroll
-    for (int q = 0; q < 12; q++) out[q] = 0.0;
-
+    // ---------------- stage A: trajectory derivatives at the sample (traj_optimizer.cpp:501-520)
+    const double invKp = 1.0 / Kp;  // exact for the power-of-two resolutions of the reference config
+    const double step = dT * invKp;
+    const double s1 = j * step;     // the reference accumulates s1 += step (quirk Q3); differs by O(j) ulp
+    const double alpha = invKp * j;
+    const double omg = (j == 0 || j == Kp) ? 0.5 : 1.0;
+    V2 sigma = mk(0.0, 0.0), dsigma = mk(0.0, 0.0), ddsigma = mk(0.0, 0.0), dddsigma = mk(0.0, 0.0);
+    bool active = false;
     if (valid) {
       const double* c = cseg + 12 * piece;
-      const double step = dT / Kp;
-      const double s1 = j * step;  // reference accumulates s1 += step (quirk Q3); differs by O(j) ulp
       const double s2 = s1 * s1, s3 = s2 * s1, s4 = s2 * s2, s5 = s4 * s1;
       const double b0[6] = {1.0, s1, s2, s3, s4, s5};
       const double b1[6] = {0.0, 1.0, 2.0 * s1, 3.0 * s2, 4.0 * s3, 5.0 * s4};
       const double b2[6] = {0.0, 0.0, 2.0, 6.0 * s1, 12.0 * s2, 20.0 * s3};
       const double b3[6] = {0.0, 0.0, 0.0, 6.0, 24.0 * s1, 60.0 * s2};
-      const double alpha = 1.0 / Kp * j;
-      V2 sigma = mk(0.0, 0.0), dsigma = mk(0.0, 0.0), ddsigma = mk(0.0, 0.0), dddsigma = mk(0.0, 0.0);
 #pragma unroll
       for (int k = 0; k < 6; k++) {
         const double cx = c[2 * k], cy = c[2 * k + 1];
@@ -569,127 +634,169 @@ __device__ __forceinline__ void sweep_segment(const ShapeDev& sh, const ParamsDe
         dddsigma.x += cx * b3[k];
         dddsigma.y += cy * b3[k];
       }
-      const double omg = (j == 0 || j == Kp) ? 0.5 : 1.0;
-      double z_h0 = norm(dsigma);
-      const bool skip = (z_h0 < P.min_speed) || (j == 0 && piece == 0) || (piece == N - 1 && j == Kp);
-      if (!skip) {
-        const double z_h1 = dot(ddsigma, dsigma);
-        const double z_h2 = dot(dddsigma, dsigma);
-        const double z_h3 = ddsigma.y * dsigma.x - ddsigma.x * dsigma.y;
-        const double vel2_reci = 1.0 / (z_h0 * z_h0);
-        const double vel2_reci_e = 1.0 / (z_h0 * z_h0 + P.help_eps);
-        const double vel3_2_reci_e = vel2_reci_e * sqrt(vel2_reci_e);
-        z_h0 = 1.0 / z_h0;
-        const double z_h4 = z_h1 * vel2_reci;
-        const double violaVel = 1.0 / vel2_reci - max_vel * max_vel;
-        const double acc2 = z_h1 * z_h1 * vel2_reci;
-        const double cur = z_h3 * vel3_2_reci_e;
-        const double violaAcc = acc2 - max_acc * max_acc;
-        const double violaCurL = cur - max_cur;
-        const double violaCurR = -cur - max_cur;
-        const double sg = (double)singul_;
-        const M2 rot = M2{dsigma.x, -dsigma.y, dsigma.y, dsigma.x};
-        const M2 ego_R = M2{sg * rot.a * z_h0, sg * rot.b * z_h0, sg * rot.c * z_h0, sg * rot.d * z_h0};
-        M2 R_dot;
-        {
-          const double f2 = vel2_reci * z_h0 * z_h1;
-          R_dot = M2{sg * (ddsigma.x * z_h0 - rot.a * f2), sg * (-ddsigma.y * z_h0 - rot.b * f2),
-                     sg * (ddsigma.y * z_h0 - rot.c * f2), sg * (ddsigma.x * z_h0 - rot.d * f2)};
-        }
-        SampleAcc acc;
-        acc.G0 = mk(0.0, 0.0);
-        acc.G1 = mk(0.0, 0.0);
-        acc.G2 = mk(0.0, 0.0);
-        acc.gdT = 0.0;
-        acc.pen0 = acc.pen1 = acc.pen2 = 0.0;
+      const double v2a = dsigma.x * dsigma.x + dsigma.y * dsigma.y;
+      // skip rule of traj_optimizer.cpp:550
+      active = !((v2a < P.min_speed * P.min_speed) || (j == 0 && piece == 0) || (piece == N - 1 && j == Kp));
+    }
 
-        // ---- static corridor (traj_optimizer.cpp:592-622).  Quirk Q1: the vertex list has 5 entries, vertex 0 twice;
-        //      the duplicate is folded into a weight of 2 on vertex 0.
-        const double wobs = omg * step * P.wei_obs;
+    // ---------------- stage B: kinematic helpers + static corridor
+    double z_h0 = 0.0, vel2_reci = 0.0, vel3_2_reci_e = 0.0, vel2_reci_e = 0.0, z_h1 = 0.0, z_h3 = 0.0, v2 = 0.0;
+    M2 ego_R = M2{0.0, 0.0, 0.0, 0.0};
+    SampleAcc acc;
+    acc.G0 = mk(0.0, 0.0);
+    acc.G1 = mk(0.0, 0.0);
+    acc.G2 = mk(0.0, 0.0);
+    acc.gdT = 0.0;
+    acc.pen0 = acc.pen1 = acc.pen2 = 0.0;
+    if (active) {
+      v2 = dsigma.x * dsigma.x + dsigma.y * dsigma.y;
+      z_h1 = dot(ddsigma, dsigma);
+      z_h3 = ddsigma.y * dsigma.x - ddsigma.x * dsigma.y;
+      // |v|, 1/|v|, 1/|v|^2 and (|v|^2+eps)^(-3/2) (traj_optimizer.cpp:527, 556-559).  With eps == 0 (what the plan
+      // manager passes, traj_manager.cpp:610) all of them follow from ONE reciprocal square root; a few ulp away
+      // from the reference's sqrt + three divisions.
+      if (P.help_eps == 0.0) {
+        z_h0 = rsqrt(v2);  // 1/|v|
+        vel2_reci = z_h0 * z_h0;
+        vel2_reci_e = vel2_reci;
+        vel3_2_reci_e = vel2_reci * z_h0;
+      } else {
+        vel2_reci = 1.0 / v2;
+        vel2_reci_e = 1.0 / (v2 + P.help_eps);
+        vel3_2_reci_e = vel2_reci_e * sqrt(vel2_reci_e);
+        z_h0 = 1.0 / sqrt(v2);
+      }
+      const M2 rot = M2{dsigma.x, -dsigma.y, dsigma.y, dsigma.x};
+      ego_R = M2{sg * rot.a * z_h0, sg * rot.b * z_h0, sg * rot.c * z_h0, sg * rot.d * z_h0};
+      M2 R_dot;
+      {
+        const double f2 = vel2_reci * z_h0 * z_h1;
+        R_dot = M2{sg * (ddsigma.x * z_h0 - rot.a * f2), sg * (-ddsigma.y * z_h0 - rot.b * f2),
+                   sg * (ddsigma.y * z_h0 - rot.c * f2), sg * (ddsigma.x * z_h0 - rot.d * f2)};
+      }
+      // ---- static corridor (traj_optimizer.cpp:592-622).  Quirk Q1: the vertex list has 5 entries, vertex 0 twice;
+      //      the duplicate is folded into a weight of 2 on vertex 0.  Planes are consumed in register chunks of 4;
+      //      chunk 0 of this pass was loaded during the previous pass (software prefetch).
+      //      Everything after the penalty is LINEAR in the plane normal, so a violated plane only adds
+      //      penaD * n and pena to per-vertex sums; the maps to d/dsigma, d/dsigma', d/dt run once per vertex.
+      const double wobs = omg * step * P.wei_obs;
+      for (int h0 = 0; h0 < H; h0 += kPlaneChunk) {
+        if (h0 > 0) load_plane_chunk(pn, pl, Mpad, store, h0, H);
+#pragma unroll
         for (int v = 0; v < 4; v++) {
           const V2 le = mk(P.le[v][0], P.le[v][1]);
-          const double mult = (v == 0) ? 2.0 : 1.0;
           const V2 q = ego_R * le;
           const V2 bpt = sigma + q;
-          const V2 rl = R_dot * le;
-          for (int h = 0; h < H; h++) {
-            const double* ph = pl + (size_t)(4 * h) * Mpad + store;
-            const V2 nrm = mk(ph[0], ph[Mpad]);
-            const V2 pnt = mk(ph[2 * Mpad], ph[3 * Mpad]);
-            const double violaPos = dot(nrm, bpt - pnt);
+          V2 Bn = mk(0.0, 0.0);  // sum penaD * n
+          double Sp = 0.0;       // sum pena
+#pragma unroll
+          for (int hh = 0; hh < kPlaneChunk; hh++) {
+            const V2 nrm = mk(pn[hh][0], pn[hh][1]);
+            const double violaPos = nrm.x * (bpt.x - pn[hh][2]) + nrm.y * (bpt.y - pn[hh][3]);
             if (violaPos > 0.0) {
               double pena, penaD;
               smoothed_l1(P.smooth_eps, violaPos, pena, penaD);
-              // n^T M,  M = singul*[l,Bl]/|v| - (R l) sigma'^T / |v|^2
-              const double nq = dot(nrm, q);
-              const V2 nM = mk(sg * z_h0 * (nrm.x * le.x + nrm.y * le.y) - vel2_reci * nq * dsigma.x,
-                               sg * z_h0 * (-nrm.x * le.y + nrm.y * le.x) - vel2_reci * nq * dsigma.y);
-              const double gradViolaPt = alpha * dot(nrm, dsigma + rl);
-              const double wc = mult * wobs * penaD;
-              acc.G0 = acc.G0 + wc * nrm;
-              acc.G1 = acc.G1 + wc * nM;
-              acc.gdT += mult * (omg * P.wei_obs * (penaD * gradViolaPt * step + pena / Kp));
-              acc.pen0 += mult * (wobs * pena);
+              Bn.x += penaD * nrm.x;
+              Bn.y += penaD * nrm.y;
+              Sp += pena;
             }
           }
-        }
-        // ---- moving obstacles (traj_optimizer.cpp:636-638)
-        if (HAS_OBS) {
-          dyn_obstacles(P, bd, prob, acc, omg, step, piece * dT + step * j, alpha, piece, Kp, sigma, dsigma, ddsigma,
-                        ego_R, singul_, s, N, trajtime);
-        }
-        // ---- velocity (642-653)
-        if (violaVel > 0.0) {
-          double pena, penaD;
-          smoothed_l1(P.smooth_eps, violaVel, pena, penaD);
-          const double wc = omg * step * P.wei_feas * penaD;
-          acc.G1 = acc.G1 + (2.0 * wc) * dsigma;
-          acc.gdT += omg * P.wei_feas * (penaD * (2.0 * alpha * z_h1) * step + pena / Kp);
-          acc.pen2 += omg * step * P.wei_feas * pena;
-        }
-        // ---- longitudinal acceleration (655-665)
-        if (violaAcc > 0.0) {
-          double pena, penaD;
-          smoothed_l1(P.smooth_eps, violaAcc, pena, penaD);
-          const double wc = omg * step * P.wei_feas * penaD;
-          const V2 w1 = z_h4 * ddsigma - (z_h4 * z_h4) * dsigma;
-          acc.G1 = acc.G1 + (2.0 * wc) * w1;
-          acc.G2 = acc.G2 + (2.0 * wc * z_h4) * dsigma;
-          const double gradViolaAt = 2.0 * alpha * (z_h4 * (dot(ddsigma, ddsigma) + z_h2) - z_h4 * z_h4 * z_h1);
-          acc.gdT += omg * P.wei_feas * (penaD * gradViolaAt * step + pena / Kp);
-          acc.pen2 += omg * step * P.wei_feas * pena;
-        }
-        // ---- curvature, both signs (684-705)
-        if (violaCurL > 0.0 || violaCurR > 0.0) {
-          const V2 aB = mk(ddsigma.y, -ddsigma.x);
-          const V2 Bv = mk(-dsigma.y, dsigma.x);
-          const double z_d3 = dddsigma.y * dsigma.x - dddsigma.x * dsigma.y;
-          const V2 w1 = vel3_2_reci_e * aB - (3.0 * vel3_2_reci_e * vel2_reci_e * z_h3) * dsigma;
-          const double gt = alpha * vel3_2_reci_e * (z_d3 - 3.0 * vel2_reci_e * z_h3 * z_h1);
-          const double wf = P.wei_feas * P.cur_weight_scale;
-          if (violaCurL > 0.0) {
-            double pena, penaD;
-            smoothed_l1(P.smooth_eps, violaCurL, pena, penaD);
-            const double wc = omg * step * wf * penaD;
-            acc.G1 = acc.G1 + wc * w1;
-            acc.G2 = acc.G2 + (wc * vel3_2_reci_e) * Bv;
-            acc.gdT += omg * wf * (penaD * gt * step + pena / Kp);
-            acc.pen2 += omg * step * wf * pena;
-          }
-          if (violaCurR > 0.0) {
-            double pena, penaD;
-            smoothed_l1(P.smooth_eps, violaCurR, pena, penaD);
-            const double wc = omg * step * wf * penaD;
-            acc.G1 = acc.G1 - wc * w1;
-            acc.G2 = acc.G2 - (wc * vel3_2_reci_e) * Bv;
-            acc.gdT += omg * wf * (penaD * (-gt) * step + pena / Kp);
-            acc.pen2 += omg * step * wf * pena;
+          if (Sp > 0.0) {
+            const double mult = (v == 0) ? 2.0 : 1.0;
+            const V2 rl = R_dot * le;
+            // n^T M,  M = singul*[l,Bl]/|v| - (R l) sigma'^T / |v|^2, applied to Bn
+            const double nq = dot(Bn, q);
+            const V2 nM = mk(sg * z_h0 * (Bn.x * le.x + Bn.y * le.y) - vel2_reci * nq * dsigma.x,
+                             sg * z_h0 * (-Bn.x * le.y + Bn.y * le.x) - vel2_reci * nq * dsigma.y);
+            const double gradViolaPt = alpha * dot(Bn, dsigma + rl);
+            const double wc = mult * wobs;
+            acc.G0 = acc.G0 + wc * Bn;
+            acc.G1 = acc.G1 + wc * nM;
+            acc.gdT += mult * (omg * P.wei_obs * (gradViolaPt * step + Sp * invKp));
+            acc.pen0 += wc * Sp;
           }
         }
-        acc_gdT += acc.gdT;
-        acc_p0 += acc.pen0;
-        acc_p1 += acc.pen1;
-        acc_p2 += acc.pen2;
+      }
+    }
+
+    // ---------------- stage C: software prefetch of the next pass's first plane chunk (registers are free now;
+    //                  its consumers are most of a pass away)
+    if (pass + 1 < npass) load_plane_chunk(pn, pl, Mpad, slot_of(pass + 1), 0, H);
+
+    // ---------------- stage D: moving obstacles, velocity / acceleration / curvature limits, expansion
+    double out[12];
+#pragma unroll
+    for (int q = 0; q < 12; q++) out[q] = 0.0;
+    if (active) {
+      if (HAS_OBS) {  // traj_optimizer.cpp:636-638
+        dyn_obstacles(P, bd, prob, acc, omg, step, piece * dT + step * j, alpha, piece, Kp, sigma, dsigma, ddsigma, ego_R,
+                      singul_, s, N, trajtime);
+      }
+      const double z_h4 = z_h1 * vel2_reci;
+      const double violaVel = v2 - max_vel * max_vel;
+      const double violaAcc = z_h1 * z_h1 * vel2_reci - max_acc * max_acc;
+      const double cur = z_h3 * vel3_2_reci_e;
+      const double violaCurL = cur - max_cur;
+      const double violaCurR = -cur - max_cur;
+      // ---- velocity (642-653)
+      if (violaVel > 0.0) {
+        double pena, penaD;
+        smoothed_l1(P.smooth_eps, violaVel, pena, penaD);
+        const double wc = omg * step * P.wei_feas * penaD;
+        acc.G1 = acc.G1 + (2.0 * wc) * dsigma;
+        acc.gdT += omg * P.wei_feas * (penaD * (2.0 * alpha * z_h1) * step + pena * invKp);
+        acc.pen2 += omg * step * P.wei_feas * pena;
+      }
+      // ---- longitudinal acceleration (655-665)
+      if (violaAcc > 0.0) {
+        double pena, penaD;
+        smoothed_l1(P.smooth_eps, violaAcc, pena, penaD);
+        const double z_h2 = dot(dddsigma, dsigma);
+        const double wc = omg * step * P.wei_feas * penaD;
+        const V2 w1 = z_h4 * ddsigma - (z_h4 * z_h4) * dsigma;
+        acc.G1 = acc.G1 + (2.0 * wc) * w1;
+        acc.G2 = acc.G2 + (2.0 * wc * z_h4) * dsigma;
+        const double gradViolaAt = 2.0 * alpha * (z_h4 * (dot(ddsigma, ddsigma) + z_h2) - z_h4 * z_h4 * z_h1);
+        acc.gdT += omg * P.wei_feas * (penaD * gradViolaAt * step + pena * invKp);
+        acc.pen2 += omg * step * P.wei_feas * pena;
+      }
+      // ---- curvature, both signs (684-705)
+      if (violaCurL > 0.0 || violaCurR > 0.0) {
+        const V2 aB = mk(ddsigma.y, -ddsigma.x);
+        const V2 Bv = mk(-dsigma.y, dsigma.x);
+        const double z_d3 = dddsigma.y * dsigma.x - dddsigma.x * dsigma.y;
+        const V2 w1 = vel3_2_reci_e * aB - (3.0 * vel3_2_reci_e * vel2_reci_e * z_h3) * dsigma;
+        const double gt = alpha * vel3_2_reci_e * (z_d3 - 3.0 * vel2_reci_e * z_h3 * z_h1);
+        const double wf = P.wei_feas * P.cur_weight_scale;
+        const bool left = violaCurL > 0.0;  // the two signs are mutually exclusive for max_cur > 0
+        double pena, penaD;
+        smoothed_l1(P.smooth_eps, left ? violaCurL : violaCurR, pena, penaD);
+        const double sgn = left ? 1.0 : -1.0;
+        const double wc = sgn * (omg * step * wf * penaD);
+        acc.G1 = acc.G1 + wc * w1;
+        acc.G2 = acc.G2 + (wc * vel3_2_reci_e) * Bv;
+        acc.gdT += omg * wf * (penaD * (sgn * gt) * step + pena * invKp);
+        acc.pen2 += omg * step * wf * pena;
+        if (left && violaCurR > 0.0) {  // only possible for a non-positive curvature limit
+          smoothed_l1(P.smooth_eps, violaCurR, pena, penaD);
+          const double wc2 = omg * step * wf * penaD;
+          acc.G1 = acc.G1 - wc2 * w1;
+          acc.G2 = acc.G2 - (wc2 * vel3_2_reci_e) * Bv;
+          acc.gdT += omg * wf * (penaD * (-gt) * step + pena * invKp);
+          acc.pen2 += omg * step * wf * pena;
+        }
+      }
+      acc_gdT += acc.gdT;
+      acc_p0 += acc.pen0;
+      acc_p1 += acc.pen1;
+      acc_p2 += acc.pen2;
+      // expansion to the 6x2 coefficient gradient: beta_0 G0^T + beta_1 G1^T + beta_2 G2^T (powers recomputed here
+      // instead of being kept live through the whole sample)
+      {
+        const double s2 = s1 * s1, s3 = s2 * s1, s4 = s2 * s2, s5 = s4 * s1;
+        const double b0[6] = {1.0, s1, s2, s3, s4, s5};
+        const double b1[6] = {0.0, 1.0, 2.0 * s1, 3.0 * s2, 4.0 * s3, 5.0 * s4};
+        const double b2[6] = {0.0, 0.0, 2.0, 6.0 * s1, 12.0 * s2, 20.0 * s3};
 #pragma unroll
         for (int k = 0; k < 6; k++) {
           out[2 * k] = b0[k] * acc.G0.x + b1[k] * acc.G1.x + b2[k] * acc.G2.x;
@@ -698,6 +805,7 @@ __device__ __forceinline__ void sweep_segment(const ShapeDev& sh, const ParamsDe
       }
     }
 
+    // ---------------- stage E: reduction into gdC
     if (endpass) {
       // every lane owns a distinct piece: direct accumulation
       if (valid) {
@@ -742,10 +850,23 @@ __device__ __forceinline__ void sweep_segment(const ShapeDev& sh, const ParamsDe
 // one cost + gradient evaluation (costFunctionCallback, traj_optimizer.cpp:206-350)
 // x, g: shared-memory vectors of the warp.  Leaves c / bt in the workspace (quirk Q8 relies on that).
 // ------------------------------------------------------------------------------------------------
+// diagnostic: when non-null, lane 0 of every warp adds the cycles spent in each phase of an evaluation
+__device__ unsigned long long* g_phase_clock = nullptr;
+__device__ __noinline__ long long phase_mark(unsigned long long* pc, int idx, long long t_prev, int lane) {
+  __syncwarp();
+  const long long now = clock64();
+  if (lane == 0) atomicAdd(pc + idx, (unsigned long long)(now - t_prev));
+  return now;
+}
+#define PHASE_MARK(idx) \
+  if (pc) t_prev = phase_mark(pc, (idx), t_prev, lane);
+
 template <bool HAS_OBS>
 __device__ double eval_cost_grad(const ShapeDev& sh, const ParamsDev& P, const BatchDev& bd, int prob,
                                  const double* __restrict__ planes, const double* __restrict__ lu, WarpWS& ws,
                                  const double* x, double* g, int lane) {
+  unsigned long long* pc = g_phase_clock;
+  long long t_prev = pc ? clock64() : 0;
   const int S = sh.S;
   const int seg0 = bd.seg_base[prob];
   const int tv0 = sh.var0[S - 1] + 2 * (sh.N[S - 1] - 1);  // offset of tau
@@ -808,12 +929,14 @@ __device__ double eval_cost_grad(const ShapeDev& sh, const ParamsDev& P, const B
     for (int i = lane; i < 2 * (N - 1); i += 32) b[2 * (6 * (i >> 1) + 5) + (i & 1)] = Pin[i];
   }
   __syncwarp();
+  PHASE_MARK(0)
   // ---- banded solve, two lanes per segment
   if (lane < 2 * S) {
     const int s = lane >> 1;
     banded_solve(lu + sh.lu_off[s], ws.bt + 2 * sh.row0[s], 6 * sh.N[s], lane & 1);
   }
   __syncwarp();
+  PHASE_MARK(1)
   // ---- c = b~ / dT^k, jerk energy, gdC / gdT initialisation (poly_traj_utils.hpp:981-984, 998-1035)
   for (int s = 0; s < S; s++) {
     const int N = sh.N[s];
@@ -857,8 +980,10 @@ __device__ double eval_cost_grad(const ShapeDev& sh, const ParamsDev& P, const B
     }
   }
   __syncwarp();
+  PHASE_MARK(2)
   // ---- constraint sweep
   for (int s = 0; s < S; s++) sweep_segment<HAS_OBS>(sh, P, bd, prob, planes, ws, s, bd.singul[seg0 + s], lane);
+  PHASE_MARK(3)
 
   // ---- MinJerkOpt::calGrads_PT (poly_traj_utils.hpp:1037-1066)
   for (int s = 0; s < S; s++) {
@@ -884,11 +1009,13 @@ __device__ double eval_cost_grad(const ShapeDev& sh, const ParamsDev& P, const B
     if (lane == 0) ws.seg[s].pad[0] = part;  // added to gdT after the boundary terms, like the reference
   }
   __syncwarp();
+  PHASE_MARK(4)
   if (lane < 2 * S) {
     const int s = lane >> 1;
     banded_solve_adj(lu + sh.lu_off[s], ws.gd + 2 * sh.row0[s], 6 * sh.N[s], lane & 1);
   }
   __syncwarp();
+  PHASE_MARK(5)
   // gdP -> g
   for (int s = 0; s < S; s++) {
     const int N = sh.N[s];
@@ -953,6 +1080,7 @@ __device__ double eval_cost_grad(const ShapeDev& sh, const ParamsDev& P, const B
     g[ab + j] = ga;
   }
   __syncwarp();
+  PHASE_MARK(6)
   // ---- total (traj_optimizer.cpp:293-294, 329, 344)
   double sm = 0.0, tc = 0.0, pen = 0.0;
   for (int s = 0; s < S; s++) {
@@ -1023,8 +1151,99 @@ __global__ void __launch_bounds__(512, 1)
 }
 
 // ------------------------------------------------------------------------------------------------
-// the solver: persistent warps, each runs lbfgs_optimize (lbfgs.hpp:440-751) for one problem at a time
+// L-BFGS two-loop recursion (lbfgs.hpp:716-739) with the direction held in registers (NPL elements per lane) and
+// the (s_j, y_j, ys_j) history stream software-prefetched two steps ahead.  alpha_j lives in shared memory.
 // ------------------------------------------------------------------------------------------------
+template <int NPL>
+struct HistStage {
+  double s[NPL], y[NPL], ys;
+};
+template <int NPL>
+__device__ __forceinline__ void hist_load(HistStage<NPL>& st, const double* __restrict__ lm_s,
+                                          const double* __restrict__ lm_y, const double* __restrict__ lm_ys, int j,
+                                          int ld, int n, int lane, bool want_s, bool want_y) {
+  const double* sj = lm_s + (size_t)j * ld;
+  const double* yj = lm_y + (size_t)j * ld;
+#pragma unroll
+  for (int e = 0; e < NPL; e++) {
+    const int i = lane + 32 * e;
+    st.s[e] = (want_s && i < n) ? sj[i] : 0.0;
+    st.y[e] = (want_y && i < n) ? yj[i] : 0.0;
+  }
+  st.ys = lm_ys[j];
+}
+
+template <int NPL>
+__device__ __noinline__ void two_loop(double* d_sm, double* alpha_sm, const double* __restrict__ lm_s,
+                                      const double* __restrict__ lm_y, const double* __restrict__ lm_ys, int ld, int m,
+                                      int end, int bound, int n, int lane, double ys, double yy) {
+  double d[NPL];
+#pragma unroll
+  for (int e = 0; e < NPL; e++) {
+    const int i = lane + 32 * e;
+    d[e] = i < n ? d_sm[i] : 0.0;
+  }
+  // ---- first loop: j = end-1, end-2, ... (newest to oldest)
+  HistStage<NPL> st0, st1, st2;
+  int j = end;
+  {
+    int jj = (j + m - 1) % m;
+    hist_load<NPL>(st0, lm_s, lm_y, lm_ys, jj, ld, n, lane, true, true);
+    jj = (jj + m - 1) % m;
+    if (1 < bound) hist_load<NPL>(st1, lm_s, lm_y, lm_ys, jj, ld, n, lane, true, true);
+  }
+  for (int i = 0; i < bound; ++i) {
+    j = (j + m - 1) % m;
+    if (i + 2 < bound) hist_load<NPL>(st2, lm_s, lm_y, lm_ys, (j + 2 * m - 2) % m, ld, n, lane, true, true);
+    double part = 0.0;
+#pragma unroll
+    for (int e = 0; e < NPL; e++) part += st0.s[e] * d[e];
+    const double a = warp_sum(part) / st0.ys;
+    if (lane == 0) alpha_sm[j] = a;
+    const double na = -a;
+#pragma unroll
+    for (int e = 0; e < NPL; e++) d[e] += na * st0.y[e];
+    st0 = st1;
+    st1 = st2;
+  }
+  const double sc = ys / yy;
+#pragma unroll
+  for (int e = 0; e < NPL; e++) d[e] *= sc;
+  __syncwarp();
+  // ---- second loop: oldest to newest, starting at the j where the first loop stopped
+  {
+    hist_load<NPL>(st0, lm_s, lm_y, lm_ys, j, ld, n, lane, true, true);
+    if (1 < bound) hist_load<NPL>(st1, lm_s, lm_y, lm_ys, (j + 1) % m, ld, n, lane, true, true);
+  }
+  for (int i = 0; i < bound; ++i) {
+    if (i + 2 < bound) hist_load<NPL>(st2, lm_s, lm_y, lm_ys, (j + 2) % m, ld, n, lane, true, true);
+    double part = 0.0;
+#pragma unroll
+    for (int e = 0; e < NPL; e++) part += st0.y[e] * d[e];
+    const double beta = warp_sum(part) / st0.ys;
+    const double a = alpha_sm[j] - beta;
+#pragma unroll
+    for (int e = 0; e < NPL; e++) d[e] += a * st0.s[e];
+    st0 = st1;
+    st1 = st2;
+    j = (j + 1) % m;
+  }
+#pragma unroll
+  for (int e = 0; e < NPL; e++) {
+    const int i = lane + 32 * e;
+    if (i < n) d_sm[i] = d[e];
+  }
+  __syncwarp();
+}
+
+// ------------------------------------------------------------------------------------------------
+// the solver: persistent warps, each runs lbfgs_optimize (lbfgs.hpp:440-751) for one problem at a time.
+// Written as a state machine around ONE call site of eval_cost_grad (keeps the kernel inside the instruction cache):
+//   FETCH -> FIRST (evaluation at x0, lbfgs.hpp:524) -> LS (line-search trial, lbfgs.hpp:312-389) -> ... -> FETCH
+// All control flow is warp-uniform: every reduction leaves bit-identical values in all lanes.
+// ------------------------------------------------------------------------------------------------
+enum { PH_FETCH = 0, PH_FIRST = 1, PH_LS = 2 };
+
 template <bool HAS_OBS>
 __global__ void __launch_bounds__(512, 1)
     solve_kernel(const __grid_constant__ ShapeDev sh, const __grid_constant__ ParamsDev P, const BatchDev bd,
@@ -1040,214 +1259,238 @@ __global__ void __launch_bounds__(512, 1)
   double* lm_s = hist.s + (size_t)slot * hist.mem * hist.ld;
   double* lm_y = hist.y + (size_t)slot * hist.mem * hist.ld;
   double* lm_ys = hist.ys + (size_t)slot * hist.mem;
-  double* lm_alpha = hist.alpha + (size_t)slot * hist.mem;
+  double* alpha_sm = ws.stage;  // free outside the sweep; the host guarantees mem_size <= 2*12*kStageLd
   const int ld = hist.ld;
+  const int npl = (n + 31) >> 5;
+
+  int phase = PH_FETCH;
+  int prob = -1, k = 0, end = 0, bound = 0, evals = 0, count = 0, ret = 0;
+  bool brackt = false, touched = false;
+  double step = 0.0, fx = 0.0, finit = 0.0, dgtest = 0.0, dstest = 0.0, mu = 0.0, nu = 0.0;
+  const double* planes = nullptr;
 
   while (true) {
-    int local = 0;
-    if (lane == 0) local = atomicAdd(work_counter, 1);
-    local = __shfl_sync(FULL, local, 0);
-    if (local >= grp.count) break;
-    const int prob = grp.prob_id[local];
-    const double* planes = grp.planes + (size_t)local * sh.H * 4 * sh.Mpad;
+    if (phase == PH_FETCH) {
+      int local = 0;
+      if (lane == 0) local = atomicAdd(work_counter, 1);
+      local = __shfl_sync(FULL, local, 0);
+      if (local >= grp.count) break;
+      prob = grp.prob_id[local];
+      planes = grp.planes + (size_t)local * sh.H * 4 * sh.Mpad;
+#pragma unroll 1
+      for (int i = lane; i < n; i += 32) ws.x[i] = bd.x0[(size_t)prob * bd.n_stride + i];
+      __syncwarp();
+      evals = 0;
+      phase = PH_FIRST;
+    }
 
-    for (int i = lane; i < n; i += 32) ws.x[i] = bd.x0[(size_t)prob * bd.n_stride + i];
-    __syncwarp();
-    int evals = 0;
-    double fx = eval_cost_grad<HAS_OBS>(sh, P, bd, prob, planes, smem, ws, ws.x, ws.g, lane);
+    // ---------------- the single evaluation site
+    fx = eval_cost_grad<HAS_OBS>(sh, P, bd, prob, planes, smem, ws, ws.x, ws.g, lane);
     evals++;
-    double pf[8];  // past <= 8 supported (host checks)
-    pf[0] = fx;
-    for (int i = lane; i < n; i += 32) ws.d[i] = -ws.g[i];
-    __syncwarp();
-    double gnorm_inf = warp_maxabs(ws.g, n, lane);
-    double xnorm_inf = warp_maxabs(ws.x, n, lane);
-    int ret = 0, k = 0;
-    if (gnorm_inf / fmax(1.0, xnorm_inf) < P.g_epsilon) {
-      ret = DFTPAV_LBFGS_CONVERGENCE;
+
+    bool start_ls = false;   // begin a new line search from the current (x, g, d, step)
+    bool finish = false;     // problem done: write results
+    bool revert = false;     // finish after restoring (xp, gp) (line-search failure, lbfgs.hpp:604-611)
+
+    if (phase == PH_FIRST) {
+      // lbfgs.hpp:524-555
+      if (lane == 0) ws.pf[0] = fx;
+#pragma unroll 1
+      for (int i = lane; i < n; i += 32) ws.d[i] = -ws.g[i];
+      __syncwarp();
+      const double gnorm_inf = warp_maxabs(ws.g, n, lane);
+      const double xnorm_inf = warp_maxabs(ws.x, n, lane);
+      k = 0;
+      if (gnorm_inf / fmax(1.0, xnorm_inf) < P.g_epsilon) {
+        ret = DFTPAV_LBFGS_CONVERGENCE;
+        finish = true;
+      } else {
+        step = 1.0 / sqrt(warp_dot(ws.d, ws.d, n, lane));
+        k = 1;
+        end = 0;
+        bound = 0;
+        start_ls = true;
+      }
     } else {
-      double step = 1.0 / sqrt(warp_dot(ws.d, ws.d, n, lane));
-      k = 1;
-      int end = 0, bound = 0;
-      while (true) {
-        for (int i = lane; i < n; i += 32) {
-          ws.xp[i] = ws.x[i];
-          ws.gp[i] = ws.g[i];
+      // ---------------- one trial of line_search_lewisoverton (lbfgs.hpp:317-388)
+      ++count;
+      int ls = 0;          // > 0: accepted with `count` evaluations, < 0: error, 0: continue with a new step
+      if (isinf(fx) || isnan(fx)) {
+        ls = DFTPAV_LBFGSERR_INVALID_FUNCVAL;
+      } else if (P.past > 0 && fabs(finit - fx) / (fabs(finit) + 1.0) < P.delta / P.past) {
+        ls = count;  // lbfgs.hpp:326-329
+      } else {
+        bool accepted = false;
+        if (fx > finit + step * dgtest) {
+          nu = step;
+          brackt = true;
+        } else if (warp_dot(ws.g, ws.d, n, lane) < dstest) {
+          mu = step;
+        } else {
+          accepted = true;
         }
-        __syncwarp();
-        // ---------------- line_search_lewisoverton (lbfgs.hpp:276-390)
-        int ls;
-        {
-          int count = 0;
-          bool brackt = false, touched = false;
-          double mu = 0.0, nu = P.max_step;
-          const double stpmin = P.min_step, stpmax = P.max_step;
-          if (!(step > 0.0)) {
-            ls = DFTPAV_LBFGSERR_INVALIDPARAMETERS;
+        if (accepted) {
+          ls = count;
+        } else if (P.max_linesearch <= count) {
+          ls = DFTPAV_LBFGSERR_MAXIMUMLINESEARCH;
+        } else if (brackt && (nu - mu) < P.machine_prec * nu) {
+          ls = DFTPAV_LBFGSERR_WIDTHTOOSMALL;
+        } else {
+          if (brackt) {
+            step = 0.5 * (mu + nu);
           } else {
-            const double dginit = warp_dot(ws.gp, ws.d, n, lane);
-            if (0.0 < dginit) {
-              ls = DFTPAV_LBFGSERR_INCREASEGRADIENT;
+            step *= 2.0;
+          }
+          if (step < P.min_step) {
+            ls = DFTPAV_LBFGSERR_MINIMUMSTEP;
+          } else if (step > P.max_step) {
+            if (touched) {
+              ls = DFTPAV_LBFGSERR_MAXIMUMSTEP;
             } else {
-              const double finit = fx;
-              const double dgtest = P.f_dec_coeff * dginit;
-              const double dstest = P.s_curv_coeff * dginit;
-              while (true) {
-                for (int i = lane; i < n; i += 32) ws.x[i] = ws.xp[i] + step * ws.d[i];
-                __syncwarp();
-                fx = eval_cost_grad<HAS_OBS>(sh, P, bd, prob, planes, smem, ws, ws.x, ws.g, lane);
-                evals++;
-                ++count;
-                if (isinf(fx) || isnan(fx)) {
-                  ls = DFTPAV_LBFGSERR_INVALID_FUNCVAL;
-                  break;
-                }
-                if (P.past > 0 && fabs(finit - fx) / (fabs(finit) + 1.0) < P.delta / P.past) {
-                  ls = count;
-                  break;
-                }
-                if (fx > finit + step * dgtest) {
-                  nu = step;
-                  brackt = true;
-                } else {
-                  if (warp_dot(ws.g, ws.d, n, lane) < dstest) {
-                    mu = step;
-                  } else {
-                    ls = count;
-                    break;
-                  }
-                }
-                if (P.max_linesearch <= count) {
-                  ls = DFTPAV_LBFGSERR_MAXIMUMLINESEARCH;
-                  break;
-                }
-                if (brackt && (nu - mu) < P.machine_prec * nu) {
-                  ls = DFTPAV_LBFGSERR_WIDTHTOOSMALL;
-                  break;
-                }
-                if (brackt) {
-                  step = 0.5 * (mu + nu);
-                } else {
-                  step *= 2.0;
-                }
-                if (step < stpmin) {
-                  ls = DFTPAV_LBFGSERR_MINIMUMSTEP;
-                  break;
-                }
-                if (step > stpmax) {
-                  if (touched) {
-                    ls = DFTPAV_LBFGSERR_MAXIMUMSTEP;
-                    break;
-                  } else {
-                    touched = true;
-                    step = stpmax;
-                  }
-                }
-              }
+              touched = true;
+              step = P.max_step;
             }
           }
         }
-        if (ls < 0) {
-          for (int i = lane; i < n; i += 32) {
-            ws.x[i] = ws.xp[i];
-            ws.g[i] = ws.gp[i];
-          }
-          __syncwarp();
-          ret = ls;
-          break;
-        }
-        gnorm_inf = warp_maxabs(ws.g, n, lane);
-        xnorm_inf = warp_maxabs(ws.x, n, lane);
+      }
+      if (ls == 0) {
+        // next trial point
+  #pragma unroll 1
+      for (int i = lane; i < n; i += 32) ws.x[i] = ws.xp[i] + step * ws.d[i];
+        __syncwarp();
+        continue;
+      }
+      if (ls < 0) {
+        ret = ls;
+        revert = true;
+        finish = true;
+      } else {
+        // ---------------- end of iteration k (lbfgs.hpp:628-743)
+        const double gnorm_inf = warp_maxabs(ws.g, n, lane);
+        const double xnorm_inf = warp_maxabs(ws.x, n, lane);
         if (gnorm_inf / fmax(1.0, xnorm_inf) < P.g_epsilon) {
           ret = DFTPAV_LBFGS_CONVERGENCE;
-          break;
+          finish = true;
         }
-        if (0 < P.past) {
+        if (!finish && 0 < P.past) {
           if (P.past <= k) {
-            const double rate = fabs(pf[k % P.past] - fx) / fmax(1.0, fabs(fx));
+            const double rate = fabs(ws.pf[k % P.past] - fx) / fmax(1.0, fabs(fx));
             if (rate < P.delta) {
               ret = DFTPAV_LBFGS_STOP;
-              break;
+              finish = true;
             }
           }
-          pf[k % P.past] = fx;
+          if (!finish) {
+            __syncwarp();
+            if (lane == 0) ws.pf[k % P.past] = fx;
+            __syncwarp();
+          }
         }
-        if (P.max_iterations != 0 && P.max_iterations <= k) {
+        if (!finish && P.max_iterations != 0 && P.max_iterations <= k) {
           ret = DFTPAV_LBFGSERR_MAXIMUMITERATION;
-          break;
+          finish = true;
         }
-        ++k;
-        // ---------------- history update (lbfgs.hpp:676-687)
-        double* se = lm_s + (size_t)end * ld;
-        double* ye = lm_y + (size_t)end * ld;
-        double ys = 0.0, yy = 0.0, ss = 0.0, gg = 0.0;
-        for (int i = lane; i < n; i += 32) {
-          const double sv = ws.x[i] - ws.xp[i];
-          const double yv = ws.g[i] - ws.gp[i];
-          se[i] = sv;
-          ye[i] = yv;
-          ys += yv * sv;
-          yy += yv * yv;
-          ss += sv * sv;
-          gg += ws.gp[i] * ws.gp[i];
-          ws.d[i] = -ws.g[i];
-        }
-        ys = warp_sum(ys);
-        yy = warp_sum(yy);
-        ss = warp_sum(ss);
-        gg = warp_sum(gg);
-        if (lane == 0) lm_ys[end] = ys;
-        __syncwarp();
-        const double cau = ss * sqrt(gg) * P.cautious_factor;
-        if (ys > cau) {
-          // ---------------- two-loop recursion (lbfgs.hpp:716-739)
-          ++bound;
-          bound = m < bound ? m : bound;
-          end = (end + 1) % m;
-          int j = end;
-          for (int i = 0; i < bound; ++i) {
-            j = (j + m - 1) % m;
-            const double* sj = lm_s + (size_t)j * ld;
-            const double* yj = lm_y + (size_t)j * ld;
-            const double ysj = (i == 0) ? ys : lm_ys[j];
-            const double a = warp_dot(sj, ws.d, n, lane) / ysj;
-            if (lane == 0) lm_alpha[j] = a;
-            const double na = -a;
-            for (int q = lane; q < n; q += 32) ws.d[q] += na * yj[q];
-            __syncwarp();
+        if (!finish) {
+          ++k;
+          // history update (lbfgs.hpp:676-687)
+          double* se = lm_s + (size_t)end * ld;
+          double* ye = lm_y + (size_t)end * ld;
+          double ys = 0.0, yy = 0.0, ss = 0.0, gg = 0.0;
+    #pragma unroll 1
+      for (int i = lane; i < n; i += 32) {
+            const double sv = ws.x[i] - ws.xp[i];
+            const double yv = ws.g[i] - ws.gp[i];
+            se[i] = sv;
+            ye[i] = yv;
+            ys += yv * sv;
+            yy += yv * yv;
+            ss += sv * sv;
+            gg += ws.gp[i] * ws.gp[i];
+            ws.d[i] = -ws.g[i];
           }
-          const double sc = ys / yy;
-          for (int q = lane; q < n; q += 32) ws.d[q] *= sc;
+          ys = warp_sum(ys);
+          yy = warp_sum(yy);
+          ss = warp_sum(ss);
+          gg = warp_sum(gg);
+          if (lane == 0) lm_ys[end] = ys;
           __syncwarp();
-          for (int i = 0; i < bound; ++i) {
-            const double* sj = lm_s + (size_t)j * ld;
-            const double* yj = lm_y + (size_t)j * ld;
-            const double beta = warp_dot(yj, ws.d, n, lane) / lm_ys[j];
-            const double a = lm_alpha[j] - beta;
-            for (int q = lane; q < n; q += 32) ws.d[q] += a * sj[q];
-            __syncwarp();
-            j = (j + 1) % m;
+          const double cau = ss * sqrt(gg) * P.cautious_factor;
+          if (ys > cau) {
+            ++bound;
+            bound = m < bound ? m : bound;
+            end = (end + 1) % m;
+            if (npl == 1) two_loop<1>(ws.d, alpha_sm, lm_s, lm_y, lm_ys, ld, m, end, bound, n, lane, ys, yy);
+            else if (npl == 2) two_loop<2>(ws.d, alpha_sm, lm_s, lm_y, lm_ys, ld, m, end, bound, n, lane, ys, yy);
+            else two_loop<3>(ws.d, alpha_sm, lm_s, lm_y, lm_ys, ld, m, end, bound, n, lane, ys, yy);
           }
+          step = 1.0;
+          start_ls = true;
         }
-        step = 1.0;
       }
     }
-    // ---------------- results (traj_optimizer.cpp:176-201)
-    bool success = (ret == DFTPAV_LBFGS_CONVERGENCE || ret == DFTPAV_LBFGS_CANCELED || ret == DFTPAV_LBFGS_STOP ||
-                    ret == DFTPAV_LBFGSERR_MAXIMUMITERATION || ret == DFTPAV_LBFGSERR_MAXIMUMLINESEARCH);
-    if (fx >= P.cost_limit) success = false;
-    for (int i = lane; i < bd.n_stride; i += 32) out.x[(size_t)prob * bd.n_stride + i] = i < n ? ws.x[i] : 0.0;
-    for (int i = lane; i < 2 * bd.row_stride; i += 32)
-      out.coeffs[(size_t)prob * bd.row_stride * 2 + i] = i < 2 * sh.rows ? ws.c[i] : 0.0;
-    if (lane < sh.S) out.piece_dT[bd.seg_base[prob] + lane] = ws.seg[lane].dT;
-    if (lane == 0) {
-      out.cost[prob] = fx;
-      out.status[prob] = ret;
-      out.success[prob] = success ? 1 : 0;
-      out.iters[prob] = k;
-      out.evals[prob] = evals;
+
+    if (start_ls) {
+      // head of line_search_lewisoverton (lbfgs.hpp:288-310) + xp/gp snapshot (lbfgs.hpp:560-561)
+#pragma unroll 1
+      for (int i = lane; i < n; i += 32) {
+        ws.xp[i] = ws.x[i];
+        ws.gp[i] = ws.g[i];
+      }
+      __syncwarp();
+      if (!(step > 0.0)) {
+        ret = DFTPAV_LBFGSERR_INVALIDPARAMETERS;
+        finish = true;
+      } else {
+        const double dginit = warp_dot(ws.gp, ws.d, n, lane);
+        if (0.0 < dginit) {
+          ret = DFTPAV_LBFGSERR_INCREASEGRADIENT;
+          finish = true;
+        } else {
+          finit = fx;
+          dgtest = P.f_dec_coeff * dginit;
+          dstest = P.s_curv_coeff * dginit;
+          count = 0;
+          brackt = false;
+          touched = false;
+          mu = 0.0;
+          nu = P.max_step;
+    #pragma unroll 1
+      for (int i = lane; i < n; i += 32) ws.x[i] = ws.xp[i] + step * ws.d[i];
+          __syncwarp();
+          phase = PH_LS;
+        }
+      }
     }
-    __syncwarp();
+
+    if (finish) {
+      if (revert) {
+  #pragma unroll 1
+      for (int i = lane; i < n; i += 32) {
+          ws.x[i] = ws.xp[i];
+          ws.g[i] = ws.gp[i];
+        }
+        __syncwarp();
+      }
+      // results (traj_optimizer.cpp:176-201); fx keeps the last tried value on failure (quirk Q8)
+      bool success = (ret == DFTPAV_LBFGS_CONVERGENCE || ret == DFTPAV_LBFGS_CANCELED || ret == DFTPAV_LBFGS_STOP ||
+                      ret == DFTPAV_LBFGSERR_MAXIMUMITERATION || ret == DFTPAV_LBFGSERR_MAXIMUMLINESEARCH);
+      if (fx >= P.cost_limit) success = false;
+#pragma unroll 1
+      for (int i = lane; i < bd.n_stride; i += 32) out.x[(size_t)prob * bd.n_stride + i] = i < n ? ws.x[i] : 0.0;
+#pragma unroll 1
+      for (int i = lane; i < 2 * bd.row_stride; i += 32)
+        out.coeffs[(size_t)prob * bd.row_stride * 2 + i] = i < 2 * sh.rows ? ws.c[i] : 0.0;
+      if (lane < sh.S) out.piece_dT[bd.seg_base[prob] + lane] = ws.seg[lane].dT;
+      if (lane == 0) {
+        out.cost[prob] = fx;
+        out.status[prob] = ret;
+        out.success[prob] = success ? 1 : 0;
+        out.iters[prob] = k;
+        out.evals[prob] = evals;
+      }
+      __syncwarp();
+      phase = PH_FETCH;
+    }
   }
 }
 
@@ -1438,5 +1681,9 @@ cudaError_t launch_prepare(int grid, int block, cudaStream_t st, const ShapeDev&
 }
 
 int ws_doubles_host(int rows, int npad) { return ws_doubles_for(rows, npad); }
+
+cudaError_t set_phase_clock(unsigned long long* dev_ptr) {
+  return cudaMemcpyToSymbol(g_phase_clock, &dev_ptr, sizeof(dev_ptr));
+}
 
 }  // namespace dftpav
