@@ -152,7 +152,8 @@ struct dftpav_handle {
   DevBuf seg_base, t_now, obs_ptr, obs_idx, singul, ini_raw, fin_raw, ini, fin, init_T, inner_base, inner_pts, samp_base,
       plane_ptr, planes_raw, obs_start, obs_dur, obs_piece_ptr, obs_piece_dur, obs_coeffs, x0, xin, fout, gout;
   DevBuf o_x, o_cost, o_status, o_success, o_iters, o_evals, o_coeffs, o_dT, counter;
-  DevBuf hist_s, hist_y, hist_ys, hist_alpha;
+  DevBuf hist_s, hist_y, hist_ys, hist_alpha, trace;
+  int trace_cap = 0;
   int hist_ld = 0, hist_slots = 0;
   int upload_launches = 0;
   BatchDev bd{};
@@ -421,7 +422,7 @@ int dftpav_destroy(dftpav_handle* h) {
                     &h->fin, &h->init_T, &h->inner_base, &h->inner_pts, &h->samp_base, &h->plane_ptr, &h->planes_raw,
                     &h->obs_start, &h->obs_dur, &h->obs_piece_ptr, &h->obs_piece_dur, &h->obs_coeffs, &h->x0, &h->xin,
                     &h->fout, &h->gout, &h->o_x, &h->o_cost, &h->o_status, &h->o_success, &h->o_iters, &h->o_evals,
-                    &h->o_coeffs, &h->o_dT, &h->counter, &h->hist_s, &h->hist_y, &h->hist_ys, &h->hist_alpha};
+                    &h->o_coeffs, &h->o_dT, &h->counter, &h->hist_s, &h->hist_y, &h->hist_ys, &h->hist_alpha, &h->trace};
   for (DevBuf* b : bufs) b->release();
   for (auto& e : h->ev)
     if (e) cudaEventDestroy(e);
@@ -599,11 +600,11 @@ int dftpav_upload_batch(dftpav_handle* h, const dftpav_batch* b) {
       sampoff += store;
       auto it = lu_of_N.find(N);
       if (it == lu_of_N.end()) {
-        // table layout per distinct N: [6 zero columns][6N packed columns][6 zero columns] so that the update-form
-        // substitutions may address columns j-6 .. j+6 without bounds checks
-        lu_of_N[N] = luoff + 6 * kLuLd;
-        sh.lu_off[s] = luoff + 6 * kLuLd;
-        luoff += (6 * N + 12) * kLuLd;
+        // table layout per distinct N: [8 zero columns][6N packed columns][8 zero columns] so that the software-
+        // pipelined update-form substitutions may address columns j-7 .. j+7 without bounds checks
+        lu_of_N[N] = luoff + 8 * kLuLd;
+        sh.lu_off[s] = luoff + 8 * kLuLd;
+        luoff += (6 * N + 16) * kLuLd;
       } else {
         sh.lu_off[s] = it->second;
       }
@@ -754,6 +755,15 @@ int dftpav_optimize(dftpav_handle* h) {
   out.evals = h->o_evals.as<int>();
   out.coeffs = h->o_coeffs.as<double>();
   out.piece_dT = h->o_dT.as<double>();
+  out.trace = nullptr;
+  out.trace_cap = 0;
+  if (h->trace_cap > 0) {
+    const size_t tb = sizeof(double) * 3 * (size_t)h->trace_cap * h->dims.B;
+    CU_TRY(h, h->trace.ensure(tb));
+    CU_TRY(h, cudaMemsetAsync(h->trace.p, 0, tb, st));
+    out.trace = h->trace.as<double>();
+    out.trace_cap = h->trace_cap;
+  }
   HistDev hist;
   hist.s = h->hist_s.as<double>();
   hist.y = h->hist_y.as<double>();
@@ -843,6 +853,19 @@ int dftpav_solve(dftpav_handle* h, const dftpav_batch* batch, const dftpav_resul
 int dftpav_last_stats(const dftpav_handle* h, dftpav_stats* stats) {
   if (!h || !stats) return DFTPAV_ERR_INVALID_ARG;
   *stats = h->stats;
+  return DFTPAV_OK;
+}
+
+// Diagnostic (not part of the drop-in ABI): per-iteration (fx, step, ls) traces of the next dftpav_optimize calls.
+int dftpav_debug_set_trace(dftpav_handle* h, int trace_cap) {
+  if (!h || trace_cap < 0) return DFTPAV_ERR_INVALID_ARG;
+  h->trace_cap = trace_cap;
+  return DFTPAV_OK;
+}
+int dftpav_debug_get_trace(dftpav_handle* h, double* out) {
+  if (!h || !out || h->trace_cap <= 0 || !h->solved) return DFTPAV_ERR_STATE;
+  CU_TRY(h, cudaSetDevice(h->device));
+  CU_TRY(h, cudaMemcpy(out, h->trace.p, sizeof(double) * 3 * (size_t)h->trace_cap * h->dims.B, cudaMemcpyDeviceToHost));
   return DFTPAV_OK;
 }
 

@@ -91,6 +91,8 @@ struct OutDev {
   int* evals;       // [B]
   double* coeffs;   // [B][row_stride][2]
   double* piece_dT; // [G]
+  double* trace;    // optional [B][trace_cap][3] = (fx, step, ls) per L-BFGS iteration (diagnostic), or nullptr
+  int trace_cap;
 };
 
 struct HistDev {

@@ -170,92 +170,140 @@ __device__ __forceinline__ unsigned order_token() {
   return t;
 }
 
+// All four substitution passes below are written in update ("column") form — exactly the reference loops
+// (poly_traj_utils.hpp:808-850): when row j is final its contribution is pushed into the six pending rows with six
+// INDEPENDENT multiply-adds, so the dependent chain per row is one FMA (+ one multiply by 1/U(j,j)); every row still
+// receives its terms in the reference order.  The loops are software-pipelined by hand: the table entries and the
+// right-hand-side row needed by step j+1 are loaded at the top of step j (the compiler does not hoist them itself and
+// the in-order issue would otherwise put the shared-memory latency on the chain of every row).
+struct Band6 {
+  double k1, k2, k3, k4, k5, k6;
+};
+
 __device__ __forceinline__ void banded_solve(const double* C, double* b, int n, int col) {
   const unsigned tok0 = order_token();
   const unsigned Ca = smem_addr(C) + tok0;  // also keeps the table reads behind the TMA completion wait
   unsigned ba = smem_addr(b) + 8u * col + tok0;
   constexpr unsigned CS = kLuLd * 8u;  // bytes per packed column
-  // forward, update form (poly_traj_utils.hpp:808-815)
+  // ---- forward (poly_traj_utils.hpp:808-815):  y_j = acc_j;  acc_{j+k} -= L(j+k, j) y_j,  L(j+k, j) = C[j][6+k]
   double w0 = b[col], w1 = b[2 + col], w2 = b[4 + col], w3 = b[6 + col], w4 = b[8 + col], w5 = b[10 + col];
   double w6 = (6 < n) ? b[12 + col] : 0.0;
-#pragma unroll 6
+  Band6 cur;
+  cur.k1 = lds_pure(Ca + 7 * 8), cur.k2 = lds_pure(Ca + 8 * 8), cur.k3 = lds_pure(Ca + 9 * 8);
+  cur.k4 = lds_pure(Ca + 10 * 8), cur.k5 = lds_pure(Ca + 11 * 8), cur.k6 = lds_pure(Ca + 12 * 8);
+#pragma unroll 2
   for (int j = 0; j < n; j++) {
-    const unsigned cj = Ca + j * CS;
+    const unsigned cn = Ca + (j + 1) * CS;  // next column (zero padding behind the table for j = n-1)
+    Band6 nxt;
+    nxt.k1 = lds_pure(cn + 7 * 8), nxt.k2 = lds_pure(cn + 8 * 8), nxt.k3 = lds_pure(cn + 9 * 8);
+    nxt.k4 = lds_pure(cn + 10 * 8), nxt.k5 = lds_pure(cn + 11 * 8), nxt.k6 = lds_pure(cn + 12 * 8);
+    const double w7 = (j + 7 < n) ? lds_pure(ba + 16u * (j + 7)) : 0.0;
     const double y = w0;
     b[2 * j + col] = y;
-    w0 = w1 - lds_pure(cj + 7 * 8) * y;
-    w1 = w2 - lds_pure(cj + 8 * 8) * y;
-    w2 = w3 - lds_pure(cj + 9 * 8) * y;
-    w3 = w4 - lds_pure(cj + 10 * 8) * y;
-    w4 = w5 - lds_pure(cj + 11 * 8) * y;
-    w5 = w6 - lds_pure(cj + 12 * 8) * y;
-    w6 = (j + 7 < n) ? lds_pure(ba + 16u * (j + 7)) : 0.0;
+    w0 = w1 - cur.k1 * y;
+    w1 = w2 - cur.k2 * y;
+    w2 = w3 - cur.k3 * y;
+    w3 = w4 - cur.k4 * y;
+    w4 = w5 - cur.k5 * y;
+    w5 = w6 - cur.k6 * y;
+    w6 = w7;
+    cur = nxt;
   }
   // (no __syncwarp here: only the two solving lanes of a segment execute this function)
   ba = smem_addr(b) + 8u * col + order_token();
-  // backward, update form (poly_traj_utils.hpp:816-824)
+  // ---- backward (poly_traj_utils.hpp:816-824):  x_j = acc_j / U(j,j);  acc_{j-k} -= U(j-k, j) x_j,  U(j-k, j) = C[j][6-k]
   double v0 = b[2 * (n - 1) + col], v1 = b[2 * (n - 2) + col], v2 = b[2 * (n - 3) + col], v3 = b[2 * (n - 4) + col];
   double v4 = b[2 * (n - 5) + col], v5 = b[2 * (n - 6) + col];
   double v6 = (n - 7 >= 0) ? b[2 * (n - 7) + col] : 0.0;
-#pragma unroll 6
+  {
+    const unsigned c0 = Ca + (n - 1) * CS;
+    cur.k1 = lds_pure(c0 + 5 * 8), cur.k2 = lds_pure(c0 + 4 * 8), cur.k3 = lds_pure(c0 + 3 * 8);
+    cur.k4 = lds_pure(c0 + 2 * 8), cur.k5 = lds_pure(c0 + 1 * 8), cur.k6 = lds_pure(c0 + 0 * 8);
+  }
+  double rd = lds_pure(Ca + (n - 1) * CS + 13 * 8);
+#pragma unroll 2
   for (int j = n - 1; j >= 0; j--) {
-    const unsigned cj = Ca + j * CS;
-    const double xj = v0 * lds_pure(cj + 13 * 8);
+    const unsigned cn = Ca + (j - 1) * CS;  // previous column (zero padding in front of the table for j = 0)
+    Band6 nxt;
+    nxt.k1 = lds_pure(cn + 5 * 8), nxt.k2 = lds_pure(cn + 4 * 8), nxt.k3 = lds_pure(cn + 3 * 8);
+    nxt.k4 = lds_pure(cn + 2 * 8), nxt.k5 = lds_pure(cn + 1 * 8), nxt.k6 = lds_pure(cn + 0 * 8);
+    const double rdn = lds_pure(cn + 13 * 8);
+    const double v7 = (j - 7 >= 0) ? lds_pure(ba + 16u * (j - 7)) : 0.0;
+    const double xj = v0 * rd;
     b[2 * j + col] = xj;
-    v0 = v1 - lds_pure(cj + 5 * 8) * xj;
-    v1 = v2 - lds_pure(cj + 4 * 8) * xj;
-    v2 = v3 - lds_pure(cj + 3 * 8) * xj;
-    v3 = v4 - lds_pure(cj + 2 * 8) * xj;
-    v4 = v5 - lds_pure(cj + 1 * 8) * xj;
-    v5 = v6 - lds_pure(cj + 0 * 8) * xj;
-    v6 = (j - 7 >= 0) ? lds_pure(ba + 16u * (j - 7)) : 0.0;
+    v0 = v1 - cur.k1 * xj;
+    v1 = v2 - cur.k2 * xj;
+    v2 = v3 - cur.k3 * xj;
+    v3 = v4 - cur.k4 * xj;
+    v4 = v5 - cur.k5 * xj;
+    v5 = v6 - cur.k6 * xj;
+    v6 = v7;
+    cur = nxt;
+    rd = rdn;
   }
 }
 
 __device__ __forceinline__ void banded_solve_adj(const double* C, double* b, int n, int col) {
-  // Update ("column") form, exactly the reference loops (poly_traj_utils.hpp:834-850): when row j is final its
-  // contribution is pushed into the six pending rows with six INDEPENDENT fused multiply-adds, so the dependent
-  // chain per row is one FMA (+ one multiply by 1/U(j,j)).  Row i still receives its terms in the reference order.
   const unsigned tok0 = order_token();
   const unsigned Ca = smem_addr(C) + tok0;
   unsigned ba = smem_addr(b) + 8u * col + tok0;
   constexpr unsigned CS = kLuLd * 8u;
-  // U^T z = b, ascending:  z_j = acc_j / U(j,j);  acc_{j+k} -= U(j, j+k) z_j,   U(j, j+k) = C[j+k][6-k]
-  // (columns beyond the matrix are the zero padding behind the table)
+  // ---- U^T z = b, ascending (poly_traj_utils.hpp:834-842):  z_j = acc_j / U(j,j);  acc_{j+k} -= U(j, j+k) z_j,
+  //      U(j, j+k) = C[j+k][6-k]  (columns beyond the matrix are the zero padding behind the table)
   double a0 = b[col], a1 = b[2 + col], a2 = b[4 + col], a3 = b[6 + col], a4 = b[8 + col], a5 = b[10 + col];
   double a6 = (6 < n) ? b[12 + col] : 0.0;
-#pragma unroll 6
+  Band6 cur;
+  cur.k1 = lds_pure(Ca + 1 * CS + 5 * 8), cur.k2 = lds_pure(Ca + 2 * CS + 4 * 8), cur.k3 = lds_pure(Ca + 3 * CS + 3 * 8);
+  cur.k4 = lds_pure(Ca + 4 * CS + 2 * 8), cur.k5 = lds_pure(Ca + 5 * CS + 1 * 8), cur.k6 = lds_pure(Ca + 6 * CS + 0 * 8);
+  double rd = lds_pure(Ca + 13 * 8);
+#pragma unroll 2
   for (int j = 0; j < n; j++) {
-    const unsigned cj = Ca + j * CS;
-    const double zj = a0 * lds_pure(cj + 13 * 8);
+    const unsigned cn = Ca + (j + 1) * CS;
+    Band6 nxt;
+    nxt.k1 = lds_pure(cn + 1 * CS + 5 * 8), nxt.k2 = lds_pure(cn + 2 * CS + 4 * 8), nxt.k3 = lds_pure(cn + 3 * CS + 3 * 8);
+    nxt.k4 = lds_pure(cn + 4 * CS + 2 * 8), nxt.k5 = lds_pure(cn + 5 * CS + 1 * 8), nxt.k6 = lds_pure(cn + 6 * CS + 0 * 8);
+    const double rdn = lds_pure(cn + 13 * 8);
+    const double a7 = (j + 7 < n) ? lds_pure(ba + 16u * (j + 7)) : 0.0;
+    const double zj = a0 * rd;
     b[2 * j + col] = zj;
-    a0 = a1 - lds_pure(cj + 1 * CS + 5 * 8) * zj;
-    a1 = a2 - lds_pure(cj + 2 * CS + 4 * 8) * zj;
-    a2 = a3 - lds_pure(cj + 3 * CS + 3 * 8) * zj;
-    a3 = a4 - lds_pure(cj + 4 * CS + 2 * 8) * zj;
-    a4 = a5 - lds_pure(cj + 5 * CS + 1 * 8) * zj;
-    a5 = a6 - lds_pure(cj + 6 * CS + 0 * 8) * zj;
-    a6 = (j + 7 < n) ? lds_pure(ba + 16u * (j + 7)) : 0.0;
+    a0 = a1 - cur.k1 * zj;
+    a1 = a2 - cur.k2 * zj;
+    a2 = a3 - cur.k3 * zj;
+    a3 = a4 - cur.k4 * zj;
+    a4 = a5 - cur.k5 * zj;
+    a5 = a6 - cur.k6 * zj;
+    a6 = a7;
+    cur = nxt;
+    rd = rdn;
   }
-  // (no __syncwarp here: only the two solving lanes of a segment execute this function)
   ba = smem_addr(b) + 8u * col + order_token();
-  // L^T w = z, descending:  w_j = acc_j;  acc_{j-k} -= L(j, j-k) w_j,   L(j, j-k) = C[j-k][6+k]
-  // (columns in front of the matrix are the zero padding before the table)
+  // ---- L^T w = z, descending (poly_traj_utils.hpp:843-850):  w_j = acc_j;  acc_{j-k} -= L(j, j-k) w_j,
+  //      L(j, j-k) = C[j-k][6+k]  (columns in front of the matrix are the zero padding before the table)
   double q0 = b[2 * (n - 1) + col], q1 = b[2 * (n - 2) + col], q2 = b[2 * (n - 3) + col], q3 = b[2 * (n - 4) + col];
   double q4 = b[2 * (n - 5) + col], q5 = b[2 * (n - 6) + col];
   double q6 = (n - 7 >= 0) ? b[2 * (n - 7) + col] : 0.0;
-#pragma unroll 6
+  {
+    const unsigned c0 = Ca + (n - 1) * CS;
+    cur.k1 = lds_pure(c0 - 1 * CS + 7 * 8), cur.k2 = lds_pure(c0 - 2 * CS + 8 * 8), cur.k3 = lds_pure(c0 - 3 * CS + 9 * 8);
+    cur.k4 = lds_pure(c0 - 4 * CS + 10 * 8), cur.k5 = lds_pure(c0 - 5 * CS + 11 * 8), cur.k6 = lds_pure(c0 - 6 * CS + 12 * 8);
+  }
+#pragma unroll 2
   for (int j = n - 1; j >= 0; j--) {
-    const unsigned cj = Ca + j * CS;
+    const unsigned cn = Ca + (j - 1) * CS;  // for j = 0 this addresses (unused) padding in front of the table
+    Band6 nxt;
+    nxt.k1 = lds_pure(cn - 1 * CS + 7 * 8), nxt.k2 = lds_pure(cn - 2 * CS + 8 * 8), nxt.k3 = lds_pure(cn - 3 * CS + 9 * 8);
+    nxt.k4 = lds_pure(cn - 4 * CS + 10 * 8), nxt.k5 = lds_pure(cn - 5 * CS + 11 * 8), nxt.k6 = lds_pure(cn - 6 * CS + 12 * 8);
+    const double q7 = (j - 7 >= 0) ? lds_pure(ba + 16u * (j - 7)) : 0.0;
     const double wj = q0;
     b[2 * j + col] = wj;
-    q0 = q1 - lds_pure(cj - 1 * CS + 7 * 8) * wj;
-    q1 = q2 - lds_pure(cj - 2 * CS + 8 * 8) * wj;
-    q2 = q3 - lds_pure(cj - 3 * CS + 9 * 8) * wj;
-    q3 = q4 - lds_pure(cj - 4 * CS + 10 * 8) * wj;
-    q4 = q5 - lds_pure(cj - 5 * CS + 11 * 8) * wj;
-    q5 = q6 - lds_pure(cj - 6 * CS + 12 * 8) * wj;
-    q6 = (j - 7 >= 0) ? lds_pure(ba + 16u * (j - 7)) : 0.0;
+    q0 = q1 - cur.k1 * wj;
+    q1 = q2 - cur.k2 * wj;
+    q2 = q3 - cur.k3 * wj;
+    q3 = q4 - cur.k4 * wj;
+    q4 = q5 - cur.k5 * wj;
+    q5 = q6 - cur.k6 * wj;
+    q6 = q7;
+    cur = nxt;
   }
 }
 
@@ -1351,6 +1399,14 @@ __global__ void __launch_bounds__(512, 1)
               step = P.max_step;
             }
           }
+        }
+      }
+      if (ls != 0 && out.trace && k - 1 < out.trace_cap) {
+        double* tr = out.trace + ((size_t)prob * out.trace_cap + (k - 1)) * 3;
+        if (lane == 0) {
+          tr[0] = fx;
+          tr[1] = step;
+          tr[2] = (double)ls;
         }
       }
       if (ls == 0) {

@@ -146,6 +146,18 @@ class BatchOptimizer:
         self._check(self._lib.dftpav_eval(self._h, x.ctypes.data_as(dp), f.ctypes.data_as(dp), g.ctypes.data_as(dp)))
         return f, g
 
+    # -- diagnostics (not part of the drop-in ABI) ---------------------------------------------
+    def enable_trace(self, cap: int):
+        self._lib.dftpav_debug_set_trace.argtypes = [C.c_void_p, C.c_int]
+        self._check(self._lib.dftpav_debug_set_trace(self._h, cap))
+        self._trace_cap = cap
+
+    def get_trace(self) -> np.ndarray:
+        out = np.zeros((self._dims.B, self._trace_cap, 3))
+        self._lib.dftpav_debug_get_trace.argtypes = [C.c_void_p, capi.c_double_p]
+        self._check(self._lib.dftpav_debug_get_trace(self._h, out.ctypes.data_as(capi.c_double_p)))
+        return out
+
     def initial_x(self, batch: TrajBatch) -> np.ndarray:
         d = capi.Dims()
         cb = batch.as_c()
