@@ -54,12 +54,12 @@ class ClockSampler(threading.Thread):
         super().__init__(daemon=True)
         self.gpu = gpu_index
         self.samples = []
-        self._stop = threading.Event()
+        self._halt = threading.Event()
 
     def run(self):
         q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
              "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
-        while not self._stop.is_set():
+        while not self._halt.is_set():
             try:
                 out = subprocess.run(["nvidia-smi", f"--id={self.gpu}", f"--query-gpu={q}", "--format=csv,noheader,nounits"],
                                      capture_output=True, text=True, timeout=5).stdout.strip()
@@ -67,10 +67,10 @@ class ClockSampler(threading.Thread):
                     self.samples.append([x.strip() for x in out.split(",")])
             except Exception:
                 pass
-            self._stop.wait(0.2)
+            self._halt.wait(0.2)
 
     def stop(self):
-        self._stop.set()
+        self._halt.set()
         self.join(timeout=3)
         sm, mx, reasons = [], [], set()
         for s in self.samples:
