@@ -203,7 +203,9 @@ def run_ours(args):
     batch, prm = synth.make_config(args.config, B=args.batch, seed=rank)
     pin_batch(batch)
     opt = BatchOptimizer(prm, device=local_rank)
-    stream = torch.cuda.current_stream()
+    # a dedicated (non-default) torch stream: the library launches on it, the CUDA events below are recorded on it
+    stream = torch.cuda.Stream(device=local_rank)
+    torch.cuda.set_stream(stream)
     opt.set_stream(stream.cuda_stream)
     flag = torch.ones(1, dtype=torch.int32, device="cuda")
 
