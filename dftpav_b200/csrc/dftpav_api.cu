@@ -85,6 +85,21 @@ struct BandLU {
       }
     }
   }
+  // The kernels skip structurally-zero LU entries with compile-time masks of period 6 (kBandMask in
+  // dftpav_kernels.cu); this checks that every non-zero of the factor is covered (L passes: all but the last piece).
+  bool masks_hold() const {
+    static const int LM[6] = {0x60, 0x70, 0x78, 0x3c, 0x1e, 0x0e}, UM[6] = {0x00, 0x00, 0x00, 0x56, 0x6e, 0x06};
+    static const int ULT[6] = {0x00, 0x0c, 0x06, 0x46, 0x42, 0x30}, LLT[6] = {0x7e, 0x7c, 0x78, 0x00, 0x00, 0x3e};
+    auto A = [&](int i, int j) -> double { return (i < 0 || j < 0 || i >= n || j >= n) ? 0.0 : d[(size_t)(i - j + 6) * n + j]; };
+    for (int j = 0; j < n; j++)
+      for (int k = 1; k <= 6; k++) {
+        if (j < n - 6 && A(j + k, j) != 0.0 && !((LM[j % 6] >> k) & 1)) return false;
+        if (j < n - 6 && A(j, j - k) != 0.0 && !((LLT[j % 6] >> k) & 1)) return false;
+        if (A(j - k, j) != 0.0 && !((UM[j % 6] >> k) & 1)) return false;
+        if (A(j, j + k) != 0.0 && !((ULT[j % 6] >> k) & 1)) return false;
+      }
+    return true;
+  }
   // packed column table: C[j][0..12] = band rows 0..12 of column j, C[j][13] = 1/U(j,j)
   void pack(double* C) const {
     for (int j = 0; j < n; j++) {
@@ -629,7 +644,12 @@ int dftpav_upload_batch(dftpav_handle* h, const dftpav_batch* b) {
     sh.H = Hmax;
     // LU block
     std::vector<double> lu((size_t)luoff, 0.0);
-    for (auto& kv : lu_of_N) BandLU(kv.first).pack(lu.data() + kv.second);
+    sh.band_masks_ok = 1;
+    for (auto& kv : lu_of_N) {
+      BandLU f(kv.first);
+      f.pack(lu.data() + kv.second);
+      if (!f.masks_hold()) sh.band_masks_ok = 0;
+    }
     CU_TRY(h, up(grp->d_lu, lu.data(), sizeof(double) * lu.size()));
     CU_TRY(h, up(grp->d_prob_id, grp->probs.data(), sizeof(int) * grp->probs.size()));
     const int count = (int)grp->probs.size();

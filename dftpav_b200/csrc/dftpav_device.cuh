@@ -38,6 +38,7 @@ struct ShapeDev {
   int lu_doubles;        // size of the LU block (all distinct N of this shape)
   int npad;              // n rounded up to a multiple of 4
   int ws_doubles;        // per-warp workspace size in doubles
+  int band_masks_ok;     // 1 if the LU tables satisfy the compile-time sparsity masks of the banded passes
 };
 
 // Scalar parameters reaching the arithmetic (mirror of dftpav_params, device side).

@@ -170,141 +170,130 @@ __device__ __forceinline__ unsigned order_token() {
   return t;
 }
 
-// All four substitution passes below are written in update ("column") form — exactly the reference loops
-// (poly_traj_utils.hpp:808-850): when row j is final its contribution is pushed into the six pending rows with six
-// INDEPENDENT multiply-adds, so the dependent chain per row is one FMA (+ one multiply by 1/U(j,j)); every row still
-// receives its terms in the reference order.  The loops are software-pipelined by hand: the table entries and the
-// right-hand-side row needed by step j+1 are loaded at the top of step j (the compiler does not hoist them itself and
-// the in-order issue would otherwise put the shared-memory latency on the chain of every row).
-struct Band6 {
-  double k1, k2, k3, k4, k5, k6;
+// ------------------------------------------------------------------------------------------------
+// Banded substitutions (poly_traj_utils.hpp:805-852) — pattern-specialised, software-pipelined.
+//
+// All four passes are in update ("column") form, i.e. exactly the reference loops: when row j is final its contribution is
+// pushed into the pending rows with independent multiply-adds, so the dependent chain per row is one FMA (+ one multiply
+// by the stored 1/U(j,j)); every row receives its terms in the reference order.
+// The LU factors of the MINCO matrix have a sparsity pattern of period 6 (one piece): 20 of 36 sub-diagonal and 11 of
+// 36 super-diagonal entries per piece are structurally non-zero.  The reference skips exact zeros at run time
+// (`if (A(i,j) != 0.0)`); here the pattern is a compile-time mask per position in the piece, so the zero terms cost
+// nothing — same arithmetic, fewer instructions.  The masks are supersets of the true pattern for every piece except the
+// last one in the two L passes (its columns hold the tail conditions), which runs with the full mask; the host verifies
+// the masks against the factorised table at upload (ShapeDev::band_masks_ok) and the kernel falls back to full masks
+// otherwise.  The loops are software-pipelined by hand: table entries and the right-hand-side row of step j+1 are
+// loaded at the top of step j (non-aliasing `lds_pure`), otherwise the in-order issue exposes the shared-memory latency
+// on the dependent chain of every row.
+// ------------------------------------------------------------------------------------------------
+enum { PASS_FWD = 0, PASS_BWD = 1, PASS_ADJ_U = 2, PASS_ADJ_L = 3 };
+// bit k (1..6) set <=> the k-th neighbour entry is structurally non-zero; index = (row or column) mod 6
+__device__ constexpr int kBandMask[4][6] = {
+    {0x60, 0x70, 0x78, 0x3c, 0x1e, 0x0e},  // FWD  : L(j+k, j)   by column type
+    {0x00, 0x00, 0x00, 0x56, 0x6e, 0x06},  // BWD  : U(j-k, j)   by column type
+    {0x00, 0x0c, 0x06, 0x46, 0x42, 0x30},  // ADJ_U: U(j, j+k)   by row type
+    {0x7e, 0x7c, 0x78, 0x00, 0x00, 0x3e},  // ADJ_L: L(j, j-k)   by row type
 };
+constexpr unsigned kColBytes = kLuLd * 8u;
 
-__device__ __forceinline__ void banded_solve(const double* C, double* b, int n, int col) {
-  const unsigned tok0 = order_token();
-  const unsigned Ca = smem_addr(C) + tok0;  // also keeps the table reads behind the TMA completion wait
-  unsigned ba = smem_addr(b) + 8u * col + tok0;
-  constexpr unsigned CS = kLuLd * 8u;  // bytes per packed column
-  // ---- forward (poly_traj_utils.hpp:808-815):  y_j = acc_j;  acc_{j+k} -= L(j+k, j) y_j,  L(j+k, j) = C[j][6+k]
-  double w0 = b[col], w1 = b[2 + col], w2 = b[4 + col], w3 = b[6 + col], w4 = b[8 + col], w5 = b[10 + col];
-  double w6 = (6 < n) ? b[12 + col] : 0.0;
-  Band6 cur;
-  cur.k1 = lds_pure(Ca + 7 * 8), cur.k2 = lds_pure(Ca + 8 * 8), cur.k3 = lds_pure(Ca + 9 * 8);
-  cur.k4 = lds_pure(Ca + 10 * 8), cur.k5 = lds_pure(Ca + 11 * 8), cur.k6 = lds_pure(Ca + 12 * 8);
-#pragma unroll 2
-  for (int j = 0; j < n; j++) {
-    const unsigned cn = Ca + (j + 1) * CS;  // next column (zero padding behind the table for j = n-1)
-    Band6 nxt;
-    nxt.k1 = lds_pure(cn + 7 * 8), nxt.k2 = lds_pure(cn + 8 * 8), nxt.k3 = lds_pure(cn + 9 * 8);
-    nxt.k4 = lds_pure(cn + 10 * 8), nxt.k5 = lds_pure(cn + 11 * 8), nxt.k6 = lds_pure(cn + 12 * 8);
-    const double w7 = (j + 7 < n) ? lds_pure(ba + 16u * (j + 7)) : 0.0;
-    const double y = w0;
-    b[2 * j + col] = y;
-    w0 = w1 - cur.k1 * y;
-    w1 = w2 - cur.k2 * y;
-    w2 = w3 - cur.k3 * y;
-    w3 = w4 - cur.k4 * y;
-    w4 = w5 - cur.k5 * y;
-    w5 = w6 - cur.k6 * y;
-    w6 = w7;
-    cur = nxt;
+template <int PASS>
+__device__ __forceinline__ unsigned band_coef_addr(unsigned cj, int k) {
+  if (PASS == PASS_FWD) return cj + (6 + k) * 8u;
+  if (PASS == PASS_BWD) return cj + (6 - k) * 8u;
+  if (PASS == PASS_ADJ_U) return cj + k * kColBytes + (6 - k) * 8u;
+  return cj - k * kColBytes + (6 + k) * 8u;
+}
+template <int PASS, int MASK>
+__device__ __forceinline__ void band_load(double (&c)[7], unsigned cj) {
+#pragma unroll
+  for (int k = 1; k <= 6; k++)
+    if ((MASK >> k) & 1) c[k] = lds_pure(band_coef_addr<PASS>(cj, k));
+  if (PASS == PASS_BWD || PASS == PASS_ADJ_U) c[0] = lds_pure(cj + 13 * 8u);  // 1/U(j,j)
+}
+// one row: finalise row j from the window, push its contribution into the pending rows, shift the window
+template <int PASS, int MASK>
+__device__ __forceinline__ void band_step(double (&w)[7], const double (&c)[7], unsigned b_addr, double next_in) {
+  const double out = (PASS == PASS_BWD || PASS == PASS_ADJ_U) ? w[0] * c[0] : w[0];
+  asm volatile("st.shared.f64 [%0], %1;" ::"r"(b_addr), "d"(out) : "memory");
+#pragma unroll
+  for (int k = 1; k <= 6; k++) w[k - 1] = ((MASK >> k) & 1) ? w[k] - c[k] * out : w[k];
+  w[6] = next_in;
+}
+
+// one row of a piece: T = position inside the piece in processing order
+template <int PASS, bool ALLK, int T>
+__device__ __forceinline__ void band_row(double (&w)[7], double (&c)[7], unsigned Ca, unsigned ba, int j0, int n) {
+  constexpr bool ASC = (PASS == PASS_FWD || PASS == PASS_ADJ_U);
+  constexpr int type = ASC ? T : 5 - T;
+  constexpr int mask = ALLK ? 0x7e : kBandMask[PASS][type];
+  constexpr int ntype = ASC ? (T + 1) % 6 : (10 - T) % 6;
+  // the next row may belong to a piece that runs with the full mask: prefetch everything at piece borders
+  constexpr int nmask = (T == 5 || ALLK) ? 0x7e : kBandMask[PASS][ntype];
+  const int j = ASC ? j0 + T : j0 - T;
+  const int jn = ASC ? j + 1 : j - 1;
+  const int jin = ASC ? j + 7 : j - 7;
+  double cn[7];
+  band_load<PASS, nmask>(cn, Ca + jn * kColBytes);
+  const bool in_range = ASC ? (jin < n) : (jin >= 0);
+  const double nin = in_range ? lds_pure(ba + 16u * jin) : 0.0;
+  band_step<PASS, mask>(w, c, ba + 16u * j, nin);
+#pragma unroll
+  for (int k = 0; k <= 6; k++) c[k] = cn[k];
+}
+
+// one piece = 6 rows
+template <int PASS, bool ALLK>
+__device__ __forceinline__ void band_piece(double (&w)[7], double (&c)[7], unsigned Ca, unsigned ba, int j0, int n) {
+  band_row<PASS, ALLK, 0>(w, c, Ca, ba, j0, n);
+  band_row<PASS, ALLK, 1>(w, c, Ca, ba, j0, n);
+  band_row<PASS, ALLK, 2>(w, c, Ca, ba, j0, n);
+  band_row<PASS, ALLK, 3>(w, c, Ca, ba, j0, n);
+  band_row<PASS, ALLK, 4>(w, c, Ca, ba, j0, n);
+  band_row<PASS, ALLK, 5>(w, c, Ca, ba, j0, n);
+}
+
+// a full pass over the n = 6*N rows of one right-hand-side column (`col`) of the row-major n x 2 array b
+template <int PASS>
+__device__ __forceinline__ void band_pass(const double* C, double* b, int n, int col, bool masks_ok) {
+  constexpr bool ASC = (PASS == PASS_FWD || PASS == PASS_ADJ_U);
+  constexpr bool LPASS = (PASS == PASS_FWD || PASS == PASS_ADJ_L);
+  const unsigned tok = order_token();  // keeps every lds_pure below behind the stores / barriers above
+  const unsigned Ca = smem_addr(C) + tok;
+  const unsigned ba = smem_addr(b) + 8u * col + tok;
+  const int NP = n / 6;
+  double w[7], c[7];
+  const int jstart = ASC ? 0 : n - 1;
+#pragma unroll
+  for (int k = 0; k <= 6; k++) {
+    const int r = ASC ? k : n - 1 - k;
+    w[k] = (r >= 0 && r < n) ? lds_pure(ba + 16u * r) : 0.0;
   }
-  // (no __syncwarp here: only the two solving lanes of a segment execute this function)
-  ba = smem_addr(b) + 8u * col + order_token();
-  // ---- backward (poly_traj_utils.hpp:816-824):  x_j = acc_j / U(j,j);  acc_{j-k} -= U(j-k, j) x_j,  U(j-k, j) = C[j][6-k]
-  double v0 = b[2 * (n - 1) + col], v1 = b[2 * (n - 2) + col], v2 = b[2 * (n - 3) + col], v3 = b[2 * (n - 4) + col];
-  double v4 = b[2 * (n - 5) + col], v5 = b[2 * (n - 6) + col];
-  double v6 = (n - 7 >= 0) ? b[2 * (n - 7) + col] : 0.0;
-  {
-    const unsigned c0 = Ca + (n - 1) * CS;
-    cur.k1 = lds_pure(c0 + 5 * 8), cur.k2 = lds_pure(c0 + 4 * 8), cur.k3 = lds_pure(c0 + 3 * 8);
-    cur.k4 = lds_pure(c0 + 2 * 8), cur.k5 = lds_pure(c0 + 1 * 8), cur.k6 = lds_pure(c0 + 0 * 8);
+  band_load<PASS, 0x7e>(c, Ca + jstart * kColBytes);
+  if (!masks_ok) {
+    for (int p = 0; p < NP; p++) band_piece<PASS, true>(w, c, Ca, ba, ASC ? 6 * p : n - 1 - 6 * p, n);
+    return;
   }
-  double rd = lds_pure(Ca + (n - 1) * CS + 13 * 8);
-#pragma unroll 2
-  for (int j = n - 1; j >= 0; j--) {
-    const unsigned cn = Ca + (j - 1) * CS;  // previous column (zero padding in front of the table for j = 0)
-    Band6 nxt;
-    nxt.k1 = lds_pure(cn + 5 * 8), nxt.k2 = lds_pure(cn + 4 * 8), nxt.k3 = lds_pure(cn + 3 * 8);
-    nxt.k4 = lds_pure(cn + 2 * 8), nxt.k5 = lds_pure(cn + 1 * 8), nxt.k6 = lds_pure(cn + 0 * 8);
-    const double rdn = lds_pure(cn + 13 * 8);
-    const double v7 = (j - 7 >= 0) ? lds_pure(ba + 16u * (j - 7)) : 0.0;
-    const double xj = v0 * rd;
-    b[2 * j + col] = xj;
-    v0 = v1 - cur.k1 * xj;
-    v1 = v2 - cur.k2 * xj;
-    v2 = v3 - cur.k3 * xj;
-    v3 = v4 - cur.k4 * xj;
-    v4 = v5 - cur.k5 * xj;
-    v5 = v6 - cur.k6 * xj;
-    v6 = v7;
-    cur = nxt;
-    rd = rdn;
+  if (ASC) {
+    const int nspec = LPASS ? NP - 1 : NP;  // the last piece of an L pass runs with the full mask
+    for (int p = 0; p < nspec; p++) band_piece<PASS, false>(w, c, Ca, ba, 6 * p, n);
+    if (LPASS) band_piece<PASS, true>(w, c, Ca, ba, 6 * (NP - 1), n);
+  } else {
+    int p = 0;
+    if (LPASS) {
+      band_piece<PASS, true>(w, c, Ca, ba, n - 1, n);
+      p = 1;
+    }
+    for (; p < NP; p++) band_piece<PASS, false>(w, c, Ca, ba, n - 1 - 6 * p, n);
   }
 }
 
-__device__ __forceinline__ void banded_solve_adj(const double* C, double* b, int n, int col) {
-  const unsigned tok0 = order_token();
-  const unsigned Ca = smem_addr(C) + tok0;
-  unsigned ba = smem_addr(b) + 8u * col + tok0;
-  constexpr unsigned CS = kLuLd * 8u;
-  // ---- U^T z = b, ascending (poly_traj_utils.hpp:834-842):  z_j = acc_j / U(j,j);  acc_{j+k} -= U(j, j+k) z_j,
-  //      U(j, j+k) = C[j+k][6-k]  (columns beyond the matrix are the zero padding behind the table)
-  double a0 = b[col], a1 = b[2 + col], a2 = b[4 + col], a3 = b[6 + col], a4 = b[8 + col], a5 = b[10 + col];
-  double a6 = (6 < n) ? b[12 + col] : 0.0;
-  Band6 cur;
-  cur.k1 = lds_pure(Ca + 1 * CS + 5 * 8), cur.k2 = lds_pure(Ca + 2 * CS + 4 * 8), cur.k3 = lds_pure(Ca + 3 * CS + 3 * 8);
-  cur.k4 = lds_pure(Ca + 4 * CS + 2 * 8), cur.k5 = lds_pure(Ca + 5 * CS + 1 * 8), cur.k6 = lds_pure(Ca + 6 * CS + 0 * 8);
-  double rd = lds_pure(Ca + 13 * 8);
-#pragma unroll 2
-  for (int j = 0; j < n; j++) {
-    const unsigned cn = Ca + (j + 1) * CS;
-    Band6 nxt;
-    nxt.k1 = lds_pure(cn + 1 * CS + 5 * 8), nxt.k2 = lds_pure(cn + 2 * CS + 4 * 8), nxt.k3 = lds_pure(cn + 3 * CS + 3 * 8);
-    nxt.k4 = lds_pure(cn + 4 * CS + 2 * 8), nxt.k5 = lds_pure(cn + 5 * CS + 1 * 8), nxt.k6 = lds_pure(cn + 6 * CS + 0 * 8);
-    const double rdn = lds_pure(cn + 13 * 8);
-    const double a7 = (j + 7 < n) ? lds_pure(ba + 16u * (j + 7)) : 0.0;
-    const double zj = a0 * rd;
-    b[2 * j + col] = zj;
-    a0 = a1 - cur.k1 * zj;
-    a1 = a2 - cur.k2 * zj;
-    a2 = a3 - cur.k3 * zj;
-    a3 = a4 - cur.k4 * zj;
-    a4 = a5 - cur.k5 * zj;
-    a5 = a6 - cur.k6 * zj;
-    a6 = a7;
-    cur = nxt;
-    rd = rdn;
-  }
-  ba = smem_addr(b) + 8u * col + order_token();
-  // ---- L^T w = z, descending (poly_traj_utils.hpp:843-850):  w_j = acc_j;  acc_{j-k} -= L(j, j-k) w_j,
-  //      L(j, j-k) = C[j-k][6+k]  (columns in front of the matrix are the zero padding before the table)
-  double q0 = b[2 * (n - 1) + col], q1 = b[2 * (n - 2) + col], q2 = b[2 * (n - 3) + col], q3 = b[2 * (n - 4) + col];
-  double q4 = b[2 * (n - 5) + col], q5 = b[2 * (n - 6) + col];
-  double q6 = (n - 7 >= 0) ? b[2 * (n - 7) + col] : 0.0;
-  {
-    const unsigned c0 = Ca + (n - 1) * CS;
-    cur.k1 = lds_pure(c0 - 1 * CS + 7 * 8), cur.k2 = lds_pure(c0 - 2 * CS + 8 * 8), cur.k3 = lds_pure(c0 - 3 * CS + 9 * 8);
-    cur.k4 = lds_pure(c0 - 4 * CS + 10 * 8), cur.k5 = lds_pure(c0 - 5 * CS + 11 * 8), cur.k6 = lds_pure(c0 - 6 * CS + 12 * 8);
-  }
-#pragma unroll 2
-  for (int j = n - 1; j >= 0; j--) {
-    const unsigned cn = Ca + (j - 1) * CS;  // for j = 0 this addresses (unused) padding in front of the table
-    Band6 nxt;
-    nxt.k1 = lds_pure(cn - 1 * CS + 7 * 8), nxt.k2 = lds_pure(cn - 2 * CS + 8 * 8), nxt.k3 = lds_pure(cn - 3 * CS + 9 * 8);
-    nxt.k4 = lds_pure(cn - 4 * CS + 10 * 8), nxt.k5 = lds_pure(cn - 5 * CS + 11 * 8), nxt.k6 = lds_pure(cn - 6 * CS + 12 * 8);
-    const double q7 = (j - 7 >= 0) ? lds_pure(ba + 16u * (j - 7)) : 0.0;
-    const double wj = q0;
-    b[2 * j + col] = wj;
-    q0 = q1 - cur.k1 * wj;
-    q1 = q2 - cur.k2 * wj;
-    q2 = q3 - cur.k3 * wj;
-    q3 = q4 - cur.k4 * wj;
-    q4 = q5 - cur.k5 * wj;
-    q5 = q6 - cur.k6 * wj;
-    q6 = q7;
-    cur = nxt;
-  }
+__device__ __forceinline__ void banded_solve(const double* C, double* b, int n, int col, bool masks_ok) {
+  band_pass<PASS_FWD>(C, b, n, col, masks_ok);  // L y = b      (poly_traj_utils.hpp:808-815)
+  band_pass<PASS_BWD>(C, b, n, col, masks_ok);  // U x = y      (poly_traj_utils.hpp:816-824)
+}
+__device__ __forceinline__ void banded_solve_adj(const double* C, double* b, int n, int col, bool masks_ok) {
+  band_pass<PASS_ADJ_U>(C, b, n, col, masks_ok);  // U^T z = b  (poly_traj_utils.hpp:834-842)
+  band_pass<PASS_ADJ_L>(C, b, n, col, masks_ok);  // L^T w = z  (poly_traj_utils.hpp:843-850)
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -391,10 +380,18 @@ __device__ __forceinline__ void load_plane_chunk(double (&pn)[kPlaneChunk][4], c
     const int h = h0 + hh;
     if (h < H) {
       const double* ph = pl + (size_t)(4 * h) * Mpad + store;
+      // read-only path; the streaming variant (ld.global.cs, -DDFTPAV_PLANES_LDCS) was measured and is not better
+#ifndef DFTPAV_PLANES_LDCS
       pn[hh][0] = __ldg(ph);
       pn[hh][1] = __ldg(ph + Mpad);
       pn[hh][2] = __ldg(ph + 2 * (size_t)Mpad);
       pn[hh][3] = __ldg(ph + 3 * (size_t)Mpad);
+#else
+      pn[hh][0] = __ldcs(ph);
+      pn[hh][1] = __ldcs(ph + Mpad);
+      pn[hh][2] = __ldcs(ph + 2 * (size_t)Mpad);
+      pn[hh][3] = __ldcs(ph + 3 * (size_t)Mpad);
+#endif
     } else {
       pn[hh][0] = pn[hh][1] = pn[hh][2] = pn[hh][3] = 0.0;
     }
@@ -981,7 +978,7 @@ __device__ double eval_cost_grad(const ShapeDev& sh, const ParamsDev& P, const B
   // ---- banded solve, two lanes per segment
   if (lane < 2 * S) {
     const int s = lane >> 1;
-    banded_solve(lu + sh.lu_off[s], ws.bt + 2 * sh.row0[s], 6 * sh.N[s], lane & 1);
+    banded_solve(lu + sh.lu_off[s], ws.bt + 2 * sh.row0[s], 6 * sh.N[s], lane & 1, sh.band_masks_ok != 0);
   }
   __syncwarp();
   PHASE_MARK(1)
@@ -1060,7 +1057,7 @@ __device__ double eval_cost_grad(const ShapeDev& sh, const ParamsDev& P, const B
   PHASE_MARK(4)
   if (lane < 2 * S) {
     const int s = lane >> 1;
-    banded_solve_adj(lu + sh.lu_off[s], ws.gd + 2 * sh.row0[s], 6 * sh.N[s], lane & 1);
+    banded_solve_adj(lu + sh.lu_off[s], ws.gd + 2 * sh.row0[s], 6 * sh.N[s], lane & 1, sh.band_masks_ok != 0);
   }
   __syncwarp();
   PHASE_MARK(5)
@@ -1221,60 +1218,77 @@ __device__ __forceinline__ void hist_load(HistStage<NPL>& st, const double* __re
   st.ys = lm_ys[j];
 }
 
+#ifdef DFTPAV_TL_INLINE
+#define DFTPAV_TL_ATTR __forceinline__
+#else
+#define DFTPAV_TL_ATTR __noinline__
+#endif
 template <int NPL>
-__device__ __noinline__ void two_loop(double* d_sm, double* alpha_sm, const double* __restrict__ lm_s,
+__device__ DFTPAV_TL_ATTR void two_loop(double* d_sm, double* alpha_sm, const double* __restrict__ lm_s,
                                       const double* __restrict__ lm_y, const double* __restrict__ lm_ys, int ld, int m,
                                       int end, int bound, int n, int lane, double ys, double yy) {
+#ifndef DFTPAV_TL_PF
+#define DFTPAV_TL_PF 1  // measured on B200 (batch 4096): PF=1 88 k solves/s, PF=2 65 k, PF=4 62 k (register spills in the ring)
+#endif
+  constexpr int PF = DFTPAV_TL_PF;  // prefetch distance (history entries in flight)
   double d[NPL];
 #pragma unroll
   for (int e = 0; e < NPL; e++) {
     const int i = lane + 32 * e;
     d[e] = i < n ? d_sm[i] : 0.0;
   }
+  HistStage<NPL> st[PF];
   // ---- first loop: j = end-1, end-2, ... (newest to oldest)
-  HistStage<NPL> st0, st1, st2;
   int j = end;
-  {
-    int jj = (j + m - 1) % m;
-    hist_load<NPL>(st0, lm_s, lm_y, lm_ys, jj, ld, n, lane, true, true);
-    jj = (jj + m - 1) % m;
-    if (1 < bound) hist_load<NPL>(st1, lm_s, lm_y, lm_ys, jj, ld, n, lane, true, true);
-  }
-  for (int i = 0; i < bound; ++i) {
-    j = (j + m - 1) % m;
-    if (i + 2 < bound) hist_load<NPL>(st2, lm_s, lm_y, lm_ys, (j + 2 * m - 2) % m, ld, n, lane, true, true);
-    double part = 0.0;
 #pragma unroll
-    for (int e = 0; e < NPL; e++) part += st0.s[e] * d[e];
-    const double a = warp_sum(part) / st0.ys;
-    if (lane == 0) alpha_sm[j] = a;
-    const double na = -a;
+  for (int q = 0; q < PF; q++)
+    if (q < bound) hist_load<NPL>(st[q], lm_s, lm_y, lm_ys, (end + (q + 1) * (m - 1)) % m, ld, n, lane, true, true);
+  for (int i0 = 0; i0 < bound; i0 += PF) {
 #pragma unroll
-    for (int e = 0; e < NPL; e++) d[e] += na * st0.y[e];
-    st0 = st1;
-    st1 = st2;
+    for (int q = 0; q < PF; q++) {
+      const int i = i0 + q;
+      if (i < bound) {
+        j = (j + m - 1) % m;
+        double part = 0.0;
+#pragma unroll
+        for (int e = 0; e < NPL; e++) part += st[q].s[e] * d[e];
+        const double a = warp_sum(part) / st[q].ys;
+        if (lane == 0) alpha_sm[j] = a;
+        const double na = -a;
+#pragma unroll
+        for (int e = 0; e < NPL; e++) d[e] += na * st[q].y[e];
+        if (i + PF < bound) {
+          int jn = j - PF;
+          jn = jn < 0 ? jn + m : jn;  // (j + PF*(m-1)) % m for PF <= m
+          hist_load<NPL>(st[q], lm_s, lm_y, lm_ys, jn, ld, n, lane, true, true);
+        }
+      }
+    }
   }
   const double sc = ys / yy;
 #pragma unroll
   for (int e = 0; e < NPL; e++) d[e] *= sc;
   __syncwarp();
   // ---- second loop: oldest to newest, starting at the j where the first loop stopped
-  {
-    hist_load<NPL>(st0, lm_s, lm_y, lm_ys, j, ld, n, lane, true, true);
-    if (1 < bound) hist_load<NPL>(st1, lm_s, lm_y, lm_ys, (j + 1) % m, ld, n, lane, true, true);
-  }
-  for (int i = 0; i < bound; ++i) {
-    if (i + 2 < bound) hist_load<NPL>(st2, lm_s, lm_y, lm_ys, (j + 2) % m, ld, n, lane, true, true);
-    double part = 0.0;
 #pragma unroll
-    for (int e = 0; e < NPL; e++) part += st0.y[e] * d[e];
-    const double beta = warp_sum(part) / st0.ys;
-    const double a = alpha_sm[j] - beta;
+  for (int q = 0; q < PF; q++)
+    if (q < bound) hist_load<NPL>(st[q], lm_s, lm_y, lm_ys, (j + q) % m, ld, n, lane, true, true);
+  for (int i0 = 0; i0 < bound; i0 += PF) {
 #pragma unroll
-    for (int e = 0; e < NPL; e++) d[e] += a * st0.s[e];
-    st0 = st1;
-    st1 = st2;
-    j = (j + 1) % m;
+    for (int q = 0; q < PF; q++) {
+      const int i = i0 + q;
+      if (i < bound) {
+        double part = 0.0;
+#pragma unroll
+        for (int e = 0; e < NPL; e++) part += st[q].y[e] * d[e];
+        const double beta = warp_sum(part) / st[q].ys;
+        const double a = alpha_sm[j] - beta;
+#pragma unroll
+        for (int e = 0; e < NPL; e++) d[e] += a * st[q].s[e];
+        if (i + PF < bound) hist_load<NPL>(st[q], lm_s, lm_y, lm_ys, (j + PF) % m, ld, n, lane, true, true);
+        j = (j + 1) % m;
+      }
+    }
   }
 #pragma unroll
   for (int e = 0; e < NPL; e++) {
