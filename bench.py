@@ -239,7 +239,7 @@ def run_ours(args):
         opt.optimize()
         st = opt.stats()
         kernel_ms.append(st.solve_ms)
-        launches += 1  # one persistent solve kernel per shape group (single shape here)
+        launches += int(st.kernel_launches - 2 * st.n_shapes)  # per shape: ordering evaluation + persistent solve kernel
         convergence_flag(1)
     ev1.record(stream)
     sync_all()

@@ -81,6 +81,7 @@ struct GroupDev {
   int count;
   const double* planes;         // tiled SoA: [count][H][4][Mpad]
   const double* lu;             // packed LU block of this shape
+  const int* order;             // work list: order[w] = local index served w-th (longest-expected-first), or nullptr
 };
 
 struct OutDev {

@@ -734,16 +734,23 @@ __device__ __forceinline__ void sweep_segment(const ShapeDev& sh, const ParamsDe
           const V2 bpt = sigma + q;
           V2 Bn = mk(0.0, 0.0);  // sum penaD * n
           double Sp = 0.0;       // sum pena
+          // the four plane tests of a vertex are evaluated together (independent chains) and share one branch: a
+          // sample violates a plane only occasionally, and in-order warps pay every branch with exposed latency
+          double viol[kPlaneChunk];
 #pragma unroll
-          for (int hh = 0; hh < kPlaneChunk; hh++) {
-            const V2 nrm = mk(pn[hh][0], pn[hh][1]);
-            const double violaPos = nrm.x * (bpt.x - pn[hh][2]) + nrm.y * (bpt.y - pn[hh][3]);
-            if (violaPos > 0.0) {
-              double pena, penaD;
-              smoothed_l1(P.smooth_eps, violaPos, pena, penaD);
-              Bn.x += penaD * nrm.x;
-              Bn.y += penaD * nrm.y;
-              Sp += pena;
+          for (int hh = 0; hh < kPlaneChunk; hh++)
+            viol[hh] = pn[hh][0] * (bpt.x - pn[hh][2]) + pn[hh][1] * (bpt.y - pn[hh][3]);
+          const double vmax = fmax(fmax(viol[0], viol[1]), fmax(viol[2], viol[3]));
+          if (vmax > 0.0) {
+#pragma unroll
+            for (int hh = 0; hh < kPlaneChunk; hh++) {
+              if (viol[hh] > 0.0) {
+                double pena, penaD;
+                smoothed_l1(P.smooth_eps, viol[hh], pena, penaD);
+                Bn.x += penaD * pn[hh][0];
+                Bn.y += penaD * pn[hh][1];
+                Sp += pena;
+              }
             }
           }
           if (Sp > 0.0) {
@@ -1218,82 +1225,113 @@ __device__ __forceinline__ void hist_load(HistStage<NPL>& st, const double* __re
   st.ys = lm_ys[j];
 }
 
-#ifdef DFTPAV_TL_INLINE
-#define DFTPAV_TL_ATTR __forceinline__
-#else
-#define DFTPAV_TL_ATTR __noinline__
-#endif
+// Lean hand-scheduled version: no integer modulo (wrap by compare), scalar double buffer (one history entry in flight:
+// measured best on B200 — deeper rings spill and lose 25 %), trip count read through a shuffle so that the compiler
+// treats the loop as warp-uniform and emits bare SHFL instead of WARPSYNC-guarded collectives.
 template <int NPL>
-__device__ DFTPAV_TL_ATTR void two_loop(double* d_sm, double* alpha_sm, const double* __restrict__ lm_s,
+__device__ __noinline__ void two_loop(double* d_sm, double* alpha_sm, const double* __restrict__ lm_s,
                                       const double* __restrict__ lm_y, const double* __restrict__ lm_ys, int ld, int m,
-                                      int end, int bound, int n, int lane, double ys, double yy) {
-#ifndef DFTPAV_TL_PF
-#define DFTPAV_TL_PF 1  // measured on B200 (batch 4096): PF=1 88 k solves/s, PF=2 65 k, PF=4 62 k (register spills in the ring)
-#endif
-  constexpr int PF = DFTPAV_TL_PF;  // prefetch distance (history entries in flight)
-  double d[NPL];
+                                      int end, int bound_in, int n, int lane, double ys, double yy) {
+  const int bound = __shfl_sync(FULL, bound_in, 0);
+  double d[NPL], sc_[NPL], yc_[NPL], sn_[NPL], yn_[NPL];
+  double ysc, ysn = 0.0;
+  bool ok[NPL];
 #pragma unroll
   for (int e = 0; e < NPL; e++) {
     const int i = lane + 32 * e;
-    d[e] = i < n ? d_sm[i] : 0.0;
+    ok[e] = i < n;
+    d[e] = ok[e] ? d_sm[i] : 0.0;
+    sn_[e] = yn_[e] = 0.0;
   }
-  HistStage<NPL> st[PF];
-  // ---- first loop: j = end-1, end-2, ... (newest to oldest)
-  int j = end;
+  // ---- first loop: newest to oldest
+  int j = end - 1;
+  if (j < 0) j += m;
+  {
+    const double* sj = lm_s + (size_t)j * ld + lane;
+    const double* yj = lm_y + (size_t)j * ld + lane;
 #pragma unroll
-  for (int q = 0; q < PF; q++)
-    if (q < bound) hist_load<NPL>(st[q], lm_s, lm_y, lm_ys, (end + (q + 1) * (m - 1)) % m, ld, n, lane, true, true);
-  for (int i0 = 0; i0 < bound; i0 += PF) {
-#pragma unroll
-    for (int q = 0; q < PF; q++) {
-      const int i = i0 + q;
-      if (i < bound) {
-        j = (j + m - 1) % m;
-        double part = 0.0;
-#pragma unroll
-        for (int e = 0; e < NPL; e++) part += st[q].s[e] * d[e];
-        const double a = warp_sum(part) / st[q].ys;
-        if (lane == 0) alpha_sm[j] = a;
-        const double na = -a;
-#pragma unroll
-        for (int e = 0; e < NPL; e++) d[e] += na * st[q].y[e];
-        if (i + PF < bound) {
-          int jn = j - PF;
-          jn = jn < 0 ? jn + m : jn;  // (j + PF*(m-1)) % m for PF <= m
-          hist_load<NPL>(st[q], lm_s, lm_y, lm_ys, jn, ld, n, lane, true, true);
-        }
-      }
+    for (int e = 0; e < NPL; e++) {
+      sc_[e] = ok[e] ? sj[32 * e] : 0.0;
+      yc_[e] = ok[e] ? yj[32 * e] : 0.0;
     }
+    ysc = lm_ys[j];
   }
-  const double sc = ys / yy;
+#pragma unroll 1
+  for (int i = 0; i < bound; ++i) {
+    int jn = j - 1;
+    if (jn < 0) jn += m;
+    if (i + 1 < bound) {
+      const double* sj = lm_s + (size_t)jn * ld + lane;
+      const double* yj = lm_y + (size_t)jn * ld + lane;
 #pragma unroll
-  for (int e = 0; e < NPL; e++) d[e] *= sc;
+      for (int e = 0; e < NPL; e++) {
+        sn_[e] = ok[e] ? sj[32 * e] : 0.0;
+        yn_[e] = ok[e] ? yj[32 * e] : 0.0;
+      }
+      ysn = lm_ys[jn];
+    }
+    double part = 0.0;
+#pragma unroll
+    for (int e = 0; e < NPL; e++) part += sc_[e] * d[e];
+    const double a = warp_sum(part) / ysc;
+    if (lane == 0) alpha_sm[j] = a;
+    const double na = -a;
+#pragma unroll
+    for (int e = 0; e < NPL; e++) {
+      d[e] += na * yc_[e];
+      sc_[e] = sn_[e];
+      yc_[e] = yn_[e];
+    }
+    ysc = ysn;
+    if (i + 1 < bound) j = jn;
+  }
+  const double scl = ys / yy;
+#pragma unroll
+  for (int e = 0; e < NPL; e++) d[e] *= scl;
   __syncwarp();
-  // ---- second loop: oldest to newest, starting at the j where the first loop stopped
+  // ---- second loop: oldest to newest, starting at the entry where the first loop stopped (j)
+  {
+    const double* sj = lm_s + (size_t)j * ld + lane;
+    const double* yj = lm_y + (size_t)j * ld + lane;
 #pragma unroll
-  for (int q = 0; q < PF; q++)
-    if (q < bound) hist_load<NPL>(st[q], lm_s, lm_y, lm_ys, (j + q) % m, ld, n, lane, true, true);
-  for (int i0 = 0; i0 < bound; i0 += PF) {
-#pragma unroll
-    for (int q = 0; q < PF; q++) {
-      const int i = i0 + q;
-      if (i < bound) {
-        double part = 0.0;
-#pragma unroll
-        for (int e = 0; e < NPL; e++) part += st[q].y[e] * d[e];
-        const double beta = warp_sum(part) / st[q].ys;
-        const double a = alpha_sm[j] - beta;
-#pragma unroll
-        for (int e = 0; e < NPL; e++) d[e] += a * st[q].s[e];
-        if (i + PF < bound) hist_load<NPL>(st[q], lm_s, lm_y, lm_ys, (j + PF) % m, ld, n, lane, true, true);
-        j = (j + 1) % m;
-      }
+    for (int e = 0; e < NPL; e++) {
+      sc_[e] = ok[e] ? sj[32 * e] : 0.0;
+      yc_[e] = ok[e] ? yj[32 * e] : 0.0;
     }
+    ysc = lm_ys[j];
+  }
+#pragma unroll 1
+  for (int i = 0; i < bound; ++i) {
+    int jn = j + 1;
+    if (jn >= m) jn -= m;
+    if (i + 1 < bound) {
+      const double* sj = lm_s + (size_t)jn * ld + lane;
+      const double* yj = lm_y + (size_t)jn * ld + lane;
+#pragma unroll
+      for (int e = 0; e < NPL; e++) {
+        sn_[e] = ok[e] ? sj[32 * e] : 0.0;
+        yn_[e] = ok[e] ? yj[32 * e] : 0.0;
+      }
+      ysn = lm_ys[jn];
+    }
+    double part = 0.0;
+#pragma unroll
+    for (int e = 0; e < NPL; e++) part += yc_[e] * d[e];
+    const double beta = warp_sum(part) / ysc;
+    const double a = alpha_sm[j] - beta;
+#pragma unroll
+    for (int e = 0; e < NPL; e++) {
+      d[e] += a * sc_[e];
+      sc_[e] = sn_[e];
+      yc_[e] = yn_[e];
+    }
+    ysc = ysn;
+    j = jn;
   }
 #pragma unroll
   for (int e = 0; e < NPL; e++) {
     const int i = lane + 32 * e;
-    if (i < n) d_sm[i] = d[e];
+    if (ok[e]) d_sm[i] = d[e];
   }
   __syncwarp();
 }
@@ -1330,6 +1368,7 @@ __global__ void __launch_bounds__(512, 1)
   bool brackt = false, touched = false;
   double step = 0.0, fx = 0.0, finit = 0.0, dgtest = 0.0, dstest = 0.0, mu = 0.0, nu = 0.0;
   const double* planes = nullptr;
+  long long t_logic = 0;
 
   while (true) {
     if (phase == PH_FETCH) {
@@ -1337,6 +1376,7 @@ __global__ void __launch_bounds__(512, 1)
       if (lane == 0) local = atomicAdd(work_counter, 1);
       local = __shfl_sync(FULL, local, 0);
       if (local >= grp.count) break;
+      if (grp.order) local = grp.order[local];
       prob = grp.prob_id[local];
       planes = grp.planes + (size_t)local * sh.H * 4 * sh.Mpad;
 #pragma unroll 1
@@ -1347,8 +1387,15 @@ __global__ void __launch_bounds__(512, 1)
     }
 
     // ---------------- the single evaluation site
+    if (g_phase_clock) {
+      const long long now = clock64();
+      if (t_logic) {
+        if (lane == 0) atomicAdd(g_phase_clock + 7, (unsigned long long)(now - t_logic));
+      }
+    }
     fx = eval_cost_grad<HAS_OBS>(sh, P, bd, prob, planes, smem, ws, ws.x, ws.g, lane);
     evals++;
+    if (g_phase_clock) t_logic = clock64();
 
     bool start_ls = false;   // begin a new line search from the current (x, g, d, step)
     bool finish = false;     // problem done: write results
