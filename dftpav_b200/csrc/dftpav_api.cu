@@ -13,6 +13,7 @@
 #include <algorithm>
 #include <cmath>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <map>
 #include <string>
@@ -265,6 +266,14 @@ void fill_params_dev(const dftpav_params& p, ParamsDev& d) {
   d.le[1][0] = p.veh_d_cr + length / 2.0, d.le[1][1] = -width / 2.0;
   d.le[2][0] = p.veh_d_cr - length / 2.0, d.le[2][1] = -width / 2.0;
   d.le[3][0] = p.veh_d_cr - length / 2.0, d.le[3][1] = width / 2.0;
+  {  // positiveSmoothedL1 constants, same expressions as traj_optimizer.cpp:785-790
+    const double pe = p.smooth_eps;
+    d.l1_half = 0.5 * pe;
+    d.l1_f3c = 1.0 / (pe * pe);
+    d.l1_f4c = -0.5 * d.l1_f3c / pe;
+    d.l1_d2c = 3.0 * d.l1_f3c;
+    d.l1_d3c = 4.0 * d.l1_f4c;
+  }
   d.gear_opt = p.gear_opt;
   d.mem_size = p.lbfgs_mem_size;
   d.past = p.lbfgs_past;
@@ -658,7 +667,7 @@ int dftpav_upload_batch(dftpav_handle* h, const dftpav_batch* b) {
     } else {
       Hmax = b->uniform_H;
     }
-    sh.H = Hmax;
+    sh.H = (Hmax + 3) / 4 * 4;  // padded to the register chunk of the sweep (null planes never violate)
     // LU block
     std::vector<double> lu((size_t)luoff, 0.0);
     sh.band_masks_ok = 1;
@@ -788,7 +797,7 @@ int dftpav_optimize(dftpav_handle* h) {
   // ---- scheduling heuristic (no effect on results): the batch time is the critical path of the longest solve, and the
   // number of L-BFGS evaluations a problem needs correlates with its initial cost (Spearman 0.4 at config 3), so the
   // persistent warps serve the problems in order of decreasing f(x0).  Costs one extra evaluation per problem.
-  const bool lpt = h->dims.B > h->num_sms * 4;
+  const bool lpt = h->dims.B > h->num_sms * 4 && !getenv("DFTPAV_NO_LPT");
   if (lpt) {
     const int B = h->dims.B;
     CU_TRY(h, h->fout.ensure(sizeof(double) * B));

@@ -48,6 +48,7 @@ struct ParamsDev {
   double max_vel[2], max_cur[2], max_acc[2];  // [0] forward, [1] backward
   double non_sinv, mini_T, help_eps, min_speed, smooth_eps, cur_weight_scale, lse_alpha, cull_dist, cost_limit;
   double le[4][2];                        // ego / obstacle box vertices (OPT.cpp:1765-1768), clockwise
+  double l1_half, l1_f3c, l1_f4c, l1_d2c, l1_d3c;  // constants of positiveSmoothedL1 (OPT.cpp:785-790), precomputed
   int gear_opt;
   int mem_size, past, max_iterations, max_linesearch;
   double delta, g_epsilon, min_step, max_step, f_dec_coeff, s_curv_coeff, cautious_factor, machine_prec;

@@ -45,18 +45,13 @@ __device__ __noinline__ double warp_maxabs(const double* a, int n, int lane) {
   return warp_max(m);
 }
 
-// positiveSmoothedL1 (traj_optimizer.cpp:783-806)
-__device__ __forceinline__ void smoothed_l1(double pe, double x, double& f, double& df) {
-  const double half = 0.5 * pe;
-  const double f3c = 1.0 / (pe * pe);
-  const double f4c = -0.5 * f3c / pe;
-  const double d2c = 3.0 * f3c;
-  const double d3c = 4.0 * f4c;
-  if (x < pe) {
-    f = (f4c * x + f3c) * x * x * x;
-    df = (d3c * x + d2c) * x * x;
+// positiveSmoothedL1 (traj_optimizer.cpp:783-806); the five constants are precomputed on the host (ParamsDev)
+__device__ __forceinline__ void smoothed_l1(const ParamsDev& P, double x, double& f, double& df) {
+  if (x < P.smooth_eps) {
+    f = (P.l1_f4c * x + P.l1_f3c) * x * x * x;
+    df = (P.l1_d3c * x + P.l1_d2c) * x * x;
   } else {
-    f = x - half;
+    f = x - P.l1_half;
     df = 1.0;
   }
 }
@@ -371,30 +366,25 @@ __device__ __forceinline__ double lse(double alpha, double* v, double& exp_sum) 
   return log(exp_sum) / alpha + d0;
 }
 
+// cold path (help_eps != 0, the header default of traj_optimizer.h:120): kept out of line to keep the sweep loop small
+__device__ __noinline__ void speed_helpers_eps(double v2, double eps, double& z_h0, double& vel2_reci, double& vel2_reci_e,
+                                              double& vel3_2_reci_e) {
+  vel2_reci = 1.0 / v2;
+  vel2_reci_e = 1.0 / (v2 + eps);
+  vel3_2_reci_e = vel2_reci_e * sqrt(vel2_reci_e);
+  z_h0 = 1.0 / sqrt(v2);
+}
+
 constexpr int kPlaneChunk = 4;
-// Loads planes h0..h0+3 of storage slot `store` into registers; planes beyond H read as the null plane (n = p = 0).
-__device__ __forceinline__ void load_plane_chunk(double (&pn)[kPlaneChunk][4], const double* __restrict__ pl, int Mpad,
-                                                 int store, int h0, int H) {
+// Loads planes h0..h0+3 of one storage slot into registers.  `slotp` already points at (plane 0, component 0, slot);
+// the host pads the plane count of a group to a multiple of 4 with null planes (n = p = 0), so no bounds checks.
+__device__ __forceinline__ void load_plane_chunk(double (&pn)[kPlaneChunk][4], const double* __restrict__ slotp, int Mpad,
+                                                 int h0) {
+  const double* ph = slotp + (size_t)(4 * h0) * Mpad;
 #pragma unroll
   for (int hh = 0; hh < kPlaneChunk; hh++) {
-    const int h = h0 + hh;
-    if (h < H) {
-      const double* ph = pl + (size_t)(4 * h) * Mpad + store;
-      // read-only path; the streaming variant (ld.global.cs, -DDFTPAV_PLANES_LDCS) was measured and is not better
-#ifndef DFTPAV_PLANES_LDCS
-      pn[hh][0] = __ldg(ph);
-      pn[hh][1] = __ldg(ph + Mpad);
-      pn[hh][2] = __ldg(ph + 2 * (size_t)Mpad);
-      pn[hh][3] = __ldg(ph + 3 * (size_t)Mpad);
-#else
-      pn[hh][0] = __ldcs(ph);
-      pn[hh][1] = __ldcs(ph + Mpad);
-      pn[hh][2] = __ldcs(ph + 2 * (size_t)Mpad);
-      pn[hh][3] = __ldcs(ph + 3 * (size_t)Mpad);
-#endif
-    } else {
-      pn[hh][0] = pn[hh][1] = pn[hh][2] = pn[hh][3] = 0.0;
-    }
+#pragma unroll
+    for (int cc = 0; cc < 4; cc++) pn[hh][cc] = __ldg(ph + (hh * 4 + cc) * Mpad);
   }
 }
 
@@ -510,7 +500,7 @@ __device__ __noinline__ void dyn_obstacles(const ParamsDev& P, const BatchDev& b
     const double costp = d_min - lse<8>(alpha, d_test, exp_sum_d);
     if (costp <= 0.0) continue;
     double pena, penaD;
-    smoothed_l1(P.smooth_eps, costp, pena, penaD);
+    smoothed_l1(P, costp, pena, penaD);
     acc.pen1 += omg * step * wei_surround * pena;
 
     V2 pG_sigma = mk(0.0, 0.0);
@@ -619,7 +609,7 @@ __device__ __forceinline__ void sweep_segment(const ShapeDev& sh, const ParamsDe
     return ntile * kTile + (pc < N ? pc : N - 1);
   };
   double pn[kPlaneChunk][4];
-  load_plane_chunk(pn, pl, Mpad, slot_of(0), 0, H);
+  load_plane_chunk(pn, pl + slot_of(0), Mpad, 0);
 
   for (int pass = 0; pass < npass; pass++) {
     const bool endpass = pass >= npass_reg;
@@ -706,10 +696,7 @@ __device__ __forceinline__ void sweep_segment(const ShapeDev& sh, const ParamsDe
         vel2_reci_e = vel2_reci;
         vel3_2_reci_e = vel2_reci * z_h0;
       } else {
-        vel2_reci = 1.0 / v2;
-        vel2_reci_e = 1.0 / (v2 + P.help_eps);
-        vel3_2_reci_e = vel2_reci_e * sqrt(vel2_reci_e);
-        z_h0 = 1.0 / sqrt(v2);
+        speed_helpers_eps(v2, P.help_eps, z_h0, vel2_reci, vel2_reci_e, vel3_2_reci_e);
       }
       const M2 rot = M2{dsigma.x, -dsigma.y, dsigma.y, dsigma.x};
       ego_R = M2{sg * rot.a * z_h0, sg * rot.b * z_h0, sg * rot.c * z_h0, sg * rot.d * z_h0};
@@ -726,9 +713,9 @@ __device__ __forceinline__ void sweep_segment(const ShapeDev& sh, const ParamsDe
       //      penaD * n and pena to per-vertex sums; the maps to d/dsigma, d/dsigma', d/dt run once per vertex.
       const double wobs = omg * step * P.wei_obs;
       for (int h0 = 0; h0 < H; h0 += kPlaneChunk) {
-        if (h0 > 0) load_plane_chunk(pn, pl, Mpad, store, h0, H);
-#pragma unroll
-        for (int v = 0; v < 4; v++) {
+        if (h0 > 0) load_plane_chunk(pn, pl + store, Mpad, h0);
+#pragma unroll 1
+        for (int v = 0; v < 4; v++) {  // kept rolled: the sweep loop has to fit the instruction cache
           const V2 le = mk(P.le[v][0], P.le[v][1]);
           const V2 q = ego_R * le;
           const V2 bpt = sigma + q;
@@ -746,7 +733,7 @@ __device__ __forceinline__ void sweep_segment(const ShapeDev& sh, const ParamsDe
             for (int hh = 0; hh < kPlaneChunk; hh++) {
               if (viol[hh] > 0.0) {
                 double pena, penaD;
-                smoothed_l1(P.smooth_eps, viol[hh], pena, penaD);
+                smoothed_l1(P, viol[hh], pena, penaD);
                 Bn.x += penaD * pn[hh][0];
                 Bn.y += penaD * pn[hh][1];
                 Sp += pena;
@@ -773,7 +760,7 @@ __device__ __forceinline__ void sweep_segment(const ShapeDev& sh, const ParamsDe
 
     // ---------------- stage C: software prefetch of the next pass's first plane chunk (registers are free now;
     //                  its consumers are most of a pass away)
-    if (pass + 1 < npass) load_plane_chunk(pn, pl, Mpad, slot_of(pass + 1), 0, H);
+    if (pass + 1 < npass) load_plane_chunk(pn, pl + slot_of(pass + 1), Mpad, 0);
 
     // ---------------- stage D: moving obstacles, velocity / acceleration / curvature limits, expansion
     double out[12];
@@ -793,7 +780,7 @@ __device__ __forceinline__ void sweep_segment(const ShapeDev& sh, const ParamsDe
       // ---- velocity (642-653)
       if (violaVel > 0.0) {
         double pena, penaD;
-        smoothed_l1(P.smooth_eps, violaVel, pena, penaD);
+        smoothed_l1(P, violaVel, pena, penaD);
         const double wc = omg * step * P.wei_feas * penaD;
         acc.G1 = acc.G1 + (2.0 * wc) * dsigma;
         acc.gdT += omg * P.wei_feas * (penaD * (2.0 * alpha * z_h1) * step + pena * invKp);
@@ -802,7 +789,7 @@ __device__ __forceinline__ void sweep_segment(const ShapeDev& sh, const ParamsDe
       // ---- longitudinal acceleration (655-665)
       if (violaAcc > 0.0) {
         double pena, penaD;
-        smoothed_l1(P.smooth_eps, violaAcc, pena, penaD);
+        smoothed_l1(P, violaAcc, pena, penaD);
         const double z_h2 = dot(dddsigma, dsigma);
         const double wc = omg * step * P.wei_feas * penaD;
         const V2 w1 = z_h4 * ddsigma - (z_h4 * z_h4) * dsigma;
@@ -822,7 +809,7 @@ __device__ __forceinline__ void sweep_segment(const ShapeDev& sh, const ParamsDe
         const double wf = P.wei_feas * P.cur_weight_scale;
         const bool left = violaCurL > 0.0;  // the two signs are mutually exclusive for max_cur > 0
         double pena, penaD;
-        smoothed_l1(P.smooth_eps, left ? violaCurL : violaCurR, pena, penaD);
+        smoothed_l1(P, left ? violaCurL : violaCurR, pena, penaD);
         const double sgn = left ? 1.0 : -1.0;
         const double wc = sgn * (omg * step * wf * penaD);
         acc.G1 = acc.G1 + wc * w1;
@@ -830,7 +817,7 @@ __device__ __forceinline__ void sweep_segment(const ShapeDev& sh, const ParamsDe
         acc.gdT += omg * wf * (penaD * (sgn * gt) * step + pena * invKp);
         acc.pen2 += omg * step * wf * pena;
         if (left && violaCurR > 0.0) {  // only possible for a non-positive curvature limit
-          smoothed_l1(P.smooth_eps, violaCurR, pena, penaD);
+          smoothed_l1(P, violaCurR, pena, penaD);
           const double wc2 = omg * step * wf * penaD;
           acc.G1 = acc.G1 - wc2 * w1;
           acc.G2 = acc.G2 - (wc2 * vel3_2_reci_e) * Bv;
@@ -993,7 +980,8 @@ __device__ double eval_cost_grad(const ShapeDev& sh, const ParamsDev& P, const B
   for (int s = 0; s < S; s++) {
     const int N = sh.N[s];
     const double t1 = ws.seg[s].dT, t2 = t1 * t1, t3 = t2 * t1, t4 = t2 * t2, t5 = t4 * t1;
-    const double ti1 = 1.0 / t1, ti2 = 1.0 / t2, ti3 = 1.0 / t3, ti4 = 1.0 / t4, ti5 = 1.0 / t5;
+    // 1/dT^k from ONE division (the reference takes t.cwiseInverse(); <= 2 ulp apart)
+    const double ti1 = 1.0 / t1, ti2 = ti1 * ti1, ti3 = ti2 * ti1, ti4 = ti2 * ti2, ti5 = ti4 * ti1;
     const double* b = ws.bt + 2 * sh.row0[s];
     double* c = ws.c + 2 * sh.row0[s];
     double* gd = ws.gd + 2 * sh.row0[s];
@@ -1041,7 +1029,8 @@ __device__ double eval_cost_grad(const ShapeDev& sh, const ParamsDev& P, const B
   for (int s = 0; s < S; s++) {
     const int N = sh.N[s];
     const double t1 = ws.seg[s].dT, t2 = t1 * t1, t3 = t2 * t1, t4 = t2 * t2, t5 = t4 * t1;
-    double tInv[6] = {1.0, 1.0 / t1, 1.0 / t2, 1.0 / t3, 1.0 / t4, 1.0 / t5};
+    const double ti1_ = 1.0 / t1, ti2_ = ti1_ * ti1_;
+    double tInv[6] = {1.0, ti1_, ti2_, ti2_ * ti1_, ti2_ * ti2_, ti2_ * ti2_ * ti1_};
     double gdtInv[6] = {0.0, -1.0 * tInv[2], -2.0 * tInv[3], -3.0 * tInv[4], -4.0 * tInv[5], -5.0 * tInv[5] * tInv[1]};
     const double* b = ws.bt + 2 * sh.row0[s];
     double* gd = ws.gd + 2 * sh.row0[s];
