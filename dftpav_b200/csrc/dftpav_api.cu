@@ -37,6 +37,7 @@ cudaError_t launch_prepare(int grid, int block, cudaStream_t st, const ShapeDev&
                            const double* fin_raw, const double* init_T, const long long* inner_base,
                            const double* inner_pts, double* ini, double* fin, double* x0, int n_stride);
 int ws_doubles_host(int rows, int npad);
+int max_warps_host();
 cudaError_t set_phase_clock(unsigned long long* dev_ptr);
 }  // namespace dftpav
 
@@ -685,7 +686,7 @@ int dftpav_upload_batch(dftpav_handle* h, const dftpav_batch* b) {
     const size_t ws_bytes = sizeof(double) * sh.ws_doubles, lu_bytes = sizeof(double) * sh.lu_doubles;
     const size_t cap = h->smem_optin > 2048 ? h->smem_optin - 1024 : 0;
     if (lu_bytes + ws_bytes > cap) return fail(h, DFTPAV_ERR_UNSUPPORTED, "problem shape does not fit in shared memory");
-    int W = (int)std::min<size_t>(16, (cap - lu_bytes) / ws_bytes);
+    int W = (int)std::min<size_t>(max_warps_host(), (cap - lu_bytes) / ws_bytes);
     const int want = (count + h->num_sms - 1) / h->num_sms;
     W = std::max(1, std::min(W, want));
     grp->warps = W;
