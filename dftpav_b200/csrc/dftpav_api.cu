@@ -168,7 +168,7 @@ struct dftpav_handle {
   std::vector<double> h_f0;
   // device buffers
   DevBuf seg_base, t_now, obs_ptr, obs_idx, singul, ini_raw, fin_raw, ini, fin, init_T, inner_base, inner_pts, samp_base,
-      plane_ptr, planes_raw, obs_start, obs_dur, obs_piece_ptr, obs_piece_dur, obs_coeffs, x0, xin, fout, gout;
+      plane_ptr, planes_raw, obs_start, obs_dur, obs_piece_ptr, obs_piece_dur, obs_coeffs, obs_uniform, x0, xin, fout, gout;
   DevBuf o_x, o_cost, o_status, o_success, o_iters, o_evals, o_coeffs, o_dT, counter;
   DevBuf hist_s, hist_y, hist_ys, hist_alpha, trace;
   int trace_cap = 0;
@@ -457,7 +457,7 @@ int dftpav_destroy(dftpav_handle* h) {
   free_groups(h);
   DevBuf* bufs[] = {&h->seg_base, &h->t_now, &h->obs_ptr, &h->obs_idx, &h->singul, &h->ini_raw, &h->fin_raw, &h->ini,
                     &h->fin, &h->init_T, &h->inner_base, &h->inner_pts, &h->samp_base, &h->plane_ptr, &h->planes_raw,
-                    &h->obs_start, &h->obs_dur, &h->obs_piece_ptr, &h->obs_piece_dur, &h->obs_coeffs, &h->x0, &h->xin,
+                    &h->obs_start, &h->obs_dur, &h->obs_piece_ptr, &h->obs_piece_dur, &h->obs_coeffs, &h->obs_uniform, &h->x0, &h->xin,
                     &h->fout, &h->gout, &h->o_x, &h->o_cost, &h->o_status, &h->o_success, &h->o_iters, &h->o_evals,
                     &h->o_coeffs, &h->o_dT, &h->counter, &h->hist_s, &h->hist_y, &h->hist_ys, &h->hist_alpha, &h->trace};
   for (DevBuf* b : bufs) b->release();
@@ -598,6 +598,16 @@ int dftpav_upload_batch(dftpav_handle* h, const dftpav_batch* b) {
     CU_TRY(h, up(h->obs_piece_ptr, b->obs_piece_ptr, sizeof(int) * (U + 1)));
     CU_TRY(h, up(h->obs_piece_dur, b->obs_piece_dur, sizeof(double) * NP));
     CU_TRY(h, up(h->obs_coeffs, b->obs_coeffs, sizeof(double) * 12 * NP));
+    // uniform piece duration per obstacle (enables the load-free exact locate loop in the kernel)
+    std::vector<double> uni(U);
+    for (int u = 0; u < U; u++) {
+      const int p0 = b->obs_piece_ptr[u], p1 = b->obs_piece_ptr[u + 1];
+      double d0 = p1 > p0 ? b->obs_piece_dur[p0] : std::nan("");
+      for (int q = p0 + 1; q < p1; q++)
+        if (b->obs_piece_dur[q] != d0) d0 = std::nan("");
+      uni[u] = d0;
+    }
+    CU_TRY(h, up(h->obs_uniform, uni.data(), sizeof(double) * U));
   }
   CU_TRY(h, h->ini.ensure(sizeof(double) * 6 * G));
   CU_TRY(h, h->fin.ensure(sizeof(double) * 6 * G));
@@ -637,9 +647,8 @@ int dftpav_upload_batch(dftpav_handle* h, const dftpav_batch* b) {
       rows += 6 * N;
       var += 2 * (N - 1);
       pieces += N;
-      int store = sh.ntile[s] * kTile + N;
-      store = (store + kTile - 1) / kTile * kTile;
-      sampoff += store;
+      // storage slots: 32 per sweep pass (two 16-sample tiles per regular pass, then the piece-end samples)
+      sampoff += 32 * ((sh.ntile[s] + 1) / 2 + (N + 31) / 32);
       auto it = lu_of_N.find(N);
       if (it == lu_of_N.end()) {
         // table layout per distinct N: [8 zero columns][6N packed columns][8 zero columns] so that the software-
@@ -729,6 +738,7 @@ int dftpav_upload_batch(dftpav_handle* h, const dftpav_batch* b) {
   bd.obs_piece_ptr = h->obs_piece_ptr.as<int>();
   bd.obs_piece_dur = h->obs_piece_dur.as<double>();
   bd.obs_coeffs = h->obs_coeffs.as<double>();
+  bd.obs_uniform = h->obs_uniform.as<double>();
   bd.x0 = h->x0.as<double>();
   bd.n_stride = dims.n_stride;
   bd.row_stride = dims.row_stride;

@@ -18,6 +18,7 @@ constexpr int kMaxPieces = 64;    // max pieces per segment
 constexpr int kTile = 16;         // samples per tile (half warp)
 constexpr int kLuLd = 16;         // doubles per packed LU column (13 band entries + 1/diag + pad)
 constexpr int kStageLd = 17;      // leading dimension of the tile-reduction staging rows
+constexpr int kObsCap = 16;       // obstacles per problem whose metadata is staged in shared memory (more: global reads)
 
 // Problem "shape": everything that fixes control flow and shared-memory layout.  All problems of one kernel
 // launch share one shape (the host groups the batch by shape).
@@ -71,6 +72,7 @@ struct BatchDev {
   const int* obs_piece_ptr;
   const double* obs_piece_dur;
   const double* obs_coeffs;     // [pieces][12], 2x6 column-major, highest power first
+  const double* obs_uniform;    // [pool] common piece duration if all pieces of the obstacle have bit-identical durations, else NaN
   // decision vectors
   const double* x0;             // [B][n_stride]
   int n_stride, row_stride;

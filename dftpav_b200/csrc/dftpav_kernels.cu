@@ -117,11 +117,12 @@ struct WarpWS {
   double* d;      // [npad]
   double* stage;  // [2][12][kStageLd]; doubles as the L-BFGS alpha array between evaluations
   double* pf;     // [8] past cost values (lbfgs.hpp:508, 658)
+  double* obs;    // [kObsCap][4] obstacle metadata of the current problem: start, duration, uniform piece duration, (P<<32|piece_ptr)
   SegScratch* seg;  // [kMaxSeg]
 };
 
 __host__ __device__ inline int ws_doubles_for(int rows, int npad) {
-  return 6 * rows + 5 * npad + 2 * 12 * kStageLd + 8 + kMaxSeg * (int)(sizeof(SegScratch) / sizeof(double));
+  return 6 * rows + 5 * npad + 2 * 12 * kStageLd + 8 + 4 * kObsCap + kMaxSeg * (int)(sizeof(SegScratch) / sizeof(double));
 }
 
 __device__ __forceinline__ WarpWS carve_ws(double* base, const ShapeDev& sh) {
@@ -136,7 +137,8 @@ __device__ __forceinline__ WarpWS carve_ws(double* base, const ShapeDev& sh) {
   w.d = w.gp + sh.npad;
   w.stage = w.d + sh.npad;
   w.pf = w.stage + 2 * 12 * kStageLd;
-  w.seg = reinterpret_cast<SegScratch*>(w.pf + 8);
+  w.obs = w.pf + 8;
+  w.seg = reinterpret_cast<SegScratch*>(w.obs + 4 * kObsCap);
   return w;
 }
 
@@ -234,8 +236,9 @@ __device__ __forceinline__ void band_row(double (&w)[7], double (&c)[7], unsigne
   const int jin = ASC ? j + 7 : j - 7;
   double cn[7];
   band_load<PASS, nmask>(cn, Ca + jn * kColBytes);
-  const bool in_range = ASC ? (jin < n) : (jin >= 0);
-  const double nin = in_range ? lds_pure(ba + 16u * jin) : 0.0;
+  // rows outside [0, n) belong to the neighbouring arrays of the warp workspace (c | bt | gd | x ...): readable, and
+  // they only ever feed accumulators of rows that do not exist
+  const double nin = lds_pure(ba + 16u * jin);
   band_step<PASS, mask>(w, c, ba + 16u * j, nin);
 #pragma unroll
   for (int k = 0; k <= 6; k++) c[k] = cn[k];
@@ -381,16 +384,31 @@ __device__ __noinline__ void speed_helpers_eps(double v2, double eps, double& z_
 }
 
 constexpr int kPlaneChunk = 4;
-// Loads planes h0..h0+3 of one storage slot into registers.  `slotp` already points at (plane 0, component 0, slot);
-// the host pads the plane count of a group to a multiple of 4 with null planes (n = p = 0), so no bounds checks.
-__device__ __forceinline__ void load_plane_chunk(double (&pn)[kPlaneChunk][4], const double* __restrict__ slotp, int Mpad,
-                                                 int h0) {
-  const double* ph = slotp + (size_t)(4 * h0) * Mpad;
+// Plane storage of one problem is pass-major: [pass][chunk of 4 planes][16 components][32 lanes], so the 16 values a
+// lane needs for one chunk sit at compile-time offsets k*32 doubles from one base pointer (immediate-offset LDG.64,
+// each warp-wide load is one contiguous 256 B row).  The host pads the plane count to a multiple of 4 with null planes.
+__device__ __forceinline__ void load_plane_chunk(double (&pn)[kPlaneChunk][4], const double* __restrict__ lanep) {
 #pragma unroll
   for (int hh = 0; hh < kPlaneChunk; hh++) {
 #pragma unroll
-    for (int cc = 0; cc < 4; cc++) pn[hh][cc] = __ldg(ph + (hh * 4 + cc) * Mpad);
+    for (int cc = 0; cc < 4; cc++) pn[hh][cc] = __ldg(lanep + (hh * 4 + cc) * 32);
   }
+}
+
+// Stages the obstacle metadata of a problem into the warp workspace (called once per problem).
+__device__ __forceinline__ void stage_obstacles(const BatchDev& bd, int prob, double* obs_sm, int lane) {
+  if (!bd.obs_ptr) return;
+  const int o0 = bd.obs_ptr[prob], o1 = bd.obs_ptr[prob + 1];
+  const int cnt = min(o1 - o0, kObsCap);
+  if (lane < cnt) {
+    const int u = bd.obs_idx[o0 + lane];
+    const int p0 = bd.obs_piece_ptr[u], p1 = bd.obs_piece_ptr[u + 1];
+    obs_sm[4 * lane + 0] = bd.obs_start[u];
+    obs_sm[4 * lane + 1] = bd.obs_dur[u];
+    obs_sm[4 * lane + 2] = bd.obs_uniform[u];
+    obs_sm[4 * lane + 3] = __longlong_as_double(((long long)(p1 - p0) << 32) | (long long)(unsigned)p0);
+  }
+  __syncwarp();
 }
 
 // Accumulators of one sample: G0 = d/d sigma, G1 = d/d sigma', G2 = d/d sigma'' (already weighted), plus the
@@ -405,8 +423,7 @@ struct SampleAcc {
 __device__ __noinline__ void dyn_obstacles(const ParamsDev& P, const BatchDev& bd, int prob, SampleAcc& acc, double omg,
                                            double step, double t, double gama, int pieceid, int trajres, V2 sigma,
                                            V2 dsigma, V2 ddsigma, M2 ego_R, int singul_, int trajid, int Nseg,
-                                           double trajtime) {
-  const int o0 = bd.obs_ptr[prob], o1 = bd.obs_ptr[prob + 1];
+                                           double trajtime, int o0, int o1) {
   if (o1 <= o0) return;
   const double alpha = P.lse_alpha, d_min = P.d_min, wei_surround = P.wei_surround;
   const double temp0 = norm(dsigma);
@@ -601,26 +618,23 @@ __device__ __forceinline__ void sweep_segment(const ShapeDev& sh, const ParamsDe
   const double sg = (double)singul_;
   const double* cseg = ws.c + 2 * sh.row0[s];
   double* gdseg = ws.gd + 2 * sh.row0[s];
-  const int Mpad = sh.Mpad;
+  double* stage0 = ws.stage;
+  // keep these three pointers in registers: ptxas otherwise re-derives them from the kernel parameters inside the loop
+  asm volatile("" : "+l"(cseg), "+l"(gdseg), "+l"(stage0));
   const int H = sh.H;
-  const double* pl = planes + sh.samp0[s];
+  const int nchunk = H / kPlaneChunk;
+  // this lane's column of the segment's first pass block
+  const double* pl = planes + (size_t)(sh.samp0[s] / 32) * nchunk * 512 + lane;
 
   double acc_gdT = 0.0, acc_p0 = 0.0, acc_p1 = 0.0, acc_p2 = 0.0;
   const int npass = npass_reg + npass_end;
   const double invK_ = 1.0 / K, invKd_ = 1.0 / Kd;
-  // storage slot of this lane in a given pass (regular tiles first, then the piece-endpoint samples)
-  auto slot_of = [&](int pass) -> int {
-    if (pass < npass_reg) return (2 * pass + half) * kTile + r;
-    const int pc = (pass - npass_reg) * 32 + lane;
-    return ntile * kTile + (pc < N ? pc : N - 1);
-  };
   double pn[kPlaneChunk][4];
-  load_plane_chunk(pn, pl + slot_of(0), Mpad, 0);
+  load_plane_chunk(pn, pl);
 
   for (int pass = 0; pass < npass; pass++) {
     const bool endpass = pass >= npass_reg;
     int piece, j, Kp;
-    const int store = slot_of(pass);
     bool valid;
     if (!endpass) {
       const int t = 2 * pass + half;
@@ -711,12 +725,6 @@ __device__ __forceinline__ void sweep_segment(const ShapeDev& sh, const ParamsDe
       }
       const M2 rot = M2{dsigma.x, -dsigma.y, dsigma.y, dsigma.x};
       ego_R = M2{sg * rot.a * z_h0, sg * rot.b * z_h0, sg * rot.c * z_h0, sg * rot.d * z_h0};
-      M2 R_dot;
-      {
-        const double f2 = vel2_reci * z_h0 * z_h1;
-        R_dot = M2{sg * (ddsigma.x * z_h0 - rot.a * f2), sg * (-ddsigma.y * z_h0 - rot.b * f2),
-                   sg * (ddsigma.y * z_h0 - rot.c * f2), sg * (ddsigma.x * z_h0 - rot.d * f2)};
-      }
       // ---- static corridor (traj_optimizer.cpp:592-622).  Quirk Q1: the vertex list has 5 entries, vertex 0 twice;
       //      the duplicate is folded into a weight of 2 on vertex 0.  Planes are consumed in register chunks of 4;
       //      chunk 0 of this pass was loaded during the previous pass (software prefetch).
@@ -724,9 +732,13 @@ __device__ __forceinline__ void sweep_segment(const ShapeDev& sh, const ParamsDe
       //      penaD * n and pena to per-vertex sums; the maps to d/dsigma, d/dsigma', d/dt run once per vertex.
       const double wobs = omg * step * P.wei_obs;
       for (int h0 = 0; h0 < H; h0 += kPlaneChunk) {
-        if (h0 > 0) load_plane_chunk(pn, pl + store, Mpad, h0);
-#pragma unroll 1
-        for (int v = 0; v < 4; v++) {  // kept rolled: the sweep loop has to fit the instruction cache
+        if (h0 > 0) load_plane_chunk(pn, pl + (size_t)(pass * nchunk + h0 / kPlaneChunk) * 512);
+#ifndef DFTPAV_VTX_UNROLL
+#define DFTPAV_VTX_UNROLL 1
+#endif
+        constexpr int kVtxUnroll = DFTPAV_VTX_UNROLL;
+#pragma unroll kVtxUnroll
+        for (int v = 0; v < 4; v++) {  // rolled: measured 161 k solves/s vs 152 k with 2 vertices per trip (19 vs 22 KB loop)
           const V2 le = mk(P.le[v][0], P.le[v][1]);
           const V2 q = ego_R * le;
           const V2 bpt = sigma + q;
@@ -738,10 +750,20 @@ __device__ __forceinline__ void sweep_segment(const ShapeDev& sh, const ParamsDe
 #pragma unroll
           for (int hh = 0; hh < kPlaneChunk; hh++)
             viol[hh] = pn[hh][0] * (bpt.x - pn[hh][2]) + pn[hh][1] * (bpt.y - pn[hh][3]);
-          const double vmax = fmax(fmax(viol[0], viol[1]), fmax(viol[2], viol[3]));
-          if (vmax > 0.0) {
+          if (viol[0] > 0.0 || viol[1] > 0.0 || viol[2] > 0.0 || viol[3] > 0.0) {
 #pragma unroll
             for (int hh = 0; hh < kPlaneChunk; hh++) {
+#ifdef DFTPAV_L1_BRANCHFREE
+              // branch-free positiveSmoothedL1 of max(viol, 0): f(0) = f'(0) = 0, so non-violated planes add nothing
+              const double xv = fmax(viol[hh], 0.0);
+              const double x2 = xv * xv;
+              const bool small = xv < P.smooth_eps;
+              const double pena = small ? (P.l1_f4c * xv + P.l1_f3c) * x2 * xv : xv - P.l1_half;
+              const double penaD = small ? (P.l1_d3c * xv + P.l1_d2c) * x2 : 1.0;
+              Bn.x += penaD * pn[hh][0];
+              Bn.y += penaD * pn[hh][1];
+              Sp += pena;
+#else
               if (viol[hh] > 0.0) {
                 double pena, penaD;
                 smoothed_l1(P, viol[hh], pena, penaD);
@@ -749,10 +771,15 @@ __device__ __forceinline__ void sweep_segment(const ShapeDev& sh, const ParamsDe
                 Bn.y += penaD * pn[hh][1];
                 Sp += pena;
               }
+#endif
             }
           }
           if (Sp > 0.0) {
             const double mult = (v == 0) ? 2.0 : 1.0;
+            // d(R l)/dt (traj_optimizer.cpp:590), only needed for a violated vertex
+            const double f2 = vel2_reci * z_h0 * z_h1;
+            const M2 R_dot = M2{sg * (ddsigma.x * z_h0 - rot.a * f2), sg * (-ddsigma.y * z_h0 - rot.b * f2),
+                                sg * (ddsigma.y * z_h0 - rot.c * f2), sg * (ddsigma.x * z_h0 - rot.d * f2)};
             const V2 rl = R_dot * le;
             // n^T M,  M = singul*[l,Bl]/|v| - (R l) sigma'^T / |v|^2, applied to Bn
             const double nq = dot(Bn, q);
@@ -771,7 +798,7 @@ __device__ __forceinline__ void sweep_segment(const ShapeDev& sh, const ParamsDe
 
     // ---------------- stage C: software prefetch of the next pass's first plane chunk (registers are free now;
     //                  its consumers are most of a pass away)
-    if (pass + 1 < npass) load_plane_chunk(pn, pl + slot_of(pass + 1), Mpad, 0);
+    if (pass + 1 < npass) load_plane_chunk(pn, pl + (size_t)((pass + 1) * nchunk) * 512);
 
     // ---------------- stage D: moving obstacles, velocity / acceleration / curvature limits, expansion
     double out[12];
@@ -779,8 +806,71 @@ __device__ __forceinline__ void sweep_segment(const ShapeDev& sh, const ParamsDe
     for (int q = 0; q < 12; q++) out[q] = 0.0;
     if (active) {
       if (HAS_OBS) {  // traj_optimizer.cpp:636-638
-        dyn_obstacles(P, bd, prob, acc, omg, step, piece * dT + step * j, alpha, piece, Kp, sigma, dsigma, ddsigma, ego_R,
-                      singul_, s, N, trajtime);
+        // Light filter per obstacle: obstacle position at the sample time and the distance cull of
+        // traj_optimizer.cpp:1393 (same arithmetic as the reference up to that point); only the few (sample,
+        // obstacle) pairs that survive run the full signed-distance term (out of line, dyn_obstacles).
+        const double t_samp = piece * dT + step * j;
+        const int ob0 = bd.obs_ptr[prob], ob1 = bd.obs_ptr[prob + 1];
+        const double t_now = bd.t_now[prob];
+        for (int oi = ob0; oi < ob1; oi++) {
+          double o_start, o_dur, o_uni;
+          int oP, op0;
+          if (oi - ob0 < kObsCap) {
+            const double* m4 = ws.obs + 4 * (oi - ob0);
+            o_start = m4[0];
+            o_dur = m4[1];
+            o_uni = m4[2];
+            const long long pk = __double_as_longlong(m4[3]);
+            oP = (int)(pk >> 32);
+            op0 = (int)(pk & 0xffffffffLL);
+          } else {
+            const int u = bd.obs_idx[oi];
+            o_start = bd.obs_start[u];
+            o_dur = bd.obs_dur[u];
+            o_uni = bd.obs_uniform[u];
+            op0 = bd.obs_piece_ptr[u];
+            oP = bd.obs_piece_ptr[u + 1] - op0;
+          }
+          const double offsettime = t_now - o_start + trajtime;
+          const double pt_time = offsettime + t_samp;
+          const bool inside = pt_time < o_dur;
+          double tt = inside ? pt_time : o_dur;
+          // Trajectory::locatePieceIdx (poly_traj_utils.hpp:510-528): sequential subtraction of the piece durations;
+          // with bit-identical durations the loop needs no loads and stays exact
+          int idx = 0;
+          if (o_uni == o_uni) {
+            while (idx < oP && tt > o_uni) {
+              tt -= o_uni;
+              idx++;
+            }
+            if (idx == oP) {
+              idx--;
+              tt += o_uni;
+            }
+          } else {
+            const double* dur = bd.obs_piece_dur + op0;
+            double dcur = 0.0;
+            for (idx = 0; idx < oP && tt > (dcur = dur[idx]); idx++) tt -= dcur;
+            if (idx == oP) {
+              idx--;
+              tt += dur[idx];
+            }
+          }
+          const double* cm = bd.obs_coeffs + 12L * (op0 + idx);
+          V2 sp = piece_pos(cm, tt);
+          if (!inside) {  // constant-acceleration extrapolation past the prediction (traj_optimizer.cpp:1379-1388)
+            const V2 sa = piece_acc(cm, tt);
+            const V2 vd = piece_vel(cm, tt);
+            const double exceed = pt_time - o_dur;
+            V2 h = 0.5 * sa;
+            h = mk(h.x * exceed, h.y * exceed);
+            h = mk(h.x * exceed, h.y * exceed);
+            sp = sp + exceed * vd + h;
+          }
+          if (norm(sp - sigma) > P.cull_dist) continue;
+          dyn_obstacles(P, bd, prob, acc, omg, step, t_samp, alpha, piece, Kp, sigma, dsigma, ddsigma, ego_R, singul_, s, N,
+                        trajtime, oi, oi + 1);
+        }
       }
       const double z_h4 = z_h1 * vel2_reci;
       const double violaVel = v2 - max_vel * max_vel;
@@ -865,14 +955,19 @@ __device__ __forceinline__ void sweep_segment(const ShapeDev& sh, const ParamsDe
       __syncwarp();
     } else {
       // fixed-order tile reduction: stage[half][q][r], then 12 lanes per half sum their row over r = 0..15
-      double* st = ws.stage + half * (12 * kStageLd);
+      double* st = stage0 + half * (12 * kStageLd);
 #pragma unroll
       for (int q = 0; q < 12; q++) st[q * kStageLd + r] = out[q];
       __syncwarp();
       double sum = 0.0;
-      if (r < 12) {
+      if (r < 12) {  // fixed order: (s0 + ... + s7) + (s8 + ... + s15), two independent chains
+        double s0 = 0.0, s1 = 0.0;
 #pragma unroll
-        for (int i = 0; i < kTile; i++) sum += st[r * kStageLd + i];
+        for (int i = 0; i < kTile / 2; i++) {
+          s0 += st[r * kStageLd + i];
+          s1 += st[r * kStageLd + kTile / 2 + i];
+        }
+        sum = s0 + s1;
       }
       // the two halves may hit the same piece (Kd > 16): add one after the other
       const int tvalid = (2 * pass + half) < ntile;
@@ -1191,6 +1286,7 @@ __global__ void __launch_bounds__(32 * DFTPAV_MAX_WARPS, 1)
     const double* planes = grp.planes + (size_t)local * sh.H * 4 * sh.Mpad;
     for (int i = lane; i < sh.n; i += 32) ws.x[i] = xin[(size_t)prob * bd.n_stride + i];
     __syncwarp();
+    if (HAS_OBS) stage_obstacles(bd, prob, ws.obs, lane);
     const double f = eval_cost_grad<HAS_OBS>(sh, P, bd, prob, planes, smem, ws, ws.x, ws.g, lane);
     __syncwarp();
     if (lane == 0) fout[prob] = f;
@@ -1370,21 +1466,34 @@ __global__ void __launch_bounds__(32 * DFTPAV_MAX_WARPS, 1)
   const double* planes = nullptr;
   long long t_logic = 0;
 
+  bool have_work = true;
   while (true) {
-    if (phase == PH_FETCH) {
+    if (phase == PH_FETCH && have_work) {
       int local = 0;
       if (lane == 0) local = atomicAdd(work_counter, 1);
       local = __shfl_sync(FULL, local, 0);
-      if (local >= grp.count) break;
-      if (grp.order) local = grp.order[local];
-      prob = grp.prob_id[local];
-      planes = grp.planes + (size_t)local * sh.H * 4 * sh.Mpad;
+      if (local >= grp.count) {
+        have_work = false;
+      } else {
+        if (grp.order) local = grp.order[local];
+        prob = grp.prob_id[local];
+        planes = grp.planes + (size_t)local * sh.H * 4 * sh.Mpad;
 #pragma unroll 1
-      for (int i = lane; i < n; i += 32) ws.x[i] = bd.x0[(size_t)prob * bd.n_stride + i];
-      __syncwarp();
-      evals = 0;
-      phase = PH_FIRST;
+        for (int i = lane; i < n; i += 32) ws.x[i] = bd.x0[(size_t)prob * bd.n_stride + i];
+        __syncwarp();
+        if (HAS_OBS) stage_obstacles(bd, prob, ws.obs, lane);
+        evals = 0;
+        phase = PH_FIRST;
+      }
     }
+#ifdef DFTPAV_PHASE_ALIGN
+    // loose phase alignment of the CTA: all warps enter the evaluation together, so the instruction stream of the
+    // (instruction-cache-bound) evaluation is fetched once for all of them; warps without work keep arriving
+    if (!__syncthreads_or(have_work ? 1 : 0)) break;
+    if (!have_work) continue;
+#else
+    if (!have_work) break;
+#endif
 
     // ---------------- the single evaluation site
     if (g_phase_clock) {
@@ -1612,14 +1721,17 @@ __global__ void __launch_bounds__(32 * DFTPAV_MAX_WARPS, 1)
 }
 
 // ------------------------------------------------------------------------------------------------
-// layout kernel: raw (n, p) planes [sample][h][4] -> tiled SoA [local][h][4][Mpad] with unit normals
-// (replaces the deep copy + colwise().normalize() of traj_optimizer.cpp:15, 49-52)
+// layout kernel: raw (n, p) planes [sample][h][4] -> pass-major SoA [local][pass][chunk][16][32] with unit normals
+// (replaces the deep copy + colwise().normalize() of traj_optimizer.cpp:15, 49-52).  Slot u = pass*32 + lane holds
+// the sample that lane handles in that pass of the sweep (two 16-sample tiles per regular pass, then the piece-end
+// samples); sh.Mpad = 32 * passes, sh.samp0[s] = first slot of segment s.
 // ------------------------------------------------------------------------------------------------
 __global__ void layout_planes_kernel(const ShapeDev sh, const int* __restrict__ prob_id, int count,
                                      const long long* __restrict__ samp_base,   // [B] first raw sample of the problem
                                      const long long* __restrict__ plane_ptr,   // [Q+1] or nullptr (uniform)
                                      int uniform_H, const double* __restrict__ raw, double* __restrict__ soa) {
   const int Mpad = sh.Mpad;
+  const int nchunk = sh.H / 4;
   const long long total = (long long)count * Mpad;
   for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total;
        idx += (long long)gridDim.x * blockDim.x) {
@@ -1633,29 +1745,34 @@ __global__ void layout_planes_kernel(const ShapeDev sh, const int* __restrict__ 
     const int N = sh.N[s], K = sh.K, Kd = sh.Kd;
     const int td = (Kd + kTile - 1) / kTile, tk = (K + kTile - 1) / kTile;
     const int ntile = sh.ntile[s];
+    const int npass_reg = (ntile + 1) >> 1;
+    const int pass = us >> 5, ln = us & 31;
     int piece = -1, j = 0;
-    if (us < ntile * kTile) {
-      const int t = us / kTile, r = us % kTile;
-      int j0;
-      if (t < td) {
-        piece = 0;
-        j0 = kTile * t;
-      } else if (t < td + (N - 2) * tk) {
-        const int uu = t - td;
-        piece = 1 + uu / tk;
-        j0 = kTile * (uu % tk);
-      } else {
-        piece = N - 1;
-        j0 = kTile * (t - td - (N - 2) * tk);
+    if (pass < npass_reg) {
+      const int t = 2 * pass + (ln >> 4), r = ln & 15;
+      if (t < ntile) {
+        int j0;
+        if (t < td) {
+          piece = 0;
+          j0 = kTile * t;
+        } else if (t < td + (N - 2) * tk) {
+          const int uu = t - td;
+          piece = 1 + uu / tk;
+          j0 = kTile * (uu % tk);
+        } else {
+          piece = N - 1;
+          j0 = kTile * (t - td - (N - 2) * tk);
+        }
+        j = j0 + r;
+        const int Kp = (piece == 0 || piece == N - 1) ? Kd : K;
+        if (j >= Kp) piece = -1;
       }
-      j = j0 + r;
-      const int Kp = (piece == 0 || piece == N - 1) ? Kd : K;
-      if (j >= Kp) piece = -1;
-    } else if (us < ntile * kTile + N) {
-      piece = us - ntile * kTile;
-      j = (piece == 0 || piece == N - 1) ? Kd : K;
+    } else {
+      piece = (pass - npass_reg) * 32 + ln;
+      if (piece >= N) piece = -1;
+      else j = (piece == 0 || piece == N - 1) ? Kd : K;
     }
-    double* dst = soa + (size_t)local * sh.H * 4 * Mpad + u;
+    double* dst = soa + (size_t)local * sh.H * 4 * Mpad + (size_t)(u >> 5) * nchunk * 512 + (u & 31);
     int Hs = 0;
     const double* src = nullptr;
     if (piece >= 0) {
@@ -1684,10 +1801,11 @@ __global__ void layout_planes_kernel(const ShapeDev sh, const int* __restrict__ 
           ny /= nz;
         }
       }
-      dst[(size_t)(4 * h + 0) * Mpad] = nx;
-      dst[(size_t)(4 * h + 1) * Mpad] = ny;
-      dst[(size_t)(4 * h + 2) * Mpad] = px;
-      dst[(size_t)(4 * h + 3) * Mpad] = py;
+      double* d4 = dst + (size_t)(h >> 2) * 512 + (h & 3) * 128;  // chunk h/4, plane h%4 -> components 4*(h%4)..+3
+      d4[0] = nx;
+      d4[32] = ny;
+      d4[64] = px;
+      d4[96] = py;
     }
   }
 }
