@@ -303,21 +303,36 @@ __device__ __forceinline__ void banded_solve_adj(const double* C, double* b, int
 // obstacle trajectory evaluation (Piece/Trajectory, poly_traj_utils.hpp:77-112,179-211,510-603)
 // ------------------------------------------------------------------------------------------------
 struct ObsView {
+  double uni;  // common piece duration or NaN
   int P;
   const double* dur;
   const double* cf;  // [P][12]
   double start_time, duration;
 };
-__device__ __forceinline__ int obs_locate(const ObsView& o, double& t) {
-  int idx;
-  double d = 0.0;
-  for (idx = 0; idx < o.P && t > (d = o.dur[idx]); idx++) t -= d;
-  if (idx == o.P) {
-    idx--;
-    t += o.dur[idx];
+// Trajectory::locatePieceIdx (poly_traj_utils.hpp:510-528): sequential subtraction of the piece durations.  When all
+// durations of the obstacle are bit-identical (`uni` is that value, else NaN) the loop needs no loads and is still exact.
+__device__ __forceinline__ int locate_piece(double uni, const double* __restrict__ dur, int P, double& t) {
+  int idx = 0;
+  if (uni == uni) {
+    while (idx < P && t > uni) {
+      t -= uni;
+      idx++;
+    }
+    if (idx == P) {
+      idx--;
+      t += uni;
+    }
+  } else {
+    double d = 0.0;
+    for (idx = 0; idx < P && t > (d = dur[idx]); idx++) t -= d;
+    if (idx == P) {
+      idx--;
+      t += dur[idx];
+    }
   }
   return idx;
 }
+__device__ __forceinline__ int obs_locate(const ObsView& o, double& t) { return locate_piece(o.uni, o.dur, o.P, t); }
 __device__ __forceinline__ V2 piece_pos(const double* cm, double t) {
   V2 pos = mk(0.0, 0.0);
   double tn = 1.0;
@@ -443,6 +458,7 @@ __device__ __noinline__ void dyn_obstacles(const ParamsDev& P, const BatchDev& b
     ob.cf = bd.obs_coeffs + 12L * bd.obs_piece_ptr[u];
     ob.start_time = bd.obs_start[u];
     ob.duration = bd.obs_dur[u];
+    ob.uni = bd.obs_uniform[u];
     const double offsettime = t_now - ob.start_time + trajtime;
     const double pt_time = offsettime + t;
     V2 sp, sv, sa;
@@ -473,119 +489,137 @@ __device__ __noinline__ void dyn_obstacles(const ParamsDev& P, const BatchDev& b
     const V2 ra = piece_acc(ob.cf + 12 * ir, tr);
     const double rn = norm(rv);
     M2 sur_R = M2{rv.x / rn, -rv.y / rn, rv.y / rn, rv.x / rn};
-    M2 Rud;
+    // ---- phase B: the eight smooth edge distances and their log-sum-exp (traj_optimizer.cpp:1417-1503).  Nothing
+    //      but d_test[8] is kept: most pairs that survive the distance cull are not in collision and leave here.
+    const double dnU_inv[4] = {1.0 / norm(vle[1] - vle[0]), 1.0 / norm(vle[2] - vle[1]), 1.0 / norm(vle[3] - vle[2]),
+                               1.0 / norm(vle[4] - vle[3])};
+    // ---- exp-free rejection.  LSE_{+a}(x) >= max(x) and LSE_{-a}(v) >= min(v) - log(4)/a, hence
+    //      costp = d_min - LSE_{+a}(d) <= d_min + log(4)/a - max_k(min_j v_kj + d~_k).  If that bound is negative the
+    //      reference takes `continue` at traj_optimizer.cpp:1505 as well; the margin covers rounding.  Most pairs that
+    //      pass the 1.5-car-length distance cull are still metres apart and leave here without a single exp/log.
     {
-      const double p3 = rn * rn * rn;  // pow(|v|,3)
-      const double va = dot(rv, ra);
-      M2 ta = M2{ra.x / rn, -ra.y / rn, ra.y / rn, ra.x / rn};
-      M2 tv = M2{rv.x / p3 * va, -rv.y / p3 * va, rv.y / p3 * va, rv.x / p3 * va};
-      Rud = ta - tv;
+      double best = -1.0e300;
+#pragma unroll
+      for (int e = 0; e < 4; e++) {
+        const V2 H_tilde = dnU_inv[e] * (Bh_mul(ego_R) * (vle[e + 1] - vle[e]));
+        const V2 hr = rowmul(H_tilde, sur_R);
+        double vmin = dot(hr, vle[0]);
+#pragma unroll
+        for (int o = 1; o < 4; o++) vmin = fmin(vmin, dot(hr, vle[o]));
+        best = fmax(best, vmin + dot(H_tilde, (sp - sigma) - ego_R * vle[e]));
+      }
+#pragma unroll
+      for (int o = 0; o < 4; o++) {
+        const V2 H_tilde = dnU_inv[o] * (Bh_mul(sur_R) * (vle[o + 1] - vle[o]));
+        const V2 hr = rowmul(H_tilde, ego_R);
+        double vmin = dot(hr, vle[0]);
+#pragma unroll
+        for (int e = 1; e < 4; e++) vmin = fmin(vmin, dot(hr, vle[e]));
+        best = fmax(best, vmin + dot(H_tilde, (sigma - sp) - sur_R * vle[o]));
+      }
+      if (d_min + 1.3862943611198906 / alpha - best < -1.0e-9) continue;
     }
-
-    double sum_exp_U[4], d_test[8], sum_exp_E[4];
-    V2 ego_normal[4], sur_normal[4];
-    double dUoe[4][4], dEeo[4][4];
-    M2 F_dle[4], F_le[4];
+    double d_test[8];
 #pragma unroll
     for (int e = 0; e < 4; e++) {
-      const V2 le = vle[e];
-      const V2 delta_le = vle[e + 1] - vle[e];
-      const double dn_inv = 1.0 / norm(delta_le);
-      F_dle[e] = (temp0_reci * ((double)singul_ * transpose(l_Bl(delta_le)))) - (temp3 * outer(dsigma, ego_R * delta_le));
-      F_le[e] = (temp0_reci * ((double)singul_ * transpose(l_Bl(le)))) - (temp3 * outer(dsigma, ego_R * le));
-      const V2 H_tilde = dn_inv * (Bh_mul(ego_R) * delta_le);
-      ego_normal[e] = H_tilde;
-      const double d_U_e_tilde = dot(H_tilde, (sp - sigma) - ego_R * le);
+      const V2 H_tilde = dnU_inv[e] * (Bh_mul(ego_R) * (vle[e + 1] - vle[e]));
+      const double d_U_e_tilde = dot(H_tilde, (sp - sigma) - ego_R * vle[e]);
       const V2 hr = rowmul(H_tilde, sur_R);
+      double v4[4];
 #pragma unroll
-      for (int o = 0; o < 4; o++) dUoe[e][o] = dot(hr, vle[o]);
+      for (int o = 0; o < 4; o++) v4[o] = dot(hr, vle[o]);
       double es;
-      d_test[e] = lse<4>(-alpha, dUoe[e], es) + d_U_e_tilde;
-      sum_exp_U[e] = es;
+      d_test[e] = lse<4>(-alpha, v4, es) + d_U_e_tilde;
     }
 #pragma unroll
     for (int o = 0; o < 4; o++) {
-      const V2 lo = vle[o];
-      const V2 delta_lo = vle[o + 1] - vle[o];
-      const double dn_inv = 1.0 / norm(delta_lo);
-      const V2 H_tilde = dn_inv * (Bh_mul(sur_R) * delta_lo);
-      sur_normal[o] = H_tilde;
-      const double d_E_o_tilde = dot(H_tilde, (sigma - sp) - sur_R * lo);
+      const V2 H_tilde = dnU_inv[o] * (Bh_mul(sur_R) * (vle[o + 1] - vle[o]));
+      const double d_E_o_tilde = dot(H_tilde, (sigma - sp) - sur_R * vle[o]);
       const V2 hr = rowmul(H_tilde, ego_R);
+      double v4[4];
 #pragma unroll
-      for (int e = 0; e < 4; e++) dEeo[o][e] = dot(hr, vle[e]);
+      for (int e = 0; e < 4; e++) v4[e] = dot(hr, vle[e]);
       double es;
-      d_test[4 + o] = lse<4>(-alpha, dEeo[o], es) + d_E_o_tilde;
-      sum_exp_E[o] = es;
+      d_test[4 + o] = lse<4>(-alpha, v4, es) + d_E_o_tilde;
     }
     double exp_sum_d;
-    const double costp = d_min - lse<8>(alpha, d_test, exp_sum_d);
+    const double costp = d_min - lse<8>(alpha, d_test, exp_sum_d);  // d_test now holds the exponentials (quirk Q7)
     if (costp <= 0.0) continue;
     double pena, penaD;
     smoothed_l1(P, costp, pena, penaD);
     acc.pen1 += omg * step * wei_surround * pena;
 
-    V2 pG_sigma = mk(0.0, 0.0);
-#pragma unroll
-    for (int e = 0; e < 4; e++) pG_sigma = pG_sigma - (d_test[e] / exp_sum_d) * (-ego_normal[e]);
-#pragma unroll
-    for (int o = 0; o < 4; o++) pG_sigma = pG_sigma - (d_test[o + 4] / exp_sum_d) * sur_normal[o];
-
-    V2 pG_dsigma = mk(0.0, 0.0);
-#pragma unroll
+    // ---- phase C: gradients (traj_optimizer.cpp:1510-1646); per-edge quantities are recomputed instead of stored
+    V2 pG_sigma = mk(0.0, 0.0), pG_dsigma = mk(0.0, 0.0);
+    double pG_that = 0.0;
+    // getRdot at pt_time (quirk Q6), traj_optimizer.cpp:1599
+    M2 Rud;
+    {
+      const double p3 = rn * rn * rn;  // pow(|v|,3)
+      const double va = dot(rv, ra);
+      const M2 ta = M2{ra.x / rn, -ra.y / rn, ra.y / rn, ra.x / rn};
+      const M2 tv = M2{rv.x / p3 * va, -rv.y / p3 * va, rv.y / p3 * va, rv.x / p3 * va};
+      Rud = ta - tv;
+    }
+#pragma unroll 1
     for (int e = 0; e < 4; e++) {
       const V2 le = vle[e];
       const V2 delta_le = vle[e + 1] - vle[e];
       const double dnrm = norm(delta_le);
-      const V2 a1 = mul_Bh(F_dle[e]) * ((-sp + sigma) + ego_R * le);
-      const V2 a2 = (mul_Bh(F_le[e]) * ego_R) * delta_le;
+      const V2 H_tilde = (1.0 / dnrm) * (Bh_mul(ego_R) * delta_le);
+      const V2 hr = rowmul(H_tilde, sur_R);
+      double ex[4], es;
+#pragma unroll
+      for (int o = 0; o < 4; o++) ex[o] = dot(hr, vle[o]);
+      (void)lse<4>(-alpha, ex, es);  // ex <- exponentials, es <- their sum
+      const double we = d_test[e] / exp_sum_d;
+      pG_sigma = pG_sigma - we * (-H_tilde);
+      const M2 F_dle = (temp0_reci * ((double)singul_ * transpose(l_Bl(delta_le)))) - (temp3 * outer(dsigma, ego_R * delta_le));
+      const M2 F_le = (temp0_reci * ((double)singul_ * transpose(l_Bl(le)))) - (temp3 * outer(dsigma, ego_R * le));
+      const V2 a1 = mul_Bh(F_dle) * ((-sp + sigma) + ego_R * le);
+      const V2 a2 = (mul_Bh(F_le) * ego_R) * delta_le;
       V2 pdU = (a1 - a2) / dnrm;
-      const M2 FdBt = mul_BhT(F_dle[e]);
+      const M2 FdBt = mul_BhT(F_dle);
+      double pdUt = dot(H_tilde, sv);
+      const V2 nr = rowmul(H_tilde, Rud);
 #pragma unroll
       for (int o = 0; o < 4; o++) {
         const V2 pd = (FdBt * (sur_R * vle[o])) / dnrm;
-        pdU = pdU + (dUoe[e][o] / sum_exp_U[e]) * pd;
+        pdU = pdU + (ex[o] / es) * pd;
+        pdUt += ex[o] / es * dot(nr, vle[o]);
       }
-      pG_dsigma = pG_dsigma - (d_test[e] / exp_sum_d) * pdU;
+      pG_dsigma = pG_dsigma - we * pdU;
+      pG_that -= we * pdUt;
     }
-#pragma unroll
-    for (int o = 0; o < 4; o++) {
-      const V2 delta_lo = vle[o + 1] - vle[o];
-      const double dnrm = norm(delta_lo);
-      V2 pdE = mk(0.0, 0.0);
-#pragma unroll
-      for (int e = 0; e < 4; e++) {
-        const V2 pd = ((mul_Bh(F_le[e]) * sur_R) * delta_lo) / dnrm;
-        pdE = pdE + (dEeo[o][e] / sum_exp_E[o]) * pd;
-      }
-      pG_dsigma = pG_dsigma - (d_test[o + 4] / exp_sum_d) * pdE;
-    }
-    const double pG_tbar = dot(pG_sigma, dsigma) + dot(pG_dsigma, ddsigma);
-
-    double pG_that = 0.0;
-#pragma unroll
-    for (int e = 0; e < 4; e++) {
-      double pdU = dot(ego_normal[e], sv);
-      const V2 nr = rowmul(ego_normal[e], Rud);
-#pragma unroll
-      for (int o = 0; o < 4; o++) pdU += dUoe[e][o] / sum_exp_U[e] * dot(nr, vle[o]);
-      pG_that -= d_test[e] / exp_sum_d * pdU;
-    }
-#pragma unroll
+#pragma unroll 1
     for (int o = 0; o < 4; o++) {
       const V2 lo = vle[o];
       const V2 delta_lo = vle[o + 1] - vle[o];
       const double dnrm = norm(delta_lo);
+      const V2 H_tilde = (1.0 / dnrm) * (Bh_mul(sur_R) * delta_lo);
+      const V2 hr = rowmul(H_tilde, ego_R);
+      double ex[4], es;
+#pragma unroll
+      for (int e = 0; e < 4; e++) ex[e] = dot(hr, vle[e]);
+      (void)lse<4>(-alpha, ex, es);
+      const double wo = d_test[o + 4] / exp_sum_d;
+      pG_sigma = pG_sigma - wo * H_tilde;
+      V2 pdE = mk(0.0, 0.0);
       const V2 r1 = (Bh_mul(Rud) * delta_lo) / dnrm;
       const V2 r2 = (Bh_mul(sur_R) * delta_lo) / dnrm;
-      double pdE = dot(r1, (sigma - sp) - sur_R * lo) + dot(r2, -sv - Rud * lo);
+      double pdEt = dot(r1, (sigma - sp) - sur_R * lo) + dot(r2, -sv - Rud * lo);
 #pragma unroll
       for (int e = 0; e < 4; e++) {
+        const M2 F_le = (temp0_reci * ((double)singul_ * transpose(l_Bl(vle[e])))) - (temp3 * outer(dsigma, ego_R * vle[e]));
+        const V2 pd = ((mul_Bh(F_le) * sur_R) * delta_lo) / dnrm;
+        pdE = pdE + (ex[e] / es) * pd;
         const V2 row = rowmul(rowmul(ego_R * vle[e], M2{0.0, -1.0, 1.0, 0.0}), Rud);
-        pdE += dEeo[o][e] / sum_exp_E[o] * (dot(row, delta_lo) / dnrm);
+        pdEt += ex[e] / es * (dot(row, delta_lo) / dnrm);
       }
-      pG_that -= d_test[o + 4] / exp_sum_d * pdE;
+      pG_dsigma = pG_dsigma - wo * pdE;
+      pG_that -= wo * pdEt;
     }
+    const double pG_tbar = dot(pG_sigma, dsigma) + dot(pG_dsigma, ddsigma);
 
     const double wc = omg * step * wei_surround * penaD;
     acc.G0 = acc.G0 + wc * pG_sigma;
@@ -837,25 +871,7 @@ __device__ __forceinline__ void sweep_segment(const ShapeDev& sh, const ParamsDe
           double tt = inside ? pt_time : o_dur;
           // Trajectory::locatePieceIdx (poly_traj_utils.hpp:510-528): sequential subtraction of the piece durations;
           // with bit-identical durations the loop needs no loads and stays exact
-          int idx = 0;
-          if (o_uni == o_uni) {
-            while (idx < oP && tt > o_uni) {
-              tt -= o_uni;
-              idx++;
-            }
-            if (idx == oP) {
-              idx--;
-              tt += o_uni;
-            }
-          } else {
-            const double* dur = bd.obs_piece_dur + op0;
-            double dcur = 0.0;
-            for (idx = 0; idx < oP && tt > (dcur = dur[idx]); idx++) tt -= dcur;
-            if (idx == oP) {
-              idx--;
-              tt += dur[idx];
-            }
-          }
+          const int idx = locate_piece(o_uni, bd.obs_piece_dur + op0, oP, tt);
           const double* cm = bd.obs_coeffs + 12L * (op0 + idx);
           V2 sp = piece_pos(cm, tt);
           if (!inside) {  // constant-acceleration extrapolation past the prediction (traj_optimizer.cpp:1379-1388)
