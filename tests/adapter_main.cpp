@@ -13,7 +13,8 @@ int main(int argc, char** argv) {
   if (argc < 2) return 2;
   std::ifstream in(argv[1]);
   int S, K, Kd;
-  in >> S >> K >> Kd;
+  double vmax, amax, cmax;
+  in >> S >> K >> Kd >> vmax >> amax >> cmax;
   std::vector<MatrixXd> ini(S), fin(S), inner(S);
   VectorXd T(S);
   std::vector<std::vector<MatrixXd>> hp(S);
@@ -40,6 +41,9 @@ int main(int argc, char** argv) {
   dftpav_default_params(&prm);
   prm.traj_resolution = K;
   prm.des_traj_resolution = Kd;
+  prm.max_forward_vel = vmax;
+  prm.max_forward_acc = amax;
+  prm.max_forward_cur = cmax;
   opt->setParam(prm);
   bool ok = opt->OptimizeTrajectory(ini, fin, inner, T, hp, sing, 0.0, 0.0);
   std::printf("success %d status %d cost %.17g\n", ok ? 1 : 0, opt->lastStatus(), opt->lastCost());

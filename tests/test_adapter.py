@@ -33,7 +33,7 @@ def _dump(batch, prm, p, path):
     samp_pref = np.concatenate([[0], np.cumsum(samp)])
     H = batch.uniform_H
     with open(path, "w") as f:
-        f.write(f"{g1 - g0} {K} {Kd}\n")
+        f.write(f"{g1 - g0} {K} {Kd} {prm.max_forward_vel!r} {prm.max_forward_acc!r} {prm.max_forward_cur!r}\n")
         for g in range(g0, g1):
             N, M = int(Ns[g]), int(samp[g])
             f.write(f"{N} {int(batch.singul[g])} {float(batch.init_T[g])!r} {M}\n")
