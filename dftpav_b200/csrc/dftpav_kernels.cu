@@ -389,13 +389,18 @@ __device__ __forceinline__ double lse(double alpha, double* v, double& exp_sum) 
   return log(exp_sum) / alpha + d0;
 }
 
-// cold path (help_eps != 0, the header default of traj_optimizer.h:120): kept out of line to keep the sweep loop small
-__device__ __noinline__ void speed_helpers_eps(double v2, double eps, double& z_h0, double& vel2_reci, double& vel2_reci_e,
-                                              double& vel3_2_reci_e) {
-  vel2_reci = 1.0 / v2;
-  vel2_reci_e = 1.0 / (v2 + eps);
-  vel3_2_reci_e = vel2_reci_e * sqrt(vel2_reci_e);
-  z_h0 = 1.0 / sqrt(v2);
+// cold path (help_eps != 0, the header default of traj_optimizer.h:120): kept out of line to keep the sweep loop small.
+// Returns by value: reference parameters would force the caller's four scalars into local memory on the HOT path too.
+struct SpeedHelpers {
+  double z_h0, vel2_reci, vel2_reci_e, vel3_2_reci_e;
+};
+__device__ __noinline__ SpeedHelpers speed_helpers_eps(double v2, double eps) {
+  SpeedHelpers r;
+  r.vel2_reci = 1.0 / v2;
+  r.vel2_reci_e = 1.0 / (v2 + eps);
+  r.vel3_2_reci_e = r.vel2_reci_e * sqrt(r.vel2_reci_e);
+  r.z_h0 = 1.0 / sqrt(v2);
+  return r;
 }
 
 constexpr int kPlaneChunk = 4;
@@ -755,7 +760,11 @@ __device__ __forceinline__ void sweep_segment(const ShapeDev& sh, const ParamsDe
         vel2_reci_e = vel2_reci;
         vel3_2_reci_e = vel2_reci * z_h0;
       } else {
-        speed_helpers_eps(v2, P.help_eps, z_h0, vel2_reci, vel2_reci_e, vel3_2_reci_e);
+        const SpeedHelpers sh_ = speed_helpers_eps(v2, P.help_eps);
+        z_h0 = sh_.z_h0;
+        vel2_reci = sh_.vel2_reci;
+        vel2_reci_e = sh_.vel2_reci_e;
+        vel3_2_reci_e = sh_.vel3_2_reci_e;
       }
       const M2 rot = M2{dsigma.x, -dsigma.y, dsigma.y, dsigma.x};
       ego_R = M2{sg * rot.a * z_h0, sg * rot.b * z_h0, sg * rot.c * z_h0, sg * rot.d * z_h0};
