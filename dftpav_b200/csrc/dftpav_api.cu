@@ -16,6 +16,7 @@
 #include <cstdlib>
 #include <cstring>
 #include <map>
+#include <mutex>
 #include <string>
 #include <vector>
 
@@ -48,30 +49,79 @@ namespace {
 // ---------------------------------------------------------------------------------------------
 // MinJerkOpt::reset on the host: banded matrix fill + LU (poly_traj_utils.hpp:776-800, 897-948)
 // ---------------------------------------------------------------------------------------------
+// Time-normalised minimum-jerk collocation matrix of N pieces (poly_traj_utils.hpp:913-960 with every T_i = 1; the reference
+// rebuilds and refactorises it per call with the actual durations, here the durations are moved into the right-hand side).
+template <class Setter>
+static void fill_minco_matrix(int N, Setter&& A) {
+  const int n = 6 * N;
+  A(0, 0) = 1.0;
+  A(1, 1) = 1.0;
+  A(2, 2) = 2.0;
+  for (int i = 0; i < N - 1; i++) {
+    const int r = 6 * i;
+    A(r + 3, r + 3) = 6.0, A(r + 3, r + 4) = 24.0, A(r + 3, r + 5) = 60.0, A(r + 3, r + 9) = -6.0;
+    A(r + 4, r + 4) = 24.0, A(r + 4, r + 5) = 120.0, A(r + 4, r + 10) = -24.0;
+    for (int k = 0; k < 6; k++) A(r + 5, r + k) = 1.0;
+    for (int k = 0; k < 6; k++) A(r + 6, r + k) = 1.0;
+    A(r + 6, r + 6) = -1.0;
+    A(r + 7, r + 1) = 1.0, A(r + 7, r + 2) = 2.0, A(r + 7, r + 3) = 3.0, A(r + 7, r + 4) = 4.0, A(r + 7, r + 5) = 5.0;
+    A(r + 7, r + 7) = -1.0;
+    A(r + 8, r + 2) = 2.0, A(r + 8, r + 3) = 6.0, A(r + 8, r + 4) = 12.0, A(r + 8, r + 5) = 20.0;
+    A(r + 8, r + 8) = -2.0;
+  }
+  const int m = n;
+  for (int k = 0; k < 6; k++) A(m - 3, m - 6 + k) = 1.0;
+  A(m - 2, m - 5) = 1.0, A(m - 2, m - 4) = 2.0, A(m - 2, m - 3) = 3.0, A(m - 2, m - 2) = 4.0, A(m - 2, m - 1) = 5.0;
+  A(m - 1, m - 4) = 2.0, A(m - 1, m - 3) = 6.0, A(m - 1, m - 2) = 12.0, A(m - 1, m - 1) = 20.0;
+}
+
+// Dense path of the MINCO solves.  The right-hand side of the collocation system has only N+5 non-zero rows (three head
+// rows, one position row per interior waypoint, three tail rows) and the adjoint solve is only read at the same rows
+// (gdP, gradIni, gradFin: poly_traj_utils.hpp:1037-1066), so both solves reduce to products with the constant
+// 6N x (N+5) matrix M = A^-1[:, R]:  b~ = M b_R  and  lambda_R = M^T gdC.  M is computed once per N in extended
+// precision (Gauss-Jordan with partial pivoting in long double) and rounded to double: its products are closer to the
+// exact solution than the reference's unpivoted banded LU (measured 1.5e-16 vs 2.3e-15 relative at N = 24).
+// Layout: Mt[j][row] with leading dimension 6N+1 (odd: conflict-free both along rows and along columns).
+static int dense_row_of(int j, int N) { return j < 3 ? j : (j < N + 2 ? 6 * (j - 3) + 5 : 5 * N - 5 + j); }
+static int dense_ld(int N) { return 6 * N + 1; }
+static size_t dense_doubles(int N) { return ((size_t)(N + 5) * dense_ld(N) + 1) / 2 * 2; }
+static const std::vector<double>& dense_minco_table(int N) {
+  static std::mutex mu;
+  static std::map<int, std::vector<double>> cache;
+  std::lock_guard<std::mutex> lk(mu);
+  auto it = cache.find(N);
+  if (it != cache.end()) return it->second;
+  const int n = 6 * N, nc = N + 5, w = n + nc;
+  std::vector<long double> a((size_t)n * w, 0.0L);
+  fill_minco_matrix(N, [&](int i, int j) -> long double& { return a[(size_t)i * w + j]; });
+  for (int j = 0; j < nc; j++) a[(size_t)dense_row_of(j, N) * w + n + j] = 1.0L;
+  for (int k = 0; k < n; k++) {
+    int p = k;
+    for (int i = k + 1; i < n; i++)
+      if (fabsl(a[(size_t)i * w + k]) > fabsl(a[(size_t)p * w + k])) p = i;
+    if (p != k)
+      for (int j = 0; j < w; j++) std::swap(a[(size_t)k * w + j], a[(size_t)p * w + j]);
+    const long double inv = 1.0L / a[(size_t)k * w + k];
+    for (int j = k; j < w; j++) a[(size_t)k * w + j] *= inv;
+    for (int i = 0; i < n; i++) {
+      const long double f = a[(size_t)i * w + k];
+      if (i == k || f == 0.0L) continue;
+      for (int j = k; j < w; j++) a[(size_t)i * w + j] -= f * a[(size_t)k * w + j];
+    }
+  }
+  std::vector<double> t(dense_doubles(N), 0.0);
+  const int ld = dense_ld(N);
+  for (int j = 0; j < nc; j++)
+    for (int i = 0; i < n; i++) t[(size_t)j * ld + i] = (double)a[(size_t)i * w + n + j];
+  return cache.emplace(N, std::move(t)).first->second;
+}
+
 struct BandLU {
   int n;
   std::vector<double> d;  // band storage d[(i-j+6)*n + j], lower = upper = 6
   explicit BandLU(int N) : n(6 * N), d((size_t)13 * 6 * N, 0.0) {
     auto A = [&](int i, int j) -> double& { return d[(size_t)(i - j + 6) * n + j]; };
-    A(0, 0) = 1.0;
-    A(1, 1) = 1.0;
-    A(2, 2) = 2.0;
-    for (int i = 0; i < N - 1; i++) {
-      const int r = 6 * i;
-      A(r + 3, r + 3) = 6.0, A(r + 3, r + 4) = 24.0, A(r + 3, r + 5) = 60.0, A(r + 3, r + 9) = -6.0;
-      A(r + 4, r + 4) = 24.0, A(r + 4, r + 5) = 120.0, A(r + 4, r + 10) = -24.0;
-      for (int k = 0; k < 6; k++) A(r + 5, r + k) = 1.0;
-      for (int k = 0; k < 6; k++) A(r + 6, r + k) = 1.0;
-      A(r + 6, r + 6) = -1.0;
-      A(r + 7, r + 1) = 1.0, A(r + 7, r + 2) = 2.0, A(r + 7, r + 3) = 3.0, A(r + 7, r + 4) = 4.0, A(r + 7, r + 5) = 5.0;
-      A(r + 7, r + 7) = -1.0;
-      A(r + 8, r + 2) = 2.0, A(r + 8, r + 3) = 6.0, A(r + 8, r + 4) = 12.0, A(r + 8, r + 5) = 20.0;
-      A(r + 8, r + 8) = -2.0;
-    }
-    const int m = n;
-    for (int k = 0; k < 6; k++) A(m - 3, m - 6 + k) = 1.0;
-    A(m - 2, m - 5) = 1.0, A(m - 2, m - 4) = 2.0, A(m - 2, m - 3) = 3.0, A(m - 2, m - 2) = 4.0, A(m - 2, m - 1) = 5.0;
-    A(m - 1, m - 4) = 2.0, A(m - 1, m - 3) = 6.0, A(m - 1, m - 2) = 12.0, A(m - 1, m - 1) = 20.0;
+    fill_minco_matrix(N, A);
     // factorizeLU: no pivoting, exact zeros skipped
     for (int k = 0; k <= n - 2; k++) {
       const int iM = std::min(k + 6, n - 1);
@@ -667,6 +717,23 @@ int dftpav_upload_batch(dftpav_handle* h, const dftpav_batch* b) {
     sh.Mpad = sampoff;
     sh.lu_doubles = luoff;
     sh.ws_doubles = ws_doubles_host(sh.rows, sh.npad);
+    // dense MINCO tables instead of the LU tables when they fit beside the workspaces of a full CTA
+    {
+      size_t dd = 0;
+      bool cols_ok = true;
+      for (auto& kv : lu_of_N) dd += dense_doubles(kv.first), cols_ok = cols_ok && kv.first + 5 <= 64;
+      const size_t cap0 = h->smem_optin > 2048 ? h->smem_optin - 1024 : 0;
+      const int cnt0 = (int)grp->probs.size();
+      const int wantW = std::max(1, std::min(max_warps_host(), (cnt0 + h->num_sms - 1) / h->num_sms));
+      if (cols_ok && !getenv("DFTPAV_NO_DENSE") && sizeof(double) * (dd + (size_t)sh.ws_doubles * wantW) <= cap0) {
+        sh.dense_minco = 1;
+        size_t off = 0;
+        std::map<int, int> off_of_N;
+        for (auto& kv : lu_of_N) off_of_N[kv.first] = (int)off, off += dense_doubles(kv.first);
+        for (int s = 0; s < sh.S; s++) sh.lu_off[s] = off_of_N[sh.N[s]];
+        sh.lu_doubles = (int)dd;
+      }
+    }
     // padded plane count of the group
     int Hmax = 0;
     if (b->plane_cnt) {
@@ -679,12 +746,21 @@ int dftpav_upload_batch(dftpav_handle* h, const dftpav_batch* b) {
     }
     sh.H = (Hmax + 3) / 4 * 4;  // padded to the register chunk of the sweep (null planes never violate)
     // LU block
-    std::vector<double> lu((size_t)luoff, 0.0);
+    std::vector<double> lu((size_t)sh.lu_doubles, 0.0);
     sh.band_masks_ok = 1;
-    for (auto& kv : lu_of_N) {
-      BandLU f(kv.first);
-      f.pack(lu.data() + kv.second);
-      if (!f.masks_hold()) sh.band_masks_ok = 0;
+    if (sh.dense_minco) {
+      size_t off = 0;
+      for (auto& kv : lu_of_N) {
+        const std::vector<double>& t = dense_minco_table(kv.first);
+        std::copy(t.begin(), t.end(), lu.begin() + off);
+        off += t.size();
+      }
+    } else {
+      for (auto& kv : lu_of_N) {
+        BandLU f(kv.first);
+        f.pack(lu.data() + kv.second);
+        if (!f.masks_hold()) sh.band_masks_ok = 0;
+      }
     }
     CU_TRY(h, up(grp->d_lu, lu.data(), sizeof(double) * lu.size()));
     CU_TRY(h, up(grp->d_prob_id, grp->probs.data(), sizeof(int) * grp->probs.size()));
@@ -978,6 +1054,18 @@ int dftpav_debug_phase_clock(dftpav_handle* h, int enable, unsigned long long* c
   CU_TRY(h, cudaMemset(d_clk, 0, 8 * sizeof(unsigned long long)));
   CU_TRY(h, set_phase_clock(enable ? d_clk : nullptr));
   return DFTPAV_OK;
+}
+
+// Diagnostic (host only, no GPU needed): the dense MINCO table of N pieces as the kernels read it, Mt[j][row] with
+// leading dimension 6N+1, (N+5) columns; rows_of_col[j] = matrix row of column j.  Returns the number of doubles written
+// (or needed, when out is null).
+long long dftpav_debug_minco_dense(int N, double* out, int* rows_of_col) {
+  if (N < 1 || N > kMaxPieces) return -1;
+  const std::vector<double>& t = dense_minco_table(N);
+  if (out) std::copy(t.begin(), t.end(), out);
+  if (rows_of_col)
+    for (int j = 0; j < N + 5; j++) rows_of_col[j] = dense_row_of(j, N);
+  return (long long)t.size();
 }
 
 const char* dftpav_last_error(const dftpav_handle* h) { return h ? h->err.c_str() : "null handle"; }

@@ -40,6 +40,7 @@ struct ShapeDev {
   int npad;              // n rounded up to a multiple of 4
   int ws_doubles;        // per-warp workspace size in doubles
   int band_masks_ok;     // 1 if the LU tables satisfy the compile-time sparsity masks of the banded passes
+  int dense_minco;       // 1: the table block holds the dense matrices M = A^-1[:, R] (lu_off = their offsets), not LU columns
 };
 
 // Scalar parameters reaching the arithmetic (mirror of dftpav_params, device side).

@@ -1031,6 +1031,75 @@ __device__ __noinline__ long long phase_mark(unsigned long long* pc, int idx, lo
 #define PHASE_MARK(idx) \
   if (pc) t_prev = phase_mark(pc, (idx), t_prev, lane);
 
+// ------------------------------------------------------------------------------------------------
+// dense MINCO path (ShapeDev::dense_minco): both solves as products with the constant matrix M = A^-1[:, R], R = the
+// N+5 rows where the right-hand side is non-zero and the adjoint solution is read (see dense_minco_table() in
+// dftpav_api.cu).  Mt[j][row], leading dimension 6N+1.  All 32 lanes work (the banded substitutions keep 2 busy).
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ int dense_row_of(int j, int N) { return j < 3 ? j : (j < N + 2 ? 6 * (j - 3) + 5 : 5 * N - 5 + j); }
+
+// b~[row] = sum_j Mt[j][row] * bR[j]   (x and y columns together); lanes own rows, 5 row blocks per chunk
+__device__ __forceinline__ void dense_forward(const double* __restrict__ Mt, int ld, int ncol, const double* bR,
+                                              double* out, int n, int lane) {
+  constexpr int RB = 5;
+  for (int r0 = 0; r0 < n; r0 += 32 * RB) {
+    double ax[RB], ay[RB];
+    const double* mp[RB];
+#pragma unroll
+    for (int k = 0; k < RB; k++) {
+      ax[k] = ay[k] = 0.0;
+      mp[k] = Mt + min(r0 + lane + 32 * k, n - 1);
+    }
+#pragma unroll 2
+    for (int j = 0; j < ncol; j++) {
+      const double2 b = *reinterpret_cast<const double2*>(bR + 2 * j);
+#pragma unroll
+      for (int k = 0; k < RB; k++) {
+        const double m = mp[k][(size_t)j * ld];
+        ax[k] = fma(m, b.x, ax[k]);
+        ay[k] = fma(m, b.y, ay[k]);
+      }
+    }
+#pragma unroll
+    for (int k = 0; k < RB; k++) {
+      const int row = r0 + lane + 32 * k;
+      if (row < n) *reinterpret_cast<double2*>(out + 2 * row) = make_double2(ax[k], ay[k]);
+    }
+  }
+}
+
+// lambda_R[j] = sum_row Mt[j][row] * gd[row], written over gd at row R[j]; lanes own columns j (ncol <= 64)
+__device__ __forceinline__ void dense_adjoint(const double* __restrict__ Mt, int ld, int ncol, double* gd, int n, int N,
+                                              int lane) {
+  const double* pA = Mt + (size_t)min(lane, ncol - 1) * ld;
+  double ax0 = 0.0, ay0 = 0.0, ax1 = 0.0, ay1 = 0.0, bx0 = 0.0, by0 = 0.0, bx1 = 0.0, by1 = 0.0;
+  if (ncol <= 32) {
+#pragma unroll 2
+    for (int r = 0; r < n; r += 2) {  // n = 6N is even
+      const double2 g0 = *reinterpret_cast<const double2*>(gd + 2 * r);
+      const double2 g1 = *reinterpret_cast<const double2*>(gd + 2 * r + 2);
+      const double m0 = pA[r], m1 = pA[r + 1];
+      ax0 = fma(m0, g0.x, ax0), ay0 = fma(m0, g0.y, ay0);
+      ax1 = fma(m1, g1.x, ax1), ay1 = fma(m1, g1.y, ay1);
+    }
+  } else {
+    const double* pB = Mt + (size_t)min(lane + 32, ncol - 1) * ld;
+#pragma unroll 2
+    for (int r = 0; r < n; r += 2) {
+      const double2 g0 = *reinterpret_cast<const double2*>(gd + 2 * r);
+      const double2 g1 = *reinterpret_cast<const double2*>(gd + 2 * r + 2);
+      const double m0 = pA[r], m1 = pA[r + 1], q0 = pB[r], q1 = pB[r + 1];
+      ax0 = fma(m0, g0.x, ax0), ay0 = fma(m0, g0.y, ay0);
+      ax1 = fma(m1, g1.x, ax1), ay1 = fma(m1, g1.y, ay1);
+      bx0 = fma(q0, g0.x, bx0), by0 = fma(q0, g0.y, by0);
+      bx1 = fma(q1, g1.x, bx1), by1 = fma(q1, g1.y, by1);
+    }
+  }
+  __syncwarp();  // every lane has read gd before the solution overwrites rows of it
+  if (lane < ncol) *reinterpret_cast<double2*>(gd + 2 * dense_row_of(lane, N)) = make_double2(ax0 + ax1, ay0 + ay1);
+  if (lane + 32 < ncol) *reinterpret_cast<double2*>(gd + 2 * dense_row_of(lane + 32, N)) = make_double2(bx0 + bx1, by0 + by1);
+}
+
 template <bool HAS_OBS>
 __device__ double eval_cost_grad(const ShapeDev& sh, const ParamsDev& P, const BatchDev& bd, int prob,
                                  const double* __restrict__ planes, const double* __restrict__ lu, WarpWS& ws,
@@ -1075,12 +1144,43 @@ __device__ double eval_cost_grad(const ShapeDev& sh, const ParamsDev& P, const B
       sc.tail[3] = P.non_sinv * sn;
     }
   }
-  for (int i = lane; i < 2 * sh.rows; i += 32) ws.bt[i] = 0.0;
+  const bool dense = sh.dense_minco != 0;
+  if (!dense)
+    for (int i = lane; i < 2 * sh.rows; i += 32) ws.bt[i] = 0.0;
   __syncwarp();
   if (lane < S) {
     // trajtimes (quirk Q5): T of the previous segment, not cumulative
     ws.seg[lane].trajtime = lane == 0 ? 0.0 : ws.seg[lane - 1].T;
   }
+  if (dense) {
+    // ---- non-zero rows of the right-hand side, staged in the (still unused) gdC array, then b~ = M b_R
+    for (int s = 0; s < S; s++) {
+      const int N = sh.N[s];
+      const SegScratch& sc = ws.seg[s];
+      const double t1 = sc.dT, t2 = t1 * t1;
+      double* bR = ws.gd + 2 * sh.row0[s];
+      const double* Pin = x + sh.var0[s];
+      for (int j = lane; j < N + 5; j += 32) {
+        double bx, by;
+        if (j >= 3 && j < N + 2) {
+          bx = Pin[2 * (j - 3)], by = Pin[2 * (j - 3) + 1];
+        } else {
+          const double* st = j < 3 ? sc.head : sc.tail;
+          const int k = j < 3 ? j : j - (N + 2);
+          const double scl = k == 0 ? 1.0 : (k == 1 ? t1 : t2);
+          bx = st[2 * k] * scl, by = st[2 * k + 1] * scl;
+        }
+        *reinterpret_cast<double2*>(bR + 2 * j) = make_double2(bx, by);
+      }
+    }
+    __syncwarp();
+    PHASE_MARK(0)
+    for (int s = 0; s < S; s++)
+      dense_forward(lu + sh.lu_off[s], 6 * sh.N[s] + 1, sh.N[s] + 5, ws.gd + 2 * sh.row0[s], ws.bt + 2 * sh.row0[s],
+                    6 * sh.N[s], lane);
+    __syncwarp();
+    PHASE_MARK(1)
+  } else {
   // ---- right-hand side (poly_traj_utils.hpp:968-977)
   for (int s = 0; s < S; s++) {
     const int N = sh.N[s];
@@ -1107,6 +1207,7 @@ __device__ double eval_cost_grad(const ShapeDev& sh, const ParamsDev& P, const B
   }
   __syncwarp();
   PHASE_MARK(1)
+  }  // !dense
   // ---- c = b~ / dT^k, jerk energy, gdC / gdT initialisation (poly_traj_utils.hpp:981-984, 998-1035)
   for (int s = 0; s < S; s++) {
     const int N = sh.N[s];
@@ -1182,7 +1283,10 @@ __device__ double eval_cost_grad(const ShapeDev& sh, const ParamsDev& P, const B
   }
   __syncwarp();
   PHASE_MARK(4)
-  if (lane < 2 * S) {
+  if (dense) {
+    for (int s = 0; s < S; s++)
+      dense_adjoint(lu + sh.lu_off[s], 6 * sh.N[s] + 1, sh.N[s] + 5, ws.gd + 2 * sh.row0[s], 6 * sh.N[s], sh.N[s], lane);
+  } else if (lane < 2 * S) {
     const int s = lane >> 1;
     banded_solve_adj(lu + sh.lu_off[s], ws.gd + 2 * sh.row0[s], 6 * sh.N[s], lane & 1, sh.band_masks_ok != 0);
   }
@@ -1327,6 +1431,19 @@ __global__ void __launch_bounds__(32 * DFTPAV_MAX_WARPS, 1)
 // L-BFGS two-loop recursion (lbfgs.hpp:716-739) with the direction held in registers (NPL elements per lane) and
 // the (s_j, y_j, ys_j) history stream software-prefetched two steps ahead.  alpha_j lives in shared memory.
 // ------------------------------------------------------------------------------------------------
+// The history keeps 1/ys_j (one division when the pair is stored) and the recursion multiplies by it, instead of the
+// reference's division by ys_j in both loops (lbfgs.hpp:722, 733): <= 1.5 ulp per alpha_j / beta_j, and the ~70-cycle
+// division leaves the dependent chain of every history step.  -DDFTPAV_RECIP_YS=0 restores the divisions.
+#ifndef DFTPAV_RECIP_YS
+#define DFTPAV_RECIP_YS 1
+#endif
+#if DFTPAV_RECIP_YS
+#define DFTPAV_OVER_YS(num, ysv) ((num) * (ysv))
+#define DFTPAV_STORE_YS(ysv) (1.0 / (ysv))
+#else
+#define DFTPAV_OVER_YS(num, ysv) ((num) / (ysv))
+#define DFTPAV_STORE_YS(ysv) (ysv)
+#endif
 template <int NPL>
 struct HistStage {
   double s[NPL], y[NPL], ys;
@@ -1394,7 +1511,7 @@ __device__ __noinline__ void two_loop(double* d_sm, double* alpha_sm, const doub
     double part = 0.0;
 #pragma unroll
     for (int e = 0; e < NPL; e++) part += sc_[e] * d[e];
-    const double a = warp_sum(part) / ysc;
+    const double a = DFTPAV_OVER_YS(warp_sum(part), ysc);
     if (lane == 0) alpha_sm[j] = a;
     const double na = -a;
 #pragma unroll
@@ -1438,7 +1555,7 @@ __device__ __noinline__ void two_loop(double* d_sm, double* alpha_sm, const doub
     double part = 0.0;
 #pragma unroll
     for (int e = 0; e < NPL; e++) part += yc_[e] * d[e];
-    const double beta = warp_sum(part) / ysc;
+    const double beta = DFTPAV_OVER_YS(warp_sum(part), ysc);
     const double a = alpha_sm[j] - beta;
 #pragma unroll
     for (int e = 0; e < NPL; e++) {
@@ -1663,7 +1780,7 @@ __global__ void __launch_bounds__(32 * DFTPAV_MAX_WARPS, 1)
           yy = warp_sum(yy);
           ss = warp_sum(ss);
           gg = warp_sum(gg);
-          if (lane == 0) lm_ys[end] = ys;
+          if (lane == 0) lm_ys[end] = DFTPAV_STORE_YS(ys);
           __syncwarp();
           const double cau = ss * sqrt(gg) * P.cautious_factor;
           if (ys > cau) {

@@ -1,0 +1,54 @@
+"""Host logic of the dense MINCO path (no GPU): the table M = A^-1[:, R] the kernels multiply with, computed by the
+library in extended precision, against numpy's dense inverse of the time-normalised collocation matrix
+(synth.minco_dense builds the same matrix the oracle factorises), and the two identities the kernels rely on:
+b~ = M b_R for a right-hand side supported on R, and lambda_R = M^T g for the adjoint solve."""
+import ctypes as C
+
+import numpy as np
+import pytest
+
+from dftpav_b200 import capi, synth
+
+
+def _table(N):
+    lib = capi.load_library()
+    lib.dftpav_debug_minco_dense.restype = C.c_longlong
+    lib.dftpav_debug_minco_dense.argtypes = [C.c_int, C.POINTER(C.c_double), C.POINTER(C.c_int)]
+    cnt = lib.dftpav_debug_minco_dense(N, None, None)
+    assert cnt >= (N + 5) * (6 * N + 1)
+    buf = np.zeros(cnt)
+    rows = np.zeros(N + 5, dtype=np.int32)
+    assert lib.dftpav_debug_minco_dense(N, buf.ctypes.data_as(C.POINTER(C.c_double)), rows.ctypes.data_as(C.POINTER(C.c_int))) == cnt
+    ld = 6 * N + 1
+    Mt = buf[: (N + 5) * ld].reshape(N + 5, ld)[:, : 6 * N]
+    return Mt.T.copy(), rows  # M [6N][N+5]
+
+
+@pytest.mark.parametrize("N", [1, 2, 3, 8, 24, 40])
+def test_dense_table_is_the_inverse_restricted_to_rhs_rows(N):
+    M, rows = _table(N)
+    A = synth.minco_dense(N)
+    expect_rows = [0, 1, 2] + [6 * i + 5 for i in range(N - 1)] + [6 * N - 3, 6 * N - 2, 6 * N - 1]
+    assert rows.tolist() == expect_rows
+    # A M = E_R  (columns of the identity at R), to a few ulps of cond(A) * eps
+    E = np.zeros((6 * N, N + 5))
+    E[rows, np.arange(N + 5)] = 1.0
+    res = np.abs(A @ M - E).max()
+    assert res < 1e-11, res
+    rng = np.random.default_rng(N)
+    bR = rng.normal(size=(N + 5, 2)) * 10
+    b = np.zeros((6 * N, 2))
+    b[rows] = bR
+    c = np.linalg.solve(A, b)
+    assert np.abs(M @ bR - c).max() <= 1e-11 * max(1.0, np.abs(c).max())
+    g = rng.normal(size=(6 * N, 2))
+    lam = np.linalg.solve(A.T, g)
+    assert np.abs(M.T @ g - lam[rows]).max() <= 1e-11 * max(1.0, np.abs(lam).max())
+
+
+def test_bad_piece_count_is_rejected():
+    lib = capi.load_library()
+    lib.dftpav_debug_minco_dense.restype = C.c_longlong
+    lib.dftpav_debug_minco_dense.argtypes = [C.c_int, C.POINTER(C.c_double), C.POINTER(C.c_int)]
+    assert lib.dftpav_debug_minco_dense(0, None, None) == -1
+    assert lib.dftpav_debug_minco_dense(65, None, None) == -1
