@@ -39,6 +39,7 @@ cudaError_t launch_prepare(int grid, int block, cudaStream_t st, const ShapeDev&
                            const double* inner_pts, double* ini, double* fin, double* x0, int n_stride);
 int ws_doubles_host(int rows, int npad);
 int max_warps_host();
+int team_size_host();
 cudaError_t set_phase_clock(unsigned long long* dev_ptr);
 }  // namespace dftpav
 
@@ -724,7 +725,7 @@ int dftpav_upload_batch(dftpav_handle* h, const dftpav_batch* b) {
       for (auto& kv : lu_of_N) dd += dense_doubles(kv.first), cols_ok = cols_ok && kv.first + 5 <= 64;
       const size_t cap0 = h->smem_optin > 2048 ? h->smem_optin - 1024 : 0;
       const int cnt0 = (int)grp->probs.size();
-      const int wantW = std::max(1, std::min(max_warps_host(), (cnt0 + h->num_sms - 1) / h->num_sms));
+      const int wantW = std::max(1, std::min(max_warps_host() / team_size_host(), (cnt0 + h->num_sms - 1) / h->num_sms));
       if (cols_ok && !getenv("DFTPAV_NO_DENSE") && sizeof(double) * (dd + (size_t)sh.ws_doubles * wantW) <= cap0) {
         sh.dense_minco = 1;
         size_t off = 0;
@@ -771,10 +772,12 @@ int dftpav_upload_batch(dftpav_handle* h, const dftpav_batch* b) {
     const size_t ws_bytes = sizeof(double) * sh.ws_doubles, lu_bytes = sizeof(double) * sh.lu_doubles;
     const size_t cap = h->smem_optin > 2048 ? h->smem_optin - 1024 : 0;
     if (lu_bytes + ws_bytes > cap) return fail(h, DFTPAV_ERR_UNSUPPORTED, "problem shape does not fit in shared memory");
-    int W = (int)std::min<size_t>(max_warps_host(), (cap - lu_bytes) / ws_bytes);
+    // W = teams per CTA (one trajectory per team of team_size_host() warps; sh.ws_doubles is the team's workspace)
+    const int G = team_size_host();
+    int W = (int)std::min<size_t>(max_warps_host() / G, (cap - lu_bytes) / ws_bytes);
     const int want = (count + h->num_sms - 1) / h->num_sms;
     W = std::max(1, std::min(W, want));
-    grp->warps = W;
+    grp->warps = W * G;
     grp->smem = lu_bytes + ws_bytes * W;
     grp->grid = std::min((count + W - 1) / W, h->num_sms);
     max_slots = std::max(max_slots, grp->grid * W);

@@ -95,7 +95,10 @@ __device__ __forceinline__ M2 mul_BhT(M2 m) { return M2{-m.b, m.a, -m.d, m.c}; }
 // ------------------------------------------------------------------------------------------------
 // per-warp workspace in shared memory
 // ------------------------------------------------------------------------------------------------
-struct SegScratch {   // 24 doubles per segment
+struct SegScratch {   // 38 doubles per segment
+  double ini[6], fin[6];  // clamped boundary states of the problem, staged once per problem (stage_problem)
+  double singul;          // +1 forward / -1 reverse, staged once per problem
+  double pad1;
   double head[6];
   double tail[6];
   double T, dT;
@@ -104,6 +107,26 @@ struct SegScratch {   // 24 doubles per segment
   double pen[3];      // corridor / dynamic / feasibility penalty of the segment
   double trajtime;    // quirk Q5: T of the previous segment (0 for the first)
   double pad[4];
+};
+
+// Team of kTeam warps per trajectory.  Rank 0 runs the solver (L-BFGS state machine, MINCO products, gradient assembly);
+// the constraint sweep - 80-90 % of a lone warp's evaluation time - is split pass-by-pass over all ranks: rank r takes
+// passes r, r+kTeam, ... and accumulates into a private partial gradient, merged in a fixed order after a named barrier.
+// The batch time at the reference batch sizes is set by the critical path of the longest problem (~200 sequential
+// evaluations), not by throughput (profiles/README.md: 124 k solves/s at batch 2048, 199 k at 4096, 293 k at 16384
+// with one warp per problem), so shortening every evaluation is worth more than resident problems.
+#ifndef DFTPAV_TEAM
+#define DFTPAV_TEAM 1  // measured at config 3, batch 4096: 1: 202 k, 2: 182 k, 3: 177 k, 4: 162 k, 6: 149 k solves/s (profiles/README.md)
+#endif
+constexpr int kTeam = DFTPAV_TEAM;
+static_assert(kTeam >= 1 && DFTPAV_MAX_WARPS % kTeam == 0 && (kTeam == 1 || (DFTPAV_MAX_WARPS / kTeam) * 2 + 1 <= 16), "team size");
+
+// what a rank accumulates into during the sweep
+struct SweepTarget {
+  double* gd;     // [2*rows] partial gdC (rank 0: the workspace gdC itself)
+  double* stage;  // [2][12][kStageLd] tile-reduction staging of this warp
+  double* scal;   // [kMaxSeg][4] per-segment partial (gdT, pen0, pen1, pen2)
+  int rank;
 };
 
 struct WarpWS {
@@ -119,10 +142,15 @@ struct WarpWS {
   double* pf;     // [8] past cost values (lbfgs.hpp:508, 658)
   double* obs;    // [kObsCap][4] obstacle metadata of the current problem: start, duration, uniform piece duration, (P<<32|piece_ptr)
   SegScratch* seg;  // [kMaxSeg]
+  double* scal;   // [kMaxSeg][4] rank 0's sweep partials
+  unsigned long long* ctl;  // [4] team mailbox: [0] exit flag, [1] problem id, [2] plane pointer of the current problem
+  double* part;   // (kTeam-1) x part_doubles: partial gdC, staging and scalars of ranks 1..kTeam-1
 };
+__host__ __device__ inline int part_doubles_for(int rows) { return 2 * rows + 2 * 12 * kStageLd + 4 * kMaxSeg; }
 
 __host__ __device__ inline int ws_doubles_for(int rows, int npad) {
-  return 6 * rows + 5 * npad + 2 * 12 * kStageLd + 8 + 4 * kObsCap + kMaxSeg * (int)(sizeof(SegScratch) / sizeof(double));
+  return 6 * rows + 5 * npad + 2 * 12 * kStageLd + 8 + 4 * kObsCap + kMaxSeg * (int)(sizeof(SegScratch) / sizeof(double)) +
+         4 * kMaxSeg + 4 + (kTeam - 1) * part_doubles_for(rows);
 }
 
 __device__ __forceinline__ WarpWS carve_ws(double* base, const ShapeDev& sh) {
@@ -139,7 +167,43 @@ __device__ __forceinline__ WarpWS carve_ws(double* base, const ShapeDev& sh) {
   w.pf = w.stage + 2 * 12 * kStageLd;
   w.obs = w.pf + 8;
   w.seg = reinterpret_cast<SegScratch*>(w.obs + 4 * kObsCap);
+  w.scal = w.obs + 4 * kObsCap + kMaxSeg * (int)(sizeof(SegScratch) / sizeof(double));
+  w.ctl = reinterpret_cast<unsigned long long*>(w.scal + 4 * kMaxSeg);
+  w.part = w.scal + 4 * kMaxSeg + 4;
   return w;
+}
+__device__ __forceinline__ SweepTarget sweep_target(const WarpWS& w, const ShapeDev& sh, int rank) {
+  SweepTarget t;
+  t.rank = rank;
+  if (rank == 0) {
+    t.gd = w.gd, t.stage = w.stage, t.scal = w.scal;
+  } else {
+    double* p = w.part + (size_t)(rank - 1) * part_doubles_for(sh.rows);
+    t.gd = p, t.stage = p + 2 * sh.rows, t.scal = p + 2 * sh.rows + 2 * 12 * kStageLd;
+  }
+  return t;
+}
+// named barriers of a team: A = "coefficients ready, sweep", B = "sweep partials ready"
+__device__ __forceinline__ void team_bar(int id) {
+  asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(32 * kTeam) : "memory");
+}
+
+
+// Per-problem constants that every evaluation needs (boundary states, direction of each gear segment): read from global
+// memory ONCE when the warp takes the problem instead of at every evaluation (the dependent seg_base -> singul load
+// alone stalled the start of every sweep for a DRAM round trip: 6 % of all stall samples, profiles/README.md).
+__device__ __forceinline__ void stage_problem(const ShapeDev& sh, const BatchDev& bd, int prob, WarpWS& ws, int lane) {
+  if (lane < sh.S) {
+    const int g = bd.seg_base[prob] + lane;
+    SegScratch& sc = ws.seg[lane];
+#pragma unroll
+    for (int k = 0; k < 6; k++) {
+      sc.ini[k] = bd.ini[6 * g + k];
+      sc.fin[k] = bd.fin[6 * g + k];
+    }
+    sc.singul = (double)bd.singul[g];
+  }
+  __syncwarp();
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -407,11 +471,21 @@ constexpr int kPlaneChunk = 4;
 // Plane storage of one problem is pass-major: [pass][chunk of 4 planes][16 components][32 lanes], so the 16 values a
 // lane needs for one chunk sit at compile-time offsets k*32 doubles from one base pointer (immediate-offset LDG.64,
 // each warp-wide load is one contiguous 256 B row).  The host pads the plane count to a multiple of 4 with null planes.
+// -DDFTPAV_PLANES_STREAM=1: planes are read with the streaming (evict-first) cache operator so that the once-per-
+// evaluation plane stream does not push the L-BFGS history of the resident problems out of L2.
+#ifndef DFTPAV_PLANES_STREAM
+#define DFTPAV_PLANES_STREAM 1  // measured: 197-199 k vs 192-193 k solves/s at config 3
+#endif
+#if DFTPAV_PLANES_STREAM
+#define DFTPAV_PLANE_LD(p) __ldcs(p)
+#else
+#define DFTPAV_PLANE_LD(p) __ldg(p)
+#endif
 __device__ __forceinline__ void load_plane_chunk(double (&pn)[kPlaneChunk][4], const double* __restrict__ lanep) {
 #pragma unroll
   for (int hh = 0; hh < kPlaneChunk; hh++) {
 #pragma unroll
-    for (int cc = 0; cc < 4; cc++) pn[hh][cc] = __ldg(lanep + (hh * 4 + cc) * 32);
+    for (int cc = 0; cc < 4; cc++) pn[hh][cc] = DFTPAV_PLANE_LD(lanep + (hh * 4 + cc) * 32);
   }
 }
 
@@ -641,8 +715,8 @@ __device__ __noinline__ void dyn_obstacles(const ParamsDev& P, const BatchDev& b
 // ------------------------------------------------------------------------------------------------
 template <bool HAS_OBS>
 __device__ __forceinline__ void sweep_segment(const ShapeDev& sh, const ParamsDev& P, const BatchDev& bd, int prob,
-                                              const double* __restrict__ planes, WarpWS& ws, int s, int singul_,
-                                              int lane) {
+                                              const double* __restrict__ planes, WarpWS& ws, const SweepTarget& tgt,
+                                              int s, int singul_, int lane) {
   const int N = sh.N[s];
   const int K = sh.K, Kd = sh.Kd;
   const int td = (Kd + kTile - 1) / kTile, tk = (K + kTile - 1) / kTile;
@@ -656,8 +730,8 @@ __device__ __forceinline__ void sweep_segment(const ShapeDev& sh, const ParamsDe
   const double max_vel = P.max_vel[sidx], max_cur = P.max_cur[sidx], max_acc = P.max_acc[sidx];
   const double sg = (double)singul_;
   const double* cseg = ws.c + 2 * sh.row0[s];
-  double* gdseg = ws.gd + 2 * sh.row0[s];
-  double* stage0 = ws.stage;
+  double* gdseg = tgt.gd + 2 * sh.row0[s];
+  double* stage0 = tgt.stage;
   // keep these three pointers in registers: ptxas otherwise re-derives them from the kernel parameters inside the loop
   asm volatile("" : "+l"(cseg), "+l"(gdseg), "+l"(stage0));
   const int H = sh.H;
@@ -669,9 +743,12 @@ __device__ __forceinline__ void sweep_segment(const ShapeDev& sh, const ParamsDe
   const int npass = npass_reg + npass_end;
   const double invK_ = 1.0 / K, invKd_ = 1.0 / Kd;
   double pn[kPlaneChunk][4];
-  load_plane_chunk(pn, pl);
+  // rank r takes passes kTeam-1-r, 2*kTeam-1-r, ...: when the pass count is not a multiple of the team size the ranks
+  // that are short one pass are the low ones, and rank 0 has the serial parts of the evaluation to do as well
+  const int pass0 = kTeam - 1 - tgt.rank;
+  if (pass0 < npass) load_plane_chunk(pn, pl + (size_t)(pass0 * nchunk) * 512);
 
-  for (int pass = 0; pass < npass; pass++) {
+  for (int pass = pass0; pass < npass; pass += kTeam) {
     const bool endpass = pass >= npass_reg;
     int piece, j, Kp;
     bool valid;
@@ -841,7 +918,7 @@ __device__ __forceinline__ void sweep_segment(const ShapeDev& sh, const ParamsDe
 
     // ---------------- stage C: software prefetch of the next pass's first plane chunk (registers are free now;
     //                  its consumers are most of a pass away)
-    if (pass + 1 < npass) load_plane_chunk(pn, pl + (size_t)((pass + 1) * nchunk) * 512);
+    if (pass + kTeam < npass) load_plane_chunk(pn, pl + (size_t)((pass + kTeam) * nchunk) * 512);
 
     // ---------------- stage D: moving obstacles, velocity / acceleration / curvature limits, expansion
     double out[12];
@@ -1008,12 +1085,24 @@ __device__ __forceinline__ void sweep_segment(const ShapeDev& sh, const ParamsDe
   acc_p2 = warp_sum(acc_p2);
   if (HAS_OBS) acc_p1 = warp_sum(acc_p1);
   if (lane == 0) {
-    ws.seg[s].gdT += acc_gdT;
-    ws.seg[s].pen[0] = acc_p0;
-    ws.seg[s].pen[1] = acc_p1;
-    ws.seg[s].pen[2] = acc_p2;
+    tgt.scal[4 * s + 0] = acc_gdT;
+    tgt.scal[4 * s + 1] = acc_p0;
+    tgt.scal[4 * s + 2] = acc_p1;
+    tgt.scal[4 * s + 3] = acc_p2;
   }
   __syncwarp();
+}
+
+// The sweep of all segments by one rank of the team (ranks > 0 start from a zeroed partial gradient).
+template <bool HAS_OBS>
+__device__ __forceinline__ void sweep_rank(const ShapeDev& sh, const ParamsDev& P, const BatchDev& bd, int prob,
+                                           const double* __restrict__ planes, WarpWS& ws, int rank, int lane) {
+  const SweepTarget tgt = sweep_target(ws, sh, rank);
+  if (rank > 0) {
+    for (int i = lane; i < 2 * sh.rows; i += 32) tgt.gd[i] = 0.0;
+    __syncwarp();
+  }
+  for (int s = 0; s < sh.S; s++) sweep_segment<HAS_OBS>(sh, P, bd, prob, planes, ws, tgt, s, (int)ws.seg[s].singul, lane);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -1100,14 +1189,12 @@ __device__ __forceinline__ void dense_adjoint(const double* __restrict__ Mt, int
   if (lane + 32 < ncol) *reinterpret_cast<double2*>(gd + 2 * dense_row_of(lane + 32, N)) = make_double2(bx0 + bx1, by0 + by1);
 }
 
-template <bool HAS_OBS>
-__device__ double eval_cost_grad(const ShapeDev& sh, const ParamsDev& P, const BatchDev& bd, int prob,
-                                 const double* __restrict__ planes, const double* __restrict__ lu, WarpWS& ws,
-                                 const double* x, double* g, int lane) {
+// Part 1 (rank 0): decision vector -> boundary states, MINCO coefficients, jerk energy, gdC initialisation.
+__device__ __forceinline__ void eval_pre(const ShapeDev& sh, const ParamsDev& P, const double* __restrict__ lu,
+                                         WarpWS& ws, const double* x, int lane, long long& t_prev) {
   unsigned long long* pc = g_phase_clock;
-  long long t_prev = pc ? clock64() : 0;
+  t_prev = pc ? clock64() : 0;
   const int S = sh.S;
-  const int seg0 = bd.seg_base[prob];
   const int tv0 = sh.var0[S - 1] + 2 * (sh.N[S - 1] - 1);  // offset of tau
   const int gb = tv0 + S;                                  // gear positions
   const int ab = gb + 2 * (S - 1);                         // angles
@@ -1122,8 +1209,8 @@ __device__ double eval_cost_grad(const ShapeDev& sh, const ParamsDev& P, const B
     sc.dT = T / sh.N[s];
 #pragma unroll
     for (int k = 0; k < 6; k++) {
-      sc.head[k] = bd.ini[6 * (seg0 + s) + k];
-      sc.tail[k] = bd.fin[6 * (seg0 + s) + k];
+      sc.head[k] = sc.ini[k];
+      sc.tail[k] = sc.fin[k];
     }
     if (s > 0) {
       const double theta = x[ab + s - 1];
@@ -1253,8 +1340,43 @@ __device__ double eval_cost_grad(const ShapeDev& sh, const ParamsDev& P, const B
   }
   __syncwarp();
   PHASE_MARK(2)
-  // ---- constraint sweep
-  for (int s = 0; s < S; s++) sweep_segment<HAS_OBS>(sh, P, bd, prob, planes, ws, s, bd.singul[seg0 + s], lane);
+}
+
+// Part 2 (rank 0, after the team's sweep): merge of the sweep partials, adjoint MINCO product, gradient assembly, cost.
+__device__ __forceinline__ double eval_post(const ShapeDev& sh, const ParamsDev& P, const double* __restrict__ lu,
+                                            WarpWS& ws, const double* x, double* g, int lane, long long t_prev) {
+  unsigned long long* pc = g_phase_clock;
+  const int S = sh.S;
+  const int tv0 = sh.var0[S - 1] + 2 * (sh.N[S - 1] - 1);  // offset of tau
+  const int gb = tv0 + S;                                  // gear positions
+  const int ab = gb + 2 * (S - 1);                         // angles
+  const bool dense = sh.dense_minco != 0;
+  if (kTeam > 1) {
+    // fixed-order merge of the partial gradients: ((rank 0 + rank 1) + rank 2) + rank 3
+    const int pd = part_doubles_for(sh.rows);
+    for (int i = lane; i < 2 * sh.rows; i += 32) {
+      double v = ws.gd[i];
+#pragma unroll
+      for (int r = 1; r < kTeam; r++) v += ws.part[(size_t)(r - 1) * pd + i];
+      ws.gd[i] = v;
+    }
+  }
+  if (lane < S) {
+    double a[4];
+#pragma unroll
+    for (int q = 0; q < 4; q++) a[q] = ws.scal[4 * lane + q];
+#pragma unroll
+    for (int r = 1; r < kTeam; r++) {
+      const double* ps = ws.part + (size_t)(r - 1) * part_doubles_for(sh.rows) + 2 * sh.rows + 2 * 12 * kStageLd;
+#pragma unroll
+      for (int q = 0; q < 4; q++) a[q] += ps[4 * lane + q];
+    }
+    ws.seg[lane].gdT += a[0];
+    ws.seg[lane].pen[0] = a[1];
+    ws.seg[lane].pen[1] = a[2];
+    ws.seg[lane].pen[2] = a[3];
+  }
+  __syncwarp();
   PHASE_MARK(3)
 
   // ---- MinJerkOpt::calGrads_PT (poly_traj_utils.hpp:1037-1066)
@@ -1408,15 +1530,26 @@ __global__ void __launch_bounds__(32 * DFTPAV_MAX_WARPS, 1)
   extern __shared__ __align__(128) double smem[];
   __shared__ __align__(8) unsigned long long mbar;
   tma_load_block(smem, grp.lu, (unsigned)(sh.lu_doubles * sizeof(double)), &mbar);
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarp = blockDim.x >> 5;
-  WarpWS ws = carve_ws(smem + sh.lu_doubles + warp * sh.ws_doubles, sh);
-  for (int local = blockIdx.x * nwarp + warp; local < grp.count; local += gridDim.x * nwarp) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nteam = (blockDim.x >> 5) / kTeam;
+  const int team = warp / kTeam, rank = warp % kTeam;
+  WarpWS ws = carve_ws(smem + sh.lu_doubles + team * sh.ws_doubles, sh);
+  // every rank walks the same loop (one sweep call site); ranks > 0 only take part in the sweep
+  for (int local = blockIdx.x * nteam + team; local < grp.count; local += gridDim.x * nteam) {
     const int prob = grp.prob_id[local];
     const double* planes = grp.planes + (size_t)local * sh.H * 4 * sh.Mpad;
-    for (int i = lane; i < sh.n; i += 32) ws.x[i] = xin[(size_t)prob * bd.n_stride + i];
-    __syncwarp();
-    if (HAS_OBS) stage_obstacles(bd, prob, ws.obs, lane);
-    const double f = eval_cost_grad<HAS_OBS>(sh, P, bd, prob, planes, smem, ws, ws.x, ws.g, lane);
+    long long t_prev = 0;
+    if (rank == 0) {
+      for (int i = lane; i < sh.n; i += 32) ws.x[i] = xin[(size_t)prob * bd.n_stride + i];
+      __syncwarp();
+      stage_problem(sh, bd, prob, ws, lane);
+      if (HAS_OBS) stage_obstacles(bd, prob, ws.obs, lane);
+      eval_pre(sh, P, smem, ws, ws.x, lane, t_prev);
+    }
+    if (kTeam > 1) team_bar(1 + 2 * team);
+    sweep_rank<HAS_OBS>(sh, P, bd, prob, planes, ws, rank, lane);
+    if (kTeam > 1) team_bar(2 + 2 * team);
+    if (rank != 0) continue;
+    const double f = eval_post(sh, P, smem, ws, ws.x, ws.g, lane, t_prev);
     __syncwarp();
     if (lane == 0) fout[prob] = f;
     for (int i = lane; i < bd.n_stride; i += 32) gout[(size_t)prob * bd.n_stride + i] = i < sh.n ? ws.g[i] : 0.0;
@@ -1434,6 +1567,15 @@ __global__ void __launch_bounds__(32 * DFTPAV_MAX_WARPS, 1)
 // The history keeps 1/ys_j (one division when the pair is stored) and the recursion multiplies by it, instead of the
 // reference's division by ys_j in both loops (lbfgs.hpp:722, 733): <= 1.5 ulp per alpha_j / beta_j, and the ~70-cycle
 // division leaves the dependent chain of every history step.  -DDFTPAV_RECIP_YS=0 restores the divisions.
+// -DDFTPAV_HIST_PREFETCH=1: L2 prefetch of the whole history window at the start of the recursion;
+// =2: L1 prefetch DFTPAV_HIST_PD entries ahead inside both loops.
+#ifndef DFTPAV_HIST_PREFETCH
+#define DFTPAV_HIST_PREFETCH 0
+#endif
+#ifndef DFTPAV_HIST_PD
+#define DFTPAV_HIST_PD 4
+#endif
+constexpr int kHistPD = DFTPAV_HIST_PD;  // prefetch distance (history entries) of -DDFTPAV_HIST_PREFETCH=2
 #ifndef DFTPAV_RECIP_YS
 #define DFTPAV_RECIP_YS 1
 #endif
@@ -1466,11 +1608,35 @@ __device__ __forceinline__ void hist_load(HistStage<NPL>& st, const double* __re
 // Lean hand-scheduled version: no integer modulo (wrap by compare), scalar double buffer (one history entry in flight:
 // measured best on B200 — deeper rings spill and lose 25 %), trip count read through a shuffle so that the compiler
 // treats the loop as warp-uniform and emits bare SHFL instead of WARPSYNC-guarded collectives.
+// L1 prefetch of history entry jj (lines of s_jj and y_jj spread over the first lanes); costs no registers
+__device__ __forceinline__ void hist_prefetch_l1(const double* lm_s, const double* lm_y, int jj, int ld, int n, int lane) {
+  const int nl = ((n * 8 - 1) >> 7) + 2;
+  if (lane < 2 * nl) {
+    const int k = lane < nl ? lane : lane - nl;
+    const double* a = (lane < nl ? lm_s : lm_y) + (size_t)jj * ld + min(16 * k, n - 1);
+    asm volatile("prefetch.global.L1 [%0];" ::"l"(a));
+  }
+}
 template <int NPL>
 __device__ __noinline__ void two_loop(double* d_sm, double* alpha_sm, const double* __restrict__ lm_s,
                                       const double* __restrict__ lm_y, const double* __restrict__ lm_ys, int ld, int m,
                                       int end, int bound_in, int n, int lane, double ys, double yy) {
   const int bound = __shfl_sync(FULL, bound_in, 0);
+#if DFTPAV_HIST_PREFETCH == 1
+  {  // pull every (s_j, y_j) line this recursion will read into L2 now: the loops below then wait for L2, not DRAM
+    const int nl = ((n * 8 - 1) >> 7) + 2;  // 128-byte lines per vector (rows are 32-byte, not 128-byte aligned)
+    const int per = 2 * nl, total = bound * per;
+    for (int t = lane; t < total; t += 32) {
+      const int e = t / per, r = t - e * per;
+      int jj = end - 1 - e;
+      if (jj < 0) jj += m;
+      const int k = r < nl ? r : r - nl;
+      const double* v = (r < nl ? lm_s : lm_y) + (size_t)jj * ld;
+      const double* a = v + min(16 * k, n - 1);
+      asm volatile("prefetch.global.L2 [%0];" ::"l"(a));
+    }
+  }
+#endif
   double d[NPL], sc_[NPL], yc_[NPL], sn_[NPL], yn_[NPL];
   double ysc, ysn = 0.0;
   bool ok[NPL];
@@ -1498,6 +1664,13 @@ __device__ __noinline__ void two_loop(double* d_sm, double* alpha_sm, const doub
   for (int i = 0; i < bound; ++i) {
     int jn = j - 1;
     if (jn < 0) jn += m;
+#if DFTPAV_HIST_PREFETCH == 2
+    if (i + kHistPD < bound) {
+      int jp = j - kHistPD;
+      if (jp < 0) jp += m;
+      hist_prefetch_l1(lm_s, lm_y, jp, ld, n, lane);
+    }
+#endif
     if (i + 1 < bound) {
       const double* sj = lm_s + (size_t)jn * ld + lane;
       const double* yj = lm_y + (size_t)jn * ld + lane;
@@ -1542,6 +1715,13 @@ __device__ __noinline__ void two_loop(double* d_sm, double* alpha_sm, const doub
   for (int i = 0; i < bound; ++i) {
     int jn = j + 1;
     if (jn >= m) jn -= m;
+#if DFTPAV_HIST_PREFETCH == 2
+    if (i + kHistPD < bound) {
+      int jp = j + kHistPD;
+      if (jp >= m) jp -= m;
+      hist_prefetch_l1(lm_s, lm_y, jp, ld, n, lane);
+    }
+#endif
     if (i + 1 < bound) {
       const double* sj = lm_s + (size_t)jn * ld + lane;
       const double* yj = lm_y + (size_t)jn * ld + lane;
@@ -1589,9 +1769,10 @@ __global__ void __launch_bounds__(32 * DFTPAV_MAX_WARPS, 1)
   extern __shared__ __align__(128) double smem[];
   __shared__ __align__(8) unsigned long long mbar;
   tma_load_block(smem, grp.lu, (unsigned)(sh.lu_doubles * sizeof(double)), &mbar);
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarp = blockDim.x >> 5;
-  WarpWS ws = carve_ws(smem + sh.lu_doubles + warp * sh.ws_doubles, sh);
-  const int slot = blockIdx.x * nwarp + warp;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nteam = (blockDim.x >> 5) / kTeam;
+  const int team = warp / kTeam, rank = warp % kTeam;
+  WarpWS ws = carve_ws(smem + sh.lu_doubles + team * sh.ws_doubles, sh);
+  const int slot = blockIdx.x * nteam + team;
   const int n = sh.n;
   const int m = P.mem_size;
   double* lm_s = hist.s + (size_t)slot * hist.mem * hist.ld;
@@ -1610,6 +1791,10 @@ __global__ void __launch_bounds__(32 * DFTPAV_MAX_WARPS, 1)
 
   bool have_work = true;
   while (true) {
+    // ---- rank 0: take a problem if needed, run the first part of the evaluation, post the team's mailbox.
+    //      Every rank then walks through the ONE sweep call site; ranks > 0 do nothing else.
+    long long t_prev = 0;
+    if (rank == 0) {
     if (phase == PH_FETCH && have_work) {
       int local = 0;
       if (lane == 0) local = atomicAdd(work_counter, 1);
@@ -1623,28 +1808,37 @@ __global__ void __launch_bounds__(32 * DFTPAV_MAX_WARPS, 1)
 #pragma unroll 1
         for (int i = lane; i < n; i += 32) ws.x[i] = bd.x0[(size_t)prob * bd.n_stride + i];
         __syncwarp();
+        stage_problem(sh, bd, prob, ws, lane);
         if (HAS_OBS) stage_obstacles(bd, prob, ws.obs, lane);
         evals = 0;
         phase = PH_FIRST;
       }
     }
-#ifdef DFTPAV_PHASE_ALIGN
-    // loose phase alignment of the CTA: all warps enter the evaluation together, so the instruction stream of the
-    // (instruction-cache-bound) evaluation is fetched once for all of them; warps without work keep arriving
-    if (!__syncthreads_or(have_work ? 1 : 0)) break;
-    if (!have_work) continue;
-#else
-    if (!have_work) break;
-#endif
-
-    // ---------------- the single evaluation site
-    if (g_phase_clock) {
-      const long long now = clock64();
-      if (t_logic) {
-        if (lane == 0) atomicAdd(g_phase_clock + 7, (unsigned long long)(now - t_logic));
+    // (aligning the evaluations of groups of warps with a named barrier so that they share instruction fetches was
+    //  measured and lost 2-16 % for groups of 3-12 warps: profiles/README.md)
+    if (have_work) {
+      if (g_phase_clock) {
+        const long long now = clock64();
+        if (t_logic) {
+          if (lane == 0) atomicAdd(g_phase_clock + 7, (unsigned long long)(now - t_logic));
+        }
       }
+      eval_pre(sh, P, smem, ws, ws.x, lane, t_prev);
     }
-    fx = eval_cost_grad<HAS_OBS>(sh, P, bd, prob, planes, smem, ws, ws.x, ws.g, lane);
+    if (lane == 0) {
+      ws.ctl[0] = have_work ? 0ull : 1ull;
+      ws.ctl[1] = (unsigned long long)prob;
+      ws.ctl[2] = reinterpret_cast<unsigned long long>(planes);
+    }
+    __syncwarp();
+    }  // rank 0
+    if (kTeam > 1) team_bar(1 + 2 * team);
+    if (ws.ctl[0] != 0ull) break;  // no problems left: the whole team leaves
+    // ---------------- the single evaluation site: sweep by all ranks, then rank 0 finishes the evaluation
+    sweep_rank<HAS_OBS>(sh, P, bd, (int)ws.ctl[1], reinterpret_cast<const double*>(ws.ctl[2]), ws, rank, lane);
+    if (kTeam > 1) team_bar(2 + 2 * team);
+    if (rank != 0) continue;
+    fx = eval_post(sh, P, smem, ws, ws.x, ws.g, lane, t_prev);
     evals++;
     if (g_phase_clock) t_logic = clock64();
 
@@ -2059,6 +2253,7 @@ cudaError_t launch_prepare(int grid, int block, cudaStream_t st, const ShapeDev&
 
 int ws_doubles_host(int rows, int npad) { return ws_doubles_for(rows, npad); }
 int max_warps_host() { return DFTPAV_MAX_WARPS; }
+int team_size_host() { return kTeam; }
 
 cudaError_t set_phase_clock(unsigned long long* dev_ptr) {
   return cudaMemcpyToSymbol(g_phase_clock, &dev_ptr, sizeof(dev_ptr));

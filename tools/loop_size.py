@@ -6,7 +6,7 @@ subprocess.run(["cuobjdump", "-xelf", "all", os.path.abspath(so)], cwd=d, captur
 cub = [f for f in os.listdir(d) if f.startswith("dftpav_kernels") and "api" not in f][0]
 sass = subprocess.run(["nvdisasm", "-g", "-c", os.path.join(d, cub)], capture_output=True, text=True).stdout.split("\n")
 src = open("dftpav_b200/csrc/dftpav_kernels.cu").read().split("\n")
-l0 = [i for i, l in enumerate(src, 1) if "for (int pass = 0; pass < npass; pass++) {" in l][0]
+l0 = [i for i, l in enumerate(src, 1) if "for (int pass = pass0; pass < npass; pass += kTeam) {" in l][0]
 l1 = [i for i, l in enumerate(src, 1) if "// segment totals" in l][0]
 for kern in ("solve_kernelILb0",):
     start = [i for i, l in enumerate(sass) if l.startswith(".text.") and kern in l][0]
