@@ -40,6 +40,7 @@ cudaError_t launch_prepare(int grid, int block, cudaStream_t st, const ShapeDev&
 int ws_doubles_host(int rows, int npad);
 int max_warps_host();
 int team_size_host();
+int drain_help_host();
 cudaError_t set_phase_clock(unsigned long long* dev_ptr);
 }  // namespace dftpav
 
@@ -193,7 +194,7 @@ struct Group {
   ShapeDev sh;
   std::vector<int> probs;
   DevBuf d_prob_id, d_planes, d_lu, d_order;
-  int warps = 0, grid = 0;
+  int warps = 0, grid = 0, owners = 0;
   size_t smem = 0;
 };
 
@@ -777,9 +778,13 @@ int dftpav_upload_batch(dftpav_handle* h, const dftpav_batch* b) {
     int W = (int)std::min<size_t>(max_warps_host() / G, (cap - lu_bytes) / ws_bytes);
     const int want = (count + h->num_sms - 1) / h->num_sms;
     W = std::max(1, std::min(W, want));
+    grp->owners = W;
+    grp->grid = std::min((count + W - 1) / W, h->num_sms);
+    // drain-phase helpers work in pairs (warp ^ 1): an odd owner count gets one more warp that never takes a problem,
+    // so that e.g. a single trajectory per SM is evaluated by two warps from the start
+    if (drain_help_host() && (W & 1) && W + 1 <= max_warps_host() && lu_bytes + ws_bytes * (W + 1) <= cap) W += 1;
     grp->warps = W * G;
     grp->smem = lu_bytes + ws_bytes * W;
-    grp->grid = std::min((count + W - 1) / W, h->num_sms);
     max_slots = std::max(max_slots, grp->grid * W);
     max_npad = std::max(max_npad, sh.npad);
     // kernels
@@ -855,6 +860,7 @@ int dftpav_eval(dftpav_handle* h, const double* x, double* f, double* g) {
     gd.planes = grp->d_planes.as<double>();
     gd.lu = grp->d_lu.as<double>();
     gd.order = nullptr;
+    gd.owners = grp->owners;
     CU_TRY(h, launch_eval(h->has_obs, grp->grid, 32 * grp->warps, grp->smem, st, grp->sh, h->pd, h->bd, gd,
                           h->xin.as<double>(), h->fout.as<double>(), h->gout.as<double>(), h->o_coeffs.as<double>(),
                           h->o_dT.as<double>()));
@@ -899,6 +905,7 @@ int dftpav_optimize(dftpav_handle* h) {
       gd.planes = grp->d_planes.as<double>();
       gd.lu = grp->d_lu.as<double>();
       gd.order = nullptr;
+      gd.owners = grp->owners;
       CU_TRY(h, launch_eval(h->has_obs, grp->grid, 32 * grp->warps, grp->smem, st, grp->sh, h->pd, h->bd, gd,
                             h->x0.as<double>(), h->fout.as<double>(), h->gout.as<double>(), nullptr, nullptr));
       launches++;
@@ -955,6 +962,7 @@ int dftpav_optimize(dftpav_handle* h) {
     gd.planes = grp->d_planes.as<double>();
     gd.lu = grp->d_lu.as<double>();
     gd.order = lpt ? grp->d_order.as<int>() : nullptr;
+    gd.owners = grp->owners;
     CU_TRY(h, launch_solve(h->has_obs, grp->grid, 32 * grp->warps, grp->smem, st, grp->sh, h->pd, h->bd, gd, out, hist,
                            h->counter.as<int>() + gi));
     launches++;

@@ -86,6 +86,7 @@ struct GroupDev {
   const double* planes;         // tiled SoA: [count][H][4][Mpad]
   const double* lu;             // packed LU block of this shape
   const int* order;             // work list: order[w] = local index served w-th (longest-expected-first), or nullptr
+  int owners;                   // warps (teams) per CTA that take problems; warps beyond start as drain-phase helpers
 };
 
 struct OutDev {

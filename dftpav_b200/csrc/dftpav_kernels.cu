@@ -119,6 +119,17 @@ struct SegScratch {   // 38 doubles per segment
 #define DFTPAV_TEAM 1  // measured at config 3, batch 4096: 1: 202 k, 2: 182 k, 3: 177 k, 4: 162 k, 6: 149 k solves/s (profiles/README.md)
 #endif
 constexpr int kTeam = DFTPAV_TEAM;
+// Drain-phase helpers (kTeam == 1 only).  Every evaluation's sweep is accumulated as TWO fixed partial sums (odd passes
+// -> partial 0, even passes -> partial 1, merged in a fixed order), normally both by the warp that owns the problem.
+// When a warp finds the work queue empty while its neighbour (warp ^ 1) is still solving, it becomes the neighbour's
+// helper for the rest of the kernel and computes partial 1 of every evaluation (pair barriers A/B, `bar.sync id, 64`).
+// The result does not depend on who computed partial 1, so the solver stays deterministic.  The batch time at the
+// reference batch sizes is dominated by the last problems leaving the queue (profiles/README.md).
+#ifndef DFTPAV_DRAIN_HELP
+#define DFTPAV_DRAIN_HELP 1
+#endif
+constexpr bool kDrainHelp = (DFTPAV_DRAIN_HELP != 0) && kTeam == 1;
+constexpr int kPart = kTeam > 1 ? kTeam : (kDrainHelp ? 2 : 1);  // partial sums of the sweep
 static_assert(kTeam >= 1 && DFTPAV_MAX_WARPS % kTeam == 0 && (kTeam == 1 || (DFTPAV_MAX_WARPS / kTeam) * 2 + 1 <= 16), "team size");
 
 // what a rank accumulates into during the sweep
@@ -144,13 +155,17 @@ struct WarpWS {
   SegScratch* seg;  // [kMaxSeg]
   double* scal;   // [kMaxSeg][4] rank 0's sweep partials
   unsigned long long* ctl;  // [4] team mailbox: [0] exit flag, [1] problem id, [2] plane pointer of the current problem
-  double* part;   // (kTeam-1) x part_doubles: partial gdC, staging and scalars of ranks 1..kTeam-1
+  double* part;   // (kPart-1) x part_doubles: partial gdC, scalars (and staging) of partial sums 1..kPart-1
 };
-__host__ __device__ inline int part_doubles_for(int rows) { return 2 * rows + 2 * 12 * kStageLd + 4 * kMaxSeg; }
+// partial gdC + scalars (+ a private tile-staging buffer for the ranks of a static team; a drain-phase helper uses the
+// staging buffer of its own, idle, workspace)
+__host__ __device__ inline int part_doubles_for(int rows) {
+  return 2 * rows + 4 * kMaxSeg + (kTeam > 1 ? 2 * 12 * kStageLd : 0);
+}
 
 __host__ __device__ inline int ws_doubles_for(int rows, int npad) {
   return 6 * rows + 5 * npad + 2 * 12 * kStageLd + 8 + 4 * kObsCap + kMaxSeg * (int)(sizeof(SegScratch) / sizeof(double)) +
-         4 * kMaxSeg + 4 + (kTeam - 1) * part_doubles_for(rows);
+         4 * kMaxSeg + 4 + (kPart - 1) * part_doubles_for(rows);
 }
 
 __device__ __forceinline__ WarpWS carve_ws(double* base, const ShapeDev& sh) {
@@ -172,17 +187,21 @@ __device__ __forceinline__ WarpWS carve_ws(double* base, const ShapeDev& sh) {
   w.part = w.scal + 4 * kMaxSeg + 4;
   return w;
 }
-__device__ __forceinline__ SweepTarget sweep_target(const WarpWS& w, const ShapeDev& sh, int rank) {
+// my_stage: tile-staging buffer of the warp that EXECUTES the sweep (its own workspace's)
+__device__ __forceinline__ SweepTarget sweep_target(const WarpWS& w, const ShapeDev& sh, int rank, double* my_stage) {
   SweepTarget t;
   t.rank = rank;
   if (rank == 0) {
-    t.gd = w.gd, t.stage = w.stage, t.scal = w.scal;
+    t.gd = w.gd, t.stage = my_stage, t.scal = w.scal;
   } else {
     double* p = w.part + (size_t)(rank - 1) * part_doubles_for(sh.rows);
-    t.gd = p, t.stage = p + 2 * sh.rows, t.scal = p + 2 * sh.rows + 2 * 12 * kStageLd;
+    t.gd = p, t.scal = p + 2 * sh.rows;
+    t.stage = kTeam > 1 ? p + 2 * sh.rows + 4 * kMaxSeg : my_stage;
   }
   return t;
 }
+// pair barrier of the drain-phase helpers (owner + helper warp)
+__device__ __forceinline__ void pair_bar(int id) { asm volatile("bar.sync %0, 64;" ::"r"(id) : "memory"); }
 // named barriers of a team: A = "coefficients ready, sweep", B = "sweep partials ready"
 __device__ __forceinline__ void team_bar(int id) {
   asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(32 * kTeam) : "memory");
@@ -745,10 +764,10 @@ __device__ __forceinline__ void sweep_segment(const ShapeDev& sh, const ParamsDe
   double pn[kPlaneChunk][4];
   // rank r takes passes kTeam-1-r, 2*kTeam-1-r, ...: when the pass count is not a multiple of the team size the ranks
   // that are short one pass are the low ones, and rank 0 has the serial parts of the evaluation to do as well
-  const int pass0 = kTeam - 1 - tgt.rank;
+  const int pass0 = kPart - 1 - tgt.rank;
   if (pass0 < npass) load_plane_chunk(pn, pl + (size_t)(pass0 * nchunk) * 512);
 
-  for (int pass = pass0; pass < npass; pass += kTeam) {
+  for (int pass = pass0; pass < npass; pass += kPart) {
     const bool endpass = pass >= npass_reg;
     int piece, j, Kp;
     bool valid;
@@ -918,7 +937,7 @@ __device__ __forceinline__ void sweep_segment(const ShapeDev& sh, const ParamsDe
 
     // ---------------- stage C: software prefetch of the next pass's first plane chunk (registers are free now;
     //                  its consumers are most of a pass away)
-    if (pass + kTeam < npass) load_plane_chunk(pn, pl + (size_t)((pass + kTeam) * nchunk) * 512);
+    if (pass + kPart < npass) load_plane_chunk(pn, pl + (size_t)((pass + kPart) * nchunk) * 512);
 
     // ---------------- stage D: moving obstacles, velocity / acceleration / curvature limits, expansion
     double out[12];
@@ -1096,8 +1115,9 @@ __device__ __forceinline__ void sweep_segment(const ShapeDev& sh, const ParamsDe
 // The sweep of all segments by one rank of the team (ranks > 0 start from a zeroed partial gradient).
 template <bool HAS_OBS>
 __device__ __forceinline__ void sweep_rank(const ShapeDev& sh, const ParamsDev& P, const BatchDev& bd, int prob,
-                                           const double* __restrict__ planes, WarpWS& ws, int rank, int lane) {
-  const SweepTarget tgt = sweep_target(ws, sh, rank);
+                                           const double* __restrict__ planes, WarpWS& ws, int rank, double* my_stage,
+                                           int lane) {
+  const SweepTarget tgt = sweep_target(ws, sh, rank, my_stage);
   if (rank > 0) {
     for (int i = lane; i < 2 * sh.rows; i += 32) tgt.gd[i] = 0.0;
     __syncwarp();
@@ -1351,13 +1371,13 @@ __device__ __forceinline__ double eval_post(const ShapeDev& sh, const ParamsDev&
   const int gb = tv0 + S;                                  // gear positions
   const int ab = gb + 2 * (S - 1);                         // angles
   const bool dense = sh.dense_minco != 0;
-  if (kTeam > 1) {
-    // fixed-order merge of the partial gradients: ((rank 0 + rank 1) + rank 2) + rank 3
+  if (kPart > 1) {
+    // fixed-order merge of the partial gradients: ((partial 0 + partial 1) + partial 2) + ...
     const int pd = part_doubles_for(sh.rows);
     for (int i = lane; i < 2 * sh.rows; i += 32) {
       double v = ws.gd[i];
 #pragma unroll
-      for (int r = 1; r < kTeam; r++) v += ws.part[(size_t)(r - 1) * pd + i];
+      for (int r = 1; r < kPart; r++) v += ws.part[(size_t)(r - 1) * pd + i];
       ws.gd[i] = v;
     }
   }
@@ -1366,8 +1386,8 @@ __device__ __forceinline__ double eval_post(const ShapeDev& sh, const ParamsDev&
 #pragma unroll
     for (int q = 0; q < 4; q++) a[q] = ws.scal[4 * lane + q];
 #pragma unroll
-    for (int r = 1; r < kTeam; r++) {
-      const double* ps = ws.part + (size_t)(r - 1) * part_doubles_for(sh.rows) + 2 * sh.rows + 2 * 12 * kStageLd;
+    for (int r = 1; r < kPart; r++) {
+      const double* ps = ws.part + (size_t)(r - 1) * part_doubles_for(sh.rows) + 2 * sh.rows;
 #pragma unroll
       for (int q = 0; q < 4; q++) a[q] += ps[4 * lane + q];
     }
@@ -1546,7 +1566,11 @@ __global__ void __launch_bounds__(32 * DFTPAV_MAX_WARPS, 1)
       eval_pre(sh, P, smem, ws, ws.x, lane, t_prev);
     }
     if (kTeam > 1) team_bar(1 + 2 * team);
-    sweep_rank<HAS_OBS>(sh, P, bd, prob, planes, ws, rank, lane);
+    {
+      const int r_end = kTeam > 1 ? rank + 1 : kPart;  // without static teams the owner computes every partial sum
+#pragma unroll 1
+      for (int r = rank; r < r_end; r++) sweep_rank<HAS_OBS>(sh, P, bd, prob, planes, ws, r, ws.stage, lane);
+    }
     if (kTeam > 1) team_bar(2 + 2 * team);
     if (rank != 0) continue;
     const double f = eval_post(sh, P, smem, ws, ws.x, ws.g, lane, t_prev);
@@ -1768,10 +1792,16 @@ __global__ void __launch_bounds__(32 * DFTPAV_MAX_WARPS, 1)
                  const GroupDev grp, const OutDev out, const HistDev hist, int* __restrict__ work_counter) {
   extern __shared__ __align__(128) double smem[];
   __shared__ __align__(8) unsigned long long mbar;
-  tma_load_block(smem, grp.lu, (unsigned)(sh.lu_doubles * sizeof(double)), &mbar);
+  __shared__ int pair_state[DFTPAV_MAX_WARPS / 2 + 1];  // 0: both warps solve; 1 + (w & 1): warp w helps its neighbour
+  if (threadIdx.x < DFTPAV_MAX_WARPS / 2 + 1) pair_state[threadIdx.x] = 0;
+  tma_load_block(smem, grp.lu, (unsigned)(sh.lu_doubles * sizeof(double)), &mbar);  // (contains a __syncthreads)
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nteam = (blockDim.x >> 5) / kTeam;
   const int team = warp / kTeam, rank = warp % kTeam;
   WarpWS ws = carve_ws(smem + sh.lu_doubles + team * sh.ws_doubles, sh);
+  double* const my_stage = ws.stage;  // stays this warp's own, also while it helps its neighbour
+  const int pair = warp >> 1;
+  const bool has_partner = kDrainHelp && ((warp ^ 1) < nteam);
+  bool helper = false;
   const int slot = blockIdx.x * nteam + team;
   const int n = sh.n;
   const int m = P.mem_size;
@@ -1789,11 +1819,13 @@ __global__ void __launch_bounds__(32 * DFTPAV_MAX_WARPS, 1)
   const double* planes = nullptr;
   long long t_logic = 0;
 
-  bool have_work = true;
+  bool have_work = team < grp.owners;  // warps beyond the owner count only ever help their neighbour
   while (true) {
     // ---- rank 0: take a problem if needed, run the first part of the evaluation, post the team's mailbox.
     //      Every rank then walks through the ONE sweep call site; ranks > 0 do nothing else.
     long long t_prev = 0;
+    bool helped = false;
+    if (!helper) {
     if (rank == 0) {
     if (phase == PH_FETCH && have_work) {
       int local = 0;
@@ -1833,9 +1865,48 @@ __global__ void __launch_bounds__(32 * DFTPAV_MAX_WARPS, 1)
     __syncwarp();
     }  // rank 0
     if (kTeam > 1) team_bar(1 + 2 * team);
-    if (ws.ctl[0] != 0ull) break;  // no problems left: the whole team leaves
-    // ---------------- the single evaluation site: sweep by all ranks, then rank 0 finishes the evaluation
-    sweep_rank<HAS_OBS>(sh, P, bd, (int)ws.ctl[1], reinterpret_cast<const double*>(ws.ctl[2]), ws, rank, lane);
+    if (ws.ctl[0] != 0ull) {  // no problems left
+      if (has_partner) {
+        int old = 0;
+        if (lane == 0) old = atomicCAS(&pair_state[pair], 0, 1 + (warp & 1));
+        old = __shfl_sync(FULL, old, 0);
+        if (old == 0) {
+          // the neighbour is still solving: help it (partial sum 1 of each of its evaluations) until it is done
+          helper = true;
+          ws = carve_ws(smem + sh.lu_doubles + (warp ^ 1) * sh.ws_doubles, sh);
+          continue;
+        }
+        pair_bar(1 + 2 * pair);  // the neighbour is my helper and waits at barrier A: it sees my exit flag
+      }
+      break;
+    }
+    if (has_partner) {
+      int st = 0;
+      if (lane == 0) st = *reinterpret_cast<volatile int*>(&pair_state[pair]);
+      st = __shfl_sync(FULL, st, 0);
+      helped = st == 1 + ((warp ^ 1) & 1);
+      if (helped) pair_bar(1 + 2 * pair);  // coefficients, problem id and plane pointer are posted: release the helper
+    }
+    } else {
+      // helper: ws is the neighbour's workspace
+      pair_bar(1 + 2 * pair);
+      if (ws.ctl[0] != 0ull) break;
+    }
+    // ---------------- the single evaluation site: the sweep (all partial sums this warp is responsible for), then the
+    //                  owner finishes the evaluation
+    {
+      const int r_begin = helper ? 1 : rank;
+      const int r_end = kTeam > 1 ? rank + 1 : (helper ? 2 : (helped ? 1 : kPart));
+      const int prob_t = (int)ws.ctl[1];
+      const double* planes_t = reinterpret_cast<const double*>(ws.ctl[2]);
+#pragma unroll 1
+      for (int r = r_begin; r < r_end; r++) sweep_rank<HAS_OBS>(sh, P, bd, prob_t, planes_t, ws, r, my_stage, lane);
+    }
+    if (helper) {
+      pair_bar(2 + 2 * pair);
+      continue;
+    }
+    if (helped) pair_bar(2 + 2 * pair);
     if (kTeam > 1) team_bar(2 + 2 * team);
     if (rank != 0) continue;
     fx = eval_post(sh, P, smem, ws, ws.x, ws.g, lane, t_prev);
@@ -2254,6 +2325,7 @@ cudaError_t launch_prepare(int grid, int block, cudaStream_t st, const ShapeDev&
 int ws_doubles_host(int rows, int npad) { return ws_doubles_for(rows, npad); }
 int max_warps_host() { return DFTPAV_MAX_WARPS; }
 int team_size_host() { return kTeam; }
+int drain_help_host() { return kDrainHelp ? 1 : 0; }
 
 cudaError_t set_phase_clock(unsigned long long* dev_ptr) {
   return cudaMemcpyToSymbol(g_phase_clock, &dev_ptr, sizeof(dev_ptr));
