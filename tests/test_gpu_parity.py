@@ -199,6 +199,23 @@ def test_determinism_and_sharding(gpu_opt_factory):
     np.testing.assert_array_equal(full.iters[40:96], part.iters)
 
 
+@pytest.mark.parametrize("cfg", [3, 4])
+def test_helped_and_unhelped_solves_are_bit_identical(cfg, gpu_opt_factory):
+    """Drain-phase helpers: whether the second partial sum of a sweep is computed by the owning warp
+    or by its idle neighbour must not change a single bit.  Tiny batches exercise the extremes: one problem per CTA
+    with a helper-only warp from the first evaluation (B = 1, 3), pairs where one warp outlives the other (B = 2, 5),
+    against the same problems solved inside a batch large enough that the queue keeps every warp busy."""
+    big, prm = synth.make_config(cfg, B=600, seed=5)
+    opt = gpu_opt_factory(prm)
+    full = opt.solve(big)
+    for lo, hi in ((0, 1), (7, 9), (10, 13), (20, 25)):
+        part = opt.solve(big.slice(lo, hi, prm.traj_resolution, prm.des_traj_resolution))
+        np.testing.assert_array_equal(full.x[lo:hi], part.x)
+        np.testing.assert_array_equal(full.cost[lo:hi], part.cost)
+        np.testing.assert_array_equal(full.evals[lo:hi], part.evals)
+        np.testing.assert_array_equal(full.coeffs[lo:hi], part.coeffs)
+
+
 def test_full_size_properties(gpu_opt_factory):
     """BASELINE.json full size (config 3, batch 4096): size-independent properties of every solve."""
     batch, prm = synth.make_config(3, B=4096, seed=0)
