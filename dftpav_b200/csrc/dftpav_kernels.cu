@@ -1778,6 +1778,132 @@ __device__ __noinline__ void two_loop(double* d_sm, double* alpha_sm, const doub
   __syncwarp();
 }
 
+// Grouped variant of the two-loop recursion: bit-identical arithmetic, but the history entries are loaded GS at a time
+// into two register groups (the next group is in flight while the current one is consumed).  With one entry in flight
+// a history step costs one L2 round trip (~475 cycles measured for a lone warp: 8.5-9.5 ms for the 130-140-iteration
+// problems that set the batch time, half of it in this function); with GS entries the round trip is shared by GS steps.
+#ifndef DFTPAV_TWO_LOOP_GROUPED
+#define DFTPAV_TWO_LOOP_GROUPED 0  // measured: the register groups end up in local memory and a lone problem gets 2x SLOWER (17.5 vs 8.5 ms)
+#endif
+#ifndef DFTPAV_TL_GS
+#define DFTPAV_TL_GS 4  // history entries per register group
+#endif
+__device__ __forceinline__ int wrap_index(int x, int m) {
+  x %= m;
+  return x < 0 ? x + m : x;
+}
+template <int NPL, int GS>
+__device__ __noinline__ void two_loop_grouped(double* d_sm, double* alpha_sm, const double* __restrict__ lm_s,
+                                              const double* __restrict__ lm_y, const double* __restrict__ lm_ys, int ld,
+                                              int m, int end, int bound_in, int n, int lane, double ys, double yy) {
+  const int bound = __shfl_sync(FULL, bound_in, 0);
+  double d[NPL];
+  bool ok[NPL];
+#pragma unroll
+  for (int e = 0; e < NPL; e++) {
+    const int i = lane + 32 * e;
+    ok[e] = i < n;
+    d[e] = ok[e] ? d_sm[i] : 0.0;
+  }
+  double sA[GS][NPL], yA[GS][NPL], rA[GS], sB[GS][NPL], yB[GS][NPL], rB[GS];
+  // entries j, j+dir, ... (cnt of them, indices wrap in [0, m))
+  auto load = [&](double (&s_)[GS][NPL], double (&y_)[GS][NPL], double (&r_)[GS], int j, int dir, int cnt) {
+#pragma unroll
+    for (int q = 0; q < GS; q++) {
+      if (q < cnt) {
+        const double* sj = lm_s + (size_t)j * ld + lane;
+        const double* yj = lm_y + (size_t)j * ld + lane;
+#pragma unroll
+        for (int e = 0; e < NPL; e++) {
+          s_[q][e] = ok[e] ? sj[32 * e] : 0.0;
+          y_[q][e] = ok[e] ? yj[32 * e] : 0.0;
+        }
+        r_[q] = lm_ys[j];
+        j += dir;
+        if (j < 0) j += m;
+        if (j >= m) j -= m;
+      }
+    }
+  };
+  // first loop (lbfgs.hpp:719-724), newest to oldest
+  auto proc1 = [&](double (&s_)[GS][NPL], double (&y_)[GS][NPL], double (&r_)[GS], int j, int cnt) {
+#pragma unroll
+    for (int q = 0; q < GS; q++) {
+      if (q < cnt) {
+        double part = 0.0;
+#pragma unroll
+        for (int e = 0; e < NPL; e++) part += s_[q][e] * d[e];
+        const double a = DFTPAV_OVER_YS(warp_sum(part), r_[q]);
+        if (lane == 0) alpha_sm[j] = a;
+        const double na = -a;
+#pragma unroll
+        for (int e = 0; e < NPL; e++) d[e] += na * y_[q][e];
+        j -= 1;
+        if (j < 0) j += m;
+      }
+    }
+  };
+  // second loop (lbfgs.hpp:730-736), oldest to newest
+  auto proc2 = [&](double (&s_)[GS][NPL], double (&y_)[GS][NPL], double (&r_)[GS], int j, int cnt) {
+#pragma unroll
+    for (int q = 0; q < GS; q++) {
+      if (q < cnt) {
+        double part = 0.0;
+#pragma unroll
+        for (int e = 0; e < NPL; e++) part += y_[q][e] * d[e];
+        const double beta = DFTPAV_OVER_YS(warp_sum(part), r_[q]);
+        const double a = alpha_sm[j] - beta;
+#pragma unroll
+        for (int e = 0; e < NPL; e++) d[e] += a * s_[q][e];
+        j += 1;
+        if (j >= m) j -= m;
+      }
+    }
+  };
+  {
+    int jA = wrap_index(end - 1, m);
+    load(sA, yA, rA, jA, -1, min(GS, bound));
+#pragma unroll 1
+    for (int done = 0; done < bound; done += 2 * GS) {
+      const int cntA = min(GS, bound - done), cntB = min(GS, bound - done - GS);
+      const int jB = wrap_index(jA - GS, m);
+      if (cntB > 0) load(sB, yB, rB, jB, -1, cntB);
+      proc1(sA, yA, rA, jA, cntA);
+      if (cntB <= 0) break;
+      jA = wrap_index(jB - GS, m);
+      const int cntA2 = min(GS, bound - done - 2 * GS);
+      if (cntA2 > 0) load(sA, yA, rA, jA, -1, cntA2);
+      proc1(sB, yB, rB, jB, cntB);
+    }
+  }
+  const double scl = ys / yy;
+#pragma unroll
+  for (int e = 0; e < NPL; e++) d[e] *= scl;
+  __syncwarp();
+  {
+    int jA = wrap_index(end - bound, m);
+    load(sA, yA, rA, jA, +1, min(GS, bound));
+#pragma unroll 1
+    for (int done = 0; done < bound; done += 2 * GS) {
+      const int cntA = min(GS, bound - done), cntB = min(GS, bound - done - GS);
+      const int jB = wrap_index(jA + GS, m);
+      if (cntB > 0) load(sB, yB, rB, jB, +1, cntB);
+      proc2(sA, yA, rA, jA, cntA);
+      if (cntB <= 0) break;
+      jA = wrap_index(jB + GS, m);
+      const int cntA2 = min(GS, bound - done - 2 * GS);
+      if (cntA2 > 0) load(sA, yA, rA, jA, +1, cntA2);
+      proc2(sB, yB, rB, jB, cntB);
+    }
+  }
+#pragma unroll
+  for (int e = 0; e < NPL; e++) {
+    const int i = lane + 32 * e;
+    if (ok[e]) d_sm[i] = d[e];
+  }
+  __syncwarp();
+}
+
 // ------------------------------------------------------------------------------------------------
 // the solver: persistent warps, each runs lbfgs_optimize (lbfgs.hpp:440-751) for one problem at a time.
 // Written as a state machine around ONE call site of eval_cost_grad (keeps the kernel inside the instruction cache):
@@ -2052,9 +2178,15 @@ __global__ void __launch_bounds__(32 * DFTPAV_MAX_WARPS, 1)
             ++bound;
             bound = m < bound ? m : bound;
             end = (end + 1) % m;
+#if DFTPAV_TWO_LOOP_GROUPED
+            if (npl == 1) two_loop_grouped<1, DFTPAV_TL_GS>(ws.d, alpha_sm, lm_s, lm_y, lm_ys, ld, m, end, bound, n, lane, ys, yy);
+            else if (npl == 2) two_loop_grouped<2, DFTPAV_TL_GS>(ws.d, alpha_sm, lm_s, lm_y, lm_ys, ld, m, end, bound, n, lane, ys, yy);
+            else two_loop_grouped<3, 2>(ws.d, alpha_sm, lm_s, lm_y, lm_ys, ld, m, end, bound, n, lane, ys, yy);
+#else
             if (npl == 1) two_loop<1>(ws.d, alpha_sm, lm_s, lm_y, lm_ys, ld, m, end, bound, n, lane, ys, yy);
             else if (npl == 2) two_loop<2>(ws.d, alpha_sm, lm_s, lm_y, lm_ys, ld, m, end, bound, n, lane, ys, yy);
             else two_loop<3>(ws.d, alpha_sm, lm_s, lm_y, lm_ys, ld, m, end, bound, n, lane, ys, yy);
+#endif
           }
           step = 1.0;
           start_ls = true;
