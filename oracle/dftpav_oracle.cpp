@@ -1380,6 +1380,53 @@ int oracle_minco_generate(int N, const double* P, double dT, const double* head,
 }
 
 
+int oracle_minco_run(int N, const double* P, double dT, const double* head, const double* tail, const double* extra_gdC,
+                     double extra_gdT, double* c, double* energy, double* gdC0, double* gdT0, double* gdP, double* gdHead,
+                     double* gdTail, double* gdT) {
+  if (N < 2 || !P || !head || !tail) return DFTPAV_ERR_INVALID_ARG;
+  MinJerk J;
+  J.reset(N);
+  J.generate(P, dT, head, tail);
+  std::memcpy(c, J.c.data(), sizeof(double) * 12 * N);
+  *energy = J.getTrajJerkCost();
+  J.initSmGradCost();
+  std::memcpy(gdC0, J.gdC.data(), sizeof(double) * 12 * N);
+  *gdT0 = J.gdT;
+  if (extra_gdC)
+    for (int i = 0; i < 12 * N; i++) J.gdC[i] += extra_gdC[i];
+  J.gdT += extra_gdT;
+  J.calGrads_PT();
+  std::memcpy(gdP, J.gdP.data(), sizeof(double) * 2 * (N - 1));
+  std::memcpy(gdHead, J.gdHead, sizeof(double) * 6);
+  std::memcpy(gdTail, J.gdTail, sizeof(double) * 6);
+  *gdT = J.gdT;
+  return DFTPAV_OK;
+}
+
+int oracle_traj_eval(int N, const double* P, double dT, const double* head, const double* tail, int singul, double t,
+                     double* out) {
+  if (N < 2 || singul != 1) return DFTPAV_ERR_INVALID_ARG;  // the hot path evaluates obstacle trajectories with singul = +1
+  MinJerk J;
+  J.reset(N);
+  J.generate(P, dT, head, tail);
+  // Piece coefficient matrix = c.block<6,2>(6i,0)^T with the columns reversed (MINCO.hpp:991): highest power first
+  std::vector<double> dur(N, dT), cm(12 * (size_t)N);
+  for (int i = 0; i < N; i++)
+    for (int k = 0; k < 6; k++)
+      for (int col = 0; col < 2; col++) cm[12 * i + 2 * k + col] = J.c[2 * (6 * i + 5 - k) + col];
+  ObsTraj tr{N, dur.data(), cm.data(), 0.0, dT * N};
+  const V2 p = tr.getPos(t), v = tr.getdSigma(t), a = tr.getddSigma(t);
+  const M2 R = tr.getR(t), Rd = tr.getRdot(t);
+  out[0] = p.x, out[1] = p.y, out[2] = v.x, out[3] = v.y, out[4] = a.x, out[5] = a.y;
+  out[6] = R.a, out[7] = R.b, out[8] = R.c, out[9] = R.d;
+  out[10] = Rd.a, out[11] = Rd.b, out[12] = Rd.c, out[13] = Rd.d;
+  out[14] = std::nan("");  // Piece::getAngle is not on the hot path
+  double tl = t;
+  out[15] = tr.locate(tl);
+  out[16] = tl;
+  return DFTPAV_OK;
+}
+
 // ---- analytic test functions (shared, via C callback, with the reference-header build) ----
 double oracle_testfunc(int id, const double* x, double* g, int n) {
   double f = 0.0;

@@ -61,6 +61,17 @@ int oracle_minco_matrix(int N, double* dense, double* lu_band);
 int oracle_minco_generate(int N, const double* P, double dT, const double* head, const double* tail,
                           double* c);
 
+/* The MinJerkOpt call sequence of one cost evaluation (generate, getTrajJerkCost, initSmGradCost, [gdC += extra_gdC,
+ * gdT += extra_gdT], calGrads_PT): same signature as ref_minco_run in oracle/ref_minco_driver.cpp, which runs the
+ * reference's own header.  Matrices 6N x 2 row-major, P 2x(N-1) / head / tail 2x3 column-major. */
+int oracle_minco_run(int N, const double* P, double dT, const double* head, const double* tail,
+                     const double* extra_gdC, double extra_gdT, double* c, double* energy, double* gdC0,
+                     double* gdT0, double* gdP, double* gdHead, double* gdTail, double* gdT);
+/* The trajectory of a generate() call sampled at t with the oracle's obstacle-trajectory evaluators (same output layout
+ * as ref_traj_eval): pos(2) dsigma(2) ddsigma(2) R(4) Rdot(4) angle piece_index local_t. */
+int oracle_traj_eval(int N, const double* P, double dT, const double* head, const double* tail, int singul, double t,
+                     double* out);
+
 /* Synthetic-test analytic functions for oracle_lbfgs / the reference header: id 0 = Rosenbrock
  * chain, 1 = ill-conditioned quadratic, 2 = nonsmooth |x| mix.  Same code is compiled into
  * oracle/_ref so both sides evaluate bit-identical f,g. */

@@ -49,6 +49,7 @@ def lib() -> C.CDLL:
         L.oracle_lbfgs.argtypes = [C.c_int, dp, dp, C.c_void_p, C.c_void_p, P, C.POINTER(C.c_int), C.POINTER(C.c_int),
                                    dp, C.c_int]
         L.oracle_minco_matrix.argtypes = [C.c_int, dp, dp]
+        _minco_sig(L.oracle_minco_run, L.oracle_traj_eval)
         L.oracle_minco_generate.argtypes = [C.c_int, dp, C.c_double, dp, dp, dp]
         L.oracle_testfunc.argtypes = [C.c_int, dp, dp, C.c_int]
         L.oracle_testfunc.restype = C.c_double
@@ -63,6 +64,66 @@ def lib() -> C.CDLL:
         L.oracle_num_threads.argtypes = []
         _lib = L
     return _lib
+
+
+REF_MINCO_SO = os.path.join(os.path.dirname(os.path.abspath(__file__)), "_ref", "libref_minco.so")
+_ref_minco = None
+
+
+def _minco_sig(fn_run, fn_eval):
+    dp = capi.c_double_p
+    fn_run.argtypes = [C.c_int, dp, C.c_double, dp, dp, dp, C.c_double, dp, dp, dp, dp, dp, dp, dp, dp]
+    fn_run.restype = C.c_int
+    fn_eval.argtypes = [C.c_int, dp, C.c_double, dp, dp, C.c_int, C.c_double, dp]
+    fn_eval.restype = C.c_int
+
+
+def ref_minco_lib():
+    """The reference MINCO header (plan_utils/poly_traj_utils.hpp) compiled in place against oracle/eigen_shim2
+    (None if it is not built here and no prebuilt copy travelled)."""
+    global _ref_minco
+    if _ref_minco is None:
+        if not os.path.exists(REF_MINCO_SO):
+            try:
+                build()
+            except Exception:
+                return None
+        if not os.path.exists(REF_MINCO_SO):
+            return None
+        R = C.CDLL(REF_MINCO_SO)
+        _minco_sig(R.ref_minco_run, R.ref_traj_eval)
+        _ref_minco = R
+    return _ref_minco
+
+
+def minco_run(fn, N, P, dT, head, tail, extra_gdC, extra_gdT):
+    """Calls ref_minco_run / oracle_minco_run (same signature).  P [N-1][2], head/tail [3][2] (p, v, a rows),
+    extra_gdC [6N][2].  Returns a dict of arrays."""
+    dp = capi.c_double_p
+    P = np.ascontiguousarray(P, dtype=np.float64)
+    head = np.ascontiguousarray(head, dtype=np.float64)
+    tail = np.ascontiguousarray(tail, dtype=np.float64)
+    ex = np.ascontiguousarray(extra_gdC, dtype=np.float64)
+    c = np.zeros((6 * N, 2)); gdC0 = np.zeros((6 * N, 2)); gdP = np.zeros((N - 1, 2)); gdH = np.zeros((3, 2)); gdTl = np.zeros((3, 2))
+    en = C.c_double(); g0 = C.c_double(); gT = C.c_double()
+    rc = fn(N, P.ctypes.data_as(dp), float(dT), head.ctypes.data_as(dp), tail.ctypes.data_as(dp), ex.ctypes.data_as(dp),
+            float(extra_gdT), c.ctypes.data_as(dp), C.cast(C.byref(en), dp), gdC0.ctypes.data_as(dp),
+            C.cast(C.byref(g0), dp), gdP.ctypes.data_as(dp), gdH.ctypes.data_as(dp), gdTl.ctypes.data_as(dp),
+            C.cast(C.byref(gT), dp))
+    assert rc == 0
+    return dict(c=c, energy=np.array(en.value), gdC0=gdC0, gdT0=np.array(g0.value), gdP=gdP, gdHead=gdH, gdTail=gdTl,
+                gdT=np.array(gT.value))
+
+
+def traj_eval(fn, N, P, dT, head, tail, t):
+    dp = capi.c_double_p
+    P = np.ascontiguousarray(P, dtype=np.float64)
+    head = np.ascontiguousarray(head, dtype=np.float64)
+    tail = np.ascontiguousarray(tail, dtype=np.float64)
+    out = np.zeros(17)
+    rc = fn(N, P.ctypes.data_as(dp), float(dT), head.ctypes.data_as(dp), tail.ctypes.data_as(dp), 1, float(t), out.ctypes.data_as(dp))
+    assert rc == 0
+    return out
 
 
 def ref_lib():

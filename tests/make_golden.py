@@ -7,6 +7,9 @@
   oracle_eval.npz            : cost / gradient / coefficients of the oracle at fixed points of every BASELINE config
                                (regression pin of the restatement itself).
   solve_small.npz            : final results of full oracle solves on small batches of every config.
+  minco_reference_header.npz : outputs of the UNMODIFIED reference MINCO header (plan_utils/poly_traj_utils.hpp compiled
+                               in place into oracle/_ref/libref_minco.so against oracle/eigen_shim2): coefficients, jerk
+                               energy, gdC / gdT initialisation, calGrads_PT outputs, trajectory samples.
 usage: python tests/make_golden.py
 """
 import ctypes as C
@@ -26,6 +29,24 @@ LB_SETTINGS = [(256, 3, 1e-4, 1e-16), (8, 3, 1e-8, 1e-16), (5, 0, 0.0, 1e-10)]
 CAP = 600
 
 
+def minco_cases():
+    """Deterministic inputs of the MINCO fixture: (N, P, dT, head, tail, extra_gdC, extra_gdT)."""
+    rng = np.random.default_rng(20240917)
+    out = []
+    for N, dT in ((2, 0.8), (3, 0.4), (8, 1.3), (24, 0.9), (24, 2.2), (40, 0.55)):
+        P = np.cumsum(rng.normal(size=(N - 1, 2)) * 2.0, axis=0)
+        head = rng.normal(size=(3, 2)) * np.array([[5.0], [3.0], [1.0]])
+        tail = rng.normal(size=(3, 2)) * np.array([[5.0], [3.0], [1.0]])
+        tail[0] += P[-1]
+        out.append((N, P, dT, head, tail, rng.normal(size=(6 * N, 2)) * 10.0, float(rng.normal())))
+    return out
+
+
+def traj_times(case):
+    N, dT = case[0], case[2]
+    return [0.0, 0.37 * dT, dT, 1.5 * dT, (N - 0.25) * dT, N * dT, N * dT + 0.9]
+
+
 def analytic_x0(n):
     return np.linspace(-1.2, 1.0, n)
 
@@ -43,7 +64,23 @@ def run_ref(n, x0, fgptr, user, mem, past, delta, geps, max_iter=12000):
     return ret, f.value, x, ev.value, tr
 
 
+def make_minco():
+    R = O.ref_minco_lib()
+    assert R is not None, "oracle/_ref/libref_minco.so missing: run `make -C oracle ref` where /root/reference exists"
+    out = {}
+    for i, case in enumerate(minco_cases()):
+        got = O.minco_run(R.ref_minco_run, *case)
+        for k, v in got.items():
+            out[f"run{i}_{k}"] = v
+        for j, t in enumerate(traj_times(case)):
+            out[f"traj{i}_{j}"] = O.traj_eval(R.ref_traj_eval, case[0], case[1], case[2], case[3], case[4], t)
+    np.savez_compressed(os.path.join(GOLD, "minco_reference_header.npz"), **out)
+
+
 def main():
+    make_minco()
+    if "--minco-only" in sys.argv:
+        return
     os.makedirs(GOLD, exist_ok=True)
     L = O.lib()
     out = {}
