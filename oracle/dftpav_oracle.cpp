@@ -1,7 +1,7 @@
 // dftpav_oracle.cpp — CPU restatement of the Dftpav MINCO / L-BFGS hot path.
 //
-// TEST INFRASTRUCTURE ONLY (see dftpav_oracle.h).  "Parity unpinned" by reference fixtures; pinned by
-// the checks listed in dftpav_oracle.h.
+// TEST INFRASTRUCTURE ONLY (see dftpav_oracle.h).  Parity PINNED: bit-identical to the reference's own sources
+// compiled in place into oracle/_ref (see dftpav_oracle.h).
 //
 // Plain C++17, no Eigen.  Every function cites the reference lines it restates; evaluation order of
 // every floating-point expression follows the reference source (left-to-right association of the

@@ -6,16 +6,23 @@
  * there only as the checker / the CPU arm.  The product path (dftpav_b200/csrc, the C-ABI of
  * include/dftpav_b200.h) never calls into this library and has no CPU fallback.
  *
- * PARITY STATUS: "parity unpinned" by the reference's own tests — the reference ships no golden
- * vectors, KATs or fixtures for this path and its implementation
- * cannot be built here (needs Eigen3, ROS1, protobuf: all absent).  What pins this restatement
- * instead (tests/test_oracle_*.py):
- *   - the L-BFGS + Lewis-Overton restatement is compared against the UNMODIFIED reference header
- *     include/geo_utils2d/lbfgs.hpp compiled in place against a minimal test-only Eigen shim
- *     (oracle/_ref, built by oracle/Makefile) — iterates are bit-identical;
- *   - central finite differences of every cost term, MINCO identities (boundary PVA, waypoint
- *     interpolation, C4 continuity, jerk energy vs quadrature), banded LU vs dense solve;
- *   - an independent numpy restatement (tests/np_restatement.py).
+ * PARITY STATUS: PINNED against the reference's own source.  The reference ships no golden vectors, KATs or
+ * fixtures for this path and its build needs Eigen3, ROS1 and protobuf (all absent), but
+ * its hot-path SOURCES compile here, unmodified and where they lie under /root/reference, against a test-only
+ * Eigen-compatible layer (oracle/eigen_shim2) and inert stubs of the ROS / protobuf / RViz dependencies
+ * (oracle/ref_stubs); recipe oracle/Makefile, outputs only into oracle/_ref/:
+ *   - libref_optimizer.so = src/traj_optimizer.cpp + plan_manage/traj_optimizer.h + poly_traj_utils.hpp +
+ *     traj_container.hpp + lbfgs.hpp, driven through the reference's public API (setParam, setSurroundTrajs,
+ *     OptimizeTrajectory, getMinJerkOptPtr).  This restatement is BIT-IDENTICAL to it: cost, gradient and
+ *     coefficients of costFunctionCallback at initial and perturbed points, and final x / cost / return code /
+ *     success flag / iteration and evaluation counts of complete solves, on all five BASELINE configurations
+ *     (tests/test_oracle_vs_reference_optimizer.py, live and against tests/golden/optimizer_reference.npz);
+ *   - libref_minco.so (MinJerkOpt, BandedSystem, Piece, Trajectory) and libref_lbfgs.so (lbfgs.hpp alone, against
+ *     the older minimal shim): bit-identical as well (tests/test_oracle_vs_reference_minco.py, test_oracle_lbfgs.py).
+ * The caveat that remains: the Eigen layer evaluates every expression element by element in the written order, real
+ * Eigen may vectorise reductions differently (rounding-level only; the algorithm is ulp-chaotic anyway).
+ * Independent checks kept as well: central finite differences of every cost term, MINCO identities, banded LU vs
+ * dense solve, an independent numpy restatement of the cost (tests/np_restatement.py).
  *
  * Input structs are those of include/dftpav_b200.h (the oracle exports the same batch format so
  * tests and the baseline timer are backend-agnostic).

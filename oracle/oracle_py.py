@@ -126,6 +126,66 @@ def traj_eval(fn, N, P, dT, head, tail, t):
     return out
 
 
+REF_OPT_SO = os.path.join(os.path.dirname(os.path.abspath(__file__)), "_ref", "libref_optimizer.so")
+_ref_opt = None
+
+
+def ref_optimizer_lib():
+    """The reference's own optimizer (src/traj_optimizer.cpp + headers) compiled in place against oracle/eigen_shim2 and
+    oracle/ref_stubs (None if it is not built here and no prebuilt copy travelled)."""
+    global _ref_opt
+    if _ref_opt is None:
+        if not os.path.exists(REF_OPT_SO):
+            try:
+                build()
+            except Exception:
+                return None
+        if not os.path.exists(REF_OPT_SO):
+            return None
+        R = C.CDLL(REF_OPT_SO)
+        dp, ip = capi.c_double_p, C.POINTER(C.c_int)
+        P, Bt = C.POINTER(capi.Params), C.POINTER(capi.Batch)
+        R.ref_opt_solve.argtypes = [P, Bt, C.c_int, dp, dp, ip, ip, ip, ip, dp, dp]
+        R.ref_opt_eval.argtypes = [P, Bt, C.c_int, dp, dp, dp, dp, dp]
+        R.ref_opt_solve.restype = R.ref_opt_eval.restype = C.c_int
+        _ref_opt = R
+    return _ref_opt
+
+
+def ref_evaluate(prm: capi.Params, batch: TrajBatch, p: int, x: np.ndarray):
+    """The reference's costFunctionCallback at x -> (f, g, coeffs [rows][2], piece_dT [S])."""
+    R = ref_optimizer_lib()
+    n, rows, _ = problem_dims(prm, batch, p)
+    S = int(batch.seg_ptr[p + 1] - batch.seg_ptr[p])
+    x = np.ascontiguousarray(x, dtype=np.float64)
+    assert x.size == n
+    g = np.zeros(n); c = np.zeros((rows, 2)); dT = np.zeros(S); f = C.c_double()
+    cb = batch.as_c()
+    dp = capi.c_double_p
+    rc = R.ref_opt_eval(C.byref(prm), C.byref(cb), p, x.ctypes.data_as(dp), C.cast(C.byref(f), dp), g.ctypes.data_as(dp),
+                        c.ctypes.data_as(dp), dT.ctypes.data_as(dp))
+    if rc != 0:
+        raise RuntimeError(f"ref_opt_eval failed: {rc}")
+    return f.value, g, c, dT
+
+
+def ref_solve(prm: capi.Params, batch: TrajBatch, p: int):
+    """One full PolyTrajOptimizer::OptimizeTrajectory of the reference -> dict(x, cost, status, success, iters, evals,
+    coeffs, piece_dT)."""
+    R = ref_optimizer_lib()
+    n, rows, _ = problem_dims(prm, batch, p)
+    S = int(batch.seg_ptr[p + 1] - batch.seg_ptr[p])
+    x = np.zeros(n); c = np.zeros((rows, 2)); dT = np.zeros(S)
+    cost = C.c_double(); st = C.c_int(); ok = C.c_int(); it = C.c_int(); ev = C.c_int()
+    cb = batch.as_c()
+    dp = capi.c_double_p
+    rc = R.ref_opt_solve(C.byref(prm), C.byref(cb), p, x.ctypes.data_as(dp), C.cast(C.byref(cost), dp), C.byref(st),
+                         C.byref(ok), C.byref(it), C.byref(ev), c.ctypes.data_as(dp), dT.ctypes.data_as(dp))
+    if rc != 0:
+        raise RuntimeError(f"ref_opt_solve failed: {rc}")
+    return dict(x=x, cost=cost.value, status=st.value, success=ok.value, iters=it.value, evals=ev.value, coeffs=c, piece_dT=dT)
+
+
 def ref_lib():
     """The reference lbfgs.hpp compiled in place (None if it could not be built and no prebuilt copy travelled)."""
     global _ref

@@ -13,6 +13,10 @@ class VehicleParam {
   double length() const { return length_; }
   double wheel_base() const { return wheel_base_; }
   double d_cr() const { return d_cr_; }
+  void set_width(double v) { width_ = v; }
+  void set_length(double v) { length_ = v; }
+  void set_wheel_base(double v) { wheel_base_ = v; }
+  void set_d_cr(double v) { d_cr_ = v; }
   double width_ = 1.9, length_ = 4.88, wheel_base_ = 3.0, d_cr_ = 1.015;
 };
 }  // namespace common

@@ -10,7 +10,10 @@
   minco_reference_header.npz : outputs of the UNMODIFIED reference MINCO header (plan_utils/poly_traj_utils.hpp compiled
                                in place into oracle/_ref/libref_minco.so against oracle/eigen_shim2): coefficients, jerk
                                energy, gdC / gdT initialisation, calGrads_PT outputs, trajectory samples.
-usage: python tests/make_golden.py
+  optimizer_reference.npz    : outputs of the UNMODIFIED reference optimizer (src/traj_optimizer.cpp compiled in place into
+                               oracle/_ref/libref_optimizer.so): costFunctionCallback values / gradients / coefficients at
+                               fixed points and complete OptimizeTrajectory results, all five configs.
+usage: python tests/make_golden.py [--reference-only]
 """
 import ctypes as C
 import os
@@ -64,6 +67,32 @@ def run_ref(n, x0, fgptr, user, mem, past, delta, geps, max_iter=12000):
     return ret, f.value, x, ev.value, tr
 
 
+OPT_CASES = [(cfg, p) for cfg in (1, 2, 3, 4, 5) for p in (0, 1)]   # (config, problem) pairs of the optimizer fixture
+
+
+def optimizer_inputs(cfg, p):
+    """Deterministic inputs of the reference-optimizer fixture: the batch and two evaluation points."""
+    batch, prm = synth.make_config(cfg, B=2, seed=21)
+    x0 = O.initial_x(prm, batch, p)
+    xs = [x0, x0 + 0.04 * np.random.default_rng(100 * cfg + p).normal(size=x0.shape)]
+    return batch, prm, xs
+
+
+def make_optimizer():
+    assert O.ref_optimizer_lib() is not None, "oracle/_ref/libref_optimizer.so missing: run `make -C oracle ref`"
+    out = {}
+    for cfg, p in OPT_CASES:
+        batch, prm, xs = optimizer_inputs(cfg, p)
+        for k, x in enumerate(xs):
+            f, g, c, dT = O.ref_evaluate(prm, batch, p, x)
+            key = f"ev_{cfg}_{p}_{k}"
+            out[key + "_f"], out[key + "_g"], out[key + "_c"], out[key + "_dT"] = f, g, c, dT
+        r = O.ref_solve(prm, batch, p)
+        for name, v in r.items():
+            out[f"sv_{cfg}_{p}_{name}"] = v
+    np.savez_compressed(os.path.join(GOLD, "optimizer_reference.npz"), **out)
+
+
 def make_minco():
     R = O.ref_minco_lib()
     assert R is not None, "oracle/_ref/libref_minco.so missing: run `make -C oracle ref` where /root/reference exists"
@@ -79,7 +108,8 @@ def make_minco():
 
 def main():
     make_minco()
-    if "--minco-only" in sys.argv:
+    make_optimizer()
+    if "--reference-only" in sys.argv or "--minco-only" in sys.argv:
         return
     os.makedirs(GOLD, exist_ok=True)
     L = O.lib()
