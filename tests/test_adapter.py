@@ -74,3 +74,24 @@ def test_adapter_matches_batch_path(tmp_path, oracle, gpu_opt_factory):
         for s, N, dT in segs:
             assert int(N) == int(batch.piece_num[g0 + int(s)])
             assert float(dT) == float(sol.piece_dT[g0 + int(s)])
+
+
+REF_INC = "/root/reference/src/Plan/traj_planner/include"
+
+
+@pytest.mark.parametrize("mode", ["reference", "dropin"])
+def test_plan_manager_call_site_compiles_against_reference_header_and_dropin(mode, tmp_path):
+    """tests/dropin_callsite.cpp is the optimizer call sequence of the reference's plan manager
+    (traj_manager.cpp:29, 604-623).  The SAME text must compile against the reference's own
+    plan_manage/traj_optimizer.h and against this repository's drop-in header in reference-types mode (Eigen / ROS /
+    protobuf come from the test-only layers under oracle/)."""
+    if not os.path.isdir(REF_INC):
+        pytest.skip("reference tree not present")
+    cxx = "/usr/bin/g++" if os.path.exists("/usr/bin/g++") else "g++"
+    cmd = [cxx, "-std=c++17", "-c", "-w", "-I", os.path.join(ROOT, "oracle", "ref_stubs"), "-I",
+           os.path.join(ROOT, "oracle", "eigen_shim2"), "-I", REF_INC, os.path.join(ROOT, "tests", "dropin_callsite.cpp"),
+           "-o", str(tmp_path / "callsite.o")]
+    if mode == "reference":
+        cmd.insert(1, "-DUSE_REFERENCE_OPTIMIZER")
+    res = subprocess.run(cmd, capture_output=True, text=True)
+    assert res.returncode == 0, res.stderr[-3000:]
