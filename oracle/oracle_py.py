@@ -148,6 +148,8 @@ def ref_optimizer_lib():
         R.ref_opt_solve.argtypes = [P, Bt, C.c_int, dp, dp, ip, ip, ip, ip, dp, dp]
         R.ref_opt_eval.argtypes = [P, Bt, C.c_int, dp, dp, dp, dp, dp]
         R.ref_opt_solve.restype = R.ref_opt_eval.restype = C.c_int
+        R.ref_opt_solve_batch.argtypes = [P, Bt, C.c_int, C.c_int, C.c_int, dp, ip, ip, ip, ip]
+        R.ref_opt_solve_batch.restype = C.c_int
         _ref_opt = R
     return _ref_opt
 
@@ -184,6 +186,21 @@ def ref_solve(prm: capi.Params, batch: TrajBatch, p: int):
     if rc != 0:
         raise RuntimeError(f"ref_opt_solve failed: {rc}")
     return dict(x=x, cost=cost.value, status=st.value, success=ok.value, iters=it.value, evals=ev.value, coeffs=c, piece_dT=dT)
+
+
+def ref_solve_batch(prm: capi.Params, batch: TrajBatch, p0: int, p1: int, threads: int = 0):
+    """Complete reference solves of problems p0..p1-1, OpenMP over problems -> dict of [p1-p0] arrays."""
+    R = ref_optimizer_lib()
+    m = p1 - p0
+    cost = np.zeros(m); st = np.zeros(m, dtype=np.int32); ok = np.zeros(m, dtype=np.int32)
+    it = np.zeros(m, dtype=np.int32); ev = np.zeros(m, dtype=np.int32)
+    cb = batch.as_c()
+    ip = C.POINTER(C.c_int)
+    rc = R.ref_opt_solve_batch(C.byref(prm), C.byref(cb), p0, p1, threads, cost.ctypes.data_as(capi.c_double_p),
+                               st.ctypes.data_as(ip), ok.ctypes.data_as(ip), it.ctypes.data_as(ip), ev.ctypes.data_as(ip))
+    if rc != 0:
+        raise RuntimeError(f"ref_opt_solve_batch failed: {rc}")
+    return dict(cost=cost, status=st, success=ok, iters=it, evals=ev)
 
 
 def ref_lib():

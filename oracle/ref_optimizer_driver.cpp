@@ -17,6 +17,9 @@
 #include <memory>
 #include <sstream>
 #include <vector>
+#ifdef _OPENMP
+#include <omp.h>
+#endif
 
 #include "../include/dftpav_b200.h"
 
@@ -34,7 +37,7 @@ struct Spy {
   lbfgs_evaluate_t eval = nullptr;
   void* inst = nullptr;
 };
-static Spy g_spy;
+static thread_local Spy g_spy;  // one per host thread: ref_opt_solve_batch runs problems concurrently
 static double spy_evaluate(void* /*inst*/, const Eigen::VectorXd& x, Eigen::VectorXd& g) {
   g_spy.evals++;
   return g_spy.eval(g_spy.inst, x, g);
@@ -248,6 +251,34 @@ int ref_opt_dims(const dftpav_params* prm, const dftpav_batch* b, int p, int* n,
   if (rc != DFTPAV_OK) return rc;
   *n = S->n, *rows = S->rows;
   return DFTPAV_OK;
+}
+
+// Problems p0..p1-1, one complete OptimizeTrajectory each, OpenMP over problems (the reference itself is single-
+// threaded per solve).  Used by bench.py --impl reference to time the reference build.  Outputs are [p1-p0] arrays.
+int ref_opt_solve_batch(const dftpav_params* prm, const dftpav_batch* b, int p0, int p1, int threads, double* cost,
+                        int* status, int* success, int* iters, int* evals) {
+  if (!prm || !b || p0 < 0 || p1 > b->B || p0 > p1) return DFTPAV_ERR_INVALID_ARG;
+  if (!representable(prm)) return DFTPAV_ERR_UNSUPPORTED;
+  Quiet q;
+  int bad = 0;
+#ifdef _OPENMP
+  if (threads <= 0) threads = omp_get_max_threads();
+#pragma omp parallel for schedule(dynamic, 1) num_threads(threads)
+#endif
+  for (int p = p0; p < p1; p++) {
+    auto S = std::make_unique<Setup>();
+    if (build(prm, b, p, *S) != DFTPAV_OK) {
+#pragma omp atomic
+      bad++;
+      continue;
+    }
+    lbfgs::g_spy.mode = 0;
+    const bool ok = S->opt.OptimizeTrajectory(S->ini, S->fin, S->inner, S->Ts, S->hpolys, S->singuls, S->now, S->help_eps);
+    const int k = p - p0;
+    cost[k] = lbfgs::g_spy.cost, status[k] = lbfgs::g_spy.ret, success[k] = ok ? 1 : 0;
+    iters[k] = lbfgs::g_spy.iters, evals[k] = lbfgs::g_spy.evals;
+  }
+  return bad ? DFTPAV_ERR_INVALID_ARG : DFTPAV_OK;
 }
 
 }  // extern "C"
