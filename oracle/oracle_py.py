@@ -90,7 +90,10 @@ def ref_minco_lib():
                 return None
         if not os.path.exists(REF_MINCO_SO):
             return None
-        R = C.CDLL(REF_MINCO_SO)
+        try:
+            R = C.CDLL(REF_MINCO_SO)
+        except OSError:
+            return None
         _minco_sig(R.ref_minco_run, R.ref_traj_eval)
         _ref_minco = R
     return _ref_minco
@@ -142,7 +145,10 @@ def ref_optimizer_lib():
                 return None
         if not os.path.exists(REF_OPT_SO):
             return None
-        R = C.CDLL(REF_OPT_SO)
+        try:
+            R = C.CDLL(REF_OPT_SO)
+        except OSError:
+            return None
         dp, ip = capi.c_double_p, C.POINTER(C.c_int)
         P, Bt = C.POINTER(capi.Params), C.POINTER(capi.Batch)
         R.ref_opt_solve.argtypes = [P, Bt, C.c_int, dp, dp, ip, ip, ip, ip, dp, dp]

@@ -86,6 +86,31 @@ def _self_consistency(oracle, prm, batch, ref):
 
 
 @pytest.mark.parametrize("cfg", [1, 2, 3, 4, 5])
+def test_eval_parity_against_the_reference_build(cfg, oracle, gpu_opt_factory):
+    """The CUDA path against the reference's OWN code: oracle/_ref/libref_optimizer.so is src/traj_optimizer.cpp compiled in
+    place (test-only Eigen layer, oracle/Makefile) and travels to the GPU box prebuilt.  One costFunctionCallback of the
+    reference vs dftpav_eval at the initial and at a perturbed point: |df| <= 1e-12 max(1,|f|), |dg|_inf <= 1e-10
+    max(1,|g|_inf), coefficients to 1e-12 (the oracle itself is bit-identical to this build, so this is the same gate as
+    test_eval_parity_at_x0_and_perturbed with the restatement taken out of the loop)."""
+    if oracle.ref_optimizer_lib() is None:
+        pytest.skip("oracle/_ref/libref_optimizer.so did not travel")
+    B = 4
+    batch, prm = synth.make_config(cfg, B=B, seed=77)
+    opt = gpu_opt_factory(prm)
+    opt.upload(batch)
+    x0 = opt.initial_x(batch)
+    rng = np.random.default_rng(cfg)
+    for scale in (0.0, 0.03):
+        x = x0 + scale * rng.normal(size=x0.shape)
+        f, g = opt.evaluate(x)
+        for p in range(B):
+            n = batch.n_of(p)
+            fr, gr, cr, _ = oracle.ref_evaluate(prm, batch, p, x[p, :n])
+            assert abs(f[p] - fr) <= EVAL_F_TOL * max(1.0, abs(fr)), (cfg, p, f[p], fr)
+            assert np.abs(g[p, :n] - gr).max() <= EVAL_G_TOL * max(1.0, np.abs(gr).max()), (cfg, p)
+
+
+@pytest.mark.parametrize("cfg", [1, 2, 3, 4, 5])
 def test_solve_parity(cfg, oracle, gpu_opt_factory):
     B = 4 if cfg == 1 else 96
     CAP = 48
