@@ -1904,6 +1904,122 @@ __device__ __noinline__ void two_loop_grouped(double* d_sm, double* alpha_sm, co
   __syncwarp();
 }
 
+// cp.async variant of the two-loop recursion (OFF: measured 180.6 k vs 198.8 k solves/s, lone problem 9.0 vs 8.5 ms): the history
+// entries are copied global -> shared with cp.async (LDGSTS: no registers in flight) D-1 entries ahead into a ring that
+// lives in workspace arrays which are dead between two evaluations (b~ and gdC, contiguous).  Arithmetic and its order
+// are those of two_loop, so results are bit-identical; only the L2 round trip (measured ~475 cycles per history step
+// for a lone warp, profiles/README.md) moves off the dependent chain.  Enable with -DDFTPAV_TWO_LOOP_ASYNC=1.
+#ifndef DFTPAV_TWO_LOOP_ASYNC
+#define DFTPAV_TWO_LOOP_ASYNC 0
+#endif
+__device__ __forceinline__ void cp_async8(double* smem_dst, const double* gsrc) {
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(smem_addr(smem_dst)), "l"(gsrc) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int PENDING>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(PENDING) : "memory"); }
+
+template <int NPL, int D>
+__device__ __noinline__ void two_loop_async(double* d_sm, double* alpha_sm, double* ring, const double* __restrict__ lm_s,
+                                            const double* __restrict__ lm_y, const double* __restrict__ lm_ys, int ld, int m,
+                                            int end, int bound_in, int n, int lane, double ys, double yy) {
+  constexpr int kSlot = 64 * NPL + 2;  // s[32*NPL], y[32*NPL], 1/ys, pad
+  const int bound = __shfl_sync(FULL, bound_in, 0);
+  double d[NPL];
+  bool ok[NPL];
+#pragma unroll
+  for (int e = 0; e < NPL; e++) {
+    const int i = lane + 32 * e;
+    ok[e] = i < n;
+    d[e] = ok[e] ? d_sm[i] : 0.0;
+  }
+  // copies history entry j into ring slot `slot` (every lane its own elements, lane 0 the scalar) and closes the group
+  auto fetch = [&](int j, int slot, bool valid) {
+    if (valid) {
+      double* dst = ring + slot * kSlot;
+      const double* sj = lm_s + (size_t)j * ld;
+      const double* yj = lm_y + (size_t)j * ld;
+#pragma unroll
+      for (int e = 0; e < NPL; e++) {
+        const int i = lane + 32 * e;
+        if (ok[e]) {
+          cp_async8(dst + i, sj + i);
+          cp_async8(dst + 32 * NPL + i, yj + i);
+        }
+      }
+      if (lane == 0) cp_async8(dst + 64 * NPL, lm_ys + j);
+    }
+    cp_async_commit();  // an empty group keeps the group count uniform at the end of the history
+  };
+  // ---- first loop: newest to oldest
+  {
+    int jf = wrap_index(end - 1, m);  // next entry to fetch
+#pragma unroll
+    for (int q = 0; q < D - 1; q++) {
+      fetch(jf, q, q < bound);
+      jf = jf == 0 ? m - 1 : jf - 1;
+    }
+    int j = wrap_index(end - 1, m);
+#pragma unroll 1
+    for (int i = 0; i < bound; ++i) {
+      fetch(jf, (i + D - 1) % D, i + D - 1 < bound);
+      jf = jf == 0 ? m - 1 : jf - 1;
+      cp_async_wait<D - 1>();
+      __syncwarp();
+      const double* slot = ring + (i % D) * kSlot;
+      double part = 0.0;
+#pragma unroll
+      for (int e = 0; e < NPL; e++) part += (ok[e] ? slot[lane + 32 * e] : 0.0) * d[e];
+      const double a = DFTPAV_OVER_YS(warp_sum(part), slot[64 * NPL]);
+      if (lane == 0) alpha_sm[j] = a;
+      const double na = -a;
+#pragma unroll
+      for (int e = 0; e < NPL; e++) d[e] += na * (ok[e] ? slot[32 * NPL + lane + 32 * e] : 0.0);
+      __syncwarp();
+      j = j == 0 ? m - 1 : j - 1;
+    }
+  }
+  cp_async_wait<0>();
+  const double scl = ys / yy;
+#pragma unroll
+  for (int e = 0; e < NPL; e++) d[e] *= scl;
+  __syncwarp();
+  // ---- second loop: oldest to newest
+  {
+    int jf = wrap_index(end - bound, m);
+#pragma unroll
+    for (int q = 0; q < D - 1; q++) {
+      fetch(jf, q, q < bound);
+      jf = jf + 1 == m ? 0 : jf + 1;
+    }
+    int j = wrap_index(end - bound, m);
+#pragma unroll 1
+    for (int i = 0; i < bound; ++i) {
+      fetch(jf, (i + D - 1) % D, i + D - 1 < bound);
+      jf = jf + 1 == m ? 0 : jf + 1;
+      cp_async_wait<D - 1>();
+      __syncwarp();
+      const double* slot = ring + (i % D) * kSlot;
+      double part = 0.0;
+#pragma unroll
+      for (int e = 0; e < NPL; e++) part += (ok[e] ? slot[32 * NPL + lane + 32 * e] : 0.0) * d[e];
+      const double beta = DFTPAV_OVER_YS(warp_sum(part), slot[64 * NPL]);
+      const double a = alpha_sm[j] - beta;
+#pragma unroll
+      for (int e = 0; e < NPL; e++) d[e] += a * (ok[e] ? slot[lane + 32 * e] : 0.0);
+      __syncwarp();
+      j = j + 1 == m ? 0 : j + 1;
+    }
+  }
+  cp_async_wait<0>();
+#pragma unroll
+  for (int e = 0; e < NPL; e++) {
+    const int i = lane + 32 * e;
+    if (ok[e]) d_sm[i] = d[e];
+  }
+  __syncwarp();
+}
+
 // ------------------------------------------------------------------------------------------------
 // the solver: persistent warps, each runs lbfgs_optimize (lbfgs.hpp:440-751) for one problem at a time.
 // Written as a state machine around ONE call site of eval_cost_grad (keeps the kernel inside the instruction cache):
@@ -2178,7 +2294,14 @@ __global__ void __launch_bounds__(32 * DFTPAV_MAX_WARPS, 1)
             ++bound;
             bound = m < bound ? m : bound;
             end = (end + 1) % m;
-#if DFTPAV_TWO_LOOP_GROUPED
+#if DFTPAV_TWO_LOOP_ASYNC
+            // ring of 4 slots in the (dead between evaluations) b~ / gdC arrays: 4 * (64*npl + 2) doubles <= 4 * rows
+            if (npl == 1 && 4 * 66 <= 4 * sh.rows) two_loop_async<1, 4>(ws.d, alpha_sm, ws.bt, lm_s, lm_y, lm_ys, ld, m, end, bound, n, lane, ys, yy);
+            else if (npl == 2 && 4 * 130 <= 4 * sh.rows) two_loop_async<2, 4>(ws.d, alpha_sm, ws.bt, lm_s, lm_y, lm_ys, ld, m, end, bound, n, lane, ys, yy);
+            else if (npl == 1) two_loop<1>(ws.d, alpha_sm, lm_s, lm_y, lm_ys, ld, m, end, bound, n, lane, ys, yy);
+            else if (npl == 2) two_loop<2>(ws.d, alpha_sm, lm_s, lm_y, lm_ys, ld, m, end, bound, n, lane, ys, yy);
+            else two_loop<3>(ws.d, alpha_sm, lm_s, lm_y, lm_ys, ld, m, end, bound, n, lane, ys, yy);
+#elif DFTPAV_TWO_LOOP_GROUPED
             if (npl == 1) two_loop_grouped<1, DFTPAV_TL_GS>(ws.d, alpha_sm, lm_s, lm_y, lm_ys, ld, m, end, bound, n, lane, ys, yy);
             else if (npl == 2) two_loop_grouped<2, DFTPAV_TL_GS>(ws.d, alpha_sm, lm_s, lm_y, lm_ys, ld, m, end, bound, n, lane, ys, yy);
             else two_loop_grouped<3, 2>(ws.d, alpha_sm, lm_s, lm_y, lm_ys, ld, m, end, bound, n, lane, ys, yy);
