@@ -1093,6 +1093,61 @@ int line_search_lewisoverton(int n, double* x, double& f, double* g, double& stp
   }
 }
 
+// ---- design study for the GPU kernel (profiles/README.md, "Next"): the two-loop recursion in blocks of BS history
+// entries.  Inside a block the alphas follow from BS independent dot products with the direction at the START of the block
+// plus the Gram products s_i . y_k of the block (alpha_1 = (s_1.q - alpha_0 s_1.y_0) / ys_1, ...), so the BS reductions no
+// longer depend on each other.  Mathematically the reference's recursion; the rounding differs.  Enabled only by the
+// environment variable DFTPAV_ORACLE_BLOCKED_TWO_LOOP=BS (tests/test_oracle_lbfgs.py measures what it does to the results).
+inline int blocked_two_loop_size() {
+  static const int bs = [] { const char* e = std::getenv("DFTPAV_ORACLE_BLOCKED_TWO_LOOP"); return e ? std::atoi(e) : 0; }();
+  return bs;
+}
+inline void blocked_two_loop(double* d, const double* S, const double* Y, const double* ysv, double* alpha, int n, int m,
+                             int end, int bound, double scale, int BS) {
+  std::vector<int> idx(BS);
+  std::vector<double> u(BS), a(BS);
+  // first loop: newest to oldest
+  int j = end;
+  for (int i0 = 0; i0 < bound; i0 += BS) {
+    const int cnt = std::min(BS, bound - i0);
+    for (int k = 0; k < cnt; k++) {
+      j = (j + m - 1) % m;
+      idx[k] = j;
+      u[k] = vdot(&S[(size_t)j * n], d, n);
+    }
+    for (int k = 0; k < cnt; k++) {
+      double v = u[k];
+      for (int l = 0; l < k; l++) v -= a[l] * vdot(&S[(size_t)idx[k] * n], &Y[(size_t)idx[l] * n], n);
+      a[k] = v / ysv[idx[k]];
+      alpha[idx[k]] = a[k];
+    }
+    for (int k = 0; k < cnt; k++) {
+      const double* y = &Y[(size_t)idx[k] * n];
+      for (int q = 0; q < n; q++) d[q] -= a[k] * y[q];
+    }
+  }
+  for (int q = 0; q < n; q++) d[q] *= scale;
+  // second loop: oldest to newest, starting where the first loop stopped
+  for (int i0 = 0; i0 < bound; i0 += BS) {
+    const int cnt = std::min(BS, bound - i0);
+    for (int k = 0; k < cnt; k++) {
+      idx[k] = j;
+      u[k] = vdot(&Y[(size_t)j * n], d, n);
+      j = (j + 1) % m;
+    }
+    for (int k = 0; k < cnt; k++) {
+      double v = u[k];
+      for (int l = 0; l < k; l++) v += a[l] * vdot(&Y[(size_t)idx[k] * n], &S[(size_t)idx[l] * n], n);
+      const double beta = v / ysv[idx[k]];
+      a[k] = alpha[idx[k]] - beta;
+    }
+    for (int k = 0; k < cnt; k++) {
+      const double* sv = &S[(size_t)idx[k] * n];
+      for (int q = 0; q < n; q++) d[q] += a[k] * sv[q];
+    }
+  }
+}
+
 template <class Eval>
 int lbfgs_optimize(int n, double* x, double& f, Eval& eval, const LbfgsParam& param, int* iters_out, double* trace,
                    int trace_cap) {
@@ -1184,6 +1239,13 @@ int lbfgs_optimize(int n, double* x, double& f, Eval& eval, const LbfgsParam& pa
         bound = m < bound ? m : bound;
         end = (end + 1) % m;
         j = end;
+        if (blocked_two_loop_size() > 1) {
+          // EXPERIMENT (round-2 design study, never used by the tests' oracle calls): blocked form of the recursion
+          blocked_two_loop(d.data(), lm_s.data(), lm_y.data(), lm_ys.data(), lm_alpha.data(), n, m, end, bound, ys / yy,
+                           blocked_two_loop_size());
+          step = 1.0;
+          continue;
+        }
         for (i = 0; i < bound; ++i) {
           j = (j + m - 1) % m;
           lm_alpha[j] = vdot(&lm_s[(size_t)j * n], d.data(), n) / lm_ys[j];
