@@ -222,7 +222,7 @@ struct dftpav_handle {
   DevBuf seg_base, t_now, obs_ptr, obs_idx, singul, ini_raw, fin_raw, ini, fin, init_T, inner_base, inner_pts, samp_base,
       plane_ptr, planes_raw, obs_start, obs_dur, obs_piece_ptr, obs_piece_dur, obs_coeffs, obs_uniform, x0, xin, fout, gout;
   DevBuf o_x, o_cost, o_status, o_success, o_iters, o_evals, o_coeffs, o_dT, counter;
-  DevBuf hist_s, hist_y, hist_ys, hist_alpha, trace;
+  DevBuf hist_s, hist_y, hist_ys, hist_alpha, hist_gram, trace;
   int trace_cap = 0;
   int hist_ld = 0, hist_slots = 0;
   int upload_launches = 0;
@@ -511,7 +511,7 @@ int dftpav_destroy(dftpav_handle* h) {
                     &h->fin, &h->init_T, &h->inner_base, &h->inner_pts, &h->samp_base, &h->plane_ptr, &h->planes_raw,
                     &h->obs_start, &h->obs_dur, &h->obs_piece_ptr, &h->obs_piece_dur, &h->obs_coeffs, &h->obs_uniform, &h->x0, &h->xin,
                     &h->fout, &h->gout, &h->o_x, &h->o_cost, &h->o_status, &h->o_success, &h->o_iters, &h->o_evals,
-                    &h->o_coeffs, &h->o_dT, &h->counter, &h->hist_s, &h->hist_y, &h->hist_ys, &h->hist_alpha, &h->trace};
+                    &h->o_coeffs, &h->o_dT, &h->counter, &h->hist_s, &h->hist_y, &h->hist_ys, &h->hist_alpha, &h->hist_gram, &h->trace};
   for (DevBuf* b : bufs) b->release();
   for (auto& e : h->ev)
     if (e) cudaEventDestroy(e);
@@ -808,6 +808,7 @@ int dftpav_upload_batch(dftpav_handle* h, const dftpav_batch* b) {
   CU_TRY(h, h->hist_y.ensure(hbytes));
   CU_TRY(h, h->hist_ys.ensure(sizeof(double) * (size_t)max_slots * h->prm.lbfgs_mem_size));
   CU_TRY(h, h->hist_alpha.ensure(sizeof(double) * (size_t)max_slots * h->prm.lbfgs_mem_size));
+  CU_TRY(h, h->hist_gram.ensure(sizeof(double) * 4 * (size_t)max_slots * h->prm.lbfgs_mem_size));
 
   BatchDev& bd = h->bd;
   bd.seg_base = h->seg_base.as<int>();
@@ -951,6 +952,7 @@ int dftpav_optimize(dftpav_handle* h) {
   hist.y = h->hist_y.as<double>();
   hist.ys = h->hist_ys.as<double>();
   hist.alpha = h->hist_alpha.as<double>();
+  hist.gram = h->hist_gram.as<double>();
   hist.ld = h->hist_ld;
   hist.mem = h->prm.lbfgs_mem_size;
   int gi = 0;

@@ -107,6 +107,7 @@ struct HistDev {
   double* y;
   double* ys;       // [slots][mem]
   double* alpha;    // [slots][mem]
+  double* gram;     // [slots][mem][4] band of Gram products s_{k-1..k-3} . y_k (blocked two-loop only)
   int ld;           // npad_max
   int mem;
 };

@@ -2020,6 +2020,161 @@ __device__ __noinline__ void two_loop_async(double* d_sm, double* alpha_sm, doub
   __syncwarp();
 }
 
+// Blocked two-loop recursion (ROUND-2 CANDIDATE, OFF by default, compiled but NOT yet run on a GPU).  Four history entries
+// per step: the four dot products with the direction at the START of the block are reduced together (interleaved
+// butterflies: the latency of one), the alphas then follow from a 4x4 triangular recurrence with the Gram products
+// s_i . y_k of the block, which are cached in the history (hist.gram[k] = {s_{k-1}.y_k, s_{k-2}.y_k, s_{k-3}.y_k},
+// computed when entry k is the newest).  Mathematically the reference's recursion; rounding differs; the oracle study in
+// profiles/README.md shows the results stay inside the algorithm's own ulp-sensitivity.  -DDFTPAV_TWO_LOOP_BLOCKED=1.
+#ifndef DFTPAV_TWO_LOOP_BLOCKED
+#define DFTPAV_TWO_LOOP_BLOCKED 0
+#endif
+template <int K>
+__device__ __forceinline__ void warp_sum_k(double (&v)[K]) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+#pragma unroll
+    for (int k = 0; k < K; k++) v[k] += __shfl_xor_sync(FULL, v[k], o);
+  }
+}
+template <int NPL>
+__device__ __noinline__ void two_loop_blocked(double* d_sm, double* alpha_sm, const double* __restrict__ lm_s,
+                                              const double* __restrict__ lm_y, const double* __restrict__ lm_ys,
+                                              double* __restrict__ lm_gram, int ld, int m, int end, int bound_in, int n,
+                                              int lane, double ys, double yy) {
+  const int bound = __shfl_sync(FULL, bound_in, 0);
+  double d[NPL];
+  bool ok[NPL];
+#pragma unroll
+  for (int e = 0; e < NPL; e++) {
+    const int i = lane + 32 * e;
+    ok[e] = i < n;
+    d[e] = ok[e] ? d_sm[i] : 0.0;
+  }
+  double sv[4][NPL], yv[4][NPL], r[4];
+  int jx[4];
+  // ---- first loop: newest to oldest; block = entries j0, j0-1, j0-2, j0-3
+  int j0 = wrap_index(end - 1, m);
+  bool first = true;
+#pragma unroll 1
+  for (int i0 = 0; i0 < bound; i0 += 4) {
+    const int cnt = min(4, bound - i0);
+#pragma unroll
+    for (int k = 0; k < 4; k++) {
+      jx[k] = wrap_index(j0 - k, m);
+      const bool v = k < cnt;
+      const double* sj = lm_s + (size_t)jx[k] * ld + lane;
+      const double* yj = lm_y + (size_t)jx[k] * ld + lane;
+#pragma unroll
+      for (int e = 0; e < NPL; e++) {
+        sv[k][e] = (v && ok[e]) ? sj[32 * e] : 0.0;
+        yv[k][e] = (v && ok[e]) ? yj[32 * e] : 0.0;
+      }
+      r[k] = v ? lm_ys[jx[k]] : 0.0;  // 1/ys (DFTPAV_RECIP_YS) : entries beyond the window get alpha = 0
+    }
+    // Gram products of the block: g_ab = s_{j_a} . y_{j_b} (a older than b)
+    double g10, g20, g30, g21 = 0.0, g31 = 0.0, g32 = 0.0;
+    double u[4];
+#pragma unroll
+    for (int k = 0; k < 4; k++) {
+      u[k] = 0.0;
+#pragma unroll
+      for (int e = 0; e < NPL; e++) u[k] += sv[k][e] * d[e];
+    }
+    if (first) {
+      // the newest entry has no cached band yet: compute it here (three more reductions, interleaved with the four)
+      double w[7];
+#pragma unroll
+      for (int k = 0; k < 4; k++) w[k] = u[k];
+#pragma unroll
+      for (int k = 1; k < 4; k++) {
+        w[3 + k] = 0.0;
+#pragma unroll
+        for (int e = 0; e < NPL; e++) w[3 + k] += sv[k][e] * yv[0][e];
+      }
+      warp_sum_k<7>(w);
+#pragma unroll
+      for (int k = 0; k < 4; k++) u[k] = w[k];
+      g10 = w[4], g20 = w[5], g30 = w[6];
+      if (lane == 0) {
+        lm_gram[4 * jx[0] + 0] = g10;
+        lm_gram[4 * jx[0] + 1] = g20;
+        lm_gram[4 * jx[0] + 2] = g30;
+      }
+    } else {
+      warp_sum_k<4>(u);
+      g10 = lm_gram[4 * jx[0] + 0], g20 = lm_gram[4 * jx[0] + 1], g30 = lm_gram[4 * jx[0] + 2];
+    }
+    if (cnt > 2) g21 = lm_gram[4 * jx[1] + 0];
+    if (cnt > 3) g31 = lm_gram[4 * jx[1] + 1], g32 = lm_gram[4 * jx[2] + 0];
+    const double a0 = DFTPAV_OVER_YS(u[0], r[0]);
+    const double a1 = DFTPAV_OVER_YS(u[1] - a0 * g10, r[1]);
+    const double a2 = DFTPAV_OVER_YS(u[2] - a0 * g20 - a1 * g21, r[2]);
+    const double a3 = DFTPAV_OVER_YS(u[3] - a0 * g30 - a1 * g31 - a2 * g32, r[3]);
+    if (lane == 0) {
+      alpha_sm[jx[0]] = a0;
+      if (cnt > 1) alpha_sm[jx[1]] = a1;
+      if (cnt > 2) alpha_sm[jx[2]] = a2;
+      if (cnt > 3) alpha_sm[jx[3]] = a3;
+    }
+#pragma unroll
+    for (int e = 0; e < NPL; e++) d[e] = (((d[e] - a0 * yv[0][e]) - a1 * yv[1][e]) - a2 * yv[2][e]) - a3 * yv[3][e];
+    j0 = wrap_index(j0 - 4, m);
+    first = false;
+  }
+  const double scl = ys / yy;
+#pragma unroll
+  for (int e = 0; e < NPL; e++) d[e] *= scl;
+  __syncwarp();
+  // ---- second loop: oldest to newest; block = entries i0, i0+1, i0+2, i0+3
+  int b0 = wrap_index(end - bound, m);
+#pragma unroll 1
+  for (int i0 = 0; i0 < bound; i0 += 4) {
+    const int cnt = min(4, bound - i0);
+    double al[4];
+#pragma unroll
+    for (int k = 0; k < 4; k++) {
+      jx[k] = wrap_index(b0 + k, m);
+      const bool v = k < cnt;
+      const double* sj = lm_s + (size_t)jx[k] * ld + lane;
+      const double* yj = lm_y + (size_t)jx[k] * ld + lane;
+#pragma unroll
+      for (int e = 0; e < NPL; e++) {
+        sv[k][e] = (v && ok[e]) ? sj[32 * e] : 0.0;
+        yv[k][e] = (v && ok[e]) ? yj[32 * e] : 0.0;
+      }
+      r[k] = v ? lm_ys[jx[k]] : 0.0;
+      al[k] = v ? alpha_sm[jx[k]] : 0.0;
+    }
+    // p_ab = y_{i_a} . s_{i_b} (b older than a) = cached band of the NEWER entry i_a
+    double p10 = 0.0, p20 = 0.0, p21 = 0.0, p30 = 0.0, p31 = 0.0, p32 = 0.0;
+    if (cnt > 1) p10 = lm_gram[4 * jx[1] + 0];
+    if (cnt > 2) p21 = lm_gram[4 * jx[2] + 0], p20 = lm_gram[4 * jx[2] + 1];
+    if (cnt > 3) p32 = lm_gram[4 * jx[3] + 0], p31 = lm_gram[4 * jx[3] + 1], p30 = lm_gram[4 * jx[3] + 2];
+    double w[4];
+#pragma unroll
+    for (int k = 0; k < 4; k++) {
+      w[k] = 0.0;
+#pragma unroll
+      for (int e = 0; e < NPL; e++) w[k] += yv[k][e] * d[e];
+    }
+    warp_sum_k<4>(w);
+    const double c0 = al[0] - DFTPAV_OVER_YS(w[0], r[0]);
+    const double c1 = al[1] - DFTPAV_OVER_YS(w[1] + c0 * p10, r[1]);
+    const double c2 = al[2] - DFTPAV_OVER_YS(w[2] + c0 * p20 + c1 * p21, r[2]);
+    const double c3 = al[3] - DFTPAV_OVER_YS(w[3] + c0 * p30 + c1 * p31 + c2 * p32, r[3]);
+#pragma unroll
+    for (int e = 0; e < NPL; e++) d[e] = (((d[e] + c0 * sv[0][e]) + c1 * sv[1][e]) + c2 * sv[2][e]) + c3 * sv[3][e];
+    b0 = wrap_index(b0 + 4, m);
+  }
+#pragma unroll
+  for (int e = 0; e < NPL; e++) {
+    const int i = lane + 32 * e;
+    if (ok[e]) d_sm[i] = d[e];
+  }
+  __syncwarp();
+}
+
 // ------------------------------------------------------------------------------------------------
 // the solver: persistent warps, each runs lbfgs_optimize (lbfgs.hpp:440-751) for one problem at a time.
 // Written as a state machine around ONE call site of eval_cost_grad (keeps the kernel inside the instruction cache):
@@ -2294,7 +2449,14 @@ __global__ void __launch_bounds__(32 * DFTPAV_MAX_WARPS, 1)
             ++bound;
             bound = m < bound ? m : bound;
             end = (end + 1) % m;
-#if DFTPAV_TWO_LOOP_ASYNC
+#if DFTPAV_TWO_LOOP_BLOCKED
+            {
+              double* lm_gram = hist.gram + (size_t)slot * hist.mem * 4;
+              if (npl == 1) two_loop_blocked<1>(ws.d, alpha_sm, lm_s, lm_y, lm_ys, lm_gram, ld, m, end, bound, n, lane, ys, yy);
+              else if (npl == 2) two_loop_blocked<2>(ws.d, alpha_sm, lm_s, lm_y, lm_ys, lm_gram, ld, m, end, bound, n, lane, ys, yy);
+              else two_loop_blocked<3>(ws.d, alpha_sm, lm_s, lm_y, lm_ys, lm_gram, ld, m, end, bound, n, lane, ys, yy);
+            }
+#elif DFTPAV_TWO_LOOP_ASYNC
             // ring of 4 slots in the (dead between evaluations) b~ / gdC arrays: 4 * (64*npl + 2) doubles <= 4 * rows
             if (npl == 1 && 4 * 66 <= 4 * sh.rows) two_loop_async<1, 4>(ws.d, alpha_sm, ws.bt, lm_s, lm_y, lm_ys, ld, m, end, bound, n, lane, ys, yy);
             else if (npl == 2 && 4 * 130 <= 4 * sh.rows) two_loop_async<2, 4>(ws.d, alpha_sm, ws.bt, lm_s, lm_y, lm_ys, ld, m, end, bound, n, lane, ys, yy);
