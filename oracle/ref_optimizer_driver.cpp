@@ -62,6 +62,10 @@ inline int lbfgs_optimize_spy(Eigen::VectorXd& x, double& f, lbfgs_evaluate_t pr
     ret = LBFGS_CONVERGENCE;
   } else {
     ret = lbfgs_optimize(x, f, spy_evaluate, proc_stepbound, spy_progress, instance, param);
+    // the solver's iteration counter k is a local of lbfgs_optimize; the progress callback sees it after every
+    // completed iteration, so when a line search fails (negative return other than the iteration limit) the counter at
+    // exit is one more than the last value seen
+    if (ret < 0 && ret != LBFGSERR_MAXIMUMITERATION) g_spy.iters += 1;
   }
   g_spy.x = x;
   g_spy.cost = f;
