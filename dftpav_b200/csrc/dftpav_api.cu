@@ -41,6 +41,7 @@ int ws_doubles_host(int rows, int npad);
 int max_warps_host();
 int team_size_host();
 int drain_help_host();
+int two_loop_blocked_host();
 cudaError_t set_phase_clock(unsigned long long* dev_ptr);
 }  // namespace dftpav
 
@@ -808,7 +809,8 @@ int dftpav_upload_batch(dftpav_handle* h, const dftpav_batch* b) {
   CU_TRY(h, h->hist_y.ensure(hbytes));
   CU_TRY(h, h->hist_ys.ensure(sizeof(double) * (size_t)max_slots * h->prm.lbfgs_mem_size));
   CU_TRY(h, h->hist_alpha.ensure(sizeof(double) * (size_t)max_slots * h->prm.lbfgs_mem_size));
-  CU_TRY(h, h->hist_gram.ensure(sizeof(double) * 4 * (size_t)max_slots * h->prm.lbfgs_mem_size));
+  if (two_loop_blocked_host())  // only the (experimental) blocked two-loop keeps a Gram band beside the history
+    CU_TRY(h, h->hist_gram.ensure(sizeof(double) * 4 * (size_t)max_slots * h->prm.lbfgs_mem_size));
 
   BatchDev& bd = h->bd;
   bd.seg_base = h->seg_base.as<int>();

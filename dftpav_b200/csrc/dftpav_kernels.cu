@@ -2743,6 +2743,7 @@ int ws_doubles_host(int rows, int npad) { return ws_doubles_for(rows, npad); }
 int max_warps_host() { return DFTPAV_MAX_WARPS; }
 int team_size_host() { return kTeam; }
 int drain_help_host() { return kDrainHelp ? 1 : 0; }
+int two_loop_blocked_host() { return DFTPAV_TWO_LOOP_BLOCKED; }
 
 cudaError_t set_phase_clock(unsigned long long* dev_ptr) {
   return cudaMemcpyToSymbol(g_phase_clock, &dev_ptr, sizeof(dev_ptr));
