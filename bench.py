@@ -38,7 +38,7 @@ def parse_args():
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
-    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference", "_refbuild"])
     ap.add_argument("--config", type=int, default=3, help="BASELINE.json config id (3 = the config the metric is quoted on)")
     ap.add_argument("--batch", type=int, default=4096, help="problems per GPU")
     ap.add_argument("--cpu-sample", type=int, default=0, help="problems of the batch used for the CPU legs (0 = auto)")
@@ -128,19 +128,23 @@ def pin_batch(batch):
     return batch
 
 
-def cpu_leg(prm, batch, sample: int, threads: int, reps: int = 1):
-    """Times the CPU oracle (the reference's algorithm restated, oracle/) on `sample` problems with `threads` threads."""
+def cpu_leg(prm, batch, sample: int, threads: int, reps: int = 1, warm: bool = False):
+    """Times the CPU oracle (the reference's algorithm restated, oracle/) on `sample` problems with `threads` threads.
+    warm: one untimed pass over a few problems per thread first (page-in of the library, OpenMP team start-up, CPU clocks).
+    Returns (solves/s of the MEDIAN pass, median seconds, solution of the last pass)."""
     from oracle import oracle_py
 
     oracle_py.build()
-    best = None
+    if warm:
+        oracle_py.optimize(prm, batch, 0, min(sample, 2 * threads), threads=threads)
+    times = []
     sol = None
-    for _ in range(reps):
+    for _ in range(max(1, reps)):
         t0 = time.perf_counter()
         sol = oracle_py.optimize(prm, batch, 0, sample, threads=threads)
-        dt = time.perf_counter() - t0
-        best = dt if best is None else min(best, dt)
-    return sample / best, best, sol
+        times.append(time.perf_counter() - t0)
+    med = statistics.median(times)
+    return sample / med, med, sol
 
 
 # ------------------------------------------------------------------------------------------------
@@ -163,7 +167,7 @@ def run_reference(args):
         times.append(dt)
     total = sum(times)
     value = sample * args.steps / total
-    ref_build = reference_build_leg(prm, batch, cores)
+    ref_build = reference_build_leg(args, cores)
     line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": 1e3 * total / args.steps, "higher_is_better": True, "scaling": "weak",
@@ -183,24 +187,42 @@ def run_reference(args):
     print(json.dumps(line))
 
 
-def reference_build_leg(prm, batch, cores):
+def reference_build_leg(args, cores):
     """The reference's OWN optimizer source compiled in place (oracle/_ref/libref_optimizer.so, test-only Eigen layer) on a
     small sample: reported for completeness - its eager matrix layer allocates per expression and runs ~100x slower than
-    the bit-identical port, so timing it as THE baseline would flatter the GPU arm."""
+    the bit-identical port, so timing it as THE baseline would flatter the GPU arm.  Runs in a SUBPROCESS with a timeout:
+    whatever happens to it (round 1: a data race in the driver's cout sink aborted the process) cannot take the
+    reference arm's result line with it."""
     try:
-        from oracle import oracle_py as O
-        if O.ref_optimizer_lib() is None:
-            return {"available": False}
-        m = min(batch.B, 2 * cores)
-        t0 = time.perf_counter()
-        r = O.ref_solve_batch(prm, batch, 0, m, threads=cores)
-        dt = time.perf_counter() - t0
-        port = O.optimize(prm, batch, 0, m, threads=cores)
-        same = bool(np.array_equal(r["cost"], port.cost[:m]) and np.array_equal(r["iters"], port.iters[:m]))
-        return {"available": True, "value": m / dt, "unit": UNIT, "cores": cores, "sample": f"first {m} problems, one pass",
-                "bit_identical_to_port": same}
+        res = subprocess.run([sys.executable, os.path.abspath(__file__), "--impl", "_refbuild", "--config", str(args.config),
+                              "--batch", str(args.batch)], capture_output=True, text=True, timeout=300)
+        for ln in reversed(res.stdout.strip().splitlines()):
+            if ln.startswith("{"):
+                return json.loads(ln)
+        return {"available": False, "error": f"rc {res.returncode}: {res.stderr.strip()[-160:]}"}
     except Exception as e:  # never let the auxiliary leg break the bench line
         return {"available": False, "error": str(e)[:200]}
+
+
+def run_refbuild(args):
+    """Child process of reference_build_leg."""
+    from dftpav_b200 import synth
+    from oracle import oracle_py as O
+
+    cores = os.cpu_count() or 1
+    if O.ref_optimizer_lib() is None:
+        print(json.dumps({"available": False}))
+        return
+    batch, prm = synth.make_config(args.config, B=args.batch, seed=0)
+    m = min(batch.B, 2 * cores)
+    t0 = time.perf_counter()
+    r = O.ref_solve_batch(prm, batch, 0, m, threads=cores)
+    dt = time.perf_counter() - t0
+    port = O.optimize(prm, batch, 0, m, threads=cores)
+    same = bool(np.array_equal(r["cost"], port.cost[:m]) and np.array_equal(r["iters"], port.iters[:m])
+                and np.array_equal(r["status"], port.status[:m]))
+    print(json.dumps({"available": True, "value": m / dt, "unit": UNIT, "cores": cores,
+                      "sample": f"first {m} problems, one pass", "bit_identical_to_port": same}))
 
 
 # ------------------------------------------------------------------------------------------------
@@ -329,10 +351,11 @@ def run_ours(args):
         if not args.no_cpu_baseline:
             cores = os.cpu_count() or 1
             sample = args.cpu_sample or min(args.batch, max(64, 64 * cores))
-            v, dt, ref = cpu_leg(prm, batch, sample, cores)
+            v, dt, ref = cpu_leg(prm, batch, sample, cores, reps=3, warm=True)
             rel = np.abs(sol.cost[:sample] - ref.cost[:sample]) / np.maximum(1.0, np.abs(ref.cost[:sample]))
             line["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": cores, "kind": "port",
-                                    "sample": f"first {sample} problems of rank 0's batch, {dt:.1f} s wall, OpenMP over problems"}
+                                    "sample": f"first {sample} problems of rank 0's batch, warmed, median of 3 passes "
+                                              f"({dt:.2f} s each), OpenMP over problems"}
             line["parity_vs_oracle"] = {"problems": int(sample), "frac_cost_within_1e-5": float(np.mean(rel <= 1e-5)),
                                         "median_rel": float(np.median(rel)), "max_rel": float(rel.max()),
                                         "status_equal_frac": float(np.mean(sol.status[:sample] == ref.status[:sample]))}
@@ -346,6 +369,8 @@ def main():
     args = parse_args()
     if args.impl == "reference":
         run_reference(args)
+    elif args.impl == "_refbuild":
+        run_refbuild(args)
     else:
         run_ours(args)
 

@@ -189,10 +189,18 @@ int build(const dftpav_params* prm, const dftpav_batch* b, int p, Setup& S) {
   return DFTPAV_OK;
 }
 
-struct Quiet {  // the reference prints progress to std::cout
+// The reference prints progress to std::cout from inside OptimizeTrajectory (traj_optimizer.cpp:34,148,158,171).
+// ref_opt_solve_batch runs several solves concurrently, so the sink must hold NO state: a streambuf without a put area
+// whose overflow()/xsputn() discard their input.  (Round 1 redirected into one std::ostringstream shared by all OpenMP
+// threads: unsynchronised writes into the same stringbuf corrupted the heap and killed bench.py --impl reference.)
+struct NullBuf : std::streambuf {
+  int_type overflow(int_type c) override { return traits_type::not_eof(c); }
+  std::streamsize xsputn(const char*, std::streamsize n) override { return n; }
+};
+NullBuf g_null_buf;
+struct Quiet {
   std::streambuf* old;
-  std::ostringstream sink;
-  Quiet() : old(std::cout.rdbuf(sink.rdbuf())) {}
+  Quiet() : old(std::cout.rdbuf(&g_null_buf)) {}
   ~Quiet() { std::cout.rdbuf(old); }
 };
 
