@@ -26,6 +26,17 @@ LBFGS_CONVERGENCE = 0
 LBFGS_STOP = 1
 LBFGS_CANCELED = 2
 LBFGSERR_UNKNOWNERROR = -1024
+LBFGSERR_INVALID_N = -1023
+LBFGSERR_INVALID_MEMSIZE = -1022
+LBFGSERR_INVALID_GEPSILON = -1021
+LBFGSERR_INVALID_TESTPERIOD = -1020
+LBFGSERR_INVALID_DELTA = -1019
+LBFGSERR_INVALID_MINSTEP = -1018
+LBFGSERR_INVALID_MAXSTEP = -1017
+LBFGSERR_INVALID_FDECCOEFF = -1016
+LBFGSERR_INVALID_SCURVCOEFF = -1015
+LBFGSERR_INVALID_MACHINEPREC = -1014
+LBFGSERR_INVALID_MAXLINESEARCH = -1013
 LBFGSERR_INVALID_FUNCVAL = -1012
 LBFGSERR_MINIMUMSTEP = -1011
 LBFGSERR_MAXIMUMSTEP = -1010
@@ -34,6 +45,7 @@ LBFGSERR_MAXIMUMITERATION = -1008
 LBFGSERR_WIDTHTOOSMALL = -1007
 LBFGSERR_INVALIDPARAMETERS = -1006
 LBFGSERR_INCREASEGRADIENT = -1005
+PROBLEM_REJECTED = -2000  # precondition of OptimizeTrajectory violated (traj_optimizer.cpp:26-48), per problem
 
 c_double_p = C.POINTER(C.c_double)
 c_int32_p = C.POINTER(C.c_int32)
@@ -203,6 +215,7 @@ class Stats(C.Structure):
 EXPORTED_SYMBOLS = [
     "dftpav_default_params",
     "dftpav_batch_dims",
+    "dftpav_batch_check",
     "dftpav_initial_x",
     "dftpav_create",
     "dftpav_destroy",
@@ -218,25 +231,31 @@ EXPORTED_SYMBOLS = [
     "dftpav_version",
 ]
 
-_LIB = None
-LIB_PATH = os.path.join(os.path.dirname(os.path.abspath(__file__)), "csrc", "libdftpav_b200.so")
+_LIBS = {}
+_CSRC = os.path.join(os.path.dirname(os.path.abspath(__file__)), "csrc")
+LIB_PATH = os.path.join(_CSRC, "libdftpav_b200.so")
+# the strict-order VERIFICATION build of the same sources (-DDFTPAV_STRICT=1 -fmad=false, dftpav_strict.cuh): complete solves
+# bit-identical to the CPU oracle; used by tests/test_gpu_strict.py only
+STRICT_LIB_PATH = os.path.join(_CSRC, "libdftpav_b200_strict.so")
 
 
-def load_library() -> C.CDLL:
-    """Loads the in-tree CUDA library; raises (never falls back) if it has not been built."""
-    global _LIB
-    if _LIB is not None:
-        return _LIB
-    if not os.path.exists(LIB_PATH):
+def load_library(variant: str = "") -> C.CDLL:
+    """Loads the in-tree CUDA library (variant "" = the product, "strict" = the verification build, or a path);
+    raises (never falls back) if it has not been built."""
+    if variant in _LIBS:
+        return _LIBS[variant]
+    path = LIB_PATH if variant == "" else (STRICT_LIB_PATH if variant == "strict" else variant)
+    if not os.path.exists(path):
         raise RuntimeError(
-            f"{LIB_PATH} is missing: run `python -c 'import __graft_entry__ as g; g.build()'` "
+            f"{path} is missing: run `python -c 'import __graft_entry__ as g; g.build()'` "
             "(nvcc, sm_100a). There is no CPU fallback for the dftpav_b200 hot path."
         )
-    lib = C.CDLL(LIB_PATH)
+    lib = C.CDLL(path)
     H = C.c_void_p
     lib.dftpav_default_params.argtypes = [C.POINTER(Params)]
     lib.dftpav_default_params.restype = None
     lib.dftpav_batch_dims.argtypes = [C.POINTER(Params), C.POINTER(Batch), C.POINTER(Dims)]
+    lib.dftpav_batch_check.argtypes = [C.POINTER(Params), C.POINTER(Batch), c_int32_p]
     lib.dftpav_initial_x.argtypes = [C.POINTER(Params), C.POINTER(Batch), c_double_p]
     lib.dftpav_create.argtypes = [C.POINTER(Params), C.c_int, C.POINTER(H)]
     lib.dftpav_destroy.argtypes = [H]
@@ -252,9 +271,9 @@ def load_library() -> C.CDLL:
     lib.dftpav_last_error.restype = C.c_char_p
     lib.dftpav_version.argtypes = []
     lib.dftpav_version.restype = C.c_char_p
+    lib.dftpav_debug_force_banded.argtypes = [H, C.c_int]
+    lib.dftpav_debug_build_flags.argtypes = []
     for name in EXPORTED_SYMBOLS:
-        fn = getattr(lib, name)
-        if fn.restype is C.c_int:
-            pass
-    _LIB = lib
+        getattr(lib, name)
+    _LIBS[variant] = lib
     return lib

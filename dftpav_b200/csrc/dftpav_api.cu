@@ -37,10 +37,10 @@ cudaError_t launch_prepare(int grid, int block, cudaStream_t st, const ShapeDev&
                            const int* prob_id, int count, const int* seg_base, const int* singul, const double* ini_raw,
                            const double* fin_raw, const double* init_T, const long long* inner_base,
                            const double* inner_pts, double* ini, double* fin, double* x0, int n_stride);
-int ws_doubles_host(int rows, int npad);
+int ws_doubles_host(int rows, int npad, int S, int has_obs);
 int max_warps_host();
-int team_size_host();
-int drain_help_host();
+int virtual_ranks_host();
+int strict_build_host();
 int two_loop_blocked_host();
 cudaError_t set_phase_clock(unsigned long long* dev_ptr);
 }  // namespace dftpav
@@ -119,24 +119,28 @@ static const std::vector<double>& dense_minco_table(int N) {
   return cache.emplace(N, std::move(t)).first->second;
 }
 
+// LU factor of the banded collocation matrix for the fallback path (tables too large for the dense products) and for the
+// strict verification build.  Doolittle without pivoting, computed row by row ("ikj" order): row i is reduced by the
+// already final rows k = i-6 .. i-1 in ascending k, so every entry receives exactly the updates
+// A(i,j) -= L(i,k) U(k,j), k ascending, followed (below the diagonal) by one division by U(k,k) - the same rounded
+// operations per entry as BandedSystem::factorizeLU (poly_traj_utils.hpp:776-800), whose right-looking loop nest visits
+// them column by column; the factors are bit-identical (tests/test_minco_dense_table.py compares them with the oracle's).
 struct BandLU {
   int n;
   std::vector<double> d;  // band storage d[(i-j+6)*n + j], lower = upper = 6
   explicit BandLU(int N) : n(6 * N), d((size_t)13 * 6 * N, 0.0) {
     auto A = [&](int i, int j) -> double& { return d[(size_t)(i - j + 6) * n + j]; };
     fill_minco_matrix(N, A);
-    // factorizeLU: no pivoting, exact zeros skipped
-    for (int k = 0; k <= n - 2; k++) {
-      const int iM = std::min(k + 6, n - 1);
-      double cVl = A(k, k);
-      for (int i = k + 1; i <= iM; i++)
-        if (A(i, k) != 0.0) A(i, k) /= cVl;
-      const int jM = std::min(k + 6, n - 1);
-      for (int j = k + 1; j <= jM; j++) {
-        cVl = A(k, j);
-        if (cVl != 0.0)
-          for (int i = k + 1; i <= iM; i++)
-            if (A(i, k) != 0.0) A(i, j) -= A(i, k) * cVl;
+    for (int i = 1; i < n; i++) {
+      for (int k = std::max(0, i - 6); k < i; k++) {
+        double& lik = A(i, k);
+        if (lik == 0.0) continue;  // structural zero: no fill-in from row k (the reference skips exact zeros as well)
+        lik /= A(k, k);
+        const int jmax = std::min(k + 6, n - 1);
+        for (int j = k + 1; j <= jmax; j++) {
+          const double ukj = A(k, j);
+          if (ukj != 0.0) A(i, j) -= lik * ukj;
+        }
       }
     }
   }
@@ -194,12 +198,14 @@ struct DevBuf {
 struct Group {
   ShapeDev sh;
   std::vector<int> probs;
-  DevBuf d_prob_id, d_planes, d_lu, d_order;
-  int warps = 0, grid = 0, owners = 0;
+  DevBuf d_prob_id, d_planes, d_lu;
+  int warps = 0, grid = 0;
   size_t smem = 0;
 };
 
 inline int samples_of(int N, int K, int Kd) { return (N - 2) * (K + 1) + 2 * (Kd + 1); }
+
+constexpr int kMaxChunks = 16;  // chunks of the plane upload that dftpav_solve overlaps with the solve
 
 }  // namespace
 
@@ -209,21 +215,29 @@ struct dftpav_handle {
   int device = 0;
   int num_sms = 0;
   size_t smem_optin = 0;
-  cudaStream_t own_stream = nullptr, stream = nullptr;
-  cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
+  cudaStream_t own_stream = nullptr, stream = nullptr, copy_stream = nullptr;
+  cudaEvent_t ev[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+  cudaEvent_t ev_copy = nullptr;
+  int epoch = 0, n_chunks = 1, chunk = 1;   // plane-upload hand-shake (BatchDev::ready / laid)
+  int* h_epoch = nullptr;                    // pinned [kMaxChunks], all = epoch (source of the arrival-flag copies)
+  std::vector<long long> h_samp_base, h_plane_ptr;
+  long long total_planes = 0;
+  int uniform_H = 0;                         // -1: ragged corridor (h_plane_ptr)
+  bool force_banded = false;                 // test hook: banded LU substitutions even where the dense tables fit
   std::string err;
   bool uploaded = false, solved = false, has_obs = false;
   dftpav_dims dims{};
   dftpav_stats stats{};
   std::vector<Group*> groups, group_pool;
   // host copies needed later
-  std::vector<int> h_seg_ptr, h_piece_num, h_n, h_evalbytes;
-  std::vector<double> h_f0;
+  std::vector<int> h_seg_ptr, h_piece_num, h_n, h_evalbytes, h_status0;
+  int param_status = 0;   // LBFGSERR_INVALID_* of the parameter block (lbfgs.hpp:456-501), 0 = parameters usable
+  int n_rejected = 0;     // problems violating a reference precondition (traj_optimizer.cpp:26-48)
   // device buffers
   DevBuf seg_base, t_now, obs_ptr, obs_idx, singul, ini_raw, fin_raw, ini, fin, init_T, inner_base, inner_pts, samp_base,
       plane_ptr, planes_raw, obs_start, obs_dur, obs_piece_ptr, obs_piece_dur, obs_coeffs, obs_uniform, x0, xin, fout, gout;
   DevBuf o_x, o_cost, o_status, o_success, o_iters, o_evals, o_coeffs, o_dT, counter;
-  DevBuf hist_s, hist_y, hist_ys, hist_alpha, hist_gram, trace;
+  DevBuf hist_s, hist_y, hist_ys, hist_gram, trace, ready, laid;
   int trace_cap = 0;
   int hist_ld = 0, hist_slots = 0;
   int upload_launches = 0;
@@ -244,8 +258,27 @@ int fail(dftpav_handle* h, int code, const std::string& msg) {
       return fail(h, DFTPAV_ERR_CUDA, std::string(#call) + ": " + cudaGetErrorString(e__));              \
   } while (0)
 
-// Validation shared by dftpav_batch_dims / upload.  Returns 0 or an error; fills dims and (optionally) bad index.
-int validate(const dftpav_params* prm, const dftpav_batch* b, dftpav_dims* dims, std::string* why) {
+// lbfgs_optimize's own parameter checks, in its order (lbfgs.hpp:456-501): the code every solve of the batch would return
+int lbfgs_param_status(const dftpav_params& p) {
+  if (p.lbfgs_mem_size <= 0) return DFTPAV_LBFGSERR_INVALID_MEMSIZE;
+  if (p.lbfgs_g_epsilon < 0.0) return DFTPAV_LBFGSERR_INVALID_GEPSILON;
+  if (p.lbfgs_past < 0) return DFTPAV_LBFGSERR_INVALID_TESTPERIOD;
+  if (p.lbfgs_delta < 0.0) return DFTPAV_LBFGSERR_INVALID_DELTA;
+  if (p.lbfgs_min_step < 0.0) return DFTPAV_LBFGSERR_INVALID_MINSTEP;
+  if (p.lbfgs_max_step < p.lbfgs_min_step) return DFTPAV_LBFGSERR_INVALID_MAXSTEP;
+  if (!(p.lbfgs_f_dec_coeff > 0.0 && p.lbfgs_f_dec_coeff < 1.0)) return DFTPAV_LBFGSERR_INVALID_FDECCOEFF;
+  if (!(p.lbfgs_s_curv_coeff < 1.0 && p.lbfgs_s_curv_coeff > p.lbfgs_f_dec_coeff)) return DFTPAV_LBFGSERR_INVALID_SCURVCOEFF;
+  if (!(p.lbfgs_machine_prec > 0.0)) return DFTPAV_LBFGSERR_INVALID_MACHINEPREC;
+  if (p.lbfgs_max_linesearch <= 0) return DFTPAV_LBFGSERR_INVALID_MAXLINESEARCH;
+  return 0;
+}
+
+// Validation shared by dftpav_batch_dims / upload.  Returns 0 or an API error (malformed arrays, compiled-in limits);
+// fills dims.  A problem that violates a precondition of OptimizeTrajectory itself (traj_optimizer.cpp:26-48: a segment
+// with a single piece, initTs < mini_T) does NOT fail the batch: the reference rejects that ONE call (`return false`), so
+// the problem is flagged in rejected[p] and reported with status DFTPAV_PROBLEM_REJECTED / success 0.
+int validate(const dftpav_params* prm, const dftpav_batch* b, dftpav_dims* dims, std::string* why,
+             std::vector<unsigned char>* rejected) {
   auto bad = [&](int code, const std::string& s) {
     if (why) *why = s;
     return code;
@@ -257,33 +290,56 @@ int validate(const dftpav_params* prm, const dftpav_batch* b, dftpav_dims* dims,
                    !b->inner_pts || !b->planes))
     return bad(DFTPAV_ERR_INVALID_ARG, "null array in batch");
   if (prm->traj_resolution < 1 || prm->des_traj_resolution < 1) return bad(DFTPAV_ERR_INVALID_ARG, "resolution < 1");
-  if (prm->lbfgs_past < 0 || prm->lbfgs_past > 8) return bad(DFTPAV_ERR_UNSUPPORTED, "lbfgs_past must be in [0,8]");
-  if (prm->lbfgs_mem_size < 1) return bad(DFTPAV_ERR_INVALID_ARG, "lbfgs_mem_size < 1");
+  if (prm->lbfgs_past > 8) return bad(DFTPAV_ERR_UNSUPPORTED, "lbfgs_past > 8");
   if (prm->lbfgs_mem_size > 2 * 12 * kStageLd)  // alpha array lives in the sweep staging buffer
     return bad(DFTPAV_ERR_UNSUPPORTED, "lbfgs_mem_size > 408");
   if (!b->plane_cnt && b->uniform_H < 0) return bad(DFTPAV_ERR_INVALID_ARG, "uniform_H < 0");
+  if (b->B > 0 && b->seg_ptr[0] != 0) return bad(DFTPAV_ERR_INVALID_ARG, "seg_ptr[0] != 0");
+  if (rejected) rejected->assign((size_t)b->B, 0);
   int n_stride = 0, row_stride = 0;
   long long samples = 0;
   for (int p = 0; p < b->B; p++) {
     const int g0 = b->seg_ptr[p], g1 = b->seg_ptr[p + 1];
     const int S = g1 - g0;
-    if (S < 1) return bad(DFTPAV_ERR_INVALID_ARG, "problem " + std::to_string(p) + ": no segments");
+    if (S < 1) return bad(DFTPAV_ERR_INVALID_ARG, "problem " + std::to_string(p) + ": no segments (seg_ptr not increasing)");
     if (S > kMaxSeg) return bad(DFTPAV_ERR_UNSUPPORTED, "problem " + std::to_string(p) + ": more than 4 gear segments");
     int n = 0, rows = 0;
+    bool rej = false;
     for (int g = g0; g < g1; g++) {
       const int N = b->piece_num[g];
-      if (N < 2)  // traj_optimizer.cpp:38-41 "There is only a piece?"
-        return bad(DFTPAV_ERR_BAD_INPUT, "problem " + std::to_string(p) + ": segment with fewer than 2 pieces");
+      if (N < 1) return bad(DFTPAV_ERR_INVALID_ARG, "problem " + std::to_string(p) + ": piece_num < 1");
       if (N > kMaxPieces) return bad(DFTPAV_ERR_UNSUPPORTED, "problem " + std::to_string(p) + ": more than 64 pieces");
-      if (!(b->init_T[g] >= prm->mini_T))  // traj_optimizer.cpp:30-33
-        return bad(DFTPAV_ERR_BAD_INPUT, "problem " + std::to_string(p) + ": initTs < mini_T");
+      if (N < 2) rej = true;                            // traj_optimizer.cpp:38-41 "There is only a piece?"
+      if (!(b->init_T[g] >= prm->mini_T)) rej = true;   // traj_optimizer.cpp:30-33
       n += 2 * (N - 1);
       rows += 6 * N;
       samples += samples_of(N, prm->traj_resolution, prm->des_traj_resolution);
     }
+    if (rej && rejected) (*rejected)[p] = 1;
     n += S + 3 * (S - 1);
     n_stride = std::max(n_stride, n);
     row_stride = std::max(row_stride, rows);
+  }
+  if (b->plane_cnt)
+    for (long long q = 0; q < samples; q++)
+      if (b->plane_cnt[q] < 0) return bad(DFTPAV_ERR_INVALID_ARG, "negative plane_cnt");
+  // obstacle CSR arrays (setSurroundTrajs, traj_optimizer.h:108): checked here so that nothing downstream dereferences them blindly
+  if (b->obs_ptr && b->B > 0) {
+    if (b->obs_ptr[0] != 0) return bad(DFTPAV_ERR_INVALID_ARG, "obs_ptr[0] != 0");
+    for (int p = 0; p < b->B; p++)
+      if (b->obs_ptr[p + 1] < b->obs_ptr[p]) return bad(DFTPAV_ERR_INVALID_ARG, "obs_ptr not monotone");
+    if (b->obs_ptr[b->B] > 0) {
+      const int U = b->n_obs_pool;
+      if (U <= 0 || !b->obs_idx || !b->obs_start_time || !b->obs_duration || !b->obs_piece_ptr || !b->obs_piece_dur ||
+          !b->obs_coeffs)
+        return bad(DFTPAV_ERR_INVALID_ARG, "obstacle arrays missing");
+      if (b->obs_piece_ptr[0] != 0) return bad(DFTPAV_ERR_INVALID_ARG, "obs_piece_ptr[0] != 0");
+      for (int u = 0; u < U; u++)
+        if (b->obs_piece_ptr[u + 1] - b->obs_piece_ptr[u] < 1)
+          return bad(DFTPAV_ERR_INVALID_ARG, "obstacle " + std::to_string(u) + " has no pieces");
+      for (int k = 0; k < b->obs_ptr[b->B]; k++)
+        if (b->obs_idx[k] < 0 || b->obs_idx[k] >= U) return bad(DFTPAV_ERR_INVALID_ARG, "obs_idx out of range");
+    }
   }
   if (dims) {
     dims->B = b->B;
@@ -358,7 +414,6 @@ void free_groups(dftpav_handle* h) {
     g->d_prob_id.release();
     g->d_planes.release();
     g->d_lu.release();
-    g->d_order.release();
     delete g;
   }
   h->group_pool.clear();
@@ -435,12 +490,20 @@ void dftpav_default_params(dftpav_params* p) {
 }
 
 int dftpav_batch_dims(const dftpav_params* prm, const dftpav_batch* batch, dftpav_dims* dims) {
-  return validate(prm, batch, dims, nullptr);
+  return validate(prm, batch, dims, nullptr, nullptr);
+}
+
+int dftpav_batch_check(const dftpav_params* prm, const dftpav_batch* batch, int32_t* rejected) {
+  std::vector<unsigned char> rej;
+  const int rc = validate(prm, batch, nullptr, nullptr, &rej);
+  if (rc == DFTPAV_OK && rejected)
+    for (int p = 0; p < batch->B; p++) rejected[p] = rej[p];
+  return rc;
 }
 
 int dftpav_initial_x(const dftpav_params* prm, const dftpav_batch* b, double* x0) {
   dftpav_dims dims;
-  int rc = validate(prm, b, &dims, nullptr);
+  int rc = validate(prm, b, &dims, nullptr, nullptr);
   if (rc) return rc;
   if (!x0) return DFTPAV_ERR_INVALID_ARG;
   long long inner = 0;
@@ -499,6 +562,12 @@ int dftpav_create(const dftpav_params* prm, int device, dftpav_handle** out) {
   }
   h->stream = h->own_stream;
   for (auto& e : h->ev) cudaEventCreate(&e);
+  if (cudaStreamCreateWithFlags(&h->copy_stream, cudaStreamNonBlocking) != cudaSuccess ||
+      cudaEventCreateWithFlags(&h->ev_copy, cudaEventDisableTiming) != cudaSuccess ||
+      cudaMallocHost(&h->h_epoch, sizeof(int) * kMaxChunks) != cudaSuccess) {
+    dftpav_destroy(h);
+    return DFTPAV_ERR_CUDA;
+  }
   *out = h;
   return DFTPAV_OK;
 }
@@ -507,15 +576,19 @@ int dftpav_destroy(dftpav_handle* h) {
   if (!h) return DFTPAV_ERR_INVALID_ARG;
   cudaSetDevice(h->device);
   cudaStreamSynchronize(h->stream);
+  if (h->copy_stream) cudaStreamSynchronize(h->copy_stream);
   free_groups(h);
   DevBuf* bufs[] = {&h->seg_base, &h->t_now, &h->obs_ptr, &h->obs_idx, &h->singul, &h->ini_raw, &h->fin_raw, &h->ini,
                     &h->fin, &h->init_T, &h->inner_base, &h->inner_pts, &h->samp_base, &h->plane_ptr, &h->planes_raw,
                     &h->obs_start, &h->obs_dur, &h->obs_piece_ptr, &h->obs_piece_dur, &h->obs_coeffs, &h->obs_uniform, &h->x0, &h->xin,
                     &h->fout, &h->gout, &h->o_x, &h->o_cost, &h->o_status, &h->o_success, &h->o_iters, &h->o_evals,
-                    &h->o_coeffs, &h->o_dT, &h->counter, &h->hist_s, &h->hist_y, &h->hist_ys, &h->hist_alpha, &h->hist_gram, &h->trace};
+                    &h->o_coeffs, &h->o_dT, &h->counter, &h->hist_s, &h->hist_y, &h->hist_ys, &h->hist_gram, &h->trace, &h->ready, &h->laid};
   for (DevBuf* b : bufs) b->release();
   for (auto& e : h->ev)
     if (e) cudaEventDestroy(e);
+  if (h->ev_copy) cudaEventDestroy(h->ev_copy);
+  if (h->copy_stream) cudaStreamDestroy(h->copy_stream);
+  if (h->h_epoch) cudaFreeHost(h->h_epoch);
   if (h->own_stream) cudaStreamDestroy(h->own_stream);
   delete h;
   return DFTPAV_OK;
@@ -534,11 +607,19 @@ int dftpav_get_dims(const dftpav_handle* h, dftpav_dims* dims) {
   return DFTPAV_OK;
 }
 
-int dftpav_upload_batch(dftpav_handle* h, const dftpav_batch* b) {
-  if (!h) return DFTPAV_ERR_INVALID_ARG;
+}  // extern "C" (reopened below)
+
+namespace {
+
+// Everything of an upload except the corridor planes themselves (the dominant bytes): validation, prefixes, shape groups,
+// MINCO tables, small arrays, boundary-state / x0 kernel, launch configurations, history.  The planes follow through
+// issue_plane_copies() - before the solve for dftpav_upload_batch, AFTER the solve kernels have been launched for
+// dftpav_solve, so that the copy runs under the solve (the kernels wait per upload chunk, layout_problem()).
+int upload_impl(dftpav_handle* h, const dftpav_batch* b, int n_chunks_wanted) {
   std::string why;
   dftpav_dims dims;
-  int rc = validate(&h->prm, b, &dims, &why);
+  std::vector<unsigned char> rejected;
+  int rc = validate(&h->prm, b, &dims, &why, &rejected);
   if (rc) return fail(h, rc, why);
   CU_TRY(h, cudaSetDevice(h->device));
   cudaStream_t st = h->stream;
@@ -546,6 +627,7 @@ int dftpav_upload_batch(dftpav_handle* h, const dftpav_batch* b) {
   h->solved = false;
   recycle_groups(h);
   h->dims = dims;
+  h->param_status = lbfgs_param_status(h->prm);
   std::memset(&h->stats, 0, sizeof(h->stats));
   CU_TRY(h, cudaEventRecord(h->ev[0], st));
   const int B = b->B, G = dims.seg_total;
@@ -555,12 +637,16 @@ int dftpav_upload_batch(dftpav_handle* h, const dftpav_batch* b) {
 
   // ---- per-problem prefixes and shape groups
   std::vector<int> seg_base(B);
-  std::vector<long long> samp_base(B), inner_base(B);
+  std::vector<long long>& samp_base = h->h_samp_base;
+  std::vector<long long> inner_base(B);
+  samp_base.assign((size_t)B + 1, 0);
   std::map<std::vector<int>, Group*> by_shape;
   long long samp = 0, inner = 0;
   h->h_seg_ptr.assign(b->seg_ptr, b->seg_ptr + B + 1);
   h->h_piece_num.assign(b->piece_num, b->piece_num + G);
   h->h_n.resize(B);
+  h->h_status0.assign(B, 0);
+  h->n_rejected = 0;
   for (int p = 0; p < B; p++) {
     const int g0 = b->seg_ptr[p], g1 = b->seg_ptr[p + 1];
     seg_base[p] = g0;
@@ -575,6 +661,12 @@ int dftpav_upload_batch(dftpav_handle* h, const dftpav_batch* b) {
     }
     n += (g1 - g0) + 3 * (g1 - g0 - 1);
     h->h_n[p] = n;
+    if (rejected[p]) {  // the reference returns false for this call alone (traj_optimizer.cpp:26-48)
+      h->h_status0[p] = DFTPAV_PROBLEM_REJECTED;
+      h->n_rejected++;
+      continue;
+    }
+    if (h->param_status) h->h_status0[p] = h->param_status;
     Group*& grp = by_shape[key];
     if (!grp) {
       if (!h->group_pool.empty()) {
@@ -587,26 +679,25 @@ int dftpav_upload_batch(dftpav_handle* h, const dftpav_batch* b) {
     }
     grp->probs.push_back(p);
   }
+  samp_base[B] = samp;
   // plane prefix (only for ragged corridors)
-  std::vector<long long> plane_ptr;
-  long long total_planes;
+  std::vector<long long>& plane_ptr = h->h_plane_ptr;
+  plane_ptr.clear();
   if (b->plane_cnt) {
     plane_ptr.resize(Q + 1);
     plane_ptr[0] = 0;
-    for (long long q = 0; q < Q; q++) {
-      if (b->plane_cnt[q] < 0) return fail(h, DFTPAV_ERR_INVALID_ARG, "negative plane_cnt");
-      plane_ptr[q + 1] = plane_ptr[q] + b->plane_cnt[q];
-    }
-    total_planes = plane_ptr[Q];
+    for (long long q = 0; q < Q; q++) plane_ptr[q + 1] = plane_ptr[q] + b->plane_cnt[q];
+    h->total_planes = plane_ptr[Q];
   } else {
-    total_planes = Q * b->uniform_H;
+    h->total_planes = Q * b->uniform_H;
   }
+  h->uniform_H = b->plane_cnt ? -1 : b->uniform_H;
   // algorithmic bytes per evaluation of each problem
   h->h_evalbytes.resize(B);
   for (int p = 0; p < B; p++) {
     const int g0 = b->seg_ptr[p], g1 = b->seg_ptr[p + 1];
-    long long q0 = samp_base[p], q1 = (p + 1 < B) ? samp_base[p + 1] : Q;
-    long long planes = b->plane_cnt ? plane_ptr[q1] - plane_ptr[q0] : (q1 - q0) * b->uniform_H;
+    const long long q0 = samp_base[p], q1 = samp_base[p + 1];
+    const long long planes = b->plane_cnt ? plane_ptr[q1] - plane_ptr[q0] : (q1 - q0) * b->uniform_H;
     long long obs = 0;
     if (b->obs_ptr)
       for (int k = b->obs_ptr[p]; k < b->obs_ptr[p + 1]; k++) {
@@ -615,8 +706,11 @@ int dftpav_upload_batch(dftpav_handle* h, const dftpav_batch* b) {
       }
     h->h_evalbytes[p] = (int)(16LL * h->h_n[p] + 32LL * planes + 96LL * (g1 - g0) + 104LL * obs);
   }
+  h->has_obs = (b->obs_ptr != nullptr) && B > 0 && b->obs_ptr[B] > 0;
+  if (h->has_obs && strict_build_host())
+    return fail(h, DFTPAV_ERR_UNSUPPORTED, "the strict verification build does not evaluate moving obstacles (exp/log)");
 
-  // ---- raw uploads
+  // ---- raw uploads (everything but the planes)
   auto up = [&](DevBuf& buf, const void* src, size_t bytes) -> cudaError_t {
     cudaError_t e = buf.ensure(bytes);
     if (e != cudaSuccess) return e;
@@ -625,24 +719,19 @@ int dftpav_upload_batch(dftpav_handle* h, const dftpav_batch* b) {
     return e;
   };
   CU_TRY(h, up(h->seg_base, seg_base.data(), sizeof(int) * B));
-  CU_TRY(h, up(h->samp_base, samp_base.data(), sizeof(long long) * B));
+  CU_TRY(h, up(h->samp_base, samp_base.data(), sizeof(long long) * (B + 1)));
   CU_TRY(h, up(h->inner_base, inner_base.data(), sizeof(long long) * B));
   CU_TRY(h, up(h->singul, b->singul, sizeof(int) * G));
   CU_TRY(h, up(h->ini_raw, b->ini_state, sizeof(double) * 6 * G));
   CU_TRY(h, up(h->fin_raw, b->fin_state, sizeof(double) * 6 * G));
   CU_TRY(h, up(h->init_T, b->init_T, sizeof(double) * G));
   CU_TRY(h, up(h->inner_pts, b->inner_pts, sizeof(double) * inner));
-  CU_TRY(h, up(h->planes_raw, b->planes, sizeof(double) * 4 * total_planes));
   if (b->plane_cnt) CU_TRY(h, up(h->plane_ptr, plane_ptr.data(), sizeof(long long) * (Q + 1)));
   std::vector<double> tnow(B, 0.0);
   if (b->t_now) std::copy(b->t_now, b->t_now + B, tnow.begin());
   CU_TRY(h, up(h->t_now, tnow.data(), sizeof(double) * B));
-  h->has_obs = (b->obs_ptr != nullptr) && B > 0 && b->obs_ptr[B] > 0;
   if (h->has_obs) {
     const int U = b->n_obs_pool;
-    if (U <= 0 || !b->obs_idx || !b->obs_start_time || !b->obs_duration || !b->obs_piece_ptr || !b->obs_piece_dur ||
-        !b->obs_coeffs)
-      return fail(h, DFTPAV_ERR_INVALID_ARG, "obstacle arrays missing");
     const int NP = b->obs_piece_ptr[U];
     CU_TRY(h, up(h->obs_ptr, b->obs_ptr, sizeof(int) * (B + 1)));
     CU_TRY(h, up(h->obs_idx, b->obs_idx, sizeof(int) * b->obs_ptr[B]));
@@ -655,13 +744,14 @@ int dftpav_upload_batch(dftpav_handle* h, const dftpav_batch* b) {
     std::vector<double> uni(U);
     for (int u = 0; u < U; u++) {
       const int p0 = b->obs_piece_ptr[u], p1 = b->obs_piece_ptr[u + 1];
-      double d0 = p1 > p0 ? b->obs_piece_dur[p0] : std::nan("");
+      double d0 = b->obs_piece_dur[p0];
       for (int q = p0 + 1; q < p1; q++)
         if (b->obs_piece_dur[q] != d0) d0 = std::nan("");
       uni[u] = d0;
     }
     CU_TRY(h, up(h->obs_uniform, uni.data(), sizeof(double) * U));
   }
+  CU_TRY(h, h->planes_raw.ensure(sizeof(double) * 4 * (size_t)h->total_planes));
   CU_TRY(h, h->ini.ensure(sizeof(double) * 6 * G));
   CU_TRY(h, h->fin.ensure(sizeof(double) * 6 * G));
   CU_TRY(h, h->x0.ensure(sizeof(double) * (size_t)B * dims.n_stride));
@@ -675,8 +765,22 @@ int dftpav_upload_batch(dftpav_handle* h, const dftpav_batch* b) {
   CU_TRY(h, h->o_coeffs.ensure(sizeof(double) * (size_t)B * dims.row_stride * 2));
   CU_TRY(h, h->o_dT.ensure(sizeof(double) * G));
   CU_TRY(h, h->counter.ensure(sizeof(int) * 64));
+  if (h->n_rejected > 0 || h->param_status) {
+    // problems no kernel touches: status from the host, everything else zero
+    CU_TRY(h, cudaMemsetAsync(h->x0.p, 0, sizeof(double) * (size_t)B * dims.n_stride, st));
+    CU_TRY(h, cudaMemsetAsync(h->o_x.p, 0, sizeof(double) * (size_t)B * dims.n_stride, st));
+    CU_TRY(h, cudaMemsetAsync(h->o_cost.p, 0, sizeof(double) * B, st));
+    CU_TRY(h, cudaMemsetAsync(h->o_success.p, 0, sizeof(int) * B, st));
+    CU_TRY(h, cudaMemsetAsync(h->o_iters.p, 0, sizeof(int) * B, st));
+    CU_TRY(h, cudaMemsetAsync(h->o_evals.p, 0, sizeof(int) * B, st));
+    CU_TRY(h, cudaMemsetAsync(h->o_coeffs.p, 0, sizeof(double) * (size_t)B * dims.row_stride * 2, st));
+    CU_TRY(h, cudaMemsetAsync(h->o_dT.p, 0, sizeof(double) * G, st));
+    CU_TRY(h, cudaMemcpyAsync(h->o_status.p, h->h_status0.data(), sizeof(int) * B, cudaMemcpyHostToDevice, st));
+  }
 
-  // ---- per-group tables, layout + state kernels
+  // ---- per-group tables, state kernel, launch configuration
+  const int VR = virtual_ranks_host();
+  const bool strict = strict_build_host() != 0;
   int max_slots = 0, max_npad = 0;
   int launches = 0;
   for (Group* grp : h->groups) {
@@ -687,7 +791,11 @@ int dftpav_upload_batch(dftpav_handle* h, const dftpav_batch* b) {
     sh.S = g1 - g0;
     sh.K = K;
     sh.Kd = Kd;
+    sh.has_obs = h->has_obs ? 1 : 0;
     const int td = (Kd + kTile - 1) / kTile, tk = (K + kTile - 1) / kTile;
+    // regular sweep passes touch disjoint pieces when every inner piece is one tile and the first / last piece fit one
+    // pass (two tiles); the tiles of the last piece are aligned to a pass by an empty tile where needed
+    sh.helpable = (tk == 1 && td <= 2) ? 1 : 0;
     std::map<int, int> lu_of_N;
     int rows = 0, var = 0, sampoff = 0, luoff = 0, pieces = 0;
     for (int s = 0; s < sh.S; s++) {
@@ -696,7 +804,8 @@ int dftpav_upload_batch(dftpav_handle* h, const dftpav_batch* b) {
       sh.row0[s] = rows;
       sh.var0[s] = var;
       sh.samp0[s] = sampoff;
-      sh.ntile[s] = 2 * td + (N - 2) * tk;
+      sh.tpad[s] = (sh.helpable && td == 2 && ((td + (N - 2) * tk) & 1)) ? 1 : 0;
+      sh.ntile[s] = 2 * td + (N - 2) * tk + sh.tpad[s];
       rows += 6 * N;
       var += 2 * (N - 1);
       pieces += N;
@@ -719,16 +828,21 @@ int dftpav_upload_batch(dftpav_handle* h, const dftpav_batch* b) {
     sh.npad = (sh.n + 3) / 4 * 4;
     sh.Mpad = sampoff;
     sh.lu_doubles = luoff;
-    sh.ws_doubles = ws_doubles_host(sh.rows, sh.npad);
-    // dense MINCO tables instead of the LU tables when they fit beside the workspaces of a full CTA
+    sh.ws_doubles = ws_doubles_host(sh.rows, sh.npad, sh.S, sh.has_obs);
+    // launch shape: one CTA per SM (or per problem), W warps; a CTA with fewer problems than warps fills up with
+    // helper-only warps (up to VR warps per trajectory), so small batches are swept by teams from the first evaluation
+    const int count = (int)grp->probs.size();
+    const size_t cap = h->smem_optin > 2048 ? h->smem_optin - 1024 : 0;
+    const int grid = std::max(1, std::min(count, h->num_sms));
+    const int per_cta = (count + grid - 1) / grid;
+    const int wantW = std::max(1, std::min(max_warps_host(), per_cta * ((sh.helpable && !strict) ? VR : 1)));
+    // dense MINCO tables instead of the LU tables when they fit beside the workspaces of the wanted warps
     {
       size_t dd = 0;
       bool cols_ok = true;
       for (auto& kv : lu_of_N) dd += dense_doubles(kv.first), cols_ok = cols_ok && kv.first + 5 <= 64;
-      const size_t cap0 = h->smem_optin > 2048 ? h->smem_optin - 1024 : 0;
-      const int cnt0 = (int)grp->probs.size();
-      const int wantW = std::max(1, std::min(max_warps_host() / team_size_host(), (cnt0 + h->num_sms - 1) / h->num_sms));
-      if (cols_ok && !getenv("DFTPAV_NO_DENSE") && sizeof(double) * (dd + (size_t)sh.ws_doubles * wantW) <= cap0) {
+      const bool want_dense = !strict && !h->force_banded;
+      if (want_dense && cols_ok && sizeof(double) * (dd + (size_t)sh.ws_doubles * wantW) <= cap) {
         sh.dense_minco = 1;
         size_t off = 0;
         std::map<int, int> off_of_N;
@@ -740,15 +854,13 @@ int dftpav_upload_batch(dftpav_handle* h, const dftpav_batch* b) {
     // padded plane count of the group
     int Hmax = 0;
     if (b->plane_cnt) {
-      for (int p : grp->probs) {
-        long long q0 = samp_base[p], q1 = (p + 1 < B) ? samp_base[p + 1] : Q;
-        for (long long q = q0; q < q1; q++) Hmax = std::max(Hmax, (int)b->plane_cnt[q]);
-      }
+      for (int p : grp->probs)
+        for (long long q = samp_base[p]; q < samp_base[p + 1]; q++) Hmax = std::max(Hmax, (int)b->plane_cnt[q]);
     } else {
       Hmax = b->uniform_H;
     }
     sh.H = (Hmax + 3) / 4 * 4;  // padded to the register chunk of the sweep (null planes never violate)
-    // LU block
+    // table block
     std::vector<double> lu((size_t)sh.lu_doubles, 0.0);
     sh.band_masks_ok = 1;
     if (sh.dense_minco) {
@@ -767,50 +879,48 @@ int dftpav_upload_batch(dftpav_handle* h, const dftpav_batch* b) {
     }
     CU_TRY(h, up(grp->d_lu, lu.data(), sizeof(double) * lu.size()));
     CU_TRY(h, up(grp->d_prob_id, grp->probs.data(), sizeof(int) * grp->probs.size()));
-    const int count = (int)grp->probs.size();
     const size_t plane_bytes = sizeof(double) * (size_t)count * std::max(1, sh.H) * 4 * sh.Mpad;
     CU_TRY(h, grp->d_planes.ensure(plane_bytes));
-    // launch configuration
     const size_t ws_bytes = sizeof(double) * sh.ws_doubles, lu_bytes = sizeof(double) * sh.lu_doubles;
-    const size_t cap = h->smem_optin > 2048 ? h->smem_optin - 1024 : 0;
     if (lu_bytes + ws_bytes > cap) return fail(h, DFTPAV_ERR_UNSUPPORTED, "problem shape does not fit in shared memory");
-    // W = teams per CTA (one trajectory per team of team_size_host() warps; sh.ws_doubles is the team's workspace)
-    const int G = team_size_host();
-    int W = (int)std::min<size_t>(max_warps_host() / G, (cap - lu_bytes) / ws_bytes);
-    const int want = (count + h->num_sms - 1) / h->num_sms;
-    W = std::max(1, std::min(W, want));
-    grp->owners = W;
-    grp->grid = std::min((count + W - 1) / W, h->num_sms);
-    // drain-phase helpers work in pairs (warp ^ 1): an odd owner count gets one more warp that never takes a problem,
-    // so that e.g. a single trajectory per SM is evaluated by two warps from the start
-    if (drain_help_host() && (W & 1) && W + 1 <= max_warps_host() && lu_bytes + ws_bytes * (W + 1) <= cap) W += 1;
-    grp->warps = W * G;
+    const int W = std::max(1, (int)std::min<size_t>((size_t)wantW, (cap - lu_bytes) / ws_bytes));
+    grp->grid = grid;
+    grp->warps = W;
     grp->smem = lu_bytes + ws_bytes * W;
     max_slots = std::max(max_slots, grp->grid * W);
     max_npad = std::max(max_npad, sh.npad);
-    // kernels
-    const long long total = (long long)count * sh.Mpad;
-    const int lgrid = (int)std::min<long long>((total + 255) / 256, 65535LL * 4);
-    CU_TRY(h, launch_layout(std::max(1, lgrid), 256, st, sh, grp->d_prob_id.as<int>(), count, h->samp_base.as<long long>(),
-                            b->plane_cnt ? h->plane_ptr.as<long long>() : nullptr, b->uniform_H,
-                            h->planes_raw.as<double>(), grp->d_planes.as<double>()));
     CU_TRY(h, launch_prepare((count + 127) / 128, 128, st, sh, h->pd, grp->d_prob_id.as<int>(), count,
                              h->seg_base.as<int>(), h->singul.as<int>(), h->ini_raw.as<double>(),
                              h->fin_raw.as<double>(), h->init_T.as<double>(), h->inner_base.as<long long>(),
                              h->inner_pts.as<double>(), h->ini.as<double>(), h->fin.as<double>(), h->x0.as<double>(),
                              dims.n_stride));
-    launches += 2;
+    launches += 1;
   }
   // L-BFGS history ring per resident warp
-  h->hist_ld = max_npad;
+  h->hist_ld = std::max(1, max_npad);
   h->hist_slots = max_slots;
-  const size_t hbytes = sizeof(double) * (size_t)max_slots * h->prm.lbfgs_mem_size * max_npad;
+  const size_t mem = (size_t)std::max(1, h->prm.lbfgs_mem_size);
+  const size_t hbytes = sizeof(double) * (size_t)max_slots * mem * h->hist_ld;
   CU_TRY(h, h->hist_s.ensure(hbytes));
   CU_TRY(h, h->hist_y.ensure(hbytes));
-  CU_TRY(h, h->hist_ys.ensure(sizeof(double) * (size_t)max_slots * h->prm.lbfgs_mem_size));
-  CU_TRY(h, h->hist_alpha.ensure(sizeof(double) * (size_t)max_slots * h->prm.lbfgs_mem_size));
-  if (two_loop_blocked_host())  // only the (experimental) blocked two-loop keeps a Gram band beside the history
-    CU_TRY(h, h->hist_gram.ensure(sizeof(double) * 4 * (size_t)max_slots * h->prm.lbfgs_mem_size));
+  CU_TRY(h, h->hist_ys.ensure(sizeof(double) * (size_t)max_slots * mem));
+  if (two_loop_blocked_host())  // only the blocked two-loop keeps a Gram band beside the history
+    CU_TRY(h, h->hist_gram.ensure(sizeof(double) * 4 * (size_t)max_slots * mem));
+
+  // ---- arrival flags of the plane upload and per-problem layout flags (epoch-stamped: nothing to clear between uploads)
+  h->epoch += 1;
+  h->n_chunks = std::max(1, std::min(std::min(n_chunks_wanted, kMaxChunks), B / 64));
+  h->chunk = std::max(1, (B + h->n_chunks - 1) / h->n_chunks);
+  h->n_chunks = B > 0 ? (B + h->chunk - 1) / h->chunk : 1;
+  if (h->ready.cap < sizeof(int) * kMaxChunks) {
+    CU_TRY(h, h->ready.ensure(sizeof(int) * kMaxChunks));
+    CU_TRY(h, cudaMemsetAsync(h->ready.p, 0, sizeof(int) * kMaxChunks, st));
+  }
+  if (h->laid.cap < sizeof(int) * (size_t)std::max(1, B)) {
+    CU_TRY(h, h->laid.ensure(sizeof(int) * (size_t)std::max(1, B)));
+    CU_TRY(h, cudaMemsetAsync(h->laid.p, 0, h->laid.cap, st));
+  }
+  for (int c = 0; c < kMaxChunks; c++) h->h_epoch[c] = h->epoch;
 
   BatchDev& bd = h->bd;
   bd.seg_base = h->seg_base.as<int>();
@@ -829,12 +939,16 @@ int dftpav_upload_batch(dftpav_handle* h, const dftpav_batch* b) {
   bd.x0 = h->x0.as<double>();
   bd.n_stride = dims.n_stride;
   bd.row_stride = dims.row_stride;
+  bd.planes_raw = h->planes_raw.as<double>();
+  bd.samp_base = h->samp_base.as<long long>();
+  bd.plane_ptr = b->plane_cnt ? h->plane_ptr.as<long long>() : nullptr;
+  bd.ready = h->ready.as<int>();
+  bd.laid = h->laid.as<int>();
+  bd.uniform_H = b->uniform_H;
+  bd.chunk = h->chunk;
+  bd.epoch = h->epoch;
 
   CU_TRY(h, cudaEventRecord(h->ev[1], st));
-  CU_TRY(h, cudaStreamSynchronize(st));  // host staging vectors above go out of scope
-  float ms = 0.f;
-  cudaEventElapsedTime(&ms, h->ev[0], h->ev[1]);
-  h->stats.upload_ms = ms;
   h->stats.h2d_bytes = h2d;
   h->upload_launches = launches;
   h->stats.kernel_launches = launches;
@@ -843,94 +957,28 @@ int dftpav_upload_batch(dftpav_handle* h, const dftpav_batch* b) {
   return DFTPAV_OK;
 }
 
-int dftpav_eval(dftpav_handle* h, const double* x, double* f, double* g) {
-  if (!h || !x || !f || !g) return DFTPAV_ERR_INVALID_ARG;
-  if (!h->uploaded) return fail(h, DFTPAV_ERR_STATE, "dftpav_eval before dftpav_upload_batch");
-  CU_TRY(h, cudaSetDevice(h->device));
-  cudaStream_t st = h->stream;
-  const int B = h->dims.B, ns = h->dims.n_stride;
-  const size_t xb = sizeof(double) * (size_t)B * ns;
-  CU_TRY(h, h->xin.ensure(xb));
-  CU_TRY(h, h->gout.ensure(xb));
-  CU_TRY(h, h->fout.ensure(sizeof(double) * B));
-  CU_TRY(h, cudaMemcpyAsync(h->xin.p, x, xb, cudaMemcpyHostToDevice, st));
-  CU_TRY(h, cudaEventRecord(h->ev[0], st));
-  int launches = 0;
-  for (Group* grp : h->groups) {
-    GroupDev gd;
-    gd.prob_id = grp->d_prob_id.as<int>();
-    gd.count = (int)grp->probs.size();
-    gd.planes = grp->d_planes.as<double>();
-    gd.lu = grp->d_lu.as<double>();
-    gd.order = nullptr;
-    gd.owners = grp->owners;
-    CU_TRY(h, launch_eval(h->has_obs, grp->grid, 32 * grp->warps, grp->smem, st, grp->sh, h->pd, h->bd, gd,
-                          h->xin.as<double>(), h->fout.as<double>(), h->gout.as<double>(), h->o_coeffs.as<double>(),
-                          h->o_dT.as<double>()));
-    launches++;
+// The corridor planes: n_chunks copies, each followed (in stream order) by its arrival flag.
+int issue_plane_copies(dftpav_handle* h, const dftpav_batch* b, cudaStream_t cs) {
+  const int B = h->dims.B;
+  for (int c = 0; c < h->n_chunks; c++) {
+    const int p0 = c * h->chunk, p1 = std::min(B, p0 + h->chunk);
+    if (p0 >= p1) break;
+    const long long q0 = h->h_samp_base[p0], q1 = h->h_samp_base[p1];
+    const long long e0 = h->uniform_H < 0 ? h->h_plane_ptr[q0] : q0 * h->uniform_H;
+    const long long e1 = h->uniform_H < 0 ? h->h_plane_ptr[q1] : q1 * h->uniform_H;
+    if (e1 > e0)
+      CU_TRY(h, cudaMemcpyAsync(h->planes_raw.as<double>() + 4 * e0, b->planes + 4 * e0, sizeof(double) * 4 * (size_t)(e1 - e0),
+                                cudaMemcpyHostToDevice, cs));
+    CU_TRY(h, cudaMemcpyAsync(h->ready.as<int>() + c, h->h_epoch + c, sizeof(int), cudaMemcpyHostToDevice, cs));
   }
-  CU_TRY(h, cudaEventRecord(h->ev[1], st));
-  CU_TRY(h, cudaMemcpyAsync(f, h->fout.p, sizeof(double) * B, cudaMemcpyDeviceToHost, st));
-  CU_TRY(h, cudaMemcpyAsync(g, h->gout.p, xb, cudaMemcpyDeviceToHost, st));
-  CU_TRY(h, cudaStreamSynchronize(st));
-  float ms = 0.f;
-  cudaEventElapsedTime(&ms, h->ev[0], h->ev[1]);
-  h->stats.solve_ms = ms;
-  h->stats.kernel_launches = launches;
-  h->stats.total_evals = B;
-  h->stats.total_iters = 0;
-  long long ab = 0;
-  for (int p = 0; p < B; p++) ab += h->h_evalbytes[p];
-  h->stats.algorithmic_bytes = ab;
+  h->stats.h2d_bytes += (long long)sizeof(double) * 4 * h->total_planes;
   return DFTPAV_OK;
 }
 
-int dftpav_optimize(dftpav_handle* h) {
-  if (!h) return DFTPAV_ERR_INVALID_ARG;
-  if (!h->uploaded) return fail(h, DFTPAV_ERR_STATE, "dftpav_optimize before dftpav_upload_batch");
-  CU_TRY(h, cudaSetDevice(h->device));
+// launches the solver kernels of every shape group on the handle's stream (no synchronisation)
+int launch_solve_kernels(dftpav_handle* h, int* launches_out) {
   cudaStream_t st = h->stream;
   CU_TRY(h, cudaMemsetAsync(h->counter.p, 0, sizeof(int) * 64, st));
-  CU_TRY(h, cudaEventRecord(h->ev[0], st));
-  int launches = 0;
-  // ---- scheduling heuristic (no effect on results): the batch time is the critical path of the longest solve, and the
-  // number of L-BFGS evaluations a problem needs correlates with its initial cost (Spearman 0.4 at config 3), so the
-  // persistent warps serve the problems in order of decreasing f(x0).  Costs one extra evaluation per problem.
-  const bool lpt = h->dims.B > h->num_sms * 4 && !getenv("DFTPAV_NO_LPT");
-  if (lpt) {
-    const int B = h->dims.B;
-    CU_TRY(h, h->fout.ensure(sizeof(double) * B));
-    CU_TRY(h, h->gout.ensure(sizeof(double) * (size_t)B * h->dims.n_stride));
-    for (Group* grp : h->groups) {
-      GroupDev gd;
-      gd.prob_id = grp->d_prob_id.as<int>();
-      gd.count = (int)grp->probs.size();
-      gd.planes = grp->d_planes.as<double>();
-      gd.lu = grp->d_lu.as<double>();
-      gd.order = nullptr;
-      gd.owners = grp->owners;
-      CU_TRY(h, launch_eval(h->has_obs, grp->grid, 32 * grp->warps, grp->smem, st, grp->sh, h->pd, h->bd, gd,
-                            h->x0.as<double>(), h->fout.as<double>(), h->gout.as<double>(), nullptr, nullptr));
-      launches++;
-    }
-    h->h_f0.resize(B);
-    CU_TRY(h, cudaMemcpyAsync(h->h_f0.data(), h->fout.p, sizeof(double) * B, cudaMemcpyDeviceToHost, st));
-    CU_TRY(h, cudaStreamSynchronize(st));
-    for (Group* grp : h->groups) {
-      const int cnt = (int)grp->probs.size();
-      std::vector<int> ord(cnt);
-      for (int i = 0; i < cnt; i++) ord[i] = i;
-      const std::vector<int>& probs = grp->probs;
-      const std::vector<double>& f0 = h->h_f0;
-      std::stable_sort(ord.begin(), ord.end(), [&](int a, int b) {
-        const double fa = f0[probs[a]], fb = f0[probs[b]];
-        return (fa > fb) || (fa != fa && fb == fb);  // NaN first (they finish immediately)
-      });
-      CU_TRY(h, grp->d_order.ensure(sizeof(int) * cnt));
-      CU_TRY(h, cudaMemcpyAsync(grp->d_order.p, ord.data(), sizeof(int) * cnt, cudaMemcpyHostToDevice, st));
-      CU_TRY(h, cudaStreamSynchronize(st));
-    }
-  }
   OutDev out;
   out.x = h->o_x.as<double>();
   out.cost = h->o_cost.as<double>();
@@ -953,25 +1001,109 @@ int dftpav_optimize(dftpav_handle* h) {
   hist.s = h->hist_s.as<double>();
   hist.y = h->hist_y.as<double>();
   hist.ys = h->hist_ys.as<double>();
-  hist.alpha = h->hist_alpha.as<double>();
   hist.gram = h->hist_gram.as<double>();
   hist.ld = h->hist_ld;
   hist.mem = h->prm.lbfgs_mem_size;
-  int gi = 0;
+  int launches = 0, gi = 0;
+  if (h->param_status) {
+    // lbfgs_optimize returns before touching x (lbfgs.hpp:456-501): the decision vector stays the initial packing
+    CU_TRY(h, cudaMemcpyAsync(h->o_x.p, h->x0.p, sizeof(double) * (size_t)h->dims.B * h->dims.n_stride,
+                              cudaMemcpyDeviceToDevice, st));
+  } else {
+    for (Group* grp : h->groups) {
+      if (gi >= 64) return fail(h, DFTPAV_ERR_UNSUPPORTED, "more than 64 distinct shapes in one batch");
+      GroupDev gd;
+      gd.prob_id = grp->d_prob_id.as<int>();
+      gd.count = (int)grp->probs.size();
+      gd.planes = grp->d_planes.as<double>();
+      gd.lu = grp->d_lu.as<double>();
+      gd.order = nullptr;
+      CU_TRY(h, launch_solve(h->has_obs, grp->grid, 32 * grp->warps, grp->smem, st, grp->sh, h->pd, h->bd, gd, out, hist,
+                             h->counter.as<int>() + gi));
+      launches++;
+      gi++;
+    }
+  }
+  *launches_out = launches;
+  return DFTPAV_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+int dftpav_upload_batch(dftpav_handle* h, const dftpav_batch* b) {
+  if (!h) return DFTPAV_ERR_INVALID_ARG;
+  int rc = upload_impl(h, b, 1);
+  if (rc) return rc;
+  rc = issue_plane_copies(h, b, h->stream);
+  if (rc) {
+    h->uploaded = false;
+    return rc;
+  }
+  CU_TRY(h, cudaEventRecord(h->ev[1], h->stream));
+  CU_TRY(h, cudaStreamSynchronize(h->stream));
+  float ms = 0.f;
+  cudaEventElapsedTime(&ms, h->ev[0], h->ev[1]);
+  h->stats.upload_ms = ms;
+  return DFTPAV_OK;
+}
+
+int dftpav_eval(dftpav_handle* h, const double* x, double* f, double* g) {
+  if (!h || !x || !f || !g) return DFTPAV_ERR_INVALID_ARG;
+  if (!h->uploaded) return fail(h, DFTPAV_ERR_STATE, "dftpav_eval before dftpav_upload_batch");
+  CU_TRY(h, cudaSetDevice(h->device));
+  cudaStream_t st = h->stream;
+  const int B = h->dims.B, ns = h->dims.n_stride;
+  const size_t xb = sizeof(double) * (size_t)B * ns;
+  CU_TRY(h, h->xin.ensure(xb));
+  CU_TRY(h, h->gout.ensure(xb));
+  CU_TRY(h, h->fout.ensure(sizeof(double) * B));
+  CU_TRY(h, cudaMemcpyAsync(h->xin.p, x, xb, cudaMemcpyHostToDevice, st));
+  if (h->n_rejected > 0) {  // rejected problems are not evaluated: f = 0, g = 0
+    CU_TRY(h, cudaMemsetAsync(h->fout.p, 0, sizeof(double) * B, st));
+    CU_TRY(h, cudaMemsetAsync(h->gout.p, 0, xb, st));
+  }
+  CU_TRY(h, cudaEventRecord(h->ev[0], st));
+  int launches = 0;
   for (Group* grp : h->groups) {
-    if (gi >= 64) return fail(h, DFTPAV_ERR_UNSUPPORTED, "more than 64 distinct shapes in one batch");
     GroupDev gd;
     gd.prob_id = grp->d_prob_id.as<int>();
     gd.count = (int)grp->probs.size();
     gd.planes = grp->d_planes.as<double>();
     gd.lu = grp->d_lu.as<double>();
-    gd.order = lpt ? grp->d_order.as<int>() : nullptr;
-    gd.owners = grp->owners;
-    CU_TRY(h, launch_solve(h->has_obs, grp->grid, 32 * grp->warps, grp->smem, st, grp->sh, h->pd, h->bd, gd, out, hist,
-                           h->counter.as<int>() + gi));
+    gd.order = nullptr;
+    CU_TRY(h, launch_eval(h->has_obs, grp->grid, 32 * grp->warps, grp->smem, st, grp->sh, h->pd, h->bd, gd,
+                          h->xin.as<double>(), h->fout.as<double>(), h->gout.as<double>(), h->o_coeffs.as<double>(),
+                          h->o_dT.as<double>()));
     launches++;
-    gi++;
   }
+  CU_TRY(h, cudaEventRecord(h->ev[1], st));
+  CU_TRY(h, cudaMemcpyAsync(f, h->fout.p, sizeof(double) * B, cudaMemcpyDeviceToHost, st));
+  CU_TRY(h, cudaMemcpyAsync(g, h->gout.p, xb, cudaMemcpyDeviceToHost, st));
+  CU_TRY(h, cudaStreamSynchronize(st));
+  float ms = 0.f;
+  cudaEventElapsedTime(&ms, h->ev[0], h->ev[1]);
+  h->stats.solve_ms = ms;
+  h->stats.kernel_launches = launches;
+  h->stats.total_evals = B - h->n_rejected;
+  h->stats.total_iters = 0;
+  long long ab = 0;
+  for (int p = 0; p < B; p++)
+    if (h->h_status0[p] != DFTPAV_PROBLEM_REJECTED) ab += h->h_evalbytes[p];
+  h->stats.algorithmic_bytes = ab;
+  return DFTPAV_OK;
+}
+
+int dftpav_optimize(dftpav_handle* h) {
+  if (!h) return DFTPAV_ERR_INVALID_ARG;
+  if (!h->uploaded) return fail(h, DFTPAV_ERR_STATE, "dftpav_optimize before dftpav_upload_batch");
+  CU_TRY(h, cudaSetDevice(h->device));
+  cudaStream_t st = h->stream;
+  CU_TRY(h, cudaEventRecord(h->ev[0], st));
+  int launches = 0;
+  int rc = launch_solve_kernels(h, &launches);
+  if (rc) return rc;
   CU_TRY(h, cudaEventRecord(h->ev[1], st));
   CU_TRY(h, cudaStreamSynchronize(st));
   float ms = 0.f;
@@ -1030,18 +1162,61 @@ int dftpav_download(dftpav_handle* h, const dftpav_result* out) {
   return DFTPAV_OK;
 }
 
+// One planner call: small arrays and state kernels first, then the solver kernels are launched, and only then the corridor
+// planes (95 % of the bytes) are copied in chunks on a second stream - the solve runs under the copy: a warp waits for
+// the arrival flag of its problem's chunk (layout_problem in dftpav_kernels.cu), the first problems start after the first
+// chunk.  Replaces the deep copy of hPoly_container at the top of OptimizeTrajectory (traj_optimizer.cpp:15).
 int dftpav_solve(dftpav_handle* h, const dftpav_batch* batch, const dftpav_result* out) {
-  int rc = dftpav_upload_batch(h, batch);
+  if (!h) return DFTPAV_ERR_INVALID_ARG;
+  int rc = upload_impl(h, batch, kMaxChunks);
   if (rc) return rc;
-  rc = dftpav_optimize(h);
+  cudaStream_t st = h->stream;
+  CU_TRY(h, cudaEventRecord(h->ev[4], st));
+  // the copy stream starts after everything already queued on the main stream (previous results are read, the old plane
+  // buffer is free) ...
+  CU_TRY(h, cudaEventRecord(h->ev_copy, st));
+  CU_TRY(h, cudaStreamWaitEvent(h->copy_stream, h->ev_copy, 0));
+  int launches = 0;
+  rc = launch_solve_kernels(h, &launches);
   if (rc) return rc;
-  return dftpav_download(h, out);
+  CU_TRY(h, cudaEventRecord(h->ev[5], st));
+  // ... and is fed only now: the persistent kernels are already resident and polling
+  rc = issue_plane_copies(h, batch, h->copy_stream);
+  if (rc) {  // release the polling kernels before reporting the failure
+    cudaMemcpyAsync(h->ready.p, h->h_epoch, sizeof(int) * kMaxChunks, cudaMemcpyHostToDevice, h->copy_stream);
+    cudaStreamSynchronize(h->copy_stream);
+    cudaStreamSynchronize(st);
+    h->solved = false;
+    return rc;
+  }
+  h->stats.kernel_launches = h->upload_launches + launches;
+  h->solved = true;
+  rc = dftpav_download(h, out);  // queued behind the kernels; synchronises the main stream
+  CU_TRY(h, cudaStreamSynchronize(h->copy_stream));
+  float ms = 0.f;
+  cudaEventElapsedTime(&ms, h->ev[4], h->ev[5]);
+  h->stats.solve_ms = ms;  // includes waiting for the plane chunks
+  cudaEventElapsedTime(&ms, h->ev[0], h->ev[1]);
+  h->stats.upload_ms = ms;  // small arrays, tables and the state kernel; the plane copy runs under the solve
+  return rc;
 }
 
 int dftpav_last_stats(const dftpav_handle* h, dftpav_stats* stats) {
   if (!h || !stats) return DFTPAV_ERR_INVALID_ARG;
   *stats = h->stats;
   return DFTPAV_OK;
+}
+
+// Test hook (not part of the drop-in ABI): use the banded LU substitutions even where the dense MINCO tables fit; takes
+// effect at the next upload.
+int dftpav_debug_force_banded(dftpav_handle* h, int on) {
+  if (!h) return DFTPAV_ERR_INVALID_ARG;
+  h->force_banded = on != 0;
+  return DFTPAV_OK;
+}
+// Build variant of the loaded library: bit 0 strict-order verification build, bit 1 blocked two-loop; bits 8.. virtual ranks
+int dftpav_debug_build_flags(void) {
+  return (strict_build_host() ? 1 : 0) | (two_loop_blocked_host() ? 2 : 0) | (virtual_ranks_host() << 8);
 }
 
 // Diagnostic (not part of the drop-in ABI): per-iteration (fx, step, ls) traces of the next dftpav_optimize calls.
@@ -1081,6 +1256,17 @@ long long dftpav_debug_minco_dense(int N, double* out, int* rows_of_col) {
   if (rows_of_col)
     for (int j = 0; j < N + 5; j++) rows_of_col[j] = dense_row_of(j, N);
   return (long long)t.size();
+}
+
+// Diagnostic (host only): the banded LU factor of N pieces as the fallback / strict kernels read it, packed columns
+// C[j][0..12] = band rows of column j (A(i,j) = C[j][i-j+6]), C[j][13] = 1/U(j,j); 6N x 16 doubles.
+long long dftpav_debug_minco_band(int N, double* out) {
+  if (N < 1 || N > kMaxPieces) return -1;
+  if (out) {
+    BandLU f(N);
+    f.pack(out);
+  }
+  return (long long)6 * N * kLuLd;
 }
 
 const char* dftpav_last_error(const dftpav_handle* h) { return h ? h->err.c_str() : "null handle"; }

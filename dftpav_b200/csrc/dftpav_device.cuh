@@ -2,8 +2,9 @@
 //
 // Mapping of the hot path onto the GPU:
 //   * one warp owns one trajectory problem for its whole L-BFGS solve (no inter-warp communication);
-//   * MINCO forward solve / adjoint solve: banded substitutions with the constant LU factor staged in
-//     shared memory once per CTA by a TMA bulk copy (cp.async.bulk), two lanes per gear segment (x / y column);
+//   * MINCO forward solve / adjoint solve: products with the constant matrix A^-1[:, R] (dense path, 32 lanes) or banded
+//     substitutions with the constant LU factor (fallback, 2 lanes per gear segment); the table is staged in shared
+//     memory once per CTA by a TMA bulk copy (cp.async.bulk);
 //   * constraint-sample sweep: lane <-> sample, 16-sample tiles, plane data read coalesced from a tiled SoA
 //     layout, fixed-order (deterministic) tile reduction of the 6x2 coefficient gradient in shared memory;
 //   * L-BFGS two-loop recursion + Lewis-Overton line search: warp-shuffle dot products, (s,y) history ring in
@@ -35,12 +36,15 @@ struct ShapeDev {
   int var0[kMaxSeg];     // offset of the segment's inner points in x
   int lu_off[kMaxSeg];   // offset (doubles) of the segment's packed LU table in the LU block
   int samp0[kMaxSeg];    // sample-storage offset of the segment
-  int ntile[kMaxSeg];    // regular 16-sample tiles of the segment
+  int ntile[kMaxSeg];    // regular 16-sample tiles of the segment (including the padding tile below)
+  int tpad[kMaxSeg];     // 1: an empty tile precedes the tiles of the last piece so that they share one sweep pass
   int lu_doubles;        // size of the LU block (all distinct N of this shape)
   int npad;              // n rounded up to a multiple of 4
   int ws_doubles;        // per-warp workspace size in doubles
   int band_masks_ok;     // 1 if the LU tables satisfy the compile-time sparsity masks of the banded passes
   int dense_minco;       // 1: the table block holds the dense matrices M = A^-1[:, R] (lu_off = their offsets), not LU columns
+  int has_obs;           // the batch carries moving obstacles (obstacle metadata array in the warp workspace)
+  int helpable;          // 1: regular sweep passes touch disjoint pieces (K <= 16 < Kd <= 32 or Kd <= 16): drain-phase helpers allowed
 };
 
 // Scalar parameters reaching the arithmetic (mirror of dftpav_params, device side).
@@ -77,16 +81,24 @@ struct BatchDev {
   // decision vectors
   const double* x0;             // [B][n_stride]
   int n_stride, row_stride;
+  // raw corridor planes as uploaded ([sample][h][4], normals not yet unit) and the hand-shake with the (possibly still
+  // running) upload: the planes of problems [c*chunk, (c+1)*chunk) have arrived when ready[c] == epoch; a problem's tiled
+  // SoA copy exists when laid[p] == epoch (written by the warp that first takes the problem)
+  const double* planes_raw;
+  const long long* samp_base;   // [B] first raw sample of the problem
+  const long long* plane_ptr;   // [Q+1] plane prefix of the samples, or nullptr (uniform_H planes per sample)
+  const int* ready;             // [chunks]
+  int* laid;                    // [B]
+  int uniform_H, chunk, epoch;
 };
 
 // One launch = one shape group.
 struct GroupDev {
   const int* prob_id;           // [count] global problem ids of this group
   int count;
-  const double* planes;         // tiled SoA: [count][H][4][Mpad]
+  double* planes;               // tiled SoA: [count][H][4][Mpad], filled by the kernels on first use (layout_problem)
   const double* lu;             // packed LU block of this shape
-  const int* order;             // work list: order[w] = local index served w-th (longest-expected-first), or nullptr
-  int owners;                   // warps (teams) per CTA that take problems; warps beyond start as drain-phase helpers
+  const int* order;             // work list: order[w] = local index served w-th, or nullptr (input order)
 };
 
 struct OutDev {
@@ -106,7 +118,6 @@ struct HistDev {
   double* s;        // [slots][mem][npad_max]
   double* y;
   double* ys;       // [slots][mem]
-  double* alpha;    // [slots][mem]
   double* gram;     // [slots][mem][4] band of Gram products s_{k-1..k-3} . y_k (blocked two-loop only)
   int ld;           // npad_max
   int mem;

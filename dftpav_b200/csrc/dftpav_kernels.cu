@@ -38,10 +38,18 @@ __device__ __forceinline__ double warp_max(double v) {
   return v;
 }
 __device__ __noinline__ double warp_dot(const double* a, const double* b, int n, int lane) {
+#if DFTPAV_STRICT
+  // the reference's sequential sum (Eigen dot of the element-by-element layer the oracle is pinned to)
+  double s = 0.0;
+  if (lane == 0)
+    for (int i = 0; i < n; i++) s += a[i] * b[i];
+  return __shfl_sync(FULL, s, 0);
+#else
   double s = 0.0;
 #pragma unroll 1
   for (int i = lane; i < n; i += 32) s += a[i] * b[i];
   return warp_sum(s);
+#endif
 }
 __device__ __noinline__ double warp_maxabs(const double* a, int n, int lane) {
   double m = 0.0;
@@ -109,35 +117,52 @@ struct SegScratch {   // 38 doubles per segment
   double pad[4];
 };
 
-// Team of kTeam warps per trajectory.  Rank 0 runs the solver (L-BFGS state machine, MINCO products, gradient assembly);
-// the constraint sweep - 80-90 % of a lone warp's evaluation time - is split pass-by-pass over all ranks: rank r takes
-// passes r, r+kTeam, ... and accumulates into a private partial gradient, merged in a fixed order after a named barrier.
-// The batch time at the reference batch sizes is set by the critical path of the longest problem (~200 sequential
-// evaluations), not by throughput (profiles/README.md: 124 k solves/s at batch 2048, 199 k at 4096, 293 k at 16384
-// with one warp per problem), so shortening every evaluation is worth more than resident problems.
-#ifndef DFTPAV_TEAM
-#define DFTPAV_TEAM 1  // measured at config 3, batch 4096: 1: 202 k, 2: 182 k, 3: 177 k, 4: 162 k, 6: 149 k solves/s (profiles/README.md)
+// ------------------------------------------------------------------------------------------------
+// Drain-phase helpers.  The batch time at the reference batch sizes is set by the last problems leaving the queue
+// (profiles/README.md): once the work queue is empty, a warp without a problem becomes a HELPER of a warp of its CTA
+// that is still solving (its OWNER) and takes a share of the regular sweep passes of each of the owner's evaluations.
+//
+// Determinism without partial buffers.  With the reference resolutions (K <= 16 < Kd <= 32) every regular pass adds into
+// the gdC rows of pieces that no other regular pass touches (one 16-sample tile per inner piece; the two tiles of the
+// first / last piece share one pass, see ShapeDev::tpad), so owner and helpers accumulate straight into the owner's gdC in
+// any interleaving; the piece-end samples (j = K_i, "end passes") are added by the owner after the helpers have
+// finished.  Every gdC entry therefore receives its terms in ONE fixed order: jerk gradient, tile sums of the piece
+// in tile order, end sample.  The scalar sums (gdT and the three penalty sums) are reduced per VIRTUAL RANK r = pass % kVR
+// (lane accumulators over the passes of the rank in pass order, one butterfly per rank) and merged by the owner in rank
+// order, whoever computed them.  A solve is bit-identical with 0 ... kVR-1 helpers (tests/test_gpu_parity.py).
+// Shapes with other resolutions (ShapeDev::helpable == 0) run without helpers.
+//
+// Protocol (shared-memory flags, no named barriers: a CTA has 16 of them, not enough for 12 owners x teams).  Owner w
+// publishes every evaluation as ctl[w].go = ++seq after writing ctl[w].h = number of helpers taking part (its snapshot
+// of ctl[w].nhelp) and the problem; helper i (attach index, from atomicAdd on nhelp) serves evaluation seq iff h > i,
+// takes virtual ranks chunk(i + 1 of h + 1), and reports with atomicAdd on ctl[w].done.  h = -1 retires the owner and
+// releases its helpers, which then look for another owner of the CTA or exit.
+// ------------------------------------------------------------------------------------------------
+#ifndef DFTPAV_VRANKS
+#define DFTPAV_VRANKS 4
 #endif
-constexpr int kTeam = DFTPAV_TEAM;
-// Drain-phase helpers (kTeam == 1 only).  Every evaluation's sweep is accumulated as TWO fixed partial sums (odd passes
-// -> partial 0, even passes -> partial 1, merged in a fixed order), normally both by the warp that owns the problem.
-// When a warp finds the work queue empty while its neighbour (warp ^ 1) is still solving, it becomes the neighbour's
-// helper for the rest of the kernel and computes partial 1 of every evaluation (pair barriers A/B, `bar.sync id, 64`).
-// The result does not depend on who computed partial 1, so the solver stays deterministic.  The batch time at the
-// reference batch sizes is dominated by the last problems leaving the queue (profiles/README.md).
-#ifndef DFTPAV_DRAIN_HELP
-#define DFTPAV_DRAIN_HELP 1
+#ifndef DFTPAV_STRICT
+#define DFTPAV_STRICT 0
 #endif
-constexpr bool kDrainHelp = (DFTPAV_DRAIN_HELP != 0) && kTeam == 1;
-constexpr int kPart = kTeam > 1 ? kTeam : (kDrainHelp ? 2 : 1);  // partial sums of the sweep
-static_assert(kTeam >= 1 && DFTPAV_MAX_WARPS % kTeam == 0 && (kTeam == 1 || (DFTPAV_MAX_WARPS / kTeam) * 2 + 1 <= 16), "team size");
+constexpr bool kStrict = DFTPAV_STRICT != 0;          // strict-order verification build (dftpav_strict.cuh)
+constexpr int kVR = kStrict ? 1 : DFTPAV_VRANKS;      // virtual ranks of the sweep = max team size (owner + kVR-1 helpers)
+constexpr int kMaxHelp = kVR - 1;
+static_assert(kVR >= 1 && kVR <= 15, "virtual ranks");
 
-// what a rank accumulates into during the sweep
-struct SweepTarget {
-  double* gd;     // [2*rows] partial gdC (rank 0: the workspace gdC itself)
-  double* stage;  // [2][12][kStageLd] tile-reduction staging of this warp
-  double* scal;   // [kMaxSeg][4] per-segment partial (gdT, pen0, pen1, pen2)
-  int rank;
+struct TeamCtl {
+  int go;       // sequence number of the owner's current evaluation
+  int h;        // helpers taking part in evaluation `go`; -1: the owner has retired
+  int nhelp;    // helpers attached to this owner
+  int done;     // cumulative number of helper completions
+  int alive;    // 1 until the warp finds the work queue empty
+  int prob;     // problem of evaluation `go`
+  unsigned long long planes;  // plane pointer of that problem
+};
+
+// where a sweep adds its results (the owner's workspace; generic pointers: a helper writes into its owner's arrays)
+struct SweepOut {
+  double* gd;     // [2*rows] gdC of the owner
+  double* rscal;  // [S][kVR+1][4] per-segment, per-virtual-rank (gdT, pen0, pen1, pen2); slot kVR = the end passes
 };
 
 struct WarpWS {
@@ -152,20 +177,15 @@ struct WarpWS {
   double* stage;  // [2][12][kStageLd]; doubles as the L-BFGS alpha array between evaluations
   double* pf;     // [8] past cost values (lbfgs.hpp:508, 658)
   double* obs;    // [kObsCap][4] obstacle metadata of the current problem: start, duration, uniform piece duration, (P<<32|piece_ptr)
-  SegScratch* seg;  // [kMaxSeg]
-  double* scal;   // [kMaxSeg][4] rank 0's sweep partials
-  unsigned long long* ctl;  // [4] team mailbox: [0] exit flag, [1] problem id, [2] plane pointer of the current problem
-  double* part;   // (kPart-1) x part_doubles: partial gdC, scalars (and staging) of partial sums 1..kPart-1
+  SegScratch* seg;  // [S]
+  double* rscal;  // [S][kVR+1][4] scalar sums of the sweep per virtual rank
+  double* adj;    // [2*rows] strict build only: the adjoint right-hand side (the reference keeps gdC beside it)
 };
-// partial gdC + scalars (+ a private tile-staging buffer for the ranks of a static team; a drain-phase helper uses the
-// staging buffer of its own, idle, workspace)
-__host__ __device__ inline int part_doubles_for(int rows) {
-  return 2 * rows + 4 * kMaxSeg + (kTeam > 1 ? 2 * 12 * kStageLd : 0);
-}
 
-__host__ __device__ inline int ws_doubles_for(int rows, int npad) {
-  return 6 * rows + 5 * npad + 2 * 12 * kStageLd + 8 + 4 * kObsCap + kMaxSeg * (int)(sizeof(SegScratch) / sizeof(double)) +
-         4 * kMaxSeg + 4 + (kPart - 1) * part_doubles_for(rows);
+// workspace size in doubles; obstacle metadata only when the batch has obstacles
+__host__ __device__ inline int ws_doubles_for(int rows, int npad, int S, int has_obs) {
+  return 6 * rows + 5 * npad + 2 * 12 * kStageLd + 8 + (has_obs ? 4 * kObsCap : 0) +
+         S * (int)(sizeof(SegScratch) / sizeof(double)) + S * (kVR + 1) * 4 + (kStrict ? 2 * rows : 0);
 }
 
 __device__ __forceinline__ WarpWS carve_ws(double* base, const ShapeDev& sh) {
@@ -181,32 +201,21 @@ __device__ __forceinline__ WarpWS carve_ws(double* base, const ShapeDev& sh) {
   w.stage = w.d + sh.npad;
   w.pf = w.stage + 2 * 12 * kStageLd;
   w.obs = w.pf + 8;
-  w.seg = reinterpret_cast<SegScratch*>(w.obs + 4 * kObsCap);
-  w.scal = w.obs + 4 * kObsCap + kMaxSeg * (int)(sizeof(SegScratch) / sizeof(double));
-  w.ctl = reinterpret_cast<unsigned long long*>(w.scal + 4 * kMaxSeg);
-  w.part = w.scal + 4 * kMaxSeg + 4;
+  double* q = w.obs + (sh.has_obs ? 4 * kObsCap : 0);
+  w.seg = reinterpret_cast<SegScratch*>(q);
+  w.rscal = q + sh.S * (int)(sizeof(SegScratch) / sizeof(double));
+  w.adj = w.rscal + sh.S * (kVR + 1) * 4;
   return w;
 }
-// my_stage: tile-staging buffer of the warp that EXECUTES the sweep (its own workspace's)
-__device__ __forceinline__ SweepTarget sweep_target(const WarpWS& w, const ShapeDev& sh, int rank, double* my_stage) {
-  SweepTarget t;
-  t.rank = rank;
-  if (rank == 0) {
-    t.gd = w.gd, t.stage = my_stage, t.scal = w.scal;
-  } else {
-    double* p = w.part + (size_t)(rank - 1) * part_doubles_for(sh.rows);
-    t.gd = p, t.scal = p + 2 * sh.rows;
-    t.stage = kTeam > 1 ? p + 2 * sh.rows + 4 * kMaxSeg : my_stage;
-  }
-  return t;
-}
-// pair barrier of the drain-phase helpers (owner + helper warp)
-__device__ __forceinline__ void pair_bar(int id) { asm volatile("bar.sync %0, 64;" ::"r"(id) : "memory"); }
-// named barriers of a team: A = "coefficients ready, sweep", B = "sweep partials ready"
-__device__ __forceinline__ void team_bar(int id) {
-  asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(32 * kTeam) : "memory");
-}
 
+// virtual ranks [r0, r1) of member `i` (0 = the owner) of a team of t: contiguous chunks, the larger ones last (the
+// owner also has the serial parts of the evaluation to do)
+__device__ __forceinline__ void rank_chunk(int i, int t, int& r0, int& r1) {
+  const int base = kVR / t, rem = kVR % t;
+  const int big0 = t - rem;  // members big0 .. t-1 get base + 1 ranks
+  r0 = i * base + max(0, i - big0);
+  r1 = r0 + base + (i >= big0 ? 1 : 0);
+}
 
 // Per-problem constants that every evaluation needs (boundary states, direction of each gear segment): read from global
 // memory ONCE when the warp takes the problem instead of at every evaluation (the dependent seg_base -> singul load
@@ -492,20 +501,114 @@ constexpr int kPlaneChunk = 4;
 // each warp-wide load is one contiguous 256 B row).  The host pads the plane count to a multiple of 4 with null planes.
 // -DDFTPAV_PLANES_STREAM=1: planes are read with the streaming (evict-first) cache operator so that the once-per-
 // evaluation plane stream does not push the L-BFGS history of the resident problems out of L2.
-#ifndef DFTPAV_PLANES_STREAM
-#define DFTPAV_PLANES_STREAM 1  // measured: 197-199 k vs 192-193 k solves/s at config 3
-#endif
-#if DFTPAV_PLANES_STREAM
+// Planes are read with the streaming (evict-first) cache operator: the once-per-evaluation plane stream must not push
+// the L-BFGS history of the resident problems out of L2 (measured 197-199 k vs 192-193 k solves/s).  Not ld.global.nc:
+// the tiled copy is written by this kernel (layout_problem).
 #define DFTPAV_PLANE_LD(p) __ldcs(p)
-#else
-#define DFTPAV_PLANE_LD(p) __ldg(p)
-#endif
 __device__ __forceinline__ void load_plane_chunk(double (&pn)[kPlaneChunk][4], const double* __restrict__ lanep) {
 #pragma unroll
   for (int hh = 0; hh < kPlaneChunk; hh++) {
 #pragma unroll
     for (int cc = 0; cc < 4; cc++) pn[hh][cc] = DFTPAV_PLANE_LD(lanep + (hh * 4 + cc) * 32);
   }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Plane layout on first use: raw (n, p) planes [sample][h][4] of ONE problem -> its pass-major SoA
+// [pass][chunk][16 components][32 lanes] with unit normals (replaces the deep copy + colwise().normalize() of
+// traj_optimizer.cpp:15, 49-52).  Slot u = pass*32 + lane holds the sample that lane handles in that pass of the sweep
+// (two 16-sample tiles per regular pass, then the piece-end samples).  Done by the warp that takes the problem, so the
+// host->device copy of the planes (the dominant bytes of an upload) can still be running while the first problems are
+// being solved: the warp first waits for the arrival flag of the problem's upload chunk.
+// ------------------------------------------------------------------------------------------------
+__device__ __noinline__ void layout_problem(const ShapeDev& sh, const BatchDev& bd, int prob, double* __restrict__ dst,
+                                            int lane) {
+  if (lane == 0) {
+    const volatile int* rd = bd.ready + prob / bd.chunk;
+    while (*rd != bd.epoch) __nanosleep(500);
+    __threadfence();
+  }
+  __syncwarp();
+  if (*reinterpret_cast<const volatile int*>(bd.laid + prob) == bd.epoch) return;
+  const int nchunk = sh.H / 4;
+  const int K = sh.K, Kd = sh.Kd;
+  const int td = (Kd + kTile - 1) / kTile, tk = (K + kTile - 1) / kTile;
+  long long pid0 = bd.samp_base[prob];
+  for (int s = 0; s < sh.S; s++) {
+    const int N = sh.N[s];
+    const int ntile = sh.ntile[s];
+    const int tlast0 = td + (N - 2) * tk + sh.tpad[s];
+    const int npass_reg = (ntile + 1) >> 1, npass = npass_reg + ((N + 31) >> 5);
+    for (int pass = 0; pass < npass; pass++) {
+      int piece = -1, j = 0;
+      if (pass < npass_reg) {
+        const int t = 2 * pass + (lane >> 4), r = lane & 15;
+        if (t < ntile) {
+          int j0;
+          if (t < td) {
+            piece = 0;
+            j0 = kTile * t;
+          } else if (t < td + (N - 2) * tk) {
+            const int uu = t - td;
+            piece = 1 + uu / tk;
+            j0 = kTile * (uu % tk);
+          } else {
+            const int uu = t - tlast0;  // -1: the padding tile
+            piece = N - 1;
+            j0 = uu < 0 ? Kd : kTile * uu;
+          }
+          j = j0 + r;
+          const int Kp = (piece == 0 || piece == N - 1) ? Kd : K;
+          if (j >= Kp) piece = -1;
+        }
+      } else {
+        piece = (pass - npass_reg) * 32 + lane;
+        if (piece >= N) piece = -1;
+        else j = (piece == 0 || piece == N - 1) ? Kd : K;
+      }
+      int Hs = 0;
+      const double* src = nullptr;
+      if (piece >= 0) {
+        // pointid inside the segment (traj_optimizer.cpp:514): pieces before contribute K_i + 1 samples each
+        long long pid = pid0 + j;
+        if (piece > 0) pid += (Kd + 1) + (long long)(piece - 1) * (K + 1);
+        if (bd.plane_ptr) {
+          Hs = (int)(bd.plane_ptr[pid + 1] - bd.plane_ptr[pid]);
+          src = bd.planes_raw + 4 * bd.plane_ptr[pid];
+        } else {
+          Hs = bd.uniform_H;
+          src = bd.planes_raw + 4 * pid * bd.uniform_H;
+        }
+      }
+      double* d0 = dst + ((size_t)(sh.samp0[s] / 32) + pass) * nchunk * 512 + lane;
+      for (int h = 0; h < sh.H; h++) {
+        double nx = 0.0, ny = 0.0, px = 0.0, py = 0.0;
+        if (h < Hs) {
+          const double2 a = *reinterpret_cast<const double2*>(src + 4 * h);
+          const double2 b = *reinterpret_cast<const double2*>(src + 4 * h + 2);
+          nx = a.x, ny = a.y, px = b.x, py = b.y;
+          const double z = nx * nx + ny * ny;
+          if (z > 0.0) {
+            const double nz = sqrt(z);
+            nx /= nz;
+            ny /= nz;
+          }
+        }
+        double* d4 = d0 + (size_t)(h >> 2) * 512 + (h & 3) * 128;  // chunk h/4, plane h%4 -> components 4*(h%4)..+3
+        d4[0] = nx;
+        d4[32] = ny;
+        d4[64] = px;
+        d4[96] = py;
+      }
+    }
+    pid0 += (long long)(N - 2) * (K + 1) + 2 * (Kd + 1);
+  }
+  __syncwarp();
+  if (lane == 0) {
+    __threadfence();
+    *reinterpret_cast<volatile int*>(bd.laid + prob) = bd.epoch;
+  }
+  __syncwarp();
 }
 
 // Stages the obstacle metadata of a problem into the warp workspace (called once per problem).
@@ -732,14 +835,19 @@ __device__ __noinline__ void dyn_obstacles(const ParamsDev& P, const BatchDev& b
 // ------------------------------------------------------------------------------------------------
 // constraint-sample sweep of one gear segment (addPVAGradCost2CT, traj_optimizer.cpp:422-779)
 // ------------------------------------------------------------------------------------------------
+// Regular passes of virtual ranks [r_begin, r_end) (rank-major: all passes of a rank, then the next rank), then - if
+// do_end - the end passes (piece-end samples).  Reads the coefficients / segment scalars / obstacle metadata of `ws`
+// (the executing warp's own workspace: a helper copies them from its owner first), adds into out.gd and stores the
+// scalar sums per virtual rank into out.rscal (both in the OWNER's workspace).
 template <bool HAS_OBS>
 __device__ __forceinline__ void sweep_segment(const ShapeDev& sh, const ParamsDev& P, const BatchDev& bd, int prob,
-                                              const double* __restrict__ planes, WarpWS& ws, const SweepTarget& tgt,
-                                              int s, int singul_, int lane) {
+                                              const double* __restrict__ planes, WarpWS& ws, const SweepOut& so,
+                                              int s, int singul_, int lane, int r_begin, int r_end, bool do_end) {
   const int N = sh.N[s];
   const int K = sh.K, Kd = sh.Kd;
   const int td = (Kd + kTile - 1) / kTile, tk = (K + kTile - 1) / kTile;
   const int ntile = sh.ntile[s];
+  const int tlast0 = td + (N - 2) * tk + sh.tpad[s];  // first tile of the last piece
   const int npass_reg = (ntile + 1) >> 1;
   const int npass_end = (N + 31) >> 5;
   const int half = lane >> 4, r = lane & 15;
@@ -749,10 +857,11 @@ __device__ __forceinline__ void sweep_segment(const ShapeDev& sh, const ParamsDe
   const double max_vel = P.max_vel[sidx], max_cur = P.max_cur[sidx], max_acc = P.max_acc[sidx];
   const double sg = (double)singul_;
   const double* cseg = ws.c + 2 * sh.row0[s];
-  double* gdseg = tgt.gd + 2 * sh.row0[s];
-  double* stage0 = tgt.stage;
-  // keep these three pointers in registers: ptxas otherwise re-derives them from the kernel parameters inside the loop
-  asm volatile("" : "+l"(cseg), "+l"(gdseg), "+l"(stage0));
+  double* gdseg = so.gd + 2 * sh.row0[s];
+  double* stage0 = ws.stage;
+  double* rsc = so.rscal + (size_t)s * (kVR + 1) * 4;
+  // keep these pointers in registers: ptxas otherwise re-derives them from the kernel parameters inside the loop
+  asm volatile("" : "+l"(cseg), "+l"(gdseg), "+l"(stage0), "+l"(rsc));
   const int H = sh.H;
   const int nchunk = H / kPlaneChunk;
   // this lane's column of the segment's first pass block
@@ -762,13 +871,38 @@ __device__ __forceinline__ void sweep_segment(const ShapeDev& sh, const ParamsDe
   const int npass = npass_reg + npass_end;
   const double invK_ = 1.0 / K, invKd_ = 1.0 / Kd;
   double pn[kPlaneChunk][4];
-  // rank r takes passes kTeam-1-r, 2*kTeam-1-r, ...: when the pass count is not a multiple of the team size the ranks
-  // that are short one pass are the low ones, and rank 0 has the serial parts of the evaluation to do as well
-  const int pass0 = kPart - 1 - tgt.rank;
-  if (pass0 < npass) load_plane_chunk(pn, pl + (size_t)(pass0 * nchunk) * 512);
+  // ---- pass sequence of this call
+  r_end = min(r_end, min(kVR, npass_reg));  // virtual ranks >= npass_reg have no passes
+  int vr = r_begin, pass = r_begin;
+  bool endpass = false;
+  if (vr >= r_end) {
+    if (!do_end) return;
+    endpass = true;
+    vr = kVR;
+    pass = npass_reg;
+  }
+  load_plane_chunk(pn, pl + (size_t)(pass * nchunk) * 512);
 
-  for (int pass = pass0; pass < npass; pass += kPart) {
-    const bool endpass = pass >= npass_reg;
+  while (true) {
+    // successor of this pass: next pass of the rank, first pass of the next rank, first end pass, or nothing
+    int pass_next, vr_next = vr;
+    bool end_next = endpass, has_next = true;
+    if (!endpass) {
+      pass_next = pass + kVR;
+      if (pass_next >= npass_reg) {
+        vr_next = vr + 1;
+        pass_next = vr_next;
+        if (vr_next >= r_end) {
+          end_next = true;
+          vr_next = kVR;
+          pass_next = npass_reg;
+          has_next = do_end;
+        }
+      }
+    } else {
+      pass_next = pass + 1;
+      has_next = pass_next < npass;
+    }
     int piece, j, Kp;
     bool valid;
     if (!endpass) {
@@ -787,9 +921,10 @@ __device__ __forceinline__ void sweep_segment(const ShapeDev& sh, const ParamsDe
           j0 = kTile * (u % tk);
         }
       } else {
-        const int u = t - td - (N - 2) * tk;
+        const int u = t - tlast0;  // -1: the padding tile (tpad)
         piece = N - 1;
-        j0 = kTile * u;
+        j0 = kTile * max(u, 0);
+        if (u < 0) j0 = Kd;  // invalid
       }
       Kp = (piece == 0 || piece == N - 1) ? Kd : K;
       j = j0 + r;
@@ -937,7 +1072,7 @@ __device__ __forceinline__ void sweep_segment(const ShapeDev& sh, const ParamsDe
 
     // ---------------- stage C: software prefetch of the next pass's first plane chunk (registers are free now;
     //                  its consumers are most of a pass away)
-    if (pass + kPart < npass) load_plane_chunk(pn, pl + (size_t)((pass + kPart) * nchunk) * 512);
+    if (has_next) load_plane_chunk(pn, pl + (size_t)(pass_next * nchunk) * 512);
 
     // ---------------- stage D: moving obstacles, velocity / acceleration / curvature limits, expansion
     double out[12];
@@ -1091,38 +1226,40 @@ __device__ __forceinline__ void sweep_segment(const ShapeDev& sh, const ParamsDe
         sum = s0 + s1;
       }
       // the two halves may hit the same piece (Kd > 16): add one after the other
-      const int tvalid = (2 * pass + half) < ntile;
+      const int tt = 2 * pass + half;
+      const bool tvalid = tt < ntile && !(tt >= td + (N - 2) * tk && tt < tlast0);
       if (half == 0 && r < 12 && tvalid) gdseg[12 * piece + r] += sum;
       __syncwarp();
       if (half == 1 && r < 12 && tvalid) gdseg[12 * piece + r] += sum;
       __syncwarp();
     }
+    // ---------------- stage F: leaving a virtual rank (or the end passes): its scalar sums, one interleaved butterfly
+    if (!has_next || vr_next != vr) {
+      double v4[4] = {acc_gdT, acc_p0, acc_p1, acc_p2};
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) {
+#pragma unroll
+        for (int q = 0; q < 4; q++)
+          if (HAS_OBS || q != 2) v4[q] += __shfl_xor_sync(FULL, v4[q], o);
+      }
+      if (lane < 4) rsc[4 * vr + lane] = lane == 0 ? v4[0] : (lane == 1 ? v4[1] : (lane == 2 ? v4[2] : v4[3]));
+      acc_gdT = acc_p0 = acc_p1 = acc_p2 = 0.0;
+      __syncwarp();
+    }
+    if (!has_next) break;
+    pass = pass_next;
+    vr = vr_next;
+    endpass = end_next;
   }
-  // segment totals
-  acc_gdT = warp_sum(acc_gdT);
-  acc_p0 = warp_sum(acc_p0);
-  acc_p2 = warp_sum(acc_p2);
-  if (HAS_OBS) acc_p1 = warp_sum(acc_p1);
-  if (lane == 0) {
-    tgt.scal[4 * s + 0] = acc_gdT;
-    tgt.scal[4 * s + 1] = acc_p0;
-    tgt.scal[4 * s + 2] = acc_p1;
-    tgt.scal[4 * s + 3] = acc_p2;
-  }
-  __syncwarp();
 }
 
-// The sweep of all segments by one rank of the team (ranks > 0 start from a zeroed partial gradient).
+// The sweep of all segments: virtual ranks [r_begin, r_end) of the regular passes and, if do_end, the end passes.
 template <bool HAS_OBS>
-__device__ __forceinline__ void sweep_rank(const ShapeDev& sh, const ParamsDev& P, const BatchDev& bd, int prob,
-                                           const double* __restrict__ planes, WarpWS& ws, int rank, double* my_stage,
-                                           int lane) {
-  const SweepTarget tgt = sweep_target(ws, sh, rank, my_stage);
-  if (rank > 0) {
-    for (int i = lane; i < 2 * sh.rows; i += 32) tgt.gd[i] = 0.0;
-    __syncwarp();
-  }
-  for (int s = 0; s < sh.S; s++) sweep_segment<HAS_OBS>(sh, P, bd, prob, planes, ws, tgt, s, (int)ws.seg[s].singul, lane);
+__device__ __forceinline__ void sweep_ranks(const ShapeDev& sh, const ParamsDev& P, const BatchDev& bd, int prob,
+                                            const double* __restrict__ planes, WarpWS& ws, const SweepOut& so, int lane,
+                                            int r_begin, int r_end, bool do_end) {
+  for (int s = 0; s < sh.S; s++)
+    sweep_segment<HAS_OBS>(sh, P, bd, prob, planes, ws, so, s, (int)ws.seg[s].singul, lane, r_begin, r_end, do_end);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -1371,26 +1508,18 @@ __device__ __forceinline__ double eval_post(const ShapeDev& sh, const ParamsDev&
   const int gb = tv0 + S;                                  // gear positions
   const int ab = gb + 2 * (S - 1);                         // angles
   const bool dense = sh.dense_minco != 0;
-  if (kPart > 1) {
-    // fixed-order merge of the partial gradients: ((partial 0 + partial 1) + partial 2) + ...
-    const int pd = part_doubles_for(sh.rows);
-    for (int i = lane; i < 2 * sh.rows; i += 32) {
-      double v = ws.gd[i];
-#pragma unroll
-      for (int r = 1; r < kPart; r++) v += ws.part[(size_t)(r - 1) * pd + i];
-      ws.gd[i] = v;
-    }
-  }
+  // fixed-order merge of the sweep's scalar sums: virtual ranks 0 .. kVR-1 in order, then the end passes (whoever
+  // computed them: the owner or its drain-phase helpers)
   if (lane < S) {
-    double a[4];
+    const double* rs = ws.rscal + (size_t)lane * (kVR + 1) * 4;
+    const int nr = min(kVR, (sh.ntile[lane] + 1) >> 1);
+    double a[4] = {0.0, 0.0, 0.0, 0.0};
+    for (int r = 0; r < nr; r++) {
 #pragma unroll
-    for (int q = 0; q < 4; q++) a[q] = ws.scal[4 * lane + q];
-#pragma unroll
-    for (int r = 1; r < kPart; r++) {
-      const double* ps = ws.part + (size_t)(r - 1) * part_doubles_for(sh.rows) + 2 * sh.rows;
-#pragma unroll
-      for (int q = 0; q < 4; q++) a[q] += ps[4 * lane + q];
+      for (int q = 0; q < 4; q++) a[q] += rs[4 * r + q];
     }
+#pragma unroll
+    for (int q = 0; q < 4; q++) a[q] += rs[4 * kVR + q];
     ws.seg[lane].gdT += a[0];
     ws.seg[lane].pen[0] = a[1];
     ws.seg[lane].pen[1] = a[2];
@@ -1539,6 +1668,12 @@ __device__ __forceinline__ void tma_load_block(double* smem_dst, const double* g
   }
 }
 
+#if DFTPAV_STRICT
+}  // namespace dftpav
+#include "dftpav_strict.cuh"
+namespace dftpav {
+#endif
+
 // ------------------------------------------------------------------------------------------------
 // standalone evaluation kernel: f, g at caller-provided x (the parity hook dftpav_eval)
 // ------------------------------------------------------------------------------------------------
@@ -1550,30 +1685,27 @@ __global__ void __launch_bounds__(32 * DFTPAV_MAX_WARPS, 1)
   extern __shared__ __align__(128) double smem[];
   __shared__ __align__(8) unsigned long long mbar;
   tma_load_block(smem, grp.lu, (unsigned)(sh.lu_doubles * sizeof(double)), &mbar);
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nteam = (blockDim.x >> 5) / kTeam;
-  const int team = warp / kTeam, rank = warp % kTeam;
-  WarpWS ws = carve_ws(smem + sh.lu_doubles + team * sh.ws_doubles, sh);
-  // every rank walks the same loop (one sweep call site); ranks > 0 only take part in the sweep
-  for (int local = blockIdx.x * nteam + team; local < grp.count; local += gridDim.x * nteam) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarp = blockDim.x >> 5;
+  WarpWS ws = carve_ws(smem + sh.lu_doubles + warp * sh.ws_doubles, sh);
+  const SweepOut so{ws.gd, ws.rscal};
+  for (int local = blockIdx.x * nwarp + warp; local < grp.count; local += gridDim.x * nwarp) {
     const int prob = grp.prob_id[local];
-    const double* planes = grp.planes + (size_t)local * sh.H * 4 * sh.Mpad;
+    double* planes = grp.planes + (size_t)local * sh.H * 4 * sh.Mpad;
+    layout_problem(sh, bd, prob, planes, lane);
     long long t_prev = 0;
-    if (rank == 0) {
-      for (int i = lane; i < sh.n; i += 32) ws.x[i] = xin[(size_t)prob * bd.n_stride + i];
-      __syncwarp();
-      stage_problem(sh, bd, prob, ws, lane);
-      if (HAS_OBS) stage_obstacles(bd, prob, ws.obs, lane);
-      eval_pre(sh, P, smem, ws, ws.x, lane, t_prev);
-    }
-    if (kTeam > 1) team_bar(1 + 2 * team);
-    {
-      const int r_end = kTeam > 1 ? rank + 1 : kPart;  // without static teams the owner computes every partial sum
-#pragma unroll 1
-      for (int r = rank; r < r_end; r++) sweep_rank<HAS_OBS>(sh, P, bd, prob, planes, ws, r, ws.stage, lane);
-    }
-    if (kTeam > 1) team_bar(2 + 2 * team);
-    if (rank != 0) continue;
-    const double f = eval_post(sh, P, smem, ws, ws.x, ws.g, lane, t_prev);
+    for (int i = lane; i < sh.n; i += 32) ws.x[i] = xin[(size_t)prob * bd.n_stride + i];
+    __syncwarp();
+    stage_problem(sh, bd, prob, ws, lane);
+    double f;
+#if DFTPAV_STRICT
+    f = strict_eval(sh, P, planes, smem, ws, ws.adj, ws.x, ws.g, lane);
+#else
+    if (HAS_OBS) stage_obstacles(bd, prob, ws.obs, lane);
+    eval_pre(sh, P, smem, ws, ws.x, lane, t_prev);
+    // the whole team's work by this warp: every virtual rank in order, then the end passes (same bits as a helped solve)
+    sweep_ranks<HAS_OBS>(sh, P, bd, prob, planes, ws, so, lane, 0, kVR, true);
+    f = eval_post(sh, P, smem, ws, ws.x, ws.g, lane, t_prev);
+#endif
     __syncwarp();
     if (lane == 0) fout[prob] = f;
     for (int i = lane; i < bd.n_stride; i += 32) gout[(size_t)prob * bd.n_stride + i] = i < sh.n ? ws.g[i] : 0.0;
@@ -1585,82 +1717,29 @@ __global__ void __launch_bounds__(32 * DFTPAV_MAX_WARPS, 1)
 }
 
 // ------------------------------------------------------------------------------------------------
-// L-BFGS two-loop recursion (lbfgs.hpp:716-739) with the direction held in registers (NPL elements per lane) and
-// the (s_j, y_j, ys_j) history stream software-prefetched two steps ahead.  alpha_j lives in shared memory.
+// L-BFGS two-loop recursion (lbfgs.hpp:716-739)
 // ------------------------------------------------------------------------------------------------
 // The history keeps 1/ys_j (one division when the pair is stored) and the recursion multiplies by it, instead of the
 // reference's division by ys_j in both loops (lbfgs.hpp:722, 733): <= 1.5 ulp per alpha_j / beta_j, and the ~70-cycle
-// division leaves the dependent chain of every history step.  -DDFTPAV_RECIP_YS=0 restores the divisions.
-// -DDFTPAV_HIST_PREFETCH=1: L2 prefetch of the whole history window at the start of the recursion;
-// =2: L1 prefetch DFTPAV_HIST_PD entries ahead inside both loops.
-#ifndef DFTPAV_HIST_PREFETCH
-#define DFTPAV_HIST_PREFETCH 0
-#endif
-#ifndef DFTPAV_HIST_PD
-#define DFTPAV_HIST_PD 4
-#endif
-constexpr int kHistPD = DFTPAV_HIST_PD;  // prefetch distance (history entries) of -DDFTPAV_HIST_PREFETCH=2
-#ifndef DFTPAV_RECIP_YS
-#define DFTPAV_RECIP_YS 1
-#endif
-#if DFTPAV_RECIP_YS
-#define DFTPAV_OVER_YS(num, ysv) ((num) * (ysv))
-#define DFTPAV_STORE_YS(ysv) (1.0 / (ysv))
-#else
+// division leaves the dependent chain of every history step.  The strict build stores ys_j and divides.
+#if DFTPAV_STRICT
 #define DFTPAV_OVER_YS(num, ysv) ((num) / (ysv))
 #define DFTPAV_STORE_YS(ysv) (ysv)
+#else
+#define DFTPAV_OVER_YS(num, ysv) ((num) * (ysv))
+#define DFTPAV_STORE_YS(ysv) (1.0 / (ysv))
 #endif
-template <int NPL>
-struct HistStage {
-  double s[NPL], y[NPL], ys;
-};
-template <int NPL>
-__device__ __forceinline__ void hist_load(HistStage<NPL>& st, const double* __restrict__ lm_s,
-                                          const double* __restrict__ lm_y, const double* __restrict__ lm_ys, int j,
-                                          int ld, int n, int lane, bool want_s, bool want_y) {
-  const double* sj = lm_s + (size_t)j * ld;
-  const double* yj = lm_y + (size_t)j * ld;
-#pragma unroll
-  for (int e = 0; e < NPL; e++) {
-    const int i = lane + 32 * e;
-    st.s[e] = (want_s && i < n) ? sj[i] : 0.0;
-    st.y[e] = (want_y && i < n) ? yj[i] : 0.0;
-  }
-  st.ys = lm_ys[j];
-}
 
-// Lean hand-scheduled version: no integer modulo (wrap by compare), scalar double buffer (one history entry in flight:
-// measured best on B200 — deeper rings spill and lose 25 %), trip count read through a shuffle so that the compiler
-// treats the loop as warp-uniform and emits bare SHFL instead of WARPSYNC-guarded collectives.
-// L1 prefetch of history entry jj (lines of s_jj and y_jj spread over the first lanes); costs no registers
-__device__ __forceinline__ void hist_prefetch_l1(const double* lm_s, const double* lm_y, int jj, int ld, int n, int lane) {
-  const int nl = ((n * 8 - 1) >> 7) + 2;
-  if (lane < 2 * nl) {
-    const int k = lane < nl ? lane : lane - nl;
-    const double* a = (lane < nl ? lm_s : lm_y) + (size_t)jj * ld + min(16 * k, n - 1);
-    asm volatile("prefetch.global.L1 [%0];" ::"l"(a));
-  }
-}
+// Register variant: the direction in registers (NPL elements per lane, n <= 32*NPL), the (s_j, y_j, 1/ys_j) stream
+// software-prefetched one entry ahead (measured best on B200: deeper register rings spill and lose 25 %; an L2 / L1
+// prefetch of the window and a cp.async ring in shared memory were measured too and do not help, profiles/README.md:
+// the step is bound by its dependent chain, not by the L2 round trip).  No integer modulo (wrap by compare); the trip
+// count is read through a shuffle so that the compiler treats the loop as warp-uniform and emits bare SHFL.
 template <int NPL>
 __device__ __noinline__ void two_loop(double* d_sm, double* alpha_sm, const double* __restrict__ lm_s,
                                       const double* __restrict__ lm_y, const double* __restrict__ lm_ys, int ld, int m,
                                       int end, int bound_in, int n, int lane, double ys, double yy) {
   const int bound = __shfl_sync(FULL, bound_in, 0);
-#if DFTPAV_HIST_PREFETCH == 1
-  {  // pull every (s_j, y_j) line this recursion will read into L2 now: the loops below then wait for L2, not DRAM
-    const int nl = ((n * 8 - 1) >> 7) + 2;  // 128-byte lines per vector (rows are 32-byte, not 128-byte aligned)
-    const int per = 2 * nl, total = bound * per;
-    for (int t = lane; t < total; t += 32) {
-      const int e = t / per, r = t - e * per;
-      int jj = end - 1 - e;
-      if (jj < 0) jj += m;
-      const int k = r < nl ? r : r - nl;
-      const double* v = (r < nl ? lm_s : lm_y) + (size_t)jj * ld;
-      const double* a = v + min(16 * k, n - 1);
-      asm volatile("prefetch.global.L2 [%0];" ::"l"(a));
-    }
-  }
-#endif
   double d[NPL], sc_[NPL], yc_[NPL], sn_[NPL], yn_[NPL];
   double ysc, ysn = 0.0;
   bool ok[NPL];
@@ -1688,13 +1767,6 @@ __device__ __noinline__ void two_loop(double* d_sm, double* alpha_sm, const doub
   for (int i = 0; i < bound; ++i) {
     int jn = j - 1;
     if (jn < 0) jn += m;
-#if DFTPAV_HIST_PREFETCH == 2
-    if (i + kHistPD < bound) {
-      int jp = j - kHistPD;
-      if (jp < 0) jp += m;
-      hist_prefetch_l1(lm_s, lm_y, jp, ld, n, lane);
-    }
-#endif
     if (i + 1 < bound) {
       const double* sj = lm_s + (size_t)jn * ld + lane;
       const double* yj = lm_y + (size_t)jn * ld + lane;
@@ -1739,13 +1811,6 @@ __device__ __noinline__ void two_loop(double* d_sm, double* alpha_sm, const doub
   for (int i = 0; i < bound; ++i) {
     int jn = j + 1;
     if (jn >= m) jn -= m;
-#if DFTPAV_HIST_PREFETCH == 2
-    if (i + kHistPD < bound) {
-      int jp = j + kHistPD;
-      if (jp >= m) jp -= m;
-      hist_prefetch_l1(lm_s, lm_y, jp, ld, n, lane);
-    }
-#endif
     if (i + 1 < bound) {
       const double* sj = lm_s + (size_t)jn * ld + lane;
       const double* yj = lm_y + (size_t)jn * ld + lane;
@@ -1778,246 +1843,45 @@ __device__ __noinline__ void two_loop(double* d_sm, double* alpha_sm, const doub
   __syncwarp();
 }
 
-// Grouped variant of the two-loop recursion: bit-identical arithmetic, but the history entries are loaded GS at a time
-// into two register groups (the next group is in flight while the current one is consumed).  With one entry in flight
-// a history step costs one L2 round trip (~475 cycles measured for a lone warp: 8.5-9.5 ms for the 130-140-iteration
-// problems that set the batch time, half of it in this function); with GS entries the round trip is shared by GS steps.
-#ifndef DFTPAV_TWO_LOOP_GROUPED
-#define DFTPAV_TWO_LOOP_GROUPED 0  // measured: the register groups end up in local memory and a lone problem gets 2x SLOWER (17.5 vs 8.5 ms)
-#endif
-#ifndef DFTPAV_TL_GS
-#define DFTPAV_TL_GS 4  // history entries per register group
-#endif
-__device__ __forceinline__ int wrap_index(int x, int m) {
-  x %= m;
-  return x < 0 ? x + m : x;
-}
-template <int NPL, int GS>
-__device__ __noinline__ void two_loop_grouped(double* d_sm, double* alpha_sm, const double* __restrict__ lm_s,
+// Generic variant for any n (up to the 517 variables of 4 segments x 64 pieces): the direction stays in shared memory.
+// Also the form of the strict build: warp_dot is then the sequential sum of the reference (lbfgs.hpp:719-736).
+__device__ __noinline__ void two_loop_generic(double* d_sm, double* alpha_sm, const double* __restrict__ lm_s,
                                               const double* __restrict__ lm_y, const double* __restrict__ lm_ys, int ld,
                                               int m, int end, int bound_in, int n, int lane, double ys, double yy) {
   const int bound = __shfl_sync(FULL, bound_in, 0);
-  double d[NPL];
-  bool ok[NPL];
-#pragma unroll
-  for (int e = 0; e < NPL; e++) {
-    const int i = lane + 32 * e;
-    ok[e] = i < n;
-    d[e] = ok[e] ? d_sm[i] : 0.0;
-  }
-  double sA[GS][NPL], yA[GS][NPL], rA[GS], sB[GS][NPL], yB[GS][NPL], rB[GS];
-  // entries j, j+dir, ... (cnt of them, indices wrap in [0, m))
-  auto load = [&](double (&s_)[GS][NPL], double (&y_)[GS][NPL], double (&r_)[GS], int j, int dir, int cnt) {
-#pragma unroll
-    for (int q = 0; q < GS; q++) {
-      if (q < cnt) {
-        const double* sj = lm_s + (size_t)j * ld + lane;
-        const double* yj = lm_y + (size_t)j * ld + lane;
-#pragma unroll
-        for (int e = 0; e < NPL; e++) {
-          s_[q][e] = ok[e] ? sj[32 * e] : 0.0;
-          y_[q][e] = ok[e] ? yj[32 * e] : 0.0;
-        }
-        r_[q] = lm_ys[j];
-        j += dir;
-        if (j < 0) j += m;
-        if (j >= m) j -= m;
-      }
-    }
-  };
-  // first loop (lbfgs.hpp:719-724), newest to oldest
-  auto proc1 = [&](double (&s_)[GS][NPL], double (&y_)[GS][NPL], double (&r_)[GS], int j, int cnt) {
-#pragma unroll
-    for (int q = 0; q < GS; q++) {
-      if (q < cnt) {
-        double part = 0.0;
-#pragma unroll
-        for (int e = 0; e < NPL; e++) part += s_[q][e] * d[e];
-        const double a = DFTPAV_OVER_YS(warp_sum(part), r_[q]);
-        if (lane == 0) alpha_sm[j] = a;
-        const double na = -a;
-#pragma unroll
-        for (int e = 0; e < NPL; e++) d[e] += na * y_[q][e];
-        j -= 1;
-        if (j < 0) j += m;
-      }
-    }
-  };
-  // second loop (lbfgs.hpp:730-736), oldest to newest
-  auto proc2 = [&](double (&s_)[GS][NPL], double (&y_)[GS][NPL], double (&r_)[GS], int j, int cnt) {
-#pragma unroll
-    for (int q = 0; q < GS; q++) {
-      if (q < cnt) {
-        double part = 0.0;
-#pragma unroll
-        for (int e = 0; e < NPL; e++) part += y_[q][e] * d[e];
-        const double beta = DFTPAV_OVER_YS(warp_sum(part), r_[q]);
-        const double a = alpha_sm[j] - beta;
-#pragma unroll
-        for (int e = 0; e < NPL; e++) d[e] += a * s_[q][e];
-        j += 1;
-        if (j >= m) j -= m;
-      }
-    }
-  };
-  {
-    int jA = wrap_index(end - 1, m);
-    load(sA, yA, rA, jA, -1, min(GS, bound));
+  int j = end;
 #pragma unroll 1
-    for (int done = 0; done < bound; done += 2 * GS) {
-      const int cntA = min(GS, bound - done), cntB = min(GS, bound - done - GS);
-      const int jB = wrap_index(jA - GS, m);
-      if (cntB > 0) load(sB, yB, rB, jB, -1, cntB);
-      proc1(sA, yA, rA, jA, cntA);
-      if (cntB <= 0) break;
-      jA = wrap_index(jB - GS, m);
-      const int cntA2 = min(GS, bound - done - 2 * GS);
-      if (cntA2 > 0) load(sA, yA, rA, jA, -1, cntA2);
-      proc1(sB, yB, rB, jB, cntB);
-    }
+  for (int i = 0; i < bound; ++i) {
+    j = j == 0 ? m - 1 : j - 1;
+    const double* sj = lm_s + (size_t)j * ld;
+    const double* yj = lm_y + (size_t)j * ld;
+    const double a = DFTPAV_OVER_YS(warp_dot(sj, d_sm, n, lane), lm_ys[j]);
+    if (lane == 0) alpha_sm[j] = a;
+    const double na = -a;
+#pragma unroll 1
+    for (int q = lane; q < n; q += 32) d_sm[q] += na * yj[q];
+    __syncwarp();
   }
   const double scl = ys / yy;
-#pragma unroll
-  for (int e = 0; e < NPL; e++) d[e] *= scl;
-  __syncwarp();
-  {
-    int jA = wrap_index(end - bound, m);
-    load(sA, yA, rA, jA, +1, min(GS, bound));
 #pragma unroll 1
-    for (int done = 0; done < bound; done += 2 * GS) {
-      const int cntA = min(GS, bound - done), cntB = min(GS, bound - done - GS);
-      const int jB = wrap_index(jA + GS, m);
-      if (cntB > 0) load(sB, yB, rB, jB, +1, cntB);
-      proc2(sA, yA, rA, jA, cntA);
-      if (cntB <= 0) break;
-      jA = wrap_index(jB + GS, m);
-      const int cntA2 = min(GS, bound - done - 2 * GS);
-      if (cntA2 > 0) load(sA, yA, rA, jA, +1, cntA2);
-      proc2(sB, yB, rB, jB, cntB);
-    }
-  }
-#pragma unroll
-  for (int e = 0; e < NPL; e++) {
-    const int i = lane + 32 * e;
-    if (ok[e]) d_sm[i] = d[e];
-  }
+  for (int q = lane; q < n; q += 32) d_sm[q] *= scl;
   __syncwarp();
+#pragma unroll 1
+  for (int i = 0; i < bound; ++i) {
+    const double* sj = lm_s + (size_t)j * ld;
+    const double* yj = lm_y + (size_t)j * ld;
+    const double beta = DFTPAV_OVER_YS(warp_dot(yj, d_sm, n, lane), lm_ys[j]);
+    const double a = alpha_sm[j] - beta;
+#pragma unroll 1
+    for (int q = lane; q < n; q += 32) d_sm[q] += a * sj[q];
+    __syncwarp();
+    j = j + 1 == m ? 0 : j + 1;
+  }
 }
 
-// cp.async variant of the two-loop recursion (OFF: measured 180.6 k vs 198.8 k solves/s, lone problem 9.0 vs 8.5 ms): the history
-// entries are copied global -> shared with cp.async (LDGSTS: no registers in flight) D-1 entries ahead into a ring that
-// lives in workspace arrays which are dead between two evaluations (b~ and gdC, contiguous).  Arithmetic and its order
-// are those of two_loop, so results are bit-identical; only the L2 round trip (measured ~475 cycles per history step
-// for a lone warp, profiles/README.md) moves off the dependent chain.  Enable with -DDFTPAV_TWO_LOOP_ASYNC=1.
-#ifndef DFTPAV_TWO_LOOP_ASYNC
-#define DFTPAV_TWO_LOOP_ASYNC 0
-#endif
-__device__ __forceinline__ void cp_async8(double* smem_dst, const double* gsrc) {
-  asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(smem_addr(smem_dst)), "l"(gsrc) : "memory");
-}
-__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
-template <int PENDING>
-__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(PENDING) : "memory"); }
-
-template <int NPL, int D>
-__device__ __noinline__ void two_loop_async(double* d_sm, double* alpha_sm, double* ring, const double* __restrict__ lm_s,
-                                            const double* __restrict__ lm_y, const double* __restrict__ lm_ys, int ld, int m,
-                                            int end, int bound_in, int n, int lane, double ys, double yy) {
-  constexpr int kSlot = 64 * NPL + 2;  // s[32*NPL], y[32*NPL], 1/ys, pad
-  const int bound = __shfl_sync(FULL, bound_in, 0);
-  double d[NPL];
-  bool ok[NPL];
-#pragma unroll
-  for (int e = 0; e < NPL; e++) {
-    const int i = lane + 32 * e;
-    ok[e] = i < n;
-    d[e] = ok[e] ? d_sm[i] : 0.0;
-  }
-  // copies history entry j into ring slot `slot` (every lane its own elements, lane 0 the scalar) and closes the group
-  auto fetch = [&](int j, int slot, bool valid) {
-    if (valid) {
-      double* dst = ring + slot * kSlot;
-      const double* sj = lm_s + (size_t)j * ld;
-      const double* yj = lm_y + (size_t)j * ld;
-#pragma unroll
-      for (int e = 0; e < NPL; e++) {
-        const int i = lane + 32 * e;
-        if (ok[e]) {
-          cp_async8(dst + i, sj + i);
-          cp_async8(dst + 32 * NPL + i, yj + i);
-        }
-      }
-      if (lane == 0) cp_async8(dst + 64 * NPL, lm_ys + j);
-    }
-    cp_async_commit();  // an empty group keeps the group count uniform at the end of the history
-  };
-  // ---- first loop: newest to oldest
-  {
-    int jf = wrap_index(end - 1, m);  // next entry to fetch
-#pragma unroll
-    for (int q = 0; q < D - 1; q++) {
-      fetch(jf, q, q < bound);
-      jf = jf == 0 ? m - 1 : jf - 1;
-    }
-    int j = wrap_index(end - 1, m);
-#pragma unroll 1
-    for (int i = 0; i < bound; ++i) {
-      fetch(jf, (i + D - 1) % D, i + D - 1 < bound);
-      jf = jf == 0 ? m - 1 : jf - 1;
-      cp_async_wait<D - 1>();
-      __syncwarp();
-      const double* slot = ring + (i % D) * kSlot;
-      double part = 0.0;
-#pragma unroll
-      for (int e = 0; e < NPL; e++) part += (ok[e] ? slot[lane + 32 * e] : 0.0) * d[e];
-      const double a = DFTPAV_OVER_YS(warp_sum(part), slot[64 * NPL]);
-      if (lane == 0) alpha_sm[j] = a;
-      const double na = -a;
-#pragma unroll
-      for (int e = 0; e < NPL; e++) d[e] += na * (ok[e] ? slot[32 * NPL + lane + 32 * e] : 0.0);
-      __syncwarp();
-      j = j == 0 ? m - 1 : j - 1;
-    }
-  }
-  cp_async_wait<0>();
-  const double scl = ys / yy;
-#pragma unroll
-  for (int e = 0; e < NPL; e++) d[e] *= scl;
-  __syncwarp();
-  // ---- second loop: oldest to newest
-  {
-    int jf = wrap_index(end - bound, m);
-#pragma unroll
-    for (int q = 0; q < D - 1; q++) {
-      fetch(jf, q, q < bound);
-      jf = jf + 1 == m ? 0 : jf + 1;
-    }
-    int j = wrap_index(end - bound, m);
-#pragma unroll 1
-    for (int i = 0; i < bound; ++i) {
-      fetch(jf, (i + D - 1) % D, i + D - 1 < bound);
-      jf = jf + 1 == m ? 0 : jf + 1;
-      cp_async_wait<D - 1>();
-      __syncwarp();
-      const double* slot = ring + (i % D) * kSlot;
-      double part = 0.0;
-#pragma unroll
-      for (int e = 0; e < NPL; e++) part += (ok[e] ? slot[32 * NPL + lane + 32 * e] : 0.0) * d[e];
-      const double beta = DFTPAV_OVER_YS(warp_sum(part), slot[64 * NPL]);
-      const double a = alpha_sm[j] - beta;
-#pragma unroll
-      for (int e = 0; e < NPL; e++) d[e] += a * (ok[e] ? slot[lane + 32 * e] : 0.0);
-      __syncwarp();
-      j = j + 1 == m ? 0 : j + 1;
-    }
-  }
-  cp_async_wait<0>();
-#pragma unroll
-  for (int e = 0; e < NPL; e++) {
-    const int i = lane + 32 * e;
-    if (ok[e]) d_sm[i] = d[e];
-  }
-  __syncwarp();
+__device__ __forceinline__ int wrap_index(int x, int m) {
+  x %= m;
+  return x < 0 ? x + m : x;
 }
 
 // Blocked two-loop recursion (ROUND-2 CANDIDATE, OFF by default, compiled but NOT yet run on a GPU).  Four history entries
@@ -2183,23 +2047,26 @@ __device__ __noinline__ void two_loop_blocked(double* d_sm, double* alpha_sm, co
 // ------------------------------------------------------------------------------------------------
 enum { PH_FETCH = 0, PH_FIRST = 1, PH_LS = 2 };
 
+// shared-memory flag helpers of the owner / helper protocol (block scope)
+__device__ __forceinline__ int ld_flag(const int* p) { return *reinterpret_cast<const volatile int*>(p); }
+__device__ __forceinline__ void st_flag(int* p, int v) { *reinterpret_cast<volatile int*>(p) = v; }
+__device__ __forceinline__ int go_word(int seq, int h) { return (seq << 4) | (h + 1); }  // h = -1: retired
+
 template <bool HAS_OBS>
 __global__ void __launch_bounds__(32 * DFTPAV_MAX_WARPS, 1)
     solve_kernel(const __grid_constant__ ShapeDev sh, const __grid_constant__ ParamsDev P, const BatchDev bd,
                  const GroupDev grp, const OutDev out, const HistDev hist, int* __restrict__ work_counter) {
   extern __shared__ __align__(128) double smem[];
   __shared__ __align__(8) unsigned long long mbar;
-  __shared__ int pair_state[DFTPAV_MAX_WARPS / 2 + 1];  // 0: both warps solve; 1 + (w & 1): warp w helps its neighbour
-  if (threadIdx.x < DFTPAV_MAX_WARPS / 2 + 1) pair_state[threadIdx.x] = 0;
+  __shared__ TeamCtl ctl[DFTPAV_MAX_WARPS];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarp = blockDim.x >> 5;
+  if (threadIdx.x < DFTPAV_MAX_WARPS) {
+    TeamCtl& c0 = ctl[threadIdx.x];
+    c0.go = go_word(0, 0), c0.h = 0, c0.nhelp = 0, c0.done = 0, c0.alive = threadIdx.x < nwarp ? 1 : 0, c0.prob = -1, c0.planes = 0ull;
+  }
   tma_load_block(smem, grp.lu, (unsigned)(sh.lu_doubles * sizeof(double)), &mbar);  // (contains a __syncthreads)
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nteam = (blockDim.x >> 5) / kTeam;
-  const int team = warp / kTeam, rank = warp % kTeam;
-  WarpWS ws = carve_ws(smem + sh.lu_doubles + team * sh.ws_doubles, sh);
-  double* const my_stage = ws.stage;  // stays this warp's own, also while it helps its neighbour
-  const int pair = warp >> 1;
-  const bool has_partner = kDrainHelp && ((warp ^ 1) < nteam);
-  bool helper = false;
-  const int slot = blockIdx.x * nteam + team;
+  WarpWS ws = carve_ws(smem + sh.lu_doubles + warp * sh.ws_doubles, sh);
+  const int slot = blockIdx.x * nwarp + warp;
   const int n = sh.n;
   const int m = P.mem_size;
   double* lm_s = hist.s + (size_t)slot * hist.mem * hist.ld;
@@ -2208,6 +2075,7 @@ __global__ void __launch_bounds__(32 * DFTPAV_MAX_WARPS, 1)
   double* alpha_sm = ws.stage;  // free outside the sweep; the host guarantees mem_size <= 2*12*kStageLd
   const int ld = hist.ld;
   const int npl = (n + 31) >> 5;
+  const bool can_help = !kStrict && kMaxHelp > 0 && sh.helpable != 0 && nwarp > 1;
 
   int phase = PH_FETCH;
   int prob = -1, k = 0, end = 0, bound = 0, evals = 0, count = 0, ret = 0;
@@ -2215,25 +2083,37 @@ __global__ void __launch_bounds__(32 * DFTPAV_MAX_WARPS, 1)
   double step = 0.0, fx = 0.0, finit = 0.0, dgtest = 0.0, dstest = 0.0, mu = 0.0, nu = 0.0;
   const double* planes = nullptr;
   long long t_logic = 0;
+  // team state: as an owner (seq, done_base), as a helper (own = my owner's warp, hidx = my attach index, seen = last go word)
+  bool helper = false;
+  int seq = 0, done_base = 0, own = -1, hidx = -1, seen = -1, hprob = -1;
 
-  bool have_work = team < grp.owners;  // warps beyond the owner count only ever help their neighbour
   while (true) {
-    // ---- rank 0: take a problem if needed, run the first part of the evaluation, post the team's mailbox.
-    //      Every rank then walks through the ONE sweep call site; ranks > 0 do nothing else.
     long long t_prev = 0;
-    bool helped = false;
+    int r0 = 0, r1 = kVR, h = 0, prob_t = prob;
+    const double* planes_t = planes;
+    SweepOut so{ws.gd, ws.rscal};
     if (!helper) {
-    if (rank == 0) {
-    if (phase == PH_FETCH && have_work) {
-      int local = 0;
-      if (lane == 0) local = atomicAdd(work_counter, 1);
-      local = __shfl_sync(FULL, local, 0);
-      if (local >= grp.count) {
-        have_work = false;
-      } else {
+      // ---------------- owner: take a problem if needed, first part of the evaluation, publish it to the team
+      if (phase == PH_FETCH) {
+        int local = 0;
+        if (lane == 0) local = atomicAdd(work_counter, 1);
+        local = __shfl_sync(FULL, local, 0);
+        if (local >= grp.count) {
+          // the queue is empty: retire as an owner (releases my helpers), help the others or leave
+          if (lane == 0) {
+            st_flag(&ctl[warp].alive, 0);
+            __threadfence_block();
+            st_flag(&ctl[warp].go, go_word(++seq, -1));
+          }
+          __syncwarp();
+          if (!can_help) break;
+          helper = true;
+          continue;
+        }
         if (grp.order) local = grp.order[local];
         prob = grp.prob_id[local];
         planes = grp.planes + (size_t)local * sh.H * 4 * sh.Mpad;
+        layout_problem(sh, bd, prob, grp.planes + (size_t)local * sh.H * 4 * sh.Mpad, lane);
 #pragma unroll 1
         for (int i = lane; i < n; i += 32) ws.x[i] = bd.x0[(size_t)prob * bd.n_stride + i];
         __syncwarp();
@@ -2241,72 +2121,130 @@ __global__ void __launch_bounds__(32 * DFTPAV_MAX_WARPS, 1)
         if (HAS_OBS) stage_obstacles(bd, prob, ws.obs, lane);
         evals = 0;
         phase = PH_FIRST;
+        prob_t = prob;
+        planes_t = planes;
       }
-    }
-    // (aligning the evaluations of groups of warps with a named barrier so that they share instruction fetches was
-    //  measured and lost 2-16 % for groups of 3-12 warps: profiles/README.md)
-    if (have_work) {
-      if (g_phase_clock) {
-        const long long now = clock64();
-        if (t_logic) {
-          if (lane == 0) atomicAdd(g_phase_clock + 7, (unsigned long long)(now - t_logic));
-        }
+      if (g_phase_clock && t_logic) {
+        if (lane == 0) atomicAdd(g_phase_clock + 7, (unsigned long long)(clock64() - t_logic));
       }
+#if !DFTPAV_STRICT
       eval_pre(sh, P, smem, ws, ws.x, lane, t_prev);
-    }
-    if (lane == 0) {
-      ws.ctl[0] = have_work ? 0ull : 1ull;
-      ws.ctl[1] = (unsigned long long)prob;
-      ws.ctl[2] = reinterpret_cast<unsigned long long>(planes);
-    }
-    __syncwarp();
-    }  // rank 0
-    if (kTeam > 1) team_bar(1 + 2 * team);
-    if (ws.ctl[0] != 0ull) {  // no problems left
-      if (has_partner) {
-        int old = 0;
-        if (lane == 0) old = atomicCAS(&pair_state[pair], 0, 1 + (warp & 1));
-        old = __shfl_sync(FULL, old, 0);
-        if (old == 0) {
-          // the neighbour is still solving: help it (partial sum 1 of each of its evaluations) until it is done
-          helper = true;
-          ws = carve_ws(smem + sh.lu_doubles + (warp ^ 1) * sh.ws_doubles, sh);
+      if (can_help) {
+        ++seq;
+        int hh = 0;
+        if (lane == 0) {
+          hh = min(ld_flag(&ctl[warp].nhelp), kMaxHelp);
+          ctl[warp].prob = prob;
+          ctl[warp].planes = reinterpret_cast<unsigned long long>(planes);
+          __threadfence_block();  // coefficients, segment scalars, problem: visible before the go word
+          st_flag(&ctl[warp].go, go_word(seq, hh));
+        }
+        h = __shfl_sync(FULL, hh, 0);
+      }
+      rank_chunk(0, h + 1, r0, r1);
+#endif
+    } else {
+      // ---------------- helper: find an owner of this CTA that is still solving, serve its evaluations
+      if (own < 0) {
+        int alive_l = 0, nh_l = 0;
+        if (lane < nwarp && lane != warp) {
+          alive_l = ld_flag(&ctl[lane].alive);
+          nh_l = ld_flag(&ctl[lane].nhelp);
+        }
+        if (__ballot_sync(FULL, alive_l != 0) == 0u) break;  // nobody left to help
+        int key = (alive_l && nh_l < kMaxHelp) ? nh_l * 64 + lane : 0x7fffffff;  // fewest helpers first
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) key = min(key, __shfl_xor_sync(FULL, key, o));
+        if (key == 0x7fffffff) {
+          __nanosleep(1000);  // every team is full: look again later
           continue;
         }
-        pair_bar(1 + 2 * pair);  // the neighbour is my helper and waits at barrier A: it sees my exit flag
+        const int o = key & 63;
+        int idx = -1;
+        if (lane == 0) {
+          int old = ld_flag(&ctl[o].nhelp);
+          while (old < kMaxHelp) {
+            const int prev = atomicCAS(&ctl[o].nhelp, old, old + 1);
+            if (prev == old) {
+              idx = old;
+              break;
+            }
+            old = prev;
+          }
+        }
+        idx = __shfl_sync(FULL, idx, 0);
+        if (idx < 0) continue;
+        own = o, hidx = idx, seen = -1, hprob = -1;
       }
-      break;
-    }
-    if (has_partner) {
-      int st = 0;
-      if (lane == 0) st = *reinterpret_cast<volatile int*>(&pair_state[pair]);
-      st = __shfl_sync(FULL, st, 0);
-      helped = st == 1 + ((warp ^ 1) & 1);
-      if (helped) pair_bar(1 + 2 * pair);  // coefficients, problem id and plane pointer are posted: release the helper
-    }
-    } else {
-      // helper: ws is the neighbour's workspace
-      pair_bar(1 + 2 * pair);
-      if (ws.ctl[0] != 0ull) break;
-    }
-    // ---------------- the single evaluation site: the sweep (all partial sums this warp is responsible for), then the
-    //                  owner finishes the evaluation
-    {
-      const int r_begin = helper ? 1 : rank;
-      const int r_end = kTeam > 1 ? rank + 1 : (helper ? 2 : (helped ? 1 : kPart));
-      const int prob_t = (int)ws.ctl[1];
-      const double* planes_t = reinterpret_cast<const double*>(ws.ctl[2]);
+      int word = 0;
+      if (lane == 0) {
+        while ((word = ld_flag(&ctl[own].go)) == seen) __nanosleep(200);
+        __threadfence_block();
+      }
+      word = __shfl_sync(FULL, word, 0);
+      __syncwarp();
+      seen = word;
+      const int hw = (word & 15) - 1;
+      if (hw < 0) {  // my owner has retired
+        own = -1;
+        continue;
+      }
+      if (hw <= hidx) continue;  // this evaluation was published before I attached
+      h = hw;
+      rank_chunk(hidx + 1, h + 1, r0, r1);
+      // what the sweep reads: the owner's coefficients and segment scalars, copied into my own (idle) workspace
+      WarpWS ows = carve_ws(smem + sh.lu_doubles + own * sh.ws_doubles, sh);
+      prob_t = ctl[own].prob;
+      planes_t = reinterpret_cast<const double*>(ctl[own].planes);
 #pragma unroll 1
-      for (int r = r_begin; r < r_end; r++) sweep_rank<HAS_OBS>(sh, P, bd, prob_t, planes_t, ws, r, my_stage, lane);
+      for (int i = lane; i < 2 * sh.rows; i += 32) ws.c[i] = ows.c[i];
+      if (lane < sh.S) {
+        ws.seg[lane].dT = ows.seg[lane].dT;
+        ws.seg[lane].trajtime = ows.seg[lane].trajtime;
+        ws.seg[lane].singul = ows.seg[lane].singul;
+      }
+      if (HAS_OBS && hprob != prob_t) {
+        for (int i = lane; i < 4 * kObsCap; i += 32) ws.obs[i] = ows.obs[i];
+      }
+      hprob = prob_t;
+      __syncwarp();
+      so.gd = ows.gd;
+      so.rscal = ows.rscal;
+    }
+    // ---------------- the single sweep site.  Owner without helpers: all virtual ranks and the end passes in one call.
+    //                  Owner with helpers: its chunk of ranks, then - once the helpers have reported - the end passes.
+    //                  Helper: its chunk of ranks.
+#if !DFTPAV_STRICT
+    {
+      const int rounds = (!helper && h > 0) ? 2 : 1;
+#pragma unroll 1
+      for (int round = 0; round < rounds; round++) {
+        bool do_end = !helper && h == 0;
+        if (round == 1) {
+          if (lane == 0) {
+            while (ld_flag(&ctl[warp].done) != done_base + h) __nanosleep(100);
+            __threadfence_block();
+          }
+          __syncwarp();
+          done_base += h;
+          r0 = r1 = kVR;
+          do_end = true;
+        }
+        sweep_ranks<HAS_OBS>(sh, P, bd, prob_t, planes_t, ws, so, lane, r0, r1, do_end);
+      }
     }
     if (helper) {
-      pair_bar(2 + 2 * pair);
+      __syncwarp();
+      if (lane == 0) {
+        __threadfence_block();
+        atomicAdd(&ctl[own].done, 1);
+      }
       continue;
     }
-    if (helped) pair_bar(2 + 2 * pair);
-    if (kTeam > 1) team_bar(2 + 2 * team);
-    if (rank != 0) continue;
     fx = eval_post(sh, P, smem, ws, ws.x, ws.g, lane, t_prev);
+#else
+    fx = strict_eval(sh, P, planes, smem, ws, ws.adj, ws.x, ws.g, lane);
+#endif
     evals++;
     if (g_phase_clock) t_logic = clock64();
 
@@ -2385,8 +2323,8 @@ __global__ void __launch_bounds__(32 * DFTPAV_MAX_WARPS, 1)
       }
       if (ls == 0) {
         // next trial point
-  #pragma unroll 1
-      for (int i = lane; i < n; i += 32) ws.x[i] = ws.xp[i] + step * ws.d[i];
+#pragma unroll 1
+        for (int i = lane; i < n; i += 32) ws.x[i] = ws.xp[i] + step * ws.d[i];
         __syncwarp();
         continue;
       }
@@ -2426,8 +2364,8 @@ __global__ void __launch_bounds__(32 * DFTPAV_MAX_WARPS, 1)
           double* se = lm_s + (size_t)end * ld;
           double* ye = lm_y + (size_t)end * ld;
           double ys = 0.0, yy = 0.0, ss = 0.0, gg = 0.0;
-    #pragma unroll 1
-      for (int i = lane; i < n; i += 32) {
+#pragma unroll 1
+          for (int i = lane; i < n; i += 32) {
             const double sv = ws.x[i] - ws.xp[i];
             const double yv = ws.g[i] - ws.gp[i];
             se[i] = sv;
@@ -2438,10 +2376,18 @@ __global__ void __launch_bounds__(32 * DFTPAV_MAX_WARPS, 1)
             gg += ws.gp[i] * ws.gp[i];
             ws.d[i] = -ws.g[i];
           }
-          ys = warp_sum(ys);
-          yy = warp_sum(yy);
-          ss = warp_sum(ss);
-          gg = warp_sum(gg);
+          if (kStrict) {  // sequential sums of the reference (lbfgs.hpp:681-704)
+            __syncwarp();
+            ys = warp_dot(ye, se, n, lane);
+            yy = warp_dot(ye, ye, n, lane);
+            ss = warp_dot(se, se, n, lane);
+            gg = warp_dot(ws.gp, ws.gp, n, lane);
+          } else {
+            ys = warp_sum(ys);
+            yy = warp_sum(yy);
+            ss = warp_sum(ss);
+            gg = warp_sum(gg);
+          }
           if (lane == 0) lm_ys[end] = DFTPAV_STORE_YS(ys);
           __syncwarp();
           const double cau = ss * sqrt(gg) * P.cautious_factor;
@@ -2449,28 +2395,22 @@ __global__ void __launch_bounds__(32 * DFTPAV_MAX_WARPS, 1)
             ++bound;
             bound = m < bound ? m : bound;
             end = (end + 1) % m;
-#if DFTPAV_TWO_LOOP_BLOCKED
+#if DFTPAV_STRICT
+            two_loop_generic(ws.d, alpha_sm, lm_s, lm_y, lm_ys, ld, m, end, bound, n, lane, ys, yy);
+#elif DFTPAV_TWO_LOOP_BLOCKED
             {
               double* lm_gram = hist.gram + (size_t)slot * hist.mem * 4;
               if (npl == 1) two_loop_blocked<1>(ws.d, alpha_sm, lm_s, lm_y, lm_ys, lm_gram, ld, m, end, bound, n, lane, ys, yy);
               else if (npl == 2) two_loop_blocked<2>(ws.d, alpha_sm, lm_s, lm_y, lm_ys, lm_gram, ld, m, end, bound, n, lane, ys, yy);
-              else two_loop_blocked<3>(ws.d, alpha_sm, lm_s, lm_y, lm_ys, lm_gram, ld, m, end, bound, n, lane, ys, yy);
+              else if (npl == 3) two_loop_blocked<3>(ws.d, alpha_sm, lm_s, lm_y, lm_ys, lm_gram, ld, m, end, bound, n, lane, ys, yy);
+              else two_loop_generic(ws.d, alpha_sm, lm_s, lm_y, lm_ys, ld, m, end, bound, n, lane, ys, yy);
             }
-#elif DFTPAV_TWO_LOOP_ASYNC
-            // ring of 4 slots in the (dead between evaluations) b~ / gdC arrays: 4 * (64*npl + 2) doubles <= 4 * rows
-            if (npl == 1 && 4 * 66 <= 4 * sh.rows) two_loop_async<1, 4>(ws.d, alpha_sm, ws.bt, lm_s, lm_y, lm_ys, ld, m, end, bound, n, lane, ys, yy);
-            else if (npl == 2 && 4 * 130 <= 4 * sh.rows) two_loop_async<2, 4>(ws.d, alpha_sm, ws.bt, lm_s, lm_y, lm_ys, ld, m, end, bound, n, lane, ys, yy);
-            else if (npl == 1) two_loop<1>(ws.d, alpha_sm, lm_s, lm_y, lm_ys, ld, m, end, bound, n, lane, ys, yy);
-            else if (npl == 2) two_loop<2>(ws.d, alpha_sm, lm_s, lm_y, lm_ys, ld, m, end, bound, n, lane, ys, yy);
-            else two_loop<3>(ws.d, alpha_sm, lm_s, lm_y, lm_ys, ld, m, end, bound, n, lane, ys, yy);
-#elif DFTPAV_TWO_LOOP_GROUPED
-            if (npl == 1) two_loop_grouped<1, DFTPAV_TL_GS>(ws.d, alpha_sm, lm_s, lm_y, lm_ys, ld, m, end, bound, n, lane, ys, yy);
-            else if (npl == 2) two_loop_grouped<2, DFTPAV_TL_GS>(ws.d, alpha_sm, lm_s, lm_y, lm_ys, ld, m, end, bound, n, lane, ys, yy);
-            else two_loop_grouped<3, 2>(ws.d, alpha_sm, lm_s, lm_y, lm_ys, ld, m, end, bound, n, lane, ys, yy);
 #else
+            // n <= 96: the direction lives in registers; larger problems (up to 4 x 64 pieces, n = 517): shared memory
             if (npl == 1) two_loop<1>(ws.d, alpha_sm, lm_s, lm_y, lm_ys, ld, m, end, bound, n, lane, ys, yy);
             else if (npl == 2) two_loop<2>(ws.d, alpha_sm, lm_s, lm_y, lm_ys, ld, m, end, bound, n, lane, ys, yy);
-            else two_loop<3>(ws.d, alpha_sm, lm_s, lm_y, lm_ys, ld, m, end, bound, n, lane, ys, yy);
+            else if (npl == 3) two_loop<3>(ws.d, alpha_sm, lm_s, lm_y, lm_ys, ld, m, end, bound, n, lane, ys, yy);
+            else two_loop_generic(ws.d, alpha_sm, lm_s, lm_y, lm_ys, ld, m, end, bound, n, lane, ys, yy);
 #endif
           }
           step = 1.0;
@@ -2504,8 +2444,8 @@ __global__ void __launch_bounds__(32 * DFTPAV_MAX_WARPS, 1)
           touched = false;
           mu = 0.0;
           nu = P.max_step;
-    #pragma unroll 1
-      for (int i = lane; i < n; i += 32) ws.x[i] = ws.xp[i] + step * ws.d[i];
+#pragma unroll 1
+          for (int i = lane; i < n; i += 32) ws.x[i] = ws.xp[i] + step * ws.d[i];
           __syncwarp();
           phase = PH_LS;
         }
@@ -2514,8 +2454,8 @@ __global__ void __launch_bounds__(32 * DFTPAV_MAX_WARPS, 1)
 
     if (finish) {
       if (revert) {
-  #pragma unroll 1
-      for (int i = lane; i < n; i += 32) {
+#pragma unroll 1
+        for (int i = lane; i < n; i += 32) {
           ws.x[i] = ws.xp[i];
           ws.g[i] = ws.gp[i];
         }
@@ -2540,96 +2480,6 @@ __global__ void __launch_bounds__(32 * DFTPAV_MAX_WARPS, 1)
       }
       __syncwarp();
       phase = PH_FETCH;
-    }
-  }
-}
-
-// ------------------------------------------------------------------------------------------------
-// layout kernel: raw (n, p) planes [sample][h][4] -> pass-major SoA [local][pass][chunk][16][32] with unit normals
-// (replaces the deep copy + colwise().normalize() of traj_optimizer.cpp:15, 49-52).  Slot u = pass*32 + lane holds
-// the sample that lane handles in that pass of the sweep (two 16-sample tiles per regular pass, then the piece-end
-// samples); sh.Mpad = 32 * passes, sh.samp0[s] = first slot of segment s.
-// ------------------------------------------------------------------------------------------------
-__global__ void layout_planes_kernel(const ShapeDev sh, const int* __restrict__ prob_id, int count,
-                                     const long long* __restrict__ samp_base,   // [B] first raw sample of the problem
-                                     const long long* __restrict__ plane_ptr,   // [Q+1] or nullptr (uniform)
-                                     int uniform_H, const double* __restrict__ raw, double* __restrict__ soa) {
-  const int Mpad = sh.Mpad;
-  const int nchunk = sh.H / 4;
-  const long long total = (long long)count * Mpad;
-  for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total;
-       idx += (long long)gridDim.x * blockDim.x) {
-    const int local = (int)(idx / Mpad);
-    const int u = (int)(idx % Mpad);
-    const int prob = prob_id[local];
-    // which segment / piece / sample does storage slot u hold?
-    int s = 0;
-    while (s + 1 < sh.S && u >= sh.samp0[s + 1]) s++;
-    const int us = u - sh.samp0[s];
-    const int N = sh.N[s], K = sh.K, Kd = sh.Kd;
-    const int td = (Kd + kTile - 1) / kTile, tk = (K + kTile - 1) / kTile;
-    const int ntile = sh.ntile[s];
-    const int npass_reg = (ntile + 1) >> 1;
-    const int pass = us >> 5, ln = us & 31;
-    int piece = -1, j = 0;
-    if (pass < npass_reg) {
-      const int t = 2 * pass + (ln >> 4), r = ln & 15;
-      if (t < ntile) {
-        int j0;
-        if (t < td) {
-          piece = 0;
-          j0 = kTile * t;
-        } else if (t < td + (N - 2) * tk) {
-          const int uu = t - td;
-          piece = 1 + uu / tk;
-          j0 = kTile * (uu % tk);
-        } else {
-          piece = N - 1;
-          j0 = kTile * (t - td - (N - 2) * tk);
-        }
-        j = j0 + r;
-        const int Kp = (piece == 0 || piece == N - 1) ? Kd : K;
-        if (j >= Kp) piece = -1;
-      }
-    } else {
-      piece = (pass - npass_reg) * 32 + ln;
-      if (piece >= N) piece = -1;
-      else j = (piece == 0 || piece == N - 1) ? Kd : K;
-    }
-    double* dst = soa + (size_t)local * sh.H * 4 * Mpad + (size_t)(u >> 5) * nchunk * 512 + (u & 31);
-    int Hs = 0;
-    const double* src = nullptr;
-    if (piece >= 0) {
-      // pointid inside the segment (traj_optimizer.cpp:514): pieces before contribute K_i + 1 samples each
-      long long pid = 0;
-      for (int ss = 0; ss < s; ss++) pid += (long long)(sh.N[ss] - 2) * (K + 1) + 2 * (Kd + 1);
-      if (piece > 0) pid += (Kd + 1) + (long long)(piece - 1) * (K + 1);
-      pid += j;
-      const long long q = samp_base[prob] + pid;
-      if (plane_ptr) {
-        Hs = (int)(plane_ptr[q + 1] - plane_ptr[q]);
-        src = raw + 4 * plane_ptr[q];
-      } else {
-        Hs = uniform_H;
-        src = raw + 4 * q * uniform_H;
-      }
-    }
-    for (int h = 0; h < sh.H; h++) {
-      double nx = 0.0, ny = 0.0, px = 0.0, py = 0.0;
-      if (h < Hs) {
-        nx = src[4 * h], ny = src[4 * h + 1], px = src[4 * h + 2], py = src[4 * h + 3];
-        const double z = nx * nx + ny * ny;
-        if (z > 0.0) {
-          const double nz = sqrt(z);
-          nx /= nz;
-          ny /= nz;
-        }
-      }
-      double* d4 = dst + (size_t)(h >> 2) * 512 + (h & 3) * 128;  // chunk h/4, plane h%4 -> components 4*(h%4)..+3
-      d4[0] = nx;
-      d4[32] = ny;
-      d4[64] = px;
-      d4[96] = py;
     }
   }
 }
@@ -2723,13 +2573,6 @@ cudaError_t launch_eval(bool has_obs, int grid, int block, size_t smem, cudaStre
   return cudaGetLastError();
 }
 
-cudaError_t launch_layout(int grid, int block, cudaStream_t st, const ShapeDev& sh, const int* prob_id, int count,
-                          const long long* samp_base, const long long* plane_ptr, int uniform_H, const double* raw,
-                          double* soa) {
-  layout_planes_kernel<<<grid, block, 0, st>>>(sh, prob_id, count, samp_base, plane_ptr, uniform_H, raw, soa);
-  return cudaGetLastError();
-}
-
 cudaError_t launch_prepare(int grid, int block, cudaStream_t st, const ShapeDev& sh, const ParamsDev& P,
                            const int* prob_id, int count, const int* seg_base, const int* singul, const double* ini_raw,
                            const double* fin_raw, const double* init_T, const long long* inner_base,
@@ -2739,10 +2582,10 @@ cudaError_t launch_prepare(int grid, int block, cudaStream_t st, const ShapeDev&
   return cudaGetLastError();
 }
 
-int ws_doubles_host(int rows, int npad) { return ws_doubles_for(rows, npad); }
+int ws_doubles_host(int rows, int npad, int S, int has_obs) { return ws_doubles_for(rows, npad, S, has_obs); }
 int max_warps_host() { return DFTPAV_MAX_WARPS; }
-int team_size_host() { return kTeam; }
-int drain_help_host() { return kDrainHelp ? 1 : 0; }
+int virtual_ranks_host() { return kVR; }
+int strict_build_host() { return kStrict ? 1 : 0; }
 int two_loop_blocked_host() { return DFTPAV_TWO_LOOP_BLOCKED; }
 
 cudaError_t set_phase_clock(unsigned long long* dev_ptr) {

@@ -72,8 +72,8 @@ class Solution:
 
 
 class BatchOptimizer:
-    def __init__(self, params: Optional[capi.Params] = None, device: int = -1):
-        self._lib = capi.load_library()
+    def __init__(self, params: Optional[capi.Params] = None, device: int = -1, variant: str = ""):
+        self._lib = capi.load_library(variant)
         self.params = params if params is not None else capi.default_params()
         self._h = C.c_void_p()
         rc = self._lib.dftpav_create(C.byref(self.params), device, C.byref(self._h))
@@ -131,10 +131,33 @@ class BatchOptimizer:
         return sol
 
     def solve(self, batch: TrajBatch, sol: Optional[Solution] = None) -> Solution:
-        """upload + optimize + download: the end-to-end call (dftpav_solve)."""
+        """The end-to-end planner call (dftpav_solve): upload, solve and read-back in ONE C-ABI call; the corridor planes are
+        copied in chunks while the solver kernels already run."""
+        self._batch = batch
+        cb = batch.as_c()
+        if sol is None:
+            d = capi.Dims()
+            self._check(self._lib.dftpav_batch_dims(C.byref(self.params), C.byref(cb), C.byref(d)))
+            sol = Solution(d.B, d.n_stride, d.row_stride, d.seg_total)
+        res = sol.as_c()
+        self._check(self._lib.dftpav_solve(self._h, C.byref(cb), C.byref(res)))
+        d = capi.Dims()
+        self._check(self._lib.dftpav_get_dims(self._h, C.byref(d)))
+        self._dims = d
+        return sol
+
+    def solve_stepwise(self, batch: TrajBatch, sol: Optional[Solution] = None) -> Solution:
+        """upload, optimize, download as three C-ABI calls (the batch stays resident for further optimize / evaluate calls)."""
         self.upload(batch)
         self.optimize()
         return self.download(sol)
+
+    def force_banded(self, on: bool = True):
+        """Test hook: banded LU substitutions (the large-N fallback) even where the dense MINCO tables fit."""
+        self._check(self._lib.dftpav_debug_force_banded(self._h, 1 if on else 0))
+
+    def build_flags(self) -> int:
+        return int(self._lib.dftpav_debug_build_flags())
 
     def evaluate(self, x: np.ndarray):
         """One cost+gradient evaluation per problem at x [B, n_stride] (dftpav_eval)."""

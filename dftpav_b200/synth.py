@@ -276,10 +276,10 @@ def _arc_segment(p0x, p0y, psi0, kappa, dist, direction, frac):
 def _parking(cfg: int, B: int, seed: int, prm: capi.Params, Ns=(12, 8, 12)) -> TrajBatch:
     st = _Streams(cfg, seed)
     K, Kd = prm.traj_resolution, prm.des_traj_resolution
-    sing = np.array([1, -1, 1])
     S = len(Ns)
-    speeds = [st.uniform("speed0", 1.8, 3.0, B), st.uniform("speed1", 0.6, 1.2, B), st.uniform("speed2", 1.8, 3.0, B)]
-    kap = [st.uniform("kappa0", -0.12, 0.12, B), st.uniform("kappa1", -0.2, 0.2, B), st.uniform("kappa2", -0.12, 0.12, B)]
+    sing = np.array([1 if i % 2 == 0 else -1 for i in range(S)])  # forward / reverse / forward (/ reverse)
+    speeds = [st.uniform(f"speed{i}", 1.8, 3.0, B) if i % 2 == 0 else st.uniform(f"speed{i}", 0.6, 1.2, B) for i in range(S)]
+    kap = [st.uniform(f"kappa{i}", -0.12, 0.12, B) if i % 2 == 0 else st.uniform(f"kappa{i}", -0.2, 0.2, B) for i in range(S)]
     px, py, psi = np.zeros(B), np.zeros(B), st.uniform("psi0", -np.pi, np.pi, B)
     ini = np.zeros((B, S, 6))
     fin = np.zeros((B, S, 6))
@@ -403,6 +403,24 @@ def make_config(cfg: int, B: int | None = None, seed: int = 0) -> Tuple[TrajBatc
     else:
         raise ValueError(f"unknown config {cfg}")
     batch.meta["description"] = CONFIG_DESCRIPTIONS[cfg]
+    return batch, prm
+
+
+def make_custom(B: int, pieces, seed: int = 0) -> Tuple[TrajBatch, capi.Params]:
+    """Shapes outside the five BASELINE configurations (tests of the compiled-in limits: up to 4 gear segments of up to 64
+    pieces): one segment with config-3 limits and rectangles, or a forward / reverse / ... parking manoeuvre."""
+    prm = capi.default_params()
+    pieces = [int(n) for n in pieces]
+    if len(pieces) == 1:
+        N = pieces[0]
+        prm.max_forward_vel = 3.0
+        prm.max_forward_acc = 2.0
+        prm.max_forward_cur = 0.3
+        batch = _single_segment(30 + N, B, seed, N, prm, length=0.8 * 3.0 * N, f_lo=1.5 * N / 24.0, f_hi=3.5 * N / 24.0,
+                                corridor="rect")
+    else:
+        batch = _parking(40 + len(pieces), B, seed, prm, Ns=tuple(pieces))
+    batch.meta["description"] = f"custom shape {pieces}"
     return batch, prm
 
 

@@ -30,7 +30,8 @@ extern "C" {
 /* ---- return codes of the API functions themselves (not of the solver) ---- */
 #define DFTPAV_OK 0
 #define DFTPAV_ERR_INVALID_ARG (-1)   /* NULL pointer, negative size, inconsistent CSR arrays       */
-#define DFTPAV_ERR_BAD_INPUT (-2)     /* a problem violates a reference precondition (OPT.cpp:26-48)  */
+#define DFTPAV_ERR_BAD_INPUT (-2)     /* reserved (round 1: a problem violating OPT.cpp:26-48 failed the whole batch;
+                                         now reported per problem as status DFTPAV_PROBLEM_REJECTED)  */
 #define DFTPAV_ERR_CUDA (-3)          /* CUDA runtime failure; see dftpav_last_error()               */
 #define DFTPAV_ERR_NO_DEVICE (-4)     /* no usable sm_100 device: there is NO CPU fallback           */
 #define DFTPAV_ERR_STATE (-5)         /* call order violated (e.g. optimize before upload)           */
@@ -60,6 +61,10 @@ extern "C" {
 #define DFTPAV_LBFGSERR_WIDTHTOOSMALL (-1007)
 #define DFTPAV_LBFGSERR_INVALIDPARAMETERS (-1006)
 #define DFTPAV_LBFGSERR_INCREASEGRADIENT (-1005)
+/* Not an L-BFGS code: the problem violates a precondition of OptimizeTrajectory itself (a segment with a single piece,
+ * initTs < mini_T: OPT.cpp:26-48 `return false`).  It is not solved; success = 0, every other output of it is zero. The
+ * other problems of the batch are unaffected. */
+#define DFTPAV_PROBLEM_REJECTED (-2000)
 
 /*
  * dftpav_params — every number that reaches the arithmetic, explicit (no hidden constants).
@@ -206,8 +211,13 @@ typedef struct dftpav_handle dftpav_handle;
 /* Fills *p with the reference defaults (CFG:65-100, OPT.cpp:127-134, OPT.h:68). */
 void dftpav_default_params(dftpav_params* p);
 
-/* Validates a batch against the preconditions of OPT.cpp:26-48 and fills *dims. No device needed. */
+/* Validates the arrays of a batch (consistent CSR pointers, compiled-in limits) and fills *dims. No device needed. */
 int dftpav_batch_dims(const dftpav_params* prm, const dftpav_batch* batch, dftpav_dims* dims);
+
+/* Which problems OptimizeTrajectory itself would refuse (OPT.cpp:26-48: a segment with one piece, initTs < mini_T):
+ * rejected[p] = 1 for those, 0 otherwise ([B], may be NULL).  Returns the same codes as dftpav_batch_dims; a rejected problem
+ * is NOT an error of the batch (it gets status DFTPAV_PROBLEM_REJECTED when the batch is solved).  No device needed. */
+int dftpav_batch_check(const dftpav_params* prm, const dftpav_batch* batch, int32_t* rejected);
 
 /* Packs the initial decision vector x0 of every problem exactly as OPT.cpp:96-115 (including the
  * ini/fin clamps of OPT.cpp:55-76 that feed Gear/theta).  x0 is [B][n_stride].  Host-only helper. */

@@ -1367,7 +1367,8 @@ int oracle_optimize(const dftpav_params* prm, const dftpav_batch* batch, int p0,
     int rc = P.setup(prm, batch, p);
     std::vector<double> x(std::max(1, P.n), 0.0);
     double final_cost = 0.0;
-    int result = DFTPAV_LBFGSERR_UNKNOWNERROR, iters = 0;
+    // a problem the reference rejects before solving (OPT.cpp:26-48 `return false`) is reported like the C-ABI does
+    int result = DFTPAV_PROBLEM_REJECTED, iters = 0;
     bool success = false;
     if (rc == 0) {
       P.initialX(x.data());

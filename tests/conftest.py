@@ -35,3 +35,21 @@ def gpu_opt_factory():
     yield make
     for o in made:
         o.close()
+
+
+@pytest.fixture(scope="session")
+def gpu_strict_factory():
+    """BatchOptimizer over the strict-order VERIFICATION build (dftpav_b200/csrc/libdftpav_b200_strict.so)."""
+    from dftpav_b200.optimizer import BatchOptimizer
+
+    made = []
+
+    def make(prm):
+        o = BatchOptimizer(prm, device=0, variant="strict")
+        assert o.build_flags() & 1, "not the strict build"
+        made.append(o)
+        return o
+
+    yield make
+    for o in made:
+        o.close()

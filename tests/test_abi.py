@@ -57,7 +57,11 @@ def test_preconditions_rejected(lib):
     d = capi.Dims()
     batch.init_T[1] = 0.05  # < mini_T  (traj_optimizer.cpp:30-33)
     cb = batch.as_c()
-    assert lib.dftpav_batch_dims(C.byref(prm), C.byref(cb), C.byref(d)) == capi.ERR_BAD_INPUT
+    # a problem the reference would refuse is flagged, not an error of the batch (per-problem status at solve time)
+    assert lib.dftpav_batch_dims(C.byref(prm), C.byref(cb), C.byref(d)) == capi.OK
+    rej = np.zeros(2, dtype=np.int32)
+    assert lib.dftpav_batch_check(C.byref(prm), C.byref(cb), rej.ctypes.data_as(capi.c_int32_p)) == capi.OK
+    assert rej.tolist() == [0, 1]
     batch.init_T[1] = 24.0
     prm.abi_version = 99
     cb = batch.as_c()

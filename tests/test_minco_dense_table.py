@@ -52,3 +52,31 @@ def test_bad_piece_count_is_rejected():
     lib.dftpav_debug_minco_dense.argtypes = [C.c_int, C.POINTER(C.c_double), C.POINTER(C.c_int)]
     assert lib.dftpav_debug_minco_dense(0, None, None) == -1
     assert lib.dftpav_debug_minco_dense(65, None, None) == -1
+
+
+def test_band_lu_factor_is_bit_identical_to_the_oracle():
+    """The host factorises the collocation matrix row by row (dftpav_api.cu, BandLU); every entry must carry the same bits
+    as BandedSystem::factorizeLU's column-oriented loop nest (poly_traj_utils.hpp:776-800, restated in the oracle), which
+    the strict verification build and the large-N fallback rely on."""
+    import ctypes as C
+
+    from dftpav_b200 import capi
+    from oracle import oracle_py
+
+    lib = capi.load_library()
+    lib.dftpav_debug_minco_band.argtypes = [C.c_int, capi.c_double_p]
+    lib.dftpav_debug_minco_band.restype = C.c_longlong
+    O = oracle_py.lib()
+    O.oracle_minco_matrix.argtypes = [C.c_int, capi.c_double_p, capi.c_double_p]
+    for N in (2, 3, 8, 16, 24, 33, 64):
+        n = 6 * N
+        packed = np.zeros((n, 16))
+        assert lib.dftpav_debug_minco_band(N, packed.ctypes.data_as(capi.c_double_p)) == n * 16
+        dense = np.zeros((n, n))
+        band = np.zeros((13, n))
+        assert O.oracle_minco_matrix(N, dense.ctypes.data_as(capi.c_double_p), band.ctypes.data_as(capi.c_double_p)) == 0
+        for j in range(n):
+            for r in range(13):
+                i = j + r - 6
+                if 0 <= i < n:
+                    assert packed[j, r] == band[r, j], (N, i, j, packed[j, r], band[r, j])
