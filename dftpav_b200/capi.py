@@ -45,6 +45,10 @@ LBFGSERR_MAXIMUMITERATION = -1008
 LBFGSERR_WIDTHTOOSMALL = -1007
 LBFGSERR_INVALIDPARAMETERS = -1006
 LBFGSERR_INCREASEGRADIENT = -1005
+STATE_DOUBLES = 12
+SAMPLE_CLAMP = 1
+SAMPLE_GETSTATE = 2
+WHEEL_BASE = 2.85  # VehicleParam::wheel_base (semantics.h:68)
 PROBLEM_REJECTED = -2000  # precondition of OptimizeTrajectory violated (traj_optimizer.cpp:26-48), per problem
 
 c_double_p = C.POINTER(C.c_double)
@@ -226,6 +230,9 @@ EXPORTED_SYMBOLS = [
     "dftpav_optimize",
     "dftpav_download",
     "dftpav_solve",
+    "dftpav_sample",
+    "dftpav_sample_uniform",
+    "dftpav_pack_polytraj",
     "dftpav_last_stats",
     "dftpav_last_error",
     "dftpav_version",
@@ -266,6 +273,9 @@ def load_library(variant: str = "") -> C.CDLL:
     lib.dftpav_optimize.argtypes = [H]
     lib.dftpav_download.argtypes = [H, C.POINTER(Result)]
     lib.dftpav_solve.argtypes = [H, C.POINTER(Batch), C.POINTER(Result)]
+    lib.dftpav_sample.argtypes = [H, C.c_int64, c_int32_p, c_double_p, C.c_int32, C.c_double, c_double_p]
+    lib.dftpav_sample_uniform.argtypes = [H, C.c_double, C.c_int32, c_double_p, c_int32_p]
+    lib.dftpav_pack_polytraj.argtypes = [H, C.POINTER(C.c_float), C.POINTER(C.c_float), C.POINTER(C.c_float)]
     lib.dftpav_last_stats.argtypes = [H, C.POINTER(Stats)]
     lib.dftpav_last_error.argtypes = [H]
     lib.dftpav_last_error.restype = C.c_char_p

@@ -35,8 +35,11 @@ cudaError_t launch_layout(int grid, int block, cudaStream_t st, const ShapeDev& 
                           double* soa);
 cudaError_t launch_prepare(int grid, int block, cudaStream_t st, const ShapeDev& sh, const ParamsDev& P,
                            const int* prob_id, int count, const int* seg_base, const int* singul, const double* ini_raw,
-                           const double* fin_raw, const double* init_T, const long long* inner_base,
-                           const double* inner_pts, double* ini, double* fin, double* x0, int n_stride);
+                           const double* fin_raw, double* ini, double* fin);
+cudaError_t launch_sample(cudaStream_t st, const SampleDev& sd, long long nq, const int* seg, const double* t, int flags,
+                          double wheel_base, double* out);
+cudaError_t launch_sample_uniform(cudaStream_t st, const SampleDev& sd, double dt, int max_per_seg, double* out, int* count);
+cudaError_t launch_pack_polytraj(cudaStream_t st, const SampleDev& sd, float* cx, float* cy, float* dur);
 int ws_doubles_host(int rows, int npad, int S, int has_obs);
 int max_warps_host();
 int virtual_ranks_host();
@@ -221,6 +224,7 @@ struct dftpav_handle {
   int epoch = 0, n_chunks = 1, chunk = 1;   // plane-upload hand-shake (BatchDev::ready / laid)
   int* h_epoch = nullptr;                    // pinned [kMaxChunks], all = epoch (source of the arrival-flag copies)
   std::vector<long long> h_samp_base, h_plane_ptr;
+  std::vector<double> h_x0;
   long long total_planes = 0;
   int uniform_H = 0;                         // -1: ragged corridor (h_plane_ptr)
   bool force_banded = false;                 // test hook: banded LU substitutions even where the dense tables fit
@@ -234,10 +238,12 @@ struct dftpav_handle {
   int param_status = 0;   // LBFGSERR_INVALID_* of the parameter block (lbfgs.hpp:456-501), 0 = parameters usable
   int n_rejected = 0;     // problems violating a reference precondition (traj_optimizer.cpp:26-48)
   // device buffers
-  DevBuf seg_base, t_now, obs_ptr, obs_idx, singul, ini_raw, fin_raw, ini, fin, init_T, inner_base, inner_pts, samp_base,
+  DevBuf seg_base, t_now, obs_ptr, obs_idx, singul, ini_raw, fin_raw, ini, fin, samp_base,
       plane_ptr, planes_raw, obs_start, obs_dur, obs_piece_ptr, obs_piece_dur, obs_coeffs, obs_uniform, x0, xin, fout, gout;
   DevBuf o_x, o_cost, o_status, o_success, o_iters, o_evals, o_coeffs, o_dT, counter;
   DevBuf hist_s, hist_y, hist_ys, hist_gram, trace, ready, laid;
+  DevBuf seg_prob, seg_row0, seg_N, seg_piece0, q_seg, q_t, q_out, q_cnt;  // trajectory evaluator (dftpav_sample*)
+  long long pieces_total = 0;
   int trace_cap = 0;
   int hist_ld = 0, hist_slots = 0;
   int upload_launches = 0;
@@ -438,6 +444,38 @@ void clamp_state(double* st, double max_vel, double max_acc) {
   }
 }
 
+// Initial decision vector of problem p exactly as traj_optimizer.cpp:96-115 (inner points, RealT2VirtualT 361-369, gear
+// positions and atan2 headings from the clamped final states 55-76).  Host code on purpose: x0 must carry glibc's atan2,
+// like the reference (the CUDA math library's atan2 differs from it by an ulp now and then).  Returns the inner-point
+// offset of the next problem.
+long long pack_x0(const dftpav_params* prm, const dftpav_batch* b, int p, long long inner, int n_stride, double* x) {
+  std::fill(x, x + n_stride, 0.0);
+  const int g0 = b->seg_ptr[p], g1 = b->seg_ptr[p + 1], S = g1 - g0;
+  int off = 0;
+  for (int g = g0; g < g1; g++) {
+    const int np = 2 * (b->piece_num[g] - 1);
+    std::memcpy(x + off, b->inner_pts + inner, sizeof(double) * np);
+    off += np;
+    inner += np;
+  }
+  for (int s = 0; s < S; s++) {  // RealT2VirtualT, traj_optimizer.cpp:361-369
+    const double RT = b->init_T[g0 + s], mini_T = prm->mini_T;
+    x[off + s] = RT > 1.0 + mini_T ? (std::sqrt(2.0 * RT - 1.0 - 2 * mini_T) - 1.0)
+                                   : (1.0 - std::sqrt(2.0 / (RT - mini_T) - 1.0));
+  }
+  off += S;
+  for (int s = 0; s < S - 1; s++) {
+    double st[6];
+    std::memcpy(st, b->fin_state + 6 * (g0 + s), sizeof(st));
+    const bool fwd = b->singul[g0 + s] > 0;
+    clamp_state(st, fwd ? prm->max_forward_vel : prm->max_backward_vel, fwd ? prm->max_forward_acc : prm->max_backward_acc);
+    x[off + 2 * s] = st[0];
+    x[off + 2 * s + 1] = st[1];
+    x[off + 2 * (S - 1) + s] = std::atan2(st[3], st[2]);
+  }
+  return inner;
+}
+
 }  // namespace
 
 extern "C" {
@@ -507,33 +545,7 @@ int dftpav_initial_x(const dftpav_params* prm, const dftpav_batch* b, double* x0
   if (rc) return rc;
   if (!x0) return DFTPAV_ERR_INVALID_ARG;
   long long inner = 0;
-  for (int p = 0; p < b->B; p++) {
-    double* x = x0 + (size_t)p * dims.n_stride;
-    std::fill(x, x + dims.n_stride, 0.0);
-    const int g0 = b->seg_ptr[p], g1 = b->seg_ptr[p + 1], S = g1 - g0;
-    int off = 0;
-    for (int g = g0; g < g1; g++) {
-      const int np = 2 * (b->piece_num[g] - 1);
-      std::memcpy(x + off, b->inner_pts + inner, sizeof(double) * np);
-      off += np;
-      inner += np;
-    }
-    for (int s = 0; s < S; s++) {  // RealT2VirtualT, traj_optimizer.cpp:361-369
-      const double RT = b->init_T[g0 + s], mini_T = prm->mini_T;
-      x[off + s] = RT > 1.0 + mini_T ? (std::sqrt(2.0 * RT - 1.0 - 2 * mini_T) - 1.0)
-                                     : (1.0 - std::sqrt(2.0 / (RT - mini_T) - 1.0));
-    }
-    off += S;
-    for (int s = 0; s < S - 1; s++) {
-      double st[6];
-      std::memcpy(st, b->fin_state + 6 * (g0 + s), sizeof(st));
-      const bool fwd = b->singul[g0 + s] > 0;
-      clamp_state(st, fwd ? prm->max_forward_vel : prm->max_backward_vel, fwd ? prm->max_forward_acc : prm->max_backward_acc);
-      x[off + 2 * s] = st[0];
-      x[off + 2 * s + 1] = st[1];
-      x[off + 2 * (S - 1) + s] = std::atan2(st[3], st[2]);
-    }
-  }
+  for (int p = 0; p < b->B; p++) inner = pack_x0(prm, b, p, inner, dims.n_stride, x0 + (size_t)p * dims.n_stride);
   return DFTPAV_OK;
 }
 
@@ -579,10 +591,11 @@ int dftpav_destroy(dftpav_handle* h) {
   if (h->copy_stream) cudaStreamSynchronize(h->copy_stream);
   free_groups(h);
   DevBuf* bufs[] = {&h->seg_base, &h->t_now, &h->obs_ptr, &h->obs_idx, &h->singul, &h->ini_raw, &h->fin_raw, &h->ini,
-                    &h->fin, &h->init_T, &h->inner_base, &h->inner_pts, &h->samp_base, &h->plane_ptr, &h->planes_raw,
+                    &h->fin, &h->samp_base, &h->plane_ptr, &h->planes_raw,
                     &h->obs_start, &h->obs_dur, &h->obs_piece_ptr, &h->obs_piece_dur, &h->obs_coeffs, &h->obs_uniform, &h->x0, &h->xin,
                     &h->fout, &h->gout, &h->o_x, &h->o_cost, &h->o_status, &h->o_success, &h->o_iters, &h->o_evals,
-                    &h->o_coeffs, &h->o_dT, &h->counter, &h->hist_s, &h->hist_y, &h->hist_ys, &h->hist_gram, &h->trace, &h->ready, &h->laid};
+                    &h->o_coeffs, &h->o_dT, &h->counter, &h->hist_s, &h->hist_y, &h->hist_ys, &h->hist_gram, &h->trace, &h->ready, &h->laid, &h->seg_prob, &h->seg_row0, &h->seg_N,
+                    &h->seg_piece0, &h->q_seg, &h->q_t, &h->q_out, &h->q_cnt};
   for (DevBuf* b : bufs) b->release();
   for (auto& e : h->ev)
     if (e) cudaEventDestroy(e);
@@ -638,7 +651,6 @@ int upload_impl(dftpav_handle* h, const dftpav_batch* b, int n_chunks_wanted) {
   // ---- per-problem prefixes and shape groups
   std::vector<int> seg_base(B);
   std::vector<long long>& samp_base = h->h_samp_base;
-  std::vector<long long> inner_base(B);
   samp_base.assign((size_t)B + 1, 0);
   std::map<std::vector<int>, Group*> by_shape;
   long long samp = 0, inner = 0;
@@ -651,7 +663,6 @@ int upload_impl(dftpav_handle* h, const dftpav_batch* b, int n_chunks_wanted) {
     const int g0 = b->seg_ptr[p], g1 = b->seg_ptr[p + 1];
     seg_base[p] = g0;
     samp_base[p] = samp;
-    inner_base[p] = inner;
     std::vector<int> key(b->piece_num + g0, b->piece_num + g1);
     int n = 0;
     for (int g = g0; g < g1; g++) {
@@ -718,14 +729,44 @@ int upload_impl(dftpav_handle* h, const dftpav_batch* b, int n_chunks_wanted) {
     h2d += (long long)bytes;
     return e;
   };
+  {  // segment directory of the trajectory evaluator
+    std::vector<int> sp(G), sr(G);
+    std::vector<long long> pc(G);
+    long long pieces = 0;
+    for (int p = 0; p < B; p++) {
+      int row = 0;
+      for (int g = b->seg_ptr[p]; g < b->seg_ptr[p + 1]; g++) {
+        sp[g] = p;
+        sr[g] = row;
+        pc[g] = pieces;
+        row += 6 * b->piece_num[g];
+        pieces += b->piece_num[g];
+      }
+    }
+    h->pieces_total = pieces;
+    CU_TRY(h, up(h->seg_prob, sp.data(), sizeof(int) * G));
+    CU_TRY(h, up(h->seg_row0, sr.data(), sizeof(int) * G));
+    CU_TRY(h, up(h->seg_piece0, pc.data(), sizeof(long long) * G));
+    CU_TRY(h, up(h->seg_N, b->piece_num, sizeof(int) * G));
+  }
   CU_TRY(h, up(h->seg_base, seg_base.data(), sizeof(int) * B));
   CU_TRY(h, up(h->samp_base, samp_base.data(), sizeof(long long) * (B + 1)));
-  CU_TRY(h, up(h->inner_base, inner_base.data(), sizeof(long long) * B));
   CU_TRY(h, up(h->singul, b->singul, sizeof(int) * G));
   CU_TRY(h, up(h->ini_raw, b->ini_state, sizeof(double) * 6 * G));
   CU_TRY(h, up(h->fin_raw, b->fin_state, sizeof(double) * 6 * G));
-  CU_TRY(h, up(h->init_T, b->init_T, sizeof(double) * G));
-  CU_TRY(h, up(h->inner_pts, b->inner_pts, sizeof(double) * inner));
+  {  // x0 packed on the host (pack_x0), rejected problems all zero
+    std::vector<double>& x0 = h->h_x0;
+    x0.assign((size_t)B * dims.n_stride, 0.0);
+    long long in_off = 0;
+    for (int p = 0; p < B; p++) {
+      if (rejected[p]) {
+        for (int g = b->seg_ptr[p]; g < b->seg_ptr[p + 1]; g++) in_off += 2LL * (b->piece_num[g] - 1);
+        continue;
+      }
+      in_off = pack_x0(&h->prm, b, p, in_off, dims.n_stride, x0.data() + (size_t)p * dims.n_stride);
+    }
+    CU_TRY(h, up(h->x0, x0.data(), sizeof(double) * x0.size()));
+  }
   if (b->plane_cnt) CU_TRY(h, up(h->plane_ptr, plane_ptr.data(), sizeof(long long) * (Q + 1)));
   std::vector<double> tnow(B, 0.0);
   if (b->t_now) std::copy(b->t_now, b->t_now + B, tnow.begin());
@@ -754,7 +795,6 @@ int upload_impl(dftpav_handle* h, const dftpav_batch* b, int n_chunks_wanted) {
   CU_TRY(h, h->planes_raw.ensure(sizeof(double) * 4 * (size_t)h->total_planes));
   CU_TRY(h, h->ini.ensure(sizeof(double) * 6 * G));
   CU_TRY(h, h->fin.ensure(sizeof(double) * 6 * G));
-  CU_TRY(h, h->x0.ensure(sizeof(double) * (size_t)B * dims.n_stride));
   // outputs
   CU_TRY(h, h->o_x.ensure(sizeof(double) * (size_t)B * dims.n_stride));
   CU_TRY(h, h->o_cost.ensure(sizeof(double) * B));
@@ -767,7 +807,6 @@ int upload_impl(dftpav_handle* h, const dftpav_batch* b, int n_chunks_wanted) {
   CU_TRY(h, h->counter.ensure(sizeof(int) * 64));
   if (h->n_rejected > 0 || h->param_status) {
     // problems no kernel touches: status from the host, everything else zero
-    CU_TRY(h, cudaMemsetAsync(h->x0.p, 0, sizeof(double) * (size_t)B * dims.n_stride, st));
     CU_TRY(h, cudaMemsetAsync(h->o_x.p, 0, sizeof(double) * (size_t)B * dims.n_stride, st));
     CU_TRY(h, cudaMemsetAsync(h->o_cost.p, 0, sizeof(double) * B, st));
     CU_TRY(h, cudaMemsetAsync(h->o_success.p, 0, sizeof(int) * B, st));
@@ -891,9 +930,7 @@ int upload_impl(dftpav_handle* h, const dftpav_batch* b, int n_chunks_wanted) {
     max_npad = std::max(max_npad, sh.npad);
     CU_TRY(h, launch_prepare((count + 127) / 128, 128, st, sh, h->pd, grp->d_prob_id.as<int>(), count,
                              h->seg_base.as<int>(), h->singul.as<int>(), h->ini_raw.as<double>(),
-                             h->fin_raw.as<double>(), h->init_T.as<double>(), h->inner_base.as<long long>(),
-                             h->inner_pts.as<double>(), h->ini.as<double>(), h->fin.as<double>(), h->x0.as<double>(),
-                             dims.n_stride));
+                             h->fin_raw.as<double>(), h->ini.as<double>(), h->fin.as<double>()));
     launches += 1;
   }
   // L-BFGS history ring per resident warp
@@ -1199,6 +1236,76 @@ int dftpav_solve(dftpav_handle* h, const dftpav_batch* batch, const dftpav_resul
   cudaEventElapsedTime(&ms, h->ev[0], h->ev[1]);
   h->stats.upload_ms = ms;  // small arrays, tables and the state kernel; the plane copy runs under the solve
   return rc;
+}
+
+static SampleDev sample_view(const dftpav_handle* h) {
+  SampleDev sd;
+  sd.coeffs = h->o_coeffs.as<double>();
+  sd.piece_dT = h->o_dT.as<double>();
+  sd.singul = h->singul.as<int>();
+  sd.seg_prob = h->seg_prob.as<int>();
+  sd.seg_row0 = h->seg_row0.as<int>();
+  sd.seg_N = h->seg_N.as<int>();
+  sd.seg_piece0 = h->seg_piece0.as<long long>();
+  sd.G = h->dims.seg_total;
+  sd.row_stride = h->dims.row_stride;
+  return sd;
+}
+
+int dftpav_sample(dftpav_handle* h, int64_t nq, const int32_t* seg, const double* t, int32_t flags, double wheel_base,
+                  double* out) {
+  if (!h || nq < 0 || (nq > 0 && (!seg || !t || !out))) return DFTPAV_ERR_INVALID_ARG;
+  if (!h->solved) return fail(h, DFTPAV_ERR_STATE, "dftpav_sample before dftpav_optimize");
+  if (nq == 0) return DFTPAV_OK;
+  CU_TRY(h, cudaSetDevice(h->device));
+  cudaStream_t st = h->stream;
+  CU_TRY(h, h->q_seg.ensure(sizeof(int) * (size_t)nq));
+  CU_TRY(h, h->q_t.ensure(sizeof(double) * (size_t)nq));
+  CU_TRY(h, h->q_out.ensure(sizeof(double) * DFTPAV_STATE_DOUBLES * (size_t)nq));
+  CU_TRY(h, cudaMemcpyAsync(h->q_seg.p, seg, sizeof(int) * (size_t)nq, cudaMemcpyHostToDevice, st));
+  CU_TRY(h, cudaMemcpyAsync(h->q_t.p, t, sizeof(double) * (size_t)nq, cudaMemcpyHostToDevice, st));
+  CU_TRY(h, launch_sample(st, sample_view(h), nq, h->q_seg.as<int>(), h->q_t.as<double>(), flags, wheel_base,
+                          h->q_out.as<double>()));
+  CU_TRY(h, cudaMemcpyAsync(out, h->q_out.p, sizeof(double) * DFTPAV_STATE_DOUBLES * (size_t)nq, cudaMemcpyDeviceToHost, st));
+  CU_TRY(h, cudaStreamSynchronize(st));
+  return DFTPAV_OK;
+}
+
+int dftpav_sample_uniform(dftpav_handle* h, double dt, int32_t max_per_seg, double* xyyaw, int32_t* count) {
+  if (!h || !(dt > 0.0) || max_per_seg < 1 || !xyyaw || !count) return DFTPAV_ERR_INVALID_ARG;
+  if (!h->solved) return fail(h, DFTPAV_ERR_STATE, "dftpav_sample_uniform before dftpav_optimize");
+  const int G = h->dims.seg_total;
+  if (G == 0) return DFTPAV_OK;
+  CU_TRY(h, cudaSetDevice(h->device));
+  cudaStream_t st = h->stream;
+  const size_t ob = sizeof(double) * 3 * (size_t)G * max_per_seg;
+  CU_TRY(h, h->q_out.ensure(ob));
+  CU_TRY(h, h->q_cnt.ensure(sizeof(int) * G));
+  CU_TRY(h, cudaMemsetAsync(h->q_out.p, 0, ob, st));
+  CU_TRY(h, launch_sample_uniform(st, sample_view(h), dt, max_per_seg, h->q_out.as<double>(), h->q_cnt.as<int>()));
+  CU_TRY(h, cudaMemcpyAsync(xyyaw, h->q_out.p, ob, cudaMemcpyDeviceToHost, st));
+  CU_TRY(h, cudaMemcpyAsync(count, h->q_cnt.p, sizeof(int) * G, cudaMemcpyDeviceToHost, st));
+  CU_TRY(h, cudaStreamSynchronize(st));
+  return DFTPAV_OK;
+}
+
+int dftpav_pack_polytraj(dftpav_handle* h, float* coef_x, float* coef_y, float* duration) {
+  if (!h || !coef_x || !coef_y || !duration) return DFTPAV_ERR_INVALID_ARG;
+  if (!h->solved) return fail(h, DFTPAV_ERR_STATE, "dftpav_pack_polytraj before dftpav_optimize");
+  const long long NP = h->pieces_total;
+  if (NP == 0) return DFTPAV_OK;
+  CU_TRY(h, cudaSetDevice(h->device));
+  cudaStream_t st = h->stream;
+  CU_TRY(h, h->q_out.ensure(sizeof(float) * 13 * (size_t)NP));
+  float* cx = h->q_out.as<float>();
+  float* cy = cx + 6 * NP;
+  float* du = cy + 6 * NP;
+  CU_TRY(h, launch_pack_polytraj(st, sample_view(h), cx, cy, du));
+  CU_TRY(h, cudaMemcpyAsync(coef_x, cx, sizeof(float) * 6 * (size_t)NP, cudaMemcpyDeviceToHost, st));
+  CU_TRY(h, cudaMemcpyAsync(coef_y, cy, sizeof(float) * 6 * (size_t)NP, cudaMemcpyDeviceToHost, st));
+  CU_TRY(h, cudaMemcpyAsync(duration, du, sizeof(float) * (size_t)NP, cudaMemcpyDeviceToHost, st));
+  CU_TRY(h, cudaStreamSynchronize(st));
+  return DFTPAV_OK;
 }
 
 int dftpav_last_stats(const dftpav_handle* h, dftpav_stats* stats) {

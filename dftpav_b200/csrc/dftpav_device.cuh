@@ -114,6 +114,18 @@ struct OutDev {
   int trace_cap;
 };
 
+// Device view for the batched trajectory evaluator (dftpav_sample*): results of the last solve + segment directory.
+struct SampleDev {
+  const double* coeffs;         // [B][row_stride][2]
+  const double* piece_dT;       // [G]
+  const int* singul;            // [G]
+  const int* seg_prob;          // [G] problem of the segment
+  const int* seg_row0;          // [G] first coefficient row of the segment inside its problem
+  const int* seg_N;             // [G] pieces
+  const long long* seg_piece0;  // [G] pieces of all earlier segments (PolyTraj packing)
+  int G, row_stride;
+};
+
 struct HistDev {
   double* s;        // [slots][mem][npad_max]
   double* y;

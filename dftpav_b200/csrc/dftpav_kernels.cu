@@ -12,6 +12,8 @@
 #include <cuda_runtime.h>
 #include <math_constants.h>
 
+#include <algorithm>
+
 #include "dftpav_device.cuh"
 #include "../../include/dftpav_b200.h"
 
@@ -2484,23 +2486,16 @@ __global__ void __launch_bounds__(32 * DFTPAV_MAX_WARPS, 1)
   }
 }
 
-// boundary-state clamps (traj_optimizer.cpp:55-76) and packing of x0 (traj_optimizer.cpp:96-115)
+// boundary-state clamps (traj_optimizer.cpp:55-76); x0 is packed on the host (pack_x0 in dftpav_api.cu: glibc atan2)
 __global__ void prepare_states_kernel(const ShapeDev sh, ParamsDev P, const int* __restrict__ prob_id, int count,
                                       const int* __restrict__ seg_base, const int* __restrict__ singul,
                                       const double* __restrict__ ini_raw, const double* __restrict__ fin_raw,
-                                      const double* __restrict__ init_T, const long long* __restrict__ inner_base,
-                                      const double* __restrict__ inner_pts, double* __restrict__ ini,
-                                      double* __restrict__ fin, double* __restrict__ x0, int n_stride) {
+                                      double* __restrict__ ini, double* __restrict__ fin) {
   const int local = blockIdx.x * blockDim.x + threadIdx.x;
   if (local >= count) return;
   const int prob = prob_id[local];
   const int g0 = seg_base[prob];
-  double* x = x0 + (size_t)prob * n_stride;
-  const int S = sh.S;
-  const int tv0 = sh.var0[S - 1] + 2 * (sh.N[S - 1] - 1);
-  const int gb = tv0 + S, ab = gb + 2 * (S - 1);
-  long long ib = inner_base[prob];
-  for (int s = 0; s < S; s++) {
+  for (int s = 0; s < sh.S; s++) {
     const int g = g0 + s;
     const int sidx = singul[g] > 0 ? 0 : 1;
     const double max_vel = P.max_vel[sidx], max_acc = P.max_acc[sidx];
@@ -2530,18 +2525,159 @@ __global__ void prepare_states_kernel(const ShapeDev sh, ParamsDev P, const int*
       ini[6 * g + k] = st[0][k];
       fin[6 * g + k] = st[1][k];
     }
-    const int np = 2 * (sh.N[s] - 1);
-    for (int i = 0; i < np; i++) x[sh.var0[s] + i] = inner_pts[ib + i];
-    ib += np;
-    const double RT = init_T[g], mini_T = P.mini_T;
-    x[tv0 + s] = RT > 1.0 + mini_T ? (sqrt(2.0 * RT - 1.0 - 2 * mini_T) - 1.0) : (1.0 - sqrt(2.0 / (RT - mini_T) - 1.0));
-    if (s < S - 1) {
-      x[gb + 2 * s] = st[1][0];
-      x[gb + 2 * s + 1] = st[1][1];
-      x[ab + s] = atan2(st[1][3], st[1][2]);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Read-back side of the path: batched evaluation of the solved trajectories straight from
+// the device-resident coefficients.  Replaces the per-sample calls consumers make on plan_utils::Trajectory -
+// getPos / getdSigma / getddSigma (poly_traj_utils.hpp:77-87, 179-211, 554-600), getAngle / getCurv / getVel / getAcc /
+// getLatAcc / getSteer (233-296, 604-645), GetState (378-406) - e.g. the 0.05 s collision re-check of the executing
+// trajectory (traj_server_ros.cpp:385-397).  Polynomial values are accumulated in the reference's order with explicitly
+// rounded multiplies / adds (no FMA contraction), so positions, derivatives, speed and accelerations are BIT-IDENTICAL to
+// the reference; angle, curvature and steer go through atan2 / pow / atan of the CUDA math library (<= 2 ulp).
+// ------------------------------------------------------------------------------------------------
+struct SegView {
+  const double* c;  // [6N][2] coefficients of the segment, row 6i+k = coefficient of t^k of piece i
+  double dT;
+  int N, singul;
+};
+__device__ __forceinline__ SegView seg_view(const SampleDev& sd, int g) {
+  SegView v;
+  v.N = sd.seg_N[g];
+  v.dT = sd.piece_dT[g];
+  v.singul = sd.singul[g];
+  v.c = sd.coeffs + ((size_t)sd.seg_prob[g] * sd.row_stride + sd.seg_row0[g]) * 2;
+  return v;
+}
+// Trajectory::getTotalDuration (poly_traj_utils.hpp:425-434): the sum, not N * dT
+__device__ __forceinline__ double seg_duration(const SegView& v) {
+  double tot = 0.0;
+  for (int i = 0; i < v.N; i++) tot = __dadd_rn(tot, v.dT);
+  return tot;
+}
+// Trajectory::locatePieceIdx (poly_traj_utils.hpp:510-528)
+__device__ __forceinline__ int seg_locate(const SegView& v, double& t) {
+  int idx;
+  for (idx = 0; idx < v.N && t > v.dT; idx++) t = __dadd_rn(t, -v.dT);
+  if (idx == v.N) {
+    idx--;
+    t = __dadd_rn(t, v.dT);
+  }
+  return idx;
+}
+// Piece::getPos / getdSigma / getddSigma: `acc += (factor * tn) * coefficient`, highest-power-first columns
+__device__ __forceinline__ void piece_eval(const double* c, double t, V2& pos, V2& ds, V2& dds) {
+  pos = ds = dds = mk(0.0, 0.0);
+  double tn = 1.0;
+#pragma unroll
+  for (int k = 0; k <= 5; k++) {  // column i = 5 - k of the reference holds the coefficient of t^k
+    pos.x = __dadd_rn(pos.x, __dmul_rn(tn, c[2 * k]));
+    pos.y = __dadd_rn(pos.y, __dmul_rn(tn, c[2 * k + 1]));
+    tn = __dmul_rn(tn, t);
+  }
+  tn = 1.0;
+#pragma unroll
+  for (int k = 1; k <= 5; k++) {
+    const double f = __dmul_rn((double)k, tn);
+    ds.x = __dadd_rn(ds.x, __dmul_rn(f, c[2 * k]));
+    ds.y = __dadd_rn(ds.y, __dmul_rn(f, c[2 * k + 1]));
+    tn = __dmul_rn(tn, t);
+  }
+  tn = 1.0;
+#pragma unroll
+  for (int k = 2; k <= 5; k++) {
+    const double f = __dmul_rn((double)((k - 1) * k), tn);
+    dds.x = __dadd_rn(dds.x, __dmul_rn(f, c[2 * k]));
+    dds.y = __dadd_rn(dds.y, __dmul_rn(f, c[2 * k + 1]));
+    tn = __dmul_rn(tn, t);
+  }
+}
+__device__ __forceinline__ double norm_rn(V2 a) { return sqrt(__dadd_rn(__dmul_rn(a.x, a.x), __dmul_rn(a.y, a.y))); }
+
+__global__ void sample_kernel(const SampleDev sd, long long nq, const int* __restrict__ seg, const double* __restrict__ tq,
+                              int flags, double wheel_base, double* __restrict__ out) {
+  for (long long q = blockIdx.x * (long long)blockDim.x + threadIdx.x; q < nq; q += (long long)gridDim.x * blockDim.x) {
+    double* o = out + q * 12;
+    const int g = seg[q];
+    if (g < 0 || g >= sd.G || sd.seg_N[g] < 1) {
+      for (int k = 0; k < 12; k++) o[k] = 0.0;
+      continue;
+    }
+    const SegView v = seg_view(sd, g);
+    double t = tq[q];
+    if (flags & (DFTPAV_SAMPLE_CLAMP | DFTPAV_SAMPLE_GETSTATE)) {
+      const double tot = seg_duration(v);
+      if (t > tot) t = tot;
+    }
+    const int idx = seg_locate(v, t);
+    V2 p, d1, d2;
+    piece_eval(v.c + 12 * idx, t, p, d1, d2);
+    const double sg = (double)v.singul;
+    const double nv = norm_rn(d1);
+    const double cross = __dadd_rn(__dmul_rn(d1.x, d2.y), -__dmul_rn(d1.y, d2.x));
+    const double dotp = __dadd_rn(__dmul_rn(d1.x, d2.x), __dmul_rn(d1.y, d2.y));
+    double curv, acc, lat;
+    const double vel = __dmul_rn(sg, nv);
+    // Piece::getCurv / getAcc / getLatAcc test norm() < 1e-6; getStateExpPos tests abs(vel) with the integer abs (quirk Q11)
+    const bool still = (flags & DFTPAV_SAMPLE_GETSTATE) ? (fabs(vel) < 1.0) : (nv < 1e-6);
+    if (still) {
+      curv = acc = lat = 0.0;
+    } else {
+      curv = __dmul_rn(sg, cross) / pow(nv, 3.0);
+      acc = __dmul_rn(sg, dotp) / nv;
+      lat = __dmul_rn(sg, cross) / nv;
+    }
+    o[0] = p.x, o[1] = p.y, o[2] = d1.x, o[3] = d1.y, o[4] = d2.x, o[5] = d2.y;
+    o[6] = atan2(__dmul_rn(sg, d1.y), __dmul_rn(sg, d1.x));
+    o[7] = curv;
+    o[8] = vel;
+    o[9] = acc;
+    o[10] = atan(__dmul_rn(wheel_base, curv));
+    o[11] = lat;
+  }
+}
+
+// The sampling loop of the collision re-check (traj_server_ros.cpp:385-397): every segment at t = 0, dt, 2 dt, ... while
+// t < duration, t accumulated like the reference's `t += 0.05`; out[g][k] = (x, y, yaw).  One thread per segment.
+__global__ void sample_uniform_kernel(const SampleDev sd, double dt, int max_per_seg, double* __restrict__ out,
+                                      int* __restrict__ count) {
+  const int g = blockIdx.x * blockDim.x + threadIdx.x;
+  if (g >= sd.G) return;
+  int k = 0;
+  if (sd.seg_N[g] >= 1) {
+    const SegView v = seg_view(sd, g);
+    const double dur = seg_duration(v);
+    double* o = out + (size_t)g * max_per_seg * 3;
+    for (double t = 0.0; t < dur && k < max_per_seg; t = __dadd_rn(t, dt), k++) {
+      double tl = t;
+      const int idx = seg_locate(v, tl);
+      V2 p, d1, d2;
+      piece_eval(v.c + 12 * idx, tl, p, d1, d2);
+      const double sg = (double)v.singul;
+      o[3 * k] = p.x;
+      o[3 * k + 1] = p.y;
+      o[3 * k + 2] = atan2(__dmul_rn(sg, d1.y), __dmul_rn(sg, d1.x));
     }
   }
-  for (int i = sh.n; i < n_stride; i++) x[i] = 0.0;
+  count[g] = k;
+}
+
+// plan_utils::Piece::getCoeffMat order for the wire format of msg/PolyTraj.msg (order, coef_x, coef_y, duration; float32):
+// per piece the six coefficients HIGHEST power first (poly_traj_utils.hpp:19, 987-997), pieces of all segments concatenated
+__global__ void pack_polytraj_kernel(const SampleDev sd, float* __restrict__ coef_x, float* __restrict__ coef_y,
+                                     float* __restrict__ duration) {
+  const int g = blockIdx.x;
+  if (g >= sd.G) return;
+  const SegView v = seg_view(sd, g);
+  const long long base = sd.seg_piece0[g];
+  for (int i = threadIdx.x; i < v.N; i += blockDim.x) {
+    duration[base + i] = (float)v.dT;
+    for (int k = 0; k < 6; k++) {
+      coef_x[(base + i) * 6 + k] = (float)v.c[2 * (6 * i + 5 - k)];
+      coef_y[(base + i) * 6 + k] = (float)v.c[2 * (6 * i + 5 - k) + 1];
+    }
+  }
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -2575,10 +2711,23 @@ cudaError_t launch_eval(bool has_obs, int grid, int block, size_t smem, cudaStre
 
 cudaError_t launch_prepare(int grid, int block, cudaStream_t st, const ShapeDev& sh, const ParamsDev& P,
                            const int* prob_id, int count, const int* seg_base, const int* singul, const double* ini_raw,
-                           const double* fin_raw, const double* init_T, const long long* inner_base,
-                           const double* inner_pts, double* ini, double* fin, double* x0, int n_stride) {
-  prepare_states_kernel<<<grid, block, 0, st>>>(sh, P, prob_id, count, seg_base, singul, ini_raw, fin_raw, init_T,
-                                                inner_base, inner_pts, ini, fin, x0, n_stride);
+                           const double* fin_raw, double* ini, double* fin) {
+  prepare_states_kernel<<<grid, block, 0, st>>>(sh, P, prob_id, count, seg_base, singul, ini_raw, fin_raw, ini, fin);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_sample(cudaStream_t st, const SampleDev& sd, long long nq, const int* seg, const double* t, int flags,
+                          double wheel_base, double* out) {
+  const int grid = (int)std::min<long long>((nq + 255) / 256, 148LL * 16);
+  sample_kernel<<<grid > 0 ? grid : 1, 256, 0, st>>>(sd, nq, seg, t, flags, wheel_base, out);
+  return cudaGetLastError();
+}
+cudaError_t launch_sample_uniform(cudaStream_t st, const SampleDev& sd, double dt, int max_per_seg, double* out, int* count) {
+  sample_uniform_kernel<<<(sd.G + 127) / 128, 128, 0, st>>>(sd, dt, max_per_seg, out, count);
+  return cudaGetLastError();
+}
+cudaError_t launch_pack_polytraj(cudaStream_t st, const SampleDev& sd, float* cx, float* cy, float* dur) {
+  pack_polytraj_kernel<<<sd.G > 0 ? sd.G : 1, 64, 0, st>>>(sd, cx, cy, dur);
   return cudaGetLastError();
 }
 

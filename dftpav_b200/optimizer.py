@@ -169,6 +169,36 @@ class BatchOptimizer:
         self._check(self._lib.dftpav_eval(self._h, x.ctypes.data_as(dp), f.ctypes.data_as(dp), g.ctypes.data_as(dp)))
         return f, g
 
+    # -- read-back: batched trajectory evaluation (Trajectory::getPos / getAngle / GetState ... on the device) ------------
+    def sample(self, seg: np.ndarray, t: np.ndarray, flags: int = 0, wheel_base: float = capi.WHEEL_BASE) -> np.ndarray:
+        """States [nq, 12] of segment seg[q] at local time t[q] (dftpav_sample)."""
+        seg = np.ascontiguousarray(seg, dtype=np.int32)
+        t = np.ascontiguousarray(t, dtype=np.float64)
+        out = np.zeros((seg.shape[0], capi.STATE_DOUBLES))
+        self._check(self._lib.dftpav_sample(self._h, seg.shape[0], seg.ctypes.data_as(capi.c_int32_p),
+                                            t.ctypes.data_as(capi.c_double_p), flags, wheel_base,
+                                            out.ctypes.data_as(capi.c_double_p)))
+        return out
+
+    def sample_uniform(self, dt: float, max_per_seg: int):
+        """(x, y, yaw) of every segment at t = 0, dt, 2 dt, ... < duration (dftpav_sample_uniform): ([G, max, 3], counts [G])."""
+        G = self._dims.seg_total
+        out = np.zeros((G, max_per_seg, 3))
+        cnt = np.zeros(G, dtype=np.int32)
+        self._check(self._lib.dftpav_sample_uniform(self._h, dt, max_per_seg, out.ctypes.data_as(capi.c_double_p),
+                                                    cnt.ctypes.data_as(capi.c_int32_p)))
+        return out, cnt
+
+    def pack_polytraj(self):
+        """msg/PolyTraj.msg fields of all segments: (coef_x [P, 6], coef_y [P, 6], duration [P]) float32, highest power first."""
+        P = int(np.sum(self._batch.piece_num))
+        cx = np.zeros((P, 6), dtype=np.float32)
+        cy = np.zeros((P, 6), dtype=np.float32)
+        du = np.zeros(P, dtype=np.float32)
+        fp = C.POINTER(C.c_float)
+        self._check(self._lib.dftpav_pack_polytraj(self._h, cx.ctypes.data_as(fp), cy.ctypes.data_as(fp), du.ctypes.data_as(fp)))
+        return cx, cy, du
+
     # -- diagnostics (not part of the drop-in ABI) ---------------------------------------------
     def enable_trace(self, cap: int):
         self._lib.dftpav_debug_set_trace.argtypes = [C.c_void_p, C.c_int]

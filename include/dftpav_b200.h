@@ -254,6 +254,35 @@ int dftpav_download(dftpav_handle* h, const dftpav_result* out);
 /* upload + optimize + download in one call (the end-to-end path a planner would use). */
 int dftpav_solve(dftpav_handle* h, const dftpav_batch* batch, const dftpav_result* out);
 
+/* ---- read-back: batched evaluation of the solved trajectories, from the device-resident coefficients ----
+ * Replaces the per-sample calls consumers make on plan_utils::Trajectory (MINCO.hpp:554-645: getPos, getdSigma, getddSigma,
+ * getAngle, getCurv, getVel, getAcc, getLatAcc, getSteer; GetState 378-406) after getMinJerkOptPtr()->at(i).getTraj(singul).
+ * A gear segment g (global index: seg_ptr[p] + s) is one Trajectory of piece_num[g] pieces with its singul; times are
+ * local to the segment.  Query q evaluates segment seg[q] at t[q]:
+ *   out[q] = { x, y, dsigma_x, dsigma_y, ddsigma_x, ddsigma_y, angle, curvature, velocity, acceleration, steer, lat_acc }
+ * Without flags the getters' semantics (time not clamped: past the end the last piece is extrapolated, MINCO.hpp:510-528;
+ * curvature / acceleration zero when |sigma'| < 1e-6).  DFTPAV_SAMPLE_CLAMP clamps t to the segment duration.
+ * DFTPAV_SAMPLE_GETSTATE gives what Trajectory::GetState stores: clamped time and getStateExpPos' threshold, which tests
+ * `abs(velocity) < 1e-6` with the unqualified (integer) abs, i.e. curvature, acceleration and steer are zero whenever
+ * |velocity| < 1 (quirk Q11).  wheel_base: VehicleParam::wheel_base (2.85, semantics.h:68) for steer = atan(L * curvature).
+ * Positions, derivatives, velocity and accelerations are bit-identical to the reference's evaluators; angle, curvature and
+ * steer within 1e-12 relative.  Call after dftpav_optimize / dftpav_solve. */
+#define DFTPAV_STATE_DOUBLES 12
+#define DFTPAV_SAMPLE_CLAMP 1
+#define DFTPAV_SAMPLE_GETSTATE 2
+int dftpav_sample(dftpav_handle* h, int64_t nq, const int32_t* seg, const double* t, int32_t flags, double wheel_base,
+                  double* out);
+
+/* The sampling loop of the collision re-check of the executing trajectory (traj_server_ros.cpp:385-397): every segment at
+ * t = 0, dt, 2 dt, ... while t < duration (t accumulated like the reference's `t += 0.05`), at most max_per_seg samples:
+ * xyyaw[g][k] = { x, y, yaw } (getPos, getAngle), count[g] = samples written. */
+int dftpav_sample_uniform(dftpav_handle* h, double dt, int32_t max_per_seg, double* xyyaw, int32_t* count);
+
+/* The fields of msg/PolyTraj.msg (uint8 order = 5, float32[] coef_x, coef_y, duration) for all segments concatenated in
+ * segment order: per piece six coefficients, highest power first like Piece::getCoeffMat (MINCO.hpp:19, 987-997).
+ * coef_x, coef_y: [6 * sum piece_num], duration: [sum piece_num]. */
+int dftpav_pack_polytraj(dftpav_handle* h, float* coef_x, float* coef_y, float* duration);
+
 int dftpav_last_stats(const dftpav_handle* h, dftpav_stats* stats);
 const char* dftpav_last_error(const dftpav_handle* h);
 const char* dftpav_version(void);

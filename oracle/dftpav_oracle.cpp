@@ -1490,6 +1490,56 @@ int oracle_traj_eval(int N, const double* P, double dT, const double* head, cons
   return DFTPAV_OK;
 }
 
+// The read-back side of the hot path: MinJerkOpt::getTraj (MINCO.hpp:987-997) followed by the Trajectory / Piece evaluators
+// consumers sample the result with (GetState 378-406; getPos, getdSigma, getddSigma, getAngle, getCurv, getVel, getAcc,
+// getLatAcc, getSteer 77-87, 179-211, 233-296, 554-645).  Same signature and output layout as ref_traj_state in
+// oracle/ref_minco_driver.cpp, which runs the reference's own header.
+int oracle_traj_state(int N, const double* c, double dT, int singul, double t, int clamp, double wheel_base, double* out,
+                      double* gs) {
+  if (N < 1 || !c || !out) return DFTPAV_ERR_INVALID_ARG;
+  std::vector<double> dur(N, dT), cm(12 * (size_t)N);
+  for (int i = 0; i < N; i++)
+    for (int k = 0; k < 6; k++)
+      for (int col = 0; col < 2; col++) cm[12 * i + 2 * k + col] = c[2 * (6 * i + 5 - k) + col];
+  ObsTraj tr{N, dur.data(), cm.data(), 0.0, 0.0};
+  double total = 0.0;  // Trajectory::getTotalDuration (MINCO.hpp:425-434)
+  for (int i = 0; i < N; i++) total += dT;
+  double tt = t;
+  if (clamp && tt > total) tt = total;
+  const double sg = (double)singul;
+  auto state_at = [&](double tq, double* o) {
+    const V2 p = tr.getPos(tq), v = tr.getdSigma(tq), a = tr.getddSigma(tq);
+    o[0] = p.x, o[1] = p.y, o[2] = v.x, o[3] = v.y, o[4] = a.x, o[5] = a.y;
+    const double nv = norm(v);
+    o[6] = std::atan2(sg * v.y, sg * v.x);                                        // getAngle, MINCO.hpp:233-241
+    o[7] = nv < 1e-6 ? 0.0 : sg * (v.x * a.y - v.y * a.x) / std::pow(nv, 3);      // getCurv, 244-256
+    o[8] = sg * nv;                                                               // getVel, 260-265
+    o[9] = nv < 1e-6 ? 0.0 : sg * (v.x * a.x + v.y * a.y) / nv;                   // getAcc, 268-278
+    o[10] = std::atan(wheel_base * o[7]);                                         // getSteer, 293-296
+    o[11] = nv < 1e-6 ? 0.0 : sg * (v.x * a.y - v.y * a.x) / nv;                  // getLatAcc, 280-290
+  };
+  state_at(tt, out);
+  if (gs) {  // Trajectory::GetState + Piece::getStateExpPos (MINCO.hpp:299-338, 378-406): always clamps
+    double ti = t;
+    if (ti > total) ti = total;
+    const V2 p = tr.getPos(ti), v = tr.getdSigma(ti), a = tr.getddSigma(ti);
+    gs[0] = std::atan2(sg * v.y, sg * v.x);
+    gs[2] = sg * norm(v);
+    // quirk Q11: getStateExpPos tests `abs(otherstate[2]) < 1e-6` with an UNQUALIFIED abs (MINCO.hpp:316); compiled as the
+    // reference writes it (oracle/_ref, g++ 13) that is ::abs(int): the speed is truncated to an integer first, so curvature,
+    // acceleration and steer are zeroed whenever |v| < 1 m/s.  (The getters getCurv / getAcc / getSteer test norm() < 1e-6.)
+    if (std::abs((int)gs[2]) < 1e-6) {
+      gs[1] = gs[3] = gs[4] = 0.0;
+    } else {
+      gs[1] = (v.x * a.y - v.y * a.x) / std::pow(gs[2], 3);
+      gs[3] = (v.x * a.x + v.y * a.y) / gs[2];
+      gs[4] = std::atan(wheel_base * gs[1]);
+    }
+    gs[5] = p.x;
+  }
+  return DFTPAV_OK;
+}
+
 // ---- analytic test functions (shared, via C callback, with the reference-header build) ----
 double oracle_testfunc(int id, const double* x, double* g, int n) {
   double f = 0.0;

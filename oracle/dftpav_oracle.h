@@ -79,6 +79,13 @@ int oracle_minco_run(int N, const double* P, double dT, const double* head, cons
 int oracle_traj_eval(int N, const double* P, double dT, const double* head, const double* tail, int singul, double t,
                      double* out);
 
+/* Trajectory / Piece evaluators on coefficients c (6N x 2 row-major, row 6i+k = coefficient of t^k of piece i, every piece
+ * of duration dT): out[12] = x y dsigma(2) ddsigma(2) angle curvature velocity acceleration steer lateral-acceleration at
+ * time t (clamped to the total duration if clamp != 0); gs[6] (optional) = Trajectory::GetState's angle curvature velocity
+ * acceleration steer, position x.  Same signature as ref_traj_state (oracle/ref_minco_driver.cpp, the reference's header). */
+int oracle_traj_state(int N, const double* c, double dT, int singul, double t, int clamp, double wheel_base, double* out,
+                      double* gs);
+
 /* Synthetic-test analytic functions for oracle_lbfgs / the reference header: id 0 = Rosenbrock
  * chain, 1 = ill-conditioned quadratic, 2 = nonsmooth |x| mix.  Same code is compiled into
  * oracle/_ref so both sides evaluate bit-identical f,g. */

@@ -62,6 +62,7 @@ def lib() -> C.CDLL:
         L.oracle_problem_initial_x.restype = None
         L.oracle_problem_fg.restype = C.c_double
         L.oracle_num_threads.argtypes = []
+        L.oracle_traj_state.argtypes = [C.c_int, dp, C.c_double, C.c_int, C.c_double, C.c_int, C.c_double, dp, dp]
         _lib = L
     return _lib
 
@@ -95,6 +96,9 @@ def ref_minco_lib():
         except OSError:
             return None
         _minco_sig(R.ref_minco_run, R.ref_traj_eval)
+        if hasattr(R, "ref_traj_state"):
+            R.ref_traj_state.argtypes = [C.c_int, capi.c_double_p, C.c_double, C.c_int, C.c_double, C.c_int,
+                                         capi.c_double_p, capi.c_double_p]
         _ref_minco = R
     return _ref_minco
 
@@ -127,6 +131,27 @@ def traj_eval(fn, N, P, dT, head, tail, t):
     rc = fn(N, P.ctypes.data_as(dp), float(dT), head.ctypes.data_as(dp), tail.ctypes.data_as(dp), 1, float(t), out.ctypes.data_as(dp))
     assert rc == 0
     return out
+
+
+def traj_state(c: np.ndarray, dT: float, singul: int, t: float, clamp: int = 0, wheel_base: float = 2.85,
+               use_ref: bool = False):
+    """Trajectory / Piece evaluators on coefficients c [6N, 2] (row 6i+k = coefficient of t^k of piece i): returns
+    (out[12], getstate[6]) from the oracle's restatement or (use_ref) from the reference's own header (oracle/_ref)."""
+    dp = capi.c_double_p
+    c = np.ascontiguousarray(c, dtype=np.float64)
+    N = c.shape[0] // 6
+    out = np.zeros(12)
+    gs = np.zeros(6)
+    if use_ref:
+        R = ref_minco_lib()
+        assert R is not None and hasattr(R, "ref_traj_state")
+        rc = R.ref_traj_state(N, c.ctypes.data_as(dp), float(dT), int(singul), float(t), int(clamp), out.ctypes.data_as(dp),
+                              gs.ctypes.data_as(dp))
+    else:
+        rc = lib().oracle_traj_state(N, c.ctypes.data_as(dp), float(dT), int(singul), float(t), int(clamp), float(wheel_base),
+                                     out.ctypes.data_as(dp), gs.ctypes.data_as(dp))
+    assert rc == 0
+    return out, gs
 
 
 REF_OPT_SO = os.path.join(os.path.dirname(os.path.abspath(__file__)), "_ref", "libref_optimizer.so")

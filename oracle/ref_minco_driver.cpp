@@ -69,4 +69,33 @@ int ref_traj_eval(int N, const double* P, double dT, const double* head, const d
   return 0;
 }
 
+// The reference's Trajectory / Piece evaluators on caller-supplied coefficients (the read-back side of the hot path:
+// MinJerkOpt::getTraj, poly_traj_utils.hpp:987-997, then Trajectory::GetState / getPos / getdSigma / getddSigma / getAngle /
+// getCurv / getVel / getAcc / getSteer / getLatAcc, 378-406 and 554-645).  c = 6N x 2 row-major (row 6i+k = coefficient of
+// t^k of piece i), all pieces of duration dT.  clamp != 0: the time is clamped to the total duration like GetState does.
+// out[12] = x y dsigma(2) ddsigma(2) angle curvature velocity acceleration steer lateral-acceleration;
+// gs[6] (optional) = what GetState writes: angle curvature velocity acceleration steer + the clamped time.
+int ref_traj_state(int N, const double* c, double dT, int singul, double t, int clamp, double* out, double* gs) {
+  plan_utils::Trajectory traj;
+  traj.reserve(N);
+  for (int i = 0; i < N; i++) {
+    plan_utils::CoefficientMat cm;
+    for (int k = 0; k < 6; k++) cm(0, 5 - k) = c[2 * (6 * i + k)], cm(1, 5 - k) = c[2 * (6 * i + k) + 1];
+    traj.emplace_back(dT, cm, singul);
+  }
+  double tt = t;
+  if (clamp && tt > traj.getTotalDuration()) tt = traj.getTotalDuration();
+  const Eigen::Vector2d pos = traj.getPos(tt), ds = traj.getdSigma(tt), dds = traj.getddSigma(tt);
+  out[0] = pos(0), out[1] = pos(1), out[2] = ds(0), out[3] = ds(1), out[4] = dds(0), out[5] = dds(1);
+  out[6] = traj.getAngle(tt), out[7] = traj.getCurv(tt), out[8] = traj.getVel(tt), out[9] = traj.getAcc(tt);
+  out[10] = traj.getSteer(tt), out[11] = traj.getLatAcc(tt);
+  if (gs) {
+    common::State st;
+    traj.GetState(t, &st);
+    gs[0] = st.angle, gs[1] = st.curvature, gs[2] = st.velocity, gs[3] = st.acceleration, gs[4] = st.steer;
+    gs[5] = st.vec_position(0);
+  }
+  return 0;
+}
+
 }  // extern "C"

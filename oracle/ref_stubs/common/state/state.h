@@ -17,6 +17,6 @@ class VehicleParam {
   void set_length(double v) { length_ = v; }
   void set_wheel_base(double v) { wheel_base_ = v; }
   void set_d_cr(double v) { d_cr_ = v; }
-  double width_ = 1.9, length_ = 4.88, wheel_base_ = 3.0, d_cr_ = 1.015;
+  double width_ = 1.9, length_ = 4.88, wheel_base_ = 2.85, d_cr_ = 1.015;
 };
 }  // namespace common

@@ -13,6 +13,8 @@
   optimizer_reference.npz    : outputs of the UNMODIFIED reference optimizer (src/traj_optimizer.cpp compiled in place into
                                oracle/_ref/libref_optimizer.so): costFunctionCallback values / gradients / coefficients at
                                fixed points and complete OptimizeTrajectory results, all five configs.
+  traj_state_reference.npz   : the reference header's Trajectory / Piece evaluators (getPos ... getSteer, GetState) on the
+                               coefficient sets of tests/test_traj_state_oracle.py::_cases (row N2 of SURVEY.md section 8f).
 usage: python tests/make_golden.py [--reference-only]
 """
 import ctypes as C
@@ -106,9 +108,22 @@ def make_minco():
     np.savez_compressed(os.path.join(GOLD, "minco_reference_header.npz"), **out)
 
 
+def make_traj_state():
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import test_traj_state_oracle as T
+
+    outs, gss = [], []
+    for c, dT, sg, t, clamp in T._cases():
+        a, g = O.traj_state(c, dT, sg, t, clamp, use_ref=True)
+        outs.append(a)
+        gss.append(g)
+    np.savez_compressed(os.path.join(GOLD, "traj_state_reference.npz"), out=np.array(outs), gs=np.array(gss))
+
+
 def main():
     make_minco()
     make_optimizer()
+    make_traj_state()
     if "--reference-only" in sys.argv or "--minco-only" in sys.argv:
         return
     os.makedirs(GOLD, exist_ok=True)

@@ -76,7 +76,7 @@ BRANCH_CASES = {
 
 @pytest.mark.parametrize("case", sorted(BRANCH_CASES))
 def test_lbfgs_branches_bit_identical(case, oracle, gpu_strict_factory):
-    batch, prm = synth.make_config(3, B=96, seed=33)
+    batch, prm = synth.make_config(3, B=128, seed=33)
     for k, v in BRANCH_CASES[case].items():
         setattr(prm, k, v)
     opt = gpu_strict_factory(prm)
