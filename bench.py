@@ -263,7 +263,8 @@ def run_ours(args):
         torch.cuda.synchronize()
 
     def convergence_flag(sol_ok: int):
-        # the single collective of the path: global "every rank's slice is done and accepted" flag (1 int, NCCL/NVLink)
+        # the single collective of the path: global "every rank's shard finished and every solve was accepted" flag
+        # (1 int, NCCL over NVLink; MIN over ranks of the local flag)
         flag.fill_(sol_ok)
         if world > 1:
             dist.all_reduce(flag, op=dist.ReduceOp.MIN)
@@ -287,17 +288,18 @@ def run_ours(args):
         st = opt.stats()
         kernel_ms.append(st.solve_ms)
         launches += int(st.n_shapes)  # one persistent solve kernel per problem shape
-        convergence_flag(1)
+        convergence_flag(int(opt.success_count() == args.batch))  # the real local flag (16 KB read-back), then MIN over ranks
     ev1.record(stream)
     sync_all()
     dev_ms = ev0.elapsed_time(ev1)
+    all_accepted = int(flag.item())
     opt.download(sol)
     st = opt.stats()
     alg_bytes = int(st.algorithmic_bytes)
     total_evals, total_iters = int(st.total_evals), int(st.total_iters)
     success = int(sol.success.sum())
 
-    # ---------------- e2e: pinned host batch in, results out, every step
+    # ---------------- e2e: pinned host batch in, results out, every step (ONE C-ABI call: dftpav_solve)
     for _ in range(2):
         opt.solve(batch, sol)
     sync_all()
@@ -305,7 +307,7 @@ def run_ours(args):
     e0.record(stream)
     for _ in range(args.steps):
         opt.solve(batch, sol)
-        convergence_flag(int(sol.status.min() > -1024))
+        convergence_flag(int(bool(np.all(sol.success != 0))))
     e1.record(stream)
     sync_all()
     e2e_ms = e0.elapsed_time(e1)
@@ -313,14 +315,21 @@ def run_ours(args):
     st2 = opt.stats()
     e2e_launches = st2.kernel_launches
 
-    # max over ranks (device-timed)
+    # max over ranks (device-timed); per-rank kernel times to name a straggler
     t = torch.tensor([dev_ms, e2e_ms], dtype=torch.float64, device="cuda")
     cnt = torch.tensor([args.batch * args.steps], dtype=torch.float64, device="cuda")
+    km = torch.tensor([statistics.mean(kernel_ms), dev_ms / args.steps], dtype=torch.float64, device="cuda")
+    km_all = [torch.zeros_like(km) for _ in range(world)]
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         dist.all_reduce(cnt, op=dist.ReduceOp.SUM)
+        dist.all_gather(km_all, km)
+    else:
+        km_all = [km]
     dev_ms, e2e_ms = float(t[0]), float(t[1])
     total_solves = float(cnt[0])
+    rank_kernel_ms = [float(x[0]) for x in km_all]
+    rank_step_ms = [float(x[1]) for x in km_all]
 
     if rank == 0:
         peaks, peak_src = measured_peaks()
@@ -347,6 +356,13 @@ def run_ours(args):
             "evals_per_s": total_evals / (kms * 1e-3) * world,
             "iters_mean": total_iters / args.batch, "evals_mean": total_evals / args.batch,
             "success_frac": success / args.batch,
+            "convergence_flag": {"all_ranks_all_accepted": all_accepted,
+                                 "note": "MIN over ranks of (success_count == batch); 0 when any solve of any shard ends "
+                                         "with a rejected L-BFGS code or a cost above the limit (traj_optimizer.cpp:176-201)"},
+            "per_rank": {"kernel_ms": {"min": min(rank_kernel_ms), "median": statistics.median(rank_kernel_ms),
+                                       "max": max(rank_kernel_ms), "all": [round(v, 3) for v in rank_kernel_ms]},
+                         "step_ms": {"min": min(rank_step_ms), "max": max(rank_step_ms)},
+                         "note": "every rank solves its own seeded batch (weak scaling); ms_per_step is the max over ranks"},
         }
         if not args.no_cpu_baseline:
             cores = os.cpu_count() or 1

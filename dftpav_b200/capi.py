@@ -230,6 +230,7 @@ EXPORTED_SYMBOLS = [
     "dftpav_optimize",
     "dftpav_download",
     "dftpav_solve",
+    "dftpav_success_count",
     "dftpav_sample",
     "dftpav_sample_uniform",
     "dftpav_pack_polytraj",
@@ -273,6 +274,7 @@ def load_library(variant: str = "") -> C.CDLL:
     lib.dftpav_optimize.argtypes = [H]
     lib.dftpav_download.argtypes = [H, C.POINTER(Result)]
     lib.dftpav_solve.argtypes = [H, C.POINTER(Batch), C.POINTER(Result)]
+    lib.dftpav_success_count.argtypes = [H, c_int32_p]
     lib.dftpav_sample.argtypes = [H, C.c_int64, c_int32_p, c_double_p, C.c_int32, C.c_double, c_double_p]
     lib.dftpav_sample_uniform.argtypes = [H, C.c_double, C.c_int32, c_double_p, c_int32_p]
     lib.dftpav_pack_polytraj.argtypes = [H, C.POINTER(C.c_float), C.POINTER(C.c_float), C.POINTER(C.c_float)]

@@ -44,7 +44,7 @@ int ws_doubles_host(int rows, int npad, int S, int has_obs);
 int max_warps_host();
 int virtual_ranks_host();
 int strict_build_host();
-int two_loop_blocked_host();
+int gram_two_loop_host();
 cudaError_t set_phase_clock(unsigned long long* dev_ptr);
 }  // namespace dftpav
 
@@ -227,6 +227,7 @@ struct dftpav_handle {
   std::vector<double> h_x0;
   long long total_planes = 0;
   int uniform_H = 0;                         // -1: ragged corridor (h_plane_ptr)
+  bool hist_gram_on = false;
   bool force_banded = false;                 // test hook: banded LU substitutions even where the dense tables fit
   std::string err;
   bool uploaded = false, solved = false, has_obs = false;
@@ -241,7 +242,7 @@ struct dftpav_handle {
   DevBuf seg_base, t_now, obs_ptr, obs_idx, singul, ini_raw, fin_raw, ini, fin, samp_base,
       plane_ptr, planes_raw, obs_start, obs_dur, obs_piece_ptr, obs_piece_dur, obs_coeffs, obs_uniform, x0, xin, fout, gout;
   DevBuf o_x, o_cost, o_status, o_success, o_iters, o_evals, o_coeffs, o_dT, counter;
-  DevBuf hist_s, hist_y, hist_ys, hist_gram, trace, ready, laid;
+  DevBuf hist_s, hist_y, hist_ys, hist_st, hist_yt, hist_g, hist_gt, trace, ready, laid;
   DevBuf seg_prob, seg_row0, seg_N, seg_piece0, q_seg, q_t, q_out, q_cnt;  // trajectory evaluator (dftpav_sample*)
   long long pieces_total = 0;
   int trace_cap = 0;
@@ -594,7 +595,7 @@ int dftpav_destroy(dftpav_handle* h) {
                     &h->fin, &h->samp_base, &h->plane_ptr, &h->planes_raw,
                     &h->obs_start, &h->obs_dur, &h->obs_piece_ptr, &h->obs_piece_dur, &h->obs_coeffs, &h->obs_uniform, &h->x0, &h->xin,
                     &h->fout, &h->gout, &h->o_x, &h->o_cost, &h->o_status, &h->o_success, &h->o_iters, &h->o_evals,
-                    &h->o_coeffs, &h->o_dT, &h->counter, &h->hist_s, &h->hist_y, &h->hist_ys, &h->hist_gram, &h->trace, &h->ready, &h->laid, &h->seg_prob, &h->seg_row0, &h->seg_N,
+                    &h->o_coeffs, &h->o_dT, &h->counter, &h->hist_s, &h->hist_y, &h->hist_ys, &h->hist_st, &h->hist_yt, &h->hist_g, &h->hist_gt, &h->trace, &h->ready, &h->laid, &h->seg_prob, &h->seg_row0, &h->seg_N,
                     &h->seg_piece0, &h->q_seg, &h->q_t, &h->q_out, &h->q_cnt};
   for (DevBuf* b : bufs) b->release();
   for (auto& e : h->ev)
@@ -941,8 +942,13 @@ int upload_impl(dftpav_handle* h, const dftpav_batch* b, int n_chunks_wanted) {
   CU_TRY(h, h->hist_s.ensure(hbytes));
   CU_TRY(h, h->hist_y.ensure(hbytes));
   CU_TRY(h, h->hist_ys.ensure(sizeof(double) * (size_t)max_slots * mem));
-  if (two_loop_blocked_host())  // only the blocked two-loop keeps a Gram band beside the history
-    CU_TRY(h, h->hist_gram.ensure(sizeof(double) * 4 * (size_t)max_slots * mem));
+  h->hist_gram_on = gram_two_loop_host() > 0 && (int)mem <= gram_two_loop_host() && max_npad <= 96;
+  if (h->hist_gram_on) {  // Gram form of the two-loop recursion: component-major history + Gram matrix and its transpose
+    CU_TRY(h, h->hist_st.ensure(hbytes));
+    CU_TRY(h, h->hist_yt.ensure(hbytes));
+    CU_TRY(h, h->hist_g.ensure(sizeof(double) * (size_t)max_slots * mem * mem));
+    CU_TRY(h, h->hist_gt.ensure(sizeof(double) * (size_t)max_slots * mem * mem));
+  }
 
   // ---- arrival flags of the plane upload and per-problem layout flags (epoch-stamped: nothing to clear between uploads)
   h->epoch += 1;
@@ -1038,7 +1044,10 @@ int launch_solve_kernels(dftpav_handle* h, int* launches_out) {
   hist.s = h->hist_s.as<double>();
   hist.y = h->hist_y.as<double>();
   hist.ys = h->hist_ys.as<double>();
-  hist.gram = h->hist_gram.as<double>();
+  hist.st = h->hist_gram_on ? h->hist_st.as<double>() : nullptr;
+  hist.yt = h->hist_gram_on ? h->hist_yt.as<double>() : nullptr;
+  hist.g = h->hist_gram_on ? h->hist_g.as<double>() : nullptr;
+  hist.gt = h->hist_gram_on ? h->hist_gt.as<double>() : nullptr;
   hist.ld = h->hist_ld;
   hist.mem = h->prm.lbfgs_mem_size;
   int launches = 0, gi = 0;
@@ -1238,6 +1247,21 @@ int dftpav_solve(dftpav_handle* h, const dftpav_batch* batch, const dftpav_resul
   return rc;
 }
 
+// The local half of the global convergence flag: how many problems of the last solve ended with
+// flag_success (traj_optimizer.cpp:176-201).  Reads B ints back; the caller all-reduces (MIN of n_success == B) over ranks.
+int dftpav_success_count(dftpav_handle* h, int32_t* n_success) {
+  if (!h || !n_success) return DFTPAV_ERR_INVALID_ARG;
+  if (!h->solved) return fail(h, DFTPAV_ERR_STATE, "dftpav_success_count before dftpav_optimize");
+  CU_TRY(h, cudaSetDevice(h->device));
+  std::vector<int> ok(h->dims.B);
+  CU_TRY(h, cudaMemcpyAsync(ok.data(), h->o_success.p, sizeof(int) * h->dims.B, cudaMemcpyDeviceToHost, h->stream));
+  CU_TRY(h, cudaStreamSynchronize(h->stream));
+  int n = 0;
+  for (int v : ok) n += v != 0;
+  *n_success = n;
+  return DFTPAV_OK;
+}
+
 static SampleDev sample_view(const dftpav_handle* h) {
   SampleDev sd;
   sd.coeffs = h->o_coeffs.as<double>();
@@ -1323,7 +1347,7 @@ int dftpav_debug_force_banded(dftpav_handle* h, int on) {
 }
 // Build variant of the loaded library: bit 0 strict-order verification build, bit 1 blocked two-loop; bits 8.. virtual ranks
 int dftpav_debug_build_flags(void) {
-  return (strict_build_host() ? 1 : 0) | (two_loop_blocked_host() ? 2 : 0) | (virtual_ranks_host() << 8);
+  return (strict_build_host() ? 1 : 0) | (gram_two_loop_host() ? 2 : 0) | (virtual_ranks_host() << 8);
 }
 
 // Diagnostic (not part of the drop-in ABI): per-iteration (fx, step, ls) traces of the next dftpav_optimize calls.

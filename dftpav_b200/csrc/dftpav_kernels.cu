@@ -34,6 +34,14 @@ __device__ __forceinline__ double warp_sum(double v) {
   for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(FULL, v, o);
   return v;
 }
+// four sums at once: the butterflies are interleaved (the latency of one)
+__device__ __noinline__ void warp_sum4(double (&v)[4]) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+#pragma unroll
+    for (int q = 0; q < 4; q++) v[q] += __shfl_xor_sync(FULL, v[q], o);
+  }
+}
 __device__ __forceinline__ double warp_max(double v) {
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) v = fmax(v, __shfl_xor_sync(FULL, v, o));
@@ -146,6 +154,10 @@ struct SegScratch {   // 38 doubles per segment
 #ifndef DFTPAV_STRICT
 #define DFTPAV_STRICT 0
 #endif
+#ifndef DFTPAV_GRAM
+#define DFTPAV_GRAM 1  // Gram form of the two-loop recursion (two_loop_gram); 0: classic recursion everywhere (A/B)
+#endif
+constexpr bool kClassicOff = false;
 constexpr bool kStrict = DFTPAV_STRICT != 0;          // strict-order verification build (dftpav_strict.cuh)
 constexpr int kVR = kStrict ? 1 : DFTPAV_VRANKS;      // virtual ranks of the sweep = max team size (owner + kVR-1 helpers)
 constexpr int kMaxHelp = kVR - 1;
@@ -1886,157 +1898,251 @@ __device__ __forceinline__ int wrap_index(int x, int m) {
   return x < 0 ? x + m : x;
 }
 
-// Blocked two-loop recursion (ROUND-2 CANDIDATE, OFF by default, compiled but NOT yet run on a GPU).  Four history entries
-// per step: the four dot products with the direction at the START of the block are reduced together (interleaved
-// butterflies: the latency of one), the alphas then follow from a 4x4 triangular recurrence with the Gram products
-// s_i . y_k of the block, which are cached in the history (hist.gram[k] = {s_{k-1}.y_k, s_{k-2}.y_k, s_{k-3}.y_k},
-// computed when entry k is the newest).  Mathematically the reference's recursion; rounding differs; the oracle study in
-// profiles/README.md shows the results stay inside the algorithm's own ulp-sensitivity.  -DDFTPAV_TWO_LOOP_BLOCKED=1.
-#ifndef DFTPAV_TWO_LOOP_BLOCKED
-#define DFTPAV_TWO_LOOP_BLOCKED 0
-#endif
-template <int K>
-__device__ __forceinline__ void warp_sum_k(double (&v)[K]) {
-#pragma unroll
-  for (int o = 16; o > 0; o >>= 1) {
-#pragma unroll
-    for (int k = 0; k < K; k++) v[k] += __shfl_xor_sync(FULL, v[k], o);
-  }
-}
+// ------------------------------------------------------------------------------------------------
+// Gram form of the two-loop recursion (the production path for mem_size <= 256, n <= 96).
+//
+// The classic recursion is a dependent chain of 2*bound history steps, each with a 5-level shuffle butterfly for its dot
+// product: 313 cycles per step for a lone warp on B200 (tools/microbench/two_loop_bench.cu: the same with the history in
+// shared memory, i.e. the chain, not the memory, is the limit), which is half of the run time of the longest problems -
+// the ones that set the batch time.  Here the dot products leave the chain:
+//   first loop :  alpha_t = rho_t (s_t.q_t),  q_t = d0 - sum_{t' newer than t} alpha_t' y_t'
+//                 =>  alpha_t = rho_t (u_t - sum_{t' newer} alpha_t' G[t'][t]),   u = S^T d0,  G[a][b] = s_b . y_a (b older than a)
+//   second loop:  beta_t = rho_t (y_t.r_t),   r_t = d1 + sum_{t' older than t} (alpha_t' - beta_t') s_t'
+//                 =>  beta_t = rho_t (w_t + sum_{t' older} c_t' G[t][t']),     w = Y^T d1,  c = alpha - beta
+// u and w are bound independent dot products computed lane <-> history entry from a component-major copy of the history
+// (coalesced, no shuffles); the Gram matrix G grows by one row per L-BFGS iteration (computed in the same pass as u); the
+// two triangular recurrences cost one multiply, one shuffle broadcast and one FMA per entry on the dependent chain (about
+// 50 cycles instead of 313) and the direction updates d -= sum alpha_t y_t, d += sum c_t s_t are plain streams.
+// Mathematically the reference's recursion (lbfgs.hpp:716-739); the rounding differs like it does for every other
+// reduction of the production build (the CPU study with the oracle's fully blocked recursion leaves 0.803 / 0.395 / 0.211
+// of the final costs of configurations 3 / 2 / 4 inside 1e-5: the algorithm's own ulp-sensitivity floors).
+// Entries are addressed by AGE t = 0 (newest) .. bound-1 (oldest), slot(t) = newest slot - t (mod m); lane l holds ages
+// l, l+32, ... in registers.  Results are deterministic (fixed orders everywhere).
+// ------------------------------------------------------------------------------------------------
+constexpr int kGramR = 8;  // ages per lane: mem_size <= 32 * kGramR
 template <int NPL>
-__device__ __noinline__ void two_loop_blocked(double* d_sm, double* alpha_sm, const double* __restrict__ lm_s,
-                                              const double* __restrict__ lm_y, const double* __restrict__ lm_ys,
-                                              double* __restrict__ lm_gram, int ld, int m, int end, int bound_in, int n,
-                                              int lane, double ys, double yy) {
-  const int bound = __shfl_sync(FULL, bound_in, 0);
+__device__ __noinline__ void two_loop_gram(double* d_sm, const double* ynew_sm, double* coef_sm, const HistDev& hist,
+                                           int slot, int m, int end, int bound_in, int n, int lane, double ys, double yy) {
+  const int k = __shfl_sync(FULL, bound_in, 0);
+  const int ld = hist.ld;
+  const double* __restrict__ S = hist.s + (size_t)slot * hist.mem * ld;
+  const double* __restrict__ Y = hist.y + (size_t)slot * hist.mem * ld;
+  const double* __restrict__ St = hist.st + (size_t)slot * hist.mem * ld;
+  const double* __restrict__ Yt = hist.yt + (size_t)slot * hist.mem * ld;
+  double* __restrict__ G = hist.g + (size_t)slot * hist.mem * hist.mem;
+  double* __restrict__ GT = hist.gt + (size_t)slot * hist.mem * hist.mem;
+  const double* __restrict__ rho_g = hist.ys + (size_t)slot * hist.mem;
+  const int e = end == 0 ? m - 1 : end - 1;  // slot of the newest pair
+  const int Rk = (k + 31) >> 5;
+  int sl[kGramR];       // slot of my age t = lane + 32 r (clamped to a valid slot beyond the window)
+  bool in[kGramR];
+#pragma unroll
+  for (int r = 0; r < kGramR; r++) {
+    const int t = lane + 32 * r;
+    in[r] = t < k;
+    int v = e - (in[r] ? t : 0);
+    if (v < 0) v += m;
+    sl[r] = v;
+  }
+  double u[kGramR], rho[kGramR], al[kGramR];
+  // ---- phase 1: u = S^T d0 and the Gram row of the newest pair, G[e][.] = S^T y_new (two accumulators each: even / odd i)
+  {
+    double ua[kGramR], ub[kGramR], ga[kGramR], gb[kGramR];
+#pragma unroll
+    for (int r = 0; r < kGramR; r++) ua[r] = ub[r] = ga[r] = gb[r] = 0.0;
+#pragma unroll 2
+    for (int i = 0; i + 1 < n; i += 2) {
+      const double d0 = d_sm[i], d1 = d_sm[i + 1], y0 = ynew_sm[i], y1 = ynew_sm[i + 1];
+#pragma unroll
+      for (int r = 0; r < kGramR; r++) {
+        if (r < Rk) {
+          const double v0 = St[(size_t)i * m + sl[r]], v1 = St[(size_t)(i + 1) * m + sl[r]];
+          ua[r] = fma(v0, d0, ua[r]);
+          ub[r] = fma(v1, d1, ub[r]);
+          ga[r] = fma(v0, y0, ga[r]);
+          gb[r] = fma(v1, y1, gb[r]);
+        }
+      }
+    }
+    if (n & 1) {
+      const int i = n - 1;
+      const double d0 = d_sm[i], y0 = ynew_sm[i];
+#pragma unroll
+      for (int r = 0; r < kGramR; r++) {
+        if (r < Rk) {
+          const double v0 = St[(size_t)i * m + sl[r]];
+          ua[r] = fma(v0, d0, ua[r]);
+          ga[r] = fma(v0, y0, ga[r]);
+        }
+      }
+    }
+#pragma unroll
+    for (int r = 0; r < kGramR; r++) {
+      u[r] = ua[r] + ub[r];
+      rho[r] = 0.0;
+      al[r] = 0.0;
+      if (r < Rk && in[r]) {
+        rho[r] = rho_g[sl[r]];
+        if (lane + 32 * r > 0) {  // entries older than the new pair
+          const double gv = ga[r] + gb[r];
+          G[(size_t)e * m + sl[r]] = gv;
+          GT[(size_t)sl[r] * m + e] = gv;
+        }
+      }
+    }
+    __syncwarp();  // the new Gram row is read below (by other lanes)
+  }
+  // ---- phase 2: first loop, newest -> oldest (lbfgs.hpp:719-724)
+#pragma unroll
+  for (int r0 = 0; r0 < kGramR; r0++) {
+    if (r0 < Rk) {
+      const int nl = min(32, k - 32 * r0);
+#pragma unroll 2
+      for (int l = 0; l < nl; l++) {
+        const int tcur = 32 * r0 + l;
+        int sc = e - tcur;
+        if (sc < 0) sc += m;
+        const double* __restrict__ row = G + (size_t)sc * m;
+        const double a = __shfl_sync(FULL, rho[r0] * u[r0], l);
+        if (lane == l) al[r0] = a;
+#pragma unroll
+        for (int r = 0; r < kGramR; r++) {
+          if (r >= r0 && r < Rk) {
+            const int t = lane + 32 * r;
+            if (t > tcur && t < k) u[r] = fma(-a, row[sl[r]], u[r]);
+          }
+        }
+      }
+    }
+  }
+  // ---- phase 3: d1 = gamma (d0 - sum_t alpha_t y_t), lane <-> component (two partial sums: even / odd ages)
+#pragma unroll
+  for (int r = 0; r < kGramR; r++)
+    if (r < Rk && in[r]) coef_sm[lane + 32 * r] = al[r];
+  __syncwarp();
   double d[NPL];
   bool ok[NPL];
 #pragma unroll
-  for (int e = 0; e < NPL; e++) {
-    const int i = lane + 32 * e;
-    ok[e] = i < n;
-    d[e] = ok[e] ? d_sm[i] : 0.0;
+  for (int q = 0; q < NPL; q++) {
+    ok[q] = lane + 32 * q < n;
+    d[q] = ok[q] ? d_sm[lane + 32 * q] : 0.0;
   }
-  double sv[4][NPL], yv[4][NPL], r[4];
-  int jx[4];
-  // ---- first loop: newest to oldest; block = entries j0, j0-1, j0-2, j0-3
-  int j0 = wrap_index(end - 1, m);
-  bool first = true;
-#pragma unroll 1
-  for (int i0 = 0; i0 < bound; i0 += 4) {
-    const int cnt = min(4, bound - i0);
+  {
+    double pa[NPL], pb[NPL];
 #pragma unroll
-    for (int k = 0; k < 4; k++) {
-      jx[k] = wrap_index(j0 - k, m);
-      const bool v = k < cnt;
-      const double* sj = lm_s + (size_t)jx[k] * ld + lane;
-      const double* yj = lm_y + (size_t)jx[k] * ld + lane;
+    for (int q = 0; q < NPL; q++) pa[q] = pb[q] = 0.0;
+    int sc = e;
+#pragma unroll 2
+    for (int t = 0; t + 1 < k; t += 2) {
+      int sc1 = sc - 1;
+      if (sc1 < 0) sc1 += m;
+      const double a0 = coef_sm[t], a1 = coef_sm[t + 1];
 #pragma unroll
-      for (int e = 0; e < NPL; e++) {
-        sv[k][e] = (v && ok[e]) ? sj[32 * e] : 0.0;
-        yv[k][e] = (v && ok[e]) ? yj[32 * e] : 0.0;
+      for (int q = 0; q < NPL; q++) {
+        if (ok[q]) {
+          pa[q] = fma(a0, Y[(size_t)sc * ld + lane + 32 * q], pa[q]);
+          pb[q] = fma(a1, Y[(size_t)sc1 * ld + lane + 32 * q], pb[q]);
+        }
       }
-      r[k] = v ? lm_ys[jx[k]] : 0.0;  // 1/ys (DFTPAV_RECIP_YS) : entries beyond the window get alpha = 0
+      sc = sc1 - 1;
+      if (sc < 0) sc += m;
     }
-    // Gram products of the block: g_ab = s_{j_a} . y_{j_b} (a older than b)
-    double g10, g20, g30, g21 = 0.0, g31 = 0.0, g32 = 0.0;
-    double u[4];
+    if (k & 1) {
+      const double a0 = coef_sm[k - 1];
 #pragma unroll
-    for (int k = 0; k < 4; k++) {
-      u[k] = 0.0;
-#pragma unroll
-      for (int e = 0; e < NPL; e++) u[k] += sv[k][e] * d[e];
+      for (int q = 0; q < NPL; q++)
+        if (ok[q]) pa[q] = fma(a0, Y[(size_t)sc * ld + lane + 32 * q], pa[q]);
     }
-    if (first) {
-      // the newest entry has no cached band yet: compute it here (three more reductions, interleaved with the four)
-      double w[7];
+    const double scl = ys / yy;
 #pragma unroll
-      for (int k = 0; k < 4; k++) w[k] = u[k];
-#pragma unroll
-      for (int k = 1; k < 4; k++) {
-        w[3 + k] = 0.0;
-#pragma unroll
-        for (int e = 0; e < NPL; e++) w[3 + k] += sv[k][e] * yv[0][e];
-      }
-      warp_sum_k<7>(w);
-#pragma unroll
-      for (int k = 0; k < 4; k++) u[k] = w[k];
-      g10 = w[4], g20 = w[5], g30 = w[6];
-      if (lane == 0) {
-        lm_gram[4 * jx[0] + 0] = g10;
-        lm_gram[4 * jx[0] + 1] = g20;
-        lm_gram[4 * jx[0] + 2] = g30;
-      }
-    } else {
-      warp_sum_k<4>(u);
-      g10 = lm_gram[4 * jx[0] + 0], g20 = lm_gram[4 * jx[0] + 1], g30 = lm_gram[4 * jx[0] + 2];
+    for (int q = 0; q < NPL; q++) {
+      d[q] = (d[q] - (pa[q] + pb[q])) * scl;
+      if (ok[q]) d_sm[lane + 32 * q] = d[q];
     }
-    if (cnt > 2) g21 = lm_gram[4 * jx[1] + 0];
-    if (cnt > 3) g31 = lm_gram[4 * jx[1] + 1], g32 = lm_gram[4 * jx[2] + 0];
-    const double a0 = DFTPAV_OVER_YS(u[0], r[0]);
-    const double a1 = DFTPAV_OVER_YS(u[1] - a0 * g10, r[1]);
-    const double a2 = DFTPAV_OVER_YS(u[2] - a0 * g20 - a1 * g21, r[2]);
-    const double a3 = DFTPAV_OVER_YS(u[3] - a0 * g30 - a1 * g31 - a2 * g32, r[3]);
-    if (lane == 0) {
-      alpha_sm[jx[0]] = a0;
-      if (cnt > 1) alpha_sm[jx[1]] = a1;
-      if (cnt > 2) alpha_sm[jx[2]] = a2;
-      if (cnt > 3) alpha_sm[jx[3]] = a3;
-    }
-#pragma unroll
-    for (int e = 0; e < NPL; e++) d[e] = (((d[e] - a0 * yv[0][e]) - a1 * yv[1][e]) - a2 * yv[2][e]) - a3 * yv[3][e];
-    j0 = wrap_index(j0 - 4, m);
-    first = false;
   }
-  const double scl = ys / yy;
-#pragma unroll
-  for (int e = 0; e < NPL; e++) d[e] *= scl;
   __syncwarp();
-  // ---- second loop: oldest to newest; block = entries i0, i0+1, i0+2, i0+3
-  int b0 = wrap_index(end - bound, m);
-#pragma unroll 1
-  for (int i0 = 0; i0 < bound; i0 += 4) {
-    const int cnt = min(4, bound - i0);
-    double al[4];
+  // ---- phase 4: w = Y^T d1 (kept in u)
+  {
+    double ua[kGramR], ub[kGramR];
 #pragma unroll
-    for (int k = 0; k < 4; k++) {
-      jx[k] = wrap_index(b0 + k, m);
-      const bool v = k < cnt;
-      const double* sj = lm_s + (size_t)jx[k] * ld + lane;
-      const double* yj = lm_y + (size_t)jx[k] * ld + lane;
+    for (int r = 0; r < kGramR; r++) ua[r] = ub[r] = 0.0;
+#pragma unroll 2
+    for (int i = 0; i + 1 < n; i += 2) {
+      const double d0 = d_sm[i], d1 = d_sm[i + 1];
 #pragma unroll
-      for (int e = 0; e < NPL; e++) {
-        sv[k][e] = (v && ok[e]) ? sj[32 * e] : 0.0;
-        yv[k][e] = (v && ok[e]) ? yj[32 * e] : 0.0;
+      for (int r = 0; r < kGramR; r++) {
+        if (r < Rk) {
+          ua[r] = fma(Yt[(size_t)i * m + sl[r]], d0, ua[r]);
+          ub[r] = fma(Yt[(size_t)(i + 1) * m + sl[r]], d1, ub[r]);
+        }
       }
-      r[k] = v ? lm_ys[jx[k]] : 0.0;
-      al[k] = v ? alpha_sm[jx[k]] : 0.0;
     }
-    // p_ab = y_{i_a} . s_{i_b} (b older than a) = cached band of the NEWER entry i_a
-    double p10 = 0.0, p20 = 0.0, p21 = 0.0, p30 = 0.0, p31 = 0.0, p32 = 0.0;
-    if (cnt > 1) p10 = lm_gram[4 * jx[1] + 0];
-    if (cnt > 2) p21 = lm_gram[4 * jx[2] + 0], p20 = lm_gram[4 * jx[2] + 1];
-    if (cnt > 3) p32 = lm_gram[4 * jx[3] + 0], p31 = lm_gram[4 * jx[3] + 1], p30 = lm_gram[4 * jx[3] + 2];
-    double w[4];
+    if (n & 1) {
+      const double d0 = d_sm[n - 1];
 #pragma unroll
-    for (int k = 0; k < 4; k++) {
-      w[k] = 0.0;
-#pragma unroll
-      for (int e = 0; e < NPL; e++) w[k] += yv[k][e] * d[e];
+      for (int r = 0; r < kGramR; r++)
+        if (r < Rk) ua[r] = fma(Yt[(size_t)(n - 1) * m + sl[r]], d0, ua[r]);
     }
-    warp_sum_k<4>(w);
-    const double c0 = al[0] - DFTPAV_OVER_YS(w[0], r[0]);
-    const double c1 = al[1] - DFTPAV_OVER_YS(w[1] + c0 * p10, r[1]);
-    const double c2 = al[2] - DFTPAV_OVER_YS(w[2] + c0 * p20 + c1 * p21, r[2]);
-    const double c3 = al[3] - DFTPAV_OVER_YS(w[3] + c0 * p30 + c1 * p31 + c2 * p32, r[3]);
 #pragma unroll
-    for (int e = 0; e < NPL; e++) d[e] = (((d[e] + c0 * sv[0][e]) + c1 * sv[1][e]) + c2 * sv[2][e]) + c3 * sv[3][e];
-    b0 = wrap_index(b0 + 4, m);
+    for (int r = 0; r < kGramR; r++) u[r] = ua[r] + ub[r];
   }
+  // ---- phase 5: second loop, oldest -> newest (lbfgs.hpp:730-736); c_t = alpha_t - beta_t replaces alpha_t
 #pragma unroll
-  for (int e = 0; e < NPL; e++) {
-    const int i = lane + 32 * e;
-    if (ok[e]) d_sm[i] = d[e];
+  for (int r0 = kGramR - 1; r0 >= 0; r0--) {
+    if (r0 < Rk) {
+      const int nl = min(32, k - 32 * r0);
+#pragma unroll 2
+      for (int l = nl - 1; l >= 0; l--) {
+        const int tcur = 32 * r0 + l;
+        int sc = e - tcur;
+        if (sc < 0) sc += m;
+        const double* __restrict__ row = GT + (size_t)sc * m;
+        const double c = __shfl_sync(FULL, al[r0] - rho[r0] * u[r0], l);
+        if (lane == l) al[r0] = c;
+#pragma unroll
+        for (int r = 0; r < kGramR; r++) {
+          if (r <= r0) {
+            const int t = lane + 32 * r;
+            if (t < tcur) u[r] = fma(c, row[sl[r]], u[r]);
+          }
+        }
+      }
+    }
+  }
+  // ---- phase 6: d = d1 + sum_t c_t s_t
+#pragma unroll
+  for (int r = 0; r < kGramR; r++)
+    if (r < Rk && in[r]) coef_sm[lane + 32 * r] = al[r];
+  __syncwarp();
+  {
+    double pa[NPL], pb[NPL];
+#pragma unroll
+    for (int q = 0; q < NPL; q++) pa[q] = pb[q] = 0.0;
+    int sc = e;
+#pragma unroll 2
+    for (int t = 0; t + 1 < k; t += 2) {
+      int sc1 = sc - 1;
+      if (sc1 < 0) sc1 += m;
+      const double a0 = coef_sm[t], a1 = coef_sm[t + 1];
+#pragma unroll
+      for (int q = 0; q < NPL; q++) {
+        if (ok[q]) {
+          pa[q] = fma(a0, S[(size_t)sc * ld + lane + 32 * q], pa[q]);
+          pb[q] = fma(a1, S[(size_t)sc1 * ld + lane + 32 * q], pb[q]);
+        }
+      }
+      sc = sc1 - 1;
+      if (sc < 0) sc += m;
+    }
+    if (k & 1) {
+      const double a0 = coef_sm[k - 1];
+#pragma unroll
+      for (int q = 0; q < NPL; q++)
+        if (ok[q]) pa[q] = fma(a0, S[(size_t)sc * ld + lane + 32 * q], pa[q]);
+    }
+#pragma unroll
+    for (int q = 0; q < NPL; q++)
+      if (ok[q]) d_sm[lane + 32 * q] = d[q] + (pa[q] + pb[q]);
   }
   __syncwarp();
 }
@@ -2077,6 +2183,10 @@ __global__ void __launch_bounds__(32 * DFTPAV_MAX_WARPS, 1)
   double* alpha_sm = ws.stage;  // free outside the sweep; the host guarantees mem_size <= 2*12*kStageLd
   const int ld = hist.ld;
   const int npl = (n + 31) >> 5;
+  // Gram form of the two-loop recursion: needs its buffers (allocated by the host for mem_size <= 32 * kGramR) and n <= 96
+  const bool use_gram = !kStrict && DFTPAV_GRAM && hist.g != nullptr && npl <= 3 && m <= 32 * kGramR;
+  double* lm_st = use_gram ? hist.st + (size_t)slot * hist.mem * hist.ld : nullptr;
+  double* lm_yt = use_gram ? hist.yt + (size_t)slot * hist.mem * hist.ld : nullptr;
   const bool can_help = !kStrict && kMaxHelp > 0 && sh.helpable != 0 && nwarp > 1;
 
   int phase = PH_FETCH;
@@ -2362,22 +2472,30 @@ __global__ void __launch_bounds__(32 * DFTPAV_MAX_WARPS, 1)
         }
         if (!finish) {
           ++k;
-          // history update (lbfgs.hpp:676-687)
+          // history update (lbfgs.hpp:676-687): the pair in entry-major form (classic recursion, direction updates) and, for
+          // the Gram form, component-major (lane <-> entry dot products); y also stays in shared memory for the Gram row
           double* se = lm_s + (size_t)end * ld;
           double* ye = lm_y + (size_t)end * ld;
-          double ys = 0.0, yy = 0.0, ss = 0.0, gg = 0.0;
+          double* ynew_sm = ws.bt;  // free between two evaluations
+          double r4[4] = {0.0, 0.0, 0.0, 0.0};  // ys, yy, ss, gg
 #pragma unroll 1
           for (int i = lane; i < n; i += 32) {
             const double sv = ws.x[i] - ws.xp[i];
             const double yv = ws.g[i] - ws.gp[i];
             se[i] = sv;
             ye[i] = yv;
-            ys += yv * sv;
-            yy += yv * yv;
-            ss += sv * sv;
-            gg += ws.gp[i] * ws.gp[i];
+            if (use_gram) {
+              ynew_sm[i] = yv;
+              lm_st[(size_t)i * m + end] = sv;
+              lm_yt[(size_t)i * m + end] = yv;
+            }
+            r4[0] += yv * sv;
+            r4[1] += yv * yv;
+            r4[2] += sv * sv;
+            r4[3] += ws.gp[i] * ws.gp[i];
             ws.d[i] = -ws.g[i];
           }
+          double ys, yy, ss, gg;
           if (kStrict) {  // sequential sums of the reference (lbfgs.hpp:681-704)
             __syncwarp();
             ys = warp_dot(ye, se, n, lane);
@@ -2385,10 +2503,8 @@ __global__ void __launch_bounds__(32 * DFTPAV_MAX_WARPS, 1)
             ss = warp_dot(se, se, n, lane);
             gg = warp_dot(ws.gp, ws.gp, n, lane);
           } else {
-            ys = warp_sum(ys);
-            yy = warp_sum(yy);
-            ss = warp_sum(ss);
-            gg = warp_sum(gg);
+            warp_sum4(r4);
+            ys = r4[0], yy = r4[1], ss = r4[2], gg = r4[3];
           }
           if (lane == 0) lm_ys[end] = DFTPAV_STORE_YS(ys);
           __syncwarp();
@@ -2399,20 +2515,21 @@ __global__ void __launch_bounds__(32 * DFTPAV_MAX_WARPS, 1)
             end = (end + 1) % m;
 #if DFTPAV_STRICT
             two_loop_generic(ws.d, alpha_sm, lm_s, lm_y, lm_ys, ld, m, end, bound, n, lane, ys, yy);
-#elif DFTPAV_TWO_LOOP_BLOCKED
-            {
-              double* lm_gram = hist.gram + (size_t)slot * hist.mem * 4;
-              if (npl == 1) two_loop_blocked<1>(ws.d, alpha_sm, lm_s, lm_y, lm_ys, lm_gram, ld, m, end, bound, n, lane, ys, yy);
-              else if (npl == 2) two_loop_blocked<2>(ws.d, alpha_sm, lm_s, lm_y, lm_ys, lm_gram, ld, m, end, bound, n, lane, ys, yy);
-              else if (npl == 3) two_loop_blocked<3>(ws.d, alpha_sm, lm_s, lm_y, lm_ys, lm_gram, ld, m, end, bound, n, lane, ys, yy);
-              else two_loop_generic(ws.d, alpha_sm, lm_s, lm_y, lm_ys, ld, m, end, bound, n, lane, ys, yy);
-            }
 #else
-            // n <= 96: the direction lives in registers; larger problems (up to 4 x 64 pieces, n = 517): shared memory
-            if (npl == 1) two_loop<1>(ws.d, alpha_sm, lm_s, lm_y, lm_ys, ld, m, end, bound, n, lane, ys, yy);
-            else if (npl == 2) two_loop<2>(ws.d, alpha_sm, lm_s, lm_y, lm_ys, ld, m, end, bound, n, lane, ys, yy);
-            else if (npl == 3) two_loop<3>(ws.d, alpha_sm, lm_s, lm_y, lm_ys, ld, m, end, bound, n, lane, ys, yy);
-            else two_loop_generic(ws.d, alpha_sm, lm_s, lm_y, lm_ys, ld, m, end, bound, n, lane, ys, yy);
+            if (use_gram) {
+              // n <= 96, mem_size <= 256: Gram form (dot products off the dependent chain)
+              if (npl == 1) two_loop_gram<1>(ws.d, ynew_sm, alpha_sm, hist, slot, m, end, bound, n, lane, ys, yy);
+              else if (npl == 2) two_loop_gram<2>(ws.d, ynew_sm, alpha_sm, hist, slot, m, end, bound, n, lane, ys, yy);
+              else two_loop_gram<3>(ws.d, ynew_sm, alpha_sm, hist, slot, m, end, bound, n, lane, ys, yy);
+            } else if (npl <= 3 && !kClassicOff) {
+              // classic recursion with the direction in registers (mem_size > 256)
+              if (npl == 1) two_loop<1>(ws.d, alpha_sm, lm_s, lm_y, lm_ys, ld, m, end, bound, n, lane, ys, yy);
+              else if (npl == 2) two_loop<2>(ws.d, alpha_sm, lm_s, lm_y, lm_ys, ld, m, end, bound, n, lane, ys, yy);
+              else two_loop<3>(ws.d, alpha_sm, lm_s, lm_y, lm_ys, ld, m, end, bound, n, lane, ys, yy);
+            } else {
+              // larger problems (up to 4 x 64 pieces, n = 517): the direction stays in shared memory
+              two_loop_generic(ws.d, alpha_sm, lm_s, lm_y, lm_ys, ld, m, end, bound, n, lane, ys, yy);
+            }
 #endif
           }
           step = 1.0;
@@ -2735,7 +2852,7 @@ int ws_doubles_host(int rows, int npad, int S, int has_obs) { return ws_doubles_
 int max_warps_host() { return DFTPAV_MAX_WARPS; }
 int virtual_ranks_host() { return kVR; }
 int strict_build_host() { return kStrict ? 1 : 0; }
-int two_loop_blocked_host() { return DFTPAV_TWO_LOOP_BLOCKED; }
+int gram_two_loop_host() { return (DFTPAV_GRAM && !kStrict) ? 32 * kGramR : 0; }  // largest mem_size of the Gram form
 
 cudaError_t set_phase_clock(unsigned long long* dev_ptr) {
   return cudaMemcpyToSymbol(g_phase_clock, &dev_ptr, sizeof(dev_ptr));

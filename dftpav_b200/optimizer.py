@@ -152,6 +152,12 @@ class BatchOptimizer:
         self.optimize()
         return self.download(sol)
 
+    def success_count(self) -> int:
+        """Problems of the last solve that ended with flag_success (dftpav_success_count)."""
+        n = C.c_int32(0)
+        self._check(self._lib.dftpav_success_count(self._h, C.byref(n)))
+        return int(n.value)
+
     def force_banded(self, on: bool = True):
         """Test hook: banded LU substitutions (the large-N fallback) even where the dense MINCO tables fit."""
         self._check(self._lib.dftpav_debug_force_banded(self._h, 1 if on else 0))

@@ -49,7 +49,9 @@ def solve_sharded(batch, K: int, Kd: int, solve_fn: Callable, gather: bool = Fal
     lo, hi = my_shard(batch.B, rank, world)
     sub = batch.slice(lo, hi, K, Kd)
     sol = solve_fn(sub)
-    ok = global_flag(bool(np.all(sol.status > -1024 + 0) and sol.status.shape[0] == hi - lo))
+    # the local half of the convergence flag: every problem of my slice finished AND was accepted (flag_success of
+    # traj_optimizer.cpp:176-201: an accepted L-BFGS return code and a final cost below the limit)
+    ok = global_flag(bool(sol.status.shape[0] == hi - lo and np.all(np.asarray(sol.success) != 0)))
     if not gather:
         return sol, (lo, hi), ok
     payload = {k: np.asarray(getattr(sol, k)) for k in ("x", "cost", "status", "success", "iters", "evals")}

@@ -251,6 +251,10 @@ int dftpav_optimize(dftpav_handle* h);
 /* [getTraj]  copies results of the last dftpav_optimize to the host. */
 int dftpav_download(dftpav_handle* h, const dftpav_result* out);
 
+/* Number of problems of the last solve with success == 1 (the local half of the global convergence flag that multi-GPU
+ * callers all-reduce: every shard finished and was accepted). */
+int dftpav_success_count(dftpav_handle* h, int32_t* n_success);
+
 /* upload + optimize + download in one call (the end-to-end path a planner would use). */
 int dftpav_solve(dftpav_handle* h, const dftpav_batch* batch, const dftpav_result* out);
 

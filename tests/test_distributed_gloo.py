@@ -27,6 +27,13 @@ def _worker(rank, world, port, out_path):
     assert ok is True
     # a failing rank flips the global flag everywhere
     assert global_flag(rank != 1) is False
+    # ... and the flag is derived from the solves, not a constant: one problem of rank 1's slice that OptimizeTrajectory
+    # rejects (initTs < mini_T) makes the global flag false on BOTH ranks (the old test `status > -1024` was
+    # true for every L-BFGS error code)
+    bad, _ = synth.make_config(3, B=7, seed=4)
+    bad.init_T[5] = 0.01
+    _, _, ok_bad = solve_sharded(bad, K, Kd, lambda sub: oracle_py.optimize(prm, sub, threads=1))
+    assert ok_bad is False
     if rank == 0:
         np.savez(out_path, lo=lo, hi=hi, **gathered)
     dist.barrier()

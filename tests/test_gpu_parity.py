@@ -163,7 +163,7 @@ def test_solve_parity(cfg, oracle, gpu_opt_factory):
     bias = sol.cost.mean() / ref.cost.mean() - 1.0
     print(f"cfg{cfg}: cost bias {bias:+.2e}, evaluations gpu/oracle {sol.evals.sum() / ref.evals.sum():.4f}")
     assert abs(bias) <= (1e-3 if B >= 64 else 1e-2), bias
-    assert abs(sol.evals.sum() / ref.evals.sum() - 1.0) <= 0.05
+    assert abs(sol.evals.sum() / ref.evals.sum() - 1.0) <= (0.05 if B >= 64 else 0.2)
     # the coefficients returned are those of the last evaluated point: re-evaluating at the final x reproduces them
     # whenever the line search did not fail (quirk Q8)
     for p in range(min(B, 8)):
