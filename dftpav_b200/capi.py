@@ -234,6 +234,13 @@ EXPORTED_SYMBOLS = [
     "dftpav_sample",
     "dftpav_sample_uniform",
     "dftpav_pack_polytraj",
+    "dftpav_create_multi",
+    "dftpav_destroy_multi",
+    "dftpav_solve_multi",
+    "dftpav_multi_uses_nccl",
+    "dftpav_multi_devices",
+    "dftpav_multi_stats",
+    "dftpav_multi_last_error",
     "dftpav_last_stats",
     "dftpav_last_error",
     "dftpav_version",
@@ -278,6 +285,14 @@ def load_library(variant: str = "") -> C.CDLL:
     lib.dftpav_sample.argtypes = [H, C.c_int64, c_int32_p, c_double_p, C.c_int32, C.c_double, c_double_p]
     lib.dftpav_sample_uniform.argtypes = [H, C.c_double, C.c_int32, c_double_p, c_int32_p]
     lib.dftpav_pack_polytraj.argtypes = [H, C.POINTER(C.c_float), C.POINTER(C.c_float), C.POINTER(C.c_float)]
+    lib.dftpav_create_multi.argtypes = [C.POINTER(Params), c_int32_p, C.c_int32, C.POINTER(H)]
+    lib.dftpav_destroy_multi.argtypes = [H]
+    lib.dftpav_solve_multi.argtypes = [H, C.POINTER(Batch), C.POINTER(Result), c_int32_p]
+    lib.dftpav_multi_uses_nccl.argtypes = [H]
+    lib.dftpav_multi_devices.argtypes = [H]
+    lib.dftpav_multi_stats.argtypes = [H, C.c_int32, C.POINTER(Stats)]
+    lib.dftpav_multi_last_error.argtypes = [H]
+    lib.dftpav_multi_last_error.restype = C.c_char_p
     lib.dftpav_last_stats.argtypes = [H, C.POINTER(Stats)]
     lib.dftpav_last_error.argtypes = [H]
     lib.dftpav_last_error.restype = C.c_char_p

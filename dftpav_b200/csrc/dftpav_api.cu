@@ -44,7 +44,6 @@ int ws_doubles_host(int rows, int npad, int S, int has_obs);
 int max_warps_host();
 int virtual_ranks_host();
 int strict_build_host();
-int gram_two_loop_host();
 cudaError_t set_phase_clock(unsigned long long* dev_ptr);
 }  // namespace dftpav
 
@@ -227,7 +226,7 @@ struct dftpav_handle {
   std::vector<double> h_x0;
   long long total_planes = 0;
   int uniform_H = 0;                         // -1: ragged corridor (h_plane_ptr)
-  bool hist_gram_on = false;
+  int min_n_stride = 0, min_row_stride = 0;   // dftpav_solve_multi: a shard uses the strides of the whole batch
   bool force_banded = false;                 // test hook: banded LU substitutions even where the dense tables fit
   std::string err;
   bool uploaded = false, solved = false, has_obs = false;
@@ -242,7 +241,7 @@ struct dftpav_handle {
   DevBuf seg_base, t_now, obs_ptr, obs_idx, singul, ini_raw, fin_raw, ini, fin, samp_base,
       plane_ptr, planes_raw, obs_start, obs_dur, obs_piece_ptr, obs_piece_dur, obs_coeffs, obs_uniform, x0, xin, fout, gout;
   DevBuf o_x, o_cost, o_status, o_success, o_iters, o_evals, o_coeffs, o_dT, counter;
-  DevBuf hist_s, hist_y, hist_ys, hist_st, hist_yt, hist_g, hist_gt, trace, ready, laid;
+  DevBuf hist_s, hist_y, hist_ys, trace, ready, laid;
   DevBuf seg_prob, seg_row0, seg_N, seg_piece0, q_seg, q_t, q_out, q_cnt;  // trajectory evaluator (dftpav_sample*)
   long long pieces_total = 0;
   int trace_cap = 0;
@@ -595,7 +594,7 @@ int dftpav_destroy(dftpav_handle* h) {
                     &h->fin, &h->samp_base, &h->plane_ptr, &h->planes_raw,
                     &h->obs_start, &h->obs_dur, &h->obs_piece_ptr, &h->obs_piece_dur, &h->obs_coeffs, &h->obs_uniform, &h->x0, &h->xin,
                     &h->fout, &h->gout, &h->o_x, &h->o_cost, &h->o_status, &h->o_success, &h->o_iters, &h->o_evals,
-                    &h->o_coeffs, &h->o_dT, &h->counter, &h->hist_s, &h->hist_y, &h->hist_ys, &h->hist_st, &h->hist_yt, &h->hist_g, &h->hist_gt, &h->trace, &h->ready, &h->laid, &h->seg_prob, &h->seg_row0, &h->seg_N,
+                    &h->o_coeffs, &h->o_dT, &h->counter, &h->hist_s, &h->hist_y, &h->hist_ys, &h->trace, &h->ready, &h->laid, &h->seg_prob, &h->seg_row0, &h->seg_N,
                     &h->seg_piece0, &h->q_seg, &h->q_t, &h->q_out, &h->q_cnt};
   for (DevBuf* b : bufs) b->release();
   for (auto& e : h->ev)
@@ -640,6 +639,8 @@ int upload_impl(dftpav_handle* h, const dftpav_batch* b, int n_chunks_wanted) {
   h->uploaded = false;
   h->solved = false;
   recycle_groups(h);
+  dims.n_stride = std::max(dims.n_stride, h->min_n_stride);
+  dims.row_stride = std::max(dims.row_stride, h->min_row_stride);
   h->dims = dims;
   h->param_status = lbfgs_param_status(h->prm);
   std::memset(&h->stats, 0, sizeof(h->stats));
@@ -942,13 +943,6 @@ int upload_impl(dftpav_handle* h, const dftpav_batch* b, int n_chunks_wanted) {
   CU_TRY(h, h->hist_s.ensure(hbytes));
   CU_TRY(h, h->hist_y.ensure(hbytes));
   CU_TRY(h, h->hist_ys.ensure(sizeof(double) * (size_t)max_slots * mem));
-  h->hist_gram_on = gram_two_loop_host() > 0 && (int)mem <= gram_two_loop_host() && max_npad <= 96;
-  if (h->hist_gram_on) {  // Gram form of the two-loop recursion: component-major history + Gram matrix and its transpose
-    CU_TRY(h, h->hist_st.ensure(hbytes));
-    CU_TRY(h, h->hist_yt.ensure(hbytes));
-    CU_TRY(h, h->hist_g.ensure(sizeof(double) * (size_t)max_slots * mem * mem));
-    CU_TRY(h, h->hist_gt.ensure(sizeof(double) * (size_t)max_slots * mem * mem));
-  }
 
   // ---- arrival flags of the plane upload and per-problem layout flags (epoch-stamped: nothing to clear between uploads)
   h->epoch += 1;
@@ -1044,10 +1038,6 @@ int launch_solve_kernels(dftpav_handle* h, int* launches_out) {
   hist.s = h->hist_s.as<double>();
   hist.y = h->hist_y.as<double>();
   hist.ys = h->hist_ys.as<double>();
-  hist.st = h->hist_gram_on ? h->hist_st.as<double>() : nullptr;
-  hist.yt = h->hist_gram_on ? h->hist_yt.as<double>() : nullptr;
-  hist.g = h->hist_gram_on ? h->hist_g.as<double>() : nullptr;
-  hist.gt = h->hist_gram_on ? h->hist_gt.as<double>() : nullptr;
   hist.ld = h->hist_ld;
   hist.mem = h->prm.lbfgs_mem_size;
   int launches = 0, gi = 0;
@@ -1338,6 +1328,14 @@ int dftpav_last_stats(const dftpav_handle* h, dftpav_stats* stats) {
   return DFTPAV_OK;
 }
 
+// Internal (dftpav_multi.cu): lower bounds for the output strides, so that a shard's rows line up with the whole batch's arrays.
+int dftpav_internal_set_min_strides(dftpav_handle* h, int n_stride, int row_stride) {
+  if (!h) return DFTPAV_ERR_INVALID_ARG;
+  h->min_n_stride = n_stride;
+  h->min_row_stride = row_stride;
+  return DFTPAV_OK;
+}
+
 // Test hook (not part of the drop-in ABI): use the banded LU substitutions even where the dense MINCO tables fit; takes
 // effect at the next upload.
 int dftpav_debug_force_banded(dftpav_handle* h, int on) {
@@ -1345,9 +1343,9 @@ int dftpav_debug_force_banded(dftpav_handle* h, int on) {
   h->force_banded = on != 0;
   return DFTPAV_OK;
 }
-// Build variant of the loaded library: bit 0 strict-order verification build, bit 1 blocked two-loop; bits 8.. virtual ranks
+// Build variant of the loaded library: bit 0 strict-order verification build; bits 8.. virtual ranks
 int dftpav_debug_build_flags(void) {
-  return (strict_build_host() ? 1 : 0) | (gram_two_loop_host() ? 2 : 0) | (virtual_ranks_host() << 8);
+  return (strict_build_host() ? 1 : 0) | (virtual_ranks_host() << 8);
 }
 
 // Diagnostic (not part of the drop-in ABI): per-iteration (fx, step, ls) traces of the next dftpav_optimize calls.

@@ -130,11 +130,6 @@ struct HistDev {
   double* s;        // [slots][mem][npad_max]
   double* y;
   double* ys;       // [slots][mem]
-  // Gram form of the two-loop recursion (two_loop_gram): component-major copies of the history and the Gram matrix
-  double* st;       // [slots][npad_max][mem]
-  double* yt;
-  double* g;        // [slots][mem][mem]  g[a][b] = s_b . y_a for b older than a
-  double* gt;       // [slots][mem][mem]  transpose
   int ld;           // npad_max
   int mem;
 };

@@ -154,10 +154,6 @@ struct SegScratch {   // 38 doubles per segment
 #ifndef DFTPAV_STRICT
 #define DFTPAV_STRICT 0
 #endif
-#ifndef DFTPAV_GRAM
-#define DFTPAV_GRAM 1  // Gram form of the two-loop recursion (two_loop_gram); 0: classic recursion everywhere (A/B)
-#endif
-constexpr bool kClassicOff = false;
 constexpr bool kStrict = DFTPAV_STRICT != 0;          // strict-order verification build (dftpav_strict.cuh)
 constexpr int kVR = kStrict ? 1 : DFTPAV_VRANKS;      // virtual ranks of the sweep = max team size (owner + kVR-1 helpers)
 constexpr int kMaxHelp = kVR - 1;
@@ -1745,9 +1741,13 @@ __global__ void __launch_bounds__(32 * DFTPAV_MAX_WARPS, 1)
 #endif
 
 // Register variant: the direction in registers (NPL elements per lane, n <= 32*NPL), the (s_j, y_j, 1/ys_j) stream
-// software-prefetched one entry ahead (measured best on B200: deeper register rings spill and lose 25 %; an L2 / L1
-// prefetch of the window and a cp.async ring in shared memory were measured too and do not help, profiles/README.md:
-// the step is bound by its dependent chain, not by the L2 round trip).  No integer modulo (wrap by compare); the trip
+// software-prefetched one entry ahead.  Measured on B200 (tools/microbench/two_loop_bench.cu, profiles/README.md): 300-313
+// cycles per history step for a lone warp, THE SAME with the history in shared memory - the step is bound by its dependent
+// chain (2 FMA, a 5-level shuffle butterfly, multiply, FMA), not by the L2 round trip.  Measured and rejected: prefetch
+// distance 2 (327), 16 lanes x 3 elements with a 4-level butterfly (297), four entries per step with a cached Gram band
+// (219 lone but 144 k vs 188 k solves/s in the solver: the extra loads are exposed), and a full Gram-matrix form with the
+// dot products lane <-> entry and the triangular recurrences on shuffle broadcasts (650-980: every recurrence step exposes
+// an L2 round trip for its Gram row; 62 k solves/s).  No integer modulo (wrap by compare); the trip
 // count is read through a shuffle so that the compiler treats the loop as warp-uniform and emits bare SHFL.
 template <int NPL>
 __device__ __noinline__ void two_loop(double* d_sm, double* alpha_sm, const double* __restrict__ lm_s,
@@ -1899,255 +1899,6 @@ __device__ __forceinline__ int wrap_index(int x, int m) {
 }
 
 // ------------------------------------------------------------------------------------------------
-// Gram form of the two-loop recursion (the production path for mem_size <= 256, n <= 96).
-//
-// The classic recursion is a dependent chain of 2*bound history steps, each with a 5-level shuffle butterfly for its dot
-// product: 313 cycles per step for a lone warp on B200 (tools/microbench/two_loop_bench.cu: the same with the history in
-// shared memory, i.e. the chain, not the memory, is the limit), which is half of the run time of the longest problems -
-// the ones that set the batch time.  Here the dot products leave the chain:
-//   first loop :  alpha_t = rho_t (s_t.q_t),  q_t = d0 - sum_{t' newer than t} alpha_t' y_t'
-//                 =>  alpha_t = rho_t (u_t - sum_{t' newer} alpha_t' G[t'][t]),   u = S^T d0,  G[a][b] = s_b . y_a (b older than a)
-//   second loop:  beta_t = rho_t (y_t.r_t),   r_t = d1 + sum_{t' older than t} (alpha_t' - beta_t') s_t'
-//                 =>  beta_t = rho_t (w_t + sum_{t' older} c_t' G[t][t']),     w = Y^T d1,  c = alpha - beta
-// u and w are bound independent dot products computed lane <-> history entry from a component-major copy of the history
-// (coalesced, no shuffles); the Gram matrix G grows by one row per L-BFGS iteration (computed in the same pass as u); the
-// two triangular recurrences cost one multiply, one shuffle broadcast and one FMA per entry on the dependent chain (about
-// 50 cycles instead of 313) and the direction updates d -= sum alpha_t y_t, d += sum c_t s_t are plain streams.
-// Mathematically the reference's recursion (lbfgs.hpp:716-739); the rounding differs like it does for every other
-// reduction of the production build (the CPU study with the oracle's fully blocked recursion leaves 0.803 / 0.395 / 0.211
-// of the final costs of configurations 3 / 2 / 4 inside 1e-5: the algorithm's own ulp-sensitivity floors).
-// Entries are addressed by AGE t = 0 (newest) .. bound-1 (oldest), slot(t) = newest slot - t (mod m); lane l holds ages
-// l, l+32, ... in registers.  Results are deterministic (fixed orders everywhere).
-// ------------------------------------------------------------------------------------------------
-constexpr int kGramR = 8;  // ages per lane: mem_size <= 32 * kGramR
-template <int NPL>
-__device__ __noinline__ void two_loop_gram(double* d_sm, const double* ynew_sm, double* coef_sm, const HistDev& hist,
-                                           int slot, int m, int end, int bound_in, int n, int lane, double ys, double yy) {
-  const int k = __shfl_sync(FULL, bound_in, 0);
-  const int ld = hist.ld;
-  const double* __restrict__ S = hist.s + (size_t)slot * hist.mem * ld;
-  const double* __restrict__ Y = hist.y + (size_t)slot * hist.mem * ld;
-  const double* __restrict__ St = hist.st + (size_t)slot * hist.mem * ld;
-  const double* __restrict__ Yt = hist.yt + (size_t)slot * hist.mem * ld;
-  double* __restrict__ G = hist.g + (size_t)slot * hist.mem * hist.mem;
-  double* __restrict__ GT = hist.gt + (size_t)slot * hist.mem * hist.mem;
-  const double* __restrict__ rho_g = hist.ys + (size_t)slot * hist.mem;
-  const int e = end == 0 ? m - 1 : end - 1;  // slot of the newest pair
-  const int Rk = (k + 31) >> 5;
-  int sl[kGramR];       // slot of my age t = lane + 32 r (clamped to a valid slot beyond the window)
-  bool in[kGramR];
-#pragma unroll
-  for (int r = 0; r < kGramR; r++) {
-    const int t = lane + 32 * r;
-    in[r] = t < k;
-    int v = e - (in[r] ? t : 0);
-    if (v < 0) v += m;
-    sl[r] = v;
-  }
-  double u[kGramR], rho[kGramR], al[kGramR];
-  // ---- phase 1: u = S^T d0 and the Gram row of the newest pair, G[e][.] = S^T y_new (two accumulators each: even / odd i)
-  {
-    double ua[kGramR], ub[kGramR], ga[kGramR], gb[kGramR];
-#pragma unroll
-    for (int r = 0; r < kGramR; r++) ua[r] = ub[r] = ga[r] = gb[r] = 0.0;
-#pragma unroll 2
-    for (int i = 0; i + 1 < n; i += 2) {
-      const double d0 = d_sm[i], d1 = d_sm[i + 1], y0 = ynew_sm[i], y1 = ynew_sm[i + 1];
-#pragma unroll
-      for (int r = 0; r < kGramR; r++) {
-        if (r < Rk) {
-          const double v0 = St[(size_t)i * m + sl[r]], v1 = St[(size_t)(i + 1) * m + sl[r]];
-          ua[r] = fma(v0, d0, ua[r]);
-          ub[r] = fma(v1, d1, ub[r]);
-          ga[r] = fma(v0, y0, ga[r]);
-          gb[r] = fma(v1, y1, gb[r]);
-        }
-      }
-    }
-    if (n & 1) {
-      const int i = n - 1;
-      const double d0 = d_sm[i], y0 = ynew_sm[i];
-#pragma unroll
-      for (int r = 0; r < kGramR; r++) {
-        if (r < Rk) {
-          const double v0 = St[(size_t)i * m + sl[r]];
-          ua[r] = fma(v0, d0, ua[r]);
-          ga[r] = fma(v0, y0, ga[r]);
-        }
-      }
-    }
-#pragma unroll
-    for (int r = 0; r < kGramR; r++) {
-      u[r] = ua[r] + ub[r];
-      rho[r] = 0.0;
-      al[r] = 0.0;
-      if (r < Rk && in[r]) {
-        rho[r] = rho_g[sl[r]];
-        if (lane + 32 * r > 0) {  // entries older than the new pair
-          const double gv = ga[r] + gb[r];
-          G[(size_t)e * m + sl[r]] = gv;
-          GT[(size_t)sl[r] * m + e] = gv;
-        }
-      }
-    }
-    __syncwarp();  // the new Gram row is read below (by other lanes)
-  }
-  // ---- phase 2: first loop, newest -> oldest (lbfgs.hpp:719-724)
-#pragma unroll
-  for (int r0 = 0; r0 < kGramR; r0++) {
-    if (r0 < Rk) {
-      const int nl = min(32, k - 32 * r0);
-#pragma unroll 2
-      for (int l = 0; l < nl; l++) {
-        const int tcur = 32 * r0 + l;
-        int sc = e - tcur;
-        if (sc < 0) sc += m;
-        const double* __restrict__ row = G + (size_t)sc * m;
-        const double a = __shfl_sync(FULL, rho[r0] * u[r0], l);
-        if (lane == l) al[r0] = a;
-#pragma unroll
-        for (int r = 0; r < kGramR; r++) {
-          if (r >= r0 && r < Rk) {
-            const int t = lane + 32 * r;
-            if (t > tcur && t < k) u[r] = fma(-a, row[sl[r]], u[r]);
-          }
-        }
-      }
-    }
-  }
-  // ---- phase 3: d1 = gamma (d0 - sum_t alpha_t y_t), lane <-> component (two partial sums: even / odd ages)
-#pragma unroll
-  for (int r = 0; r < kGramR; r++)
-    if (r < Rk && in[r]) coef_sm[lane + 32 * r] = al[r];
-  __syncwarp();
-  double d[NPL];
-  bool ok[NPL];
-#pragma unroll
-  for (int q = 0; q < NPL; q++) {
-    ok[q] = lane + 32 * q < n;
-    d[q] = ok[q] ? d_sm[lane + 32 * q] : 0.0;
-  }
-  {
-    double pa[NPL], pb[NPL];
-#pragma unroll
-    for (int q = 0; q < NPL; q++) pa[q] = pb[q] = 0.0;
-    int sc = e;
-#pragma unroll 2
-    for (int t = 0; t + 1 < k; t += 2) {
-      int sc1 = sc - 1;
-      if (sc1 < 0) sc1 += m;
-      const double a0 = coef_sm[t], a1 = coef_sm[t + 1];
-#pragma unroll
-      for (int q = 0; q < NPL; q++) {
-        if (ok[q]) {
-          pa[q] = fma(a0, Y[(size_t)sc * ld + lane + 32 * q], pa[q]);
-          pb[q] = fma(a1, Y[(size_t)sc1 * ld + lane + 32 * q], pb[q]);
-        }
-      }
-      sc = sc1 - 1;
-      if (sc < 0) sc += m;
-    }
-    if (k & 1) {
-      const double a0 = coef_sm[k - 1];
-#pragma unroll
-      for (int q = 0; q < NPL; q++)
-        if (ok[q]) pa[q] = fma(a0, Y[(size_t)sc * ld + lane + 32 * q], pa[q]);
-    }
-    const double scl = ys / yy;
-#pragma unroll
-    for (int q = 0; q < NPL; q++) {
-      d[q] = (d[q] - (pa[q] + pb[q])) * scl;
-      if (ok[q]) d_sm[lane + 32 * q] = d[q];
-    }
-  }
-  __syncwarp();
-  // ---- phase 4: w = Y^T d1 (kept in u)
-  {
-    double ua[kGramR], ub[kGramR];
-#pragma unroll
-    for (int r = 0; r < kGramR; r++) ua[r] = ub[r] = 0.0;
-#pragma unroll 2
-    for (int i = 0; i + 1 < n; i += 2) {
-      const double d0 = d_sm[i], d1 = d_sm[i + 1];
-#pragma unroll
-      for (int r = 0; r < kGramR; r++) {
-        if (r < Rk) {
-          ua[r] = fma(Yt[(size_t)i * m + sl[r]], d0, ua[r]);
-          ub[r] = fma(Yt[(size_t)(i + 1) * m + sl[r]], d1, ub[r]);
-        }
-      }
-    }
-    if (n & 1) {
-      const double d0 = d_sm[n - 1];
-#pragma unroll
-      for (int r = 0; r < kGramR; r++)
-        if (r < Rk) ua[r] = fma(Yt[(size_t)(n - 1) * m + sl[r]], d0, ua[r]);
-    }
-#pragma unroll
-    for (int r = 0; r < kGramR; r++) u[r] = ua[r] + ub[r];
-  }
-  // ---- phase 5: second loop, oldest -> newest (lbfgs.hpp:730-736); c_t = alpha_t - beta_t replaces alpha_t
-#pragma unroll
-  for (int r0 = kGramR - 1; r0 >= 0; r0--) {
-    if (r0 < Rk) {
-      const int nl = min(32, k - 32 * r0);
-#pragma unroll 2
-      for (int l = nl - 1; l >= 0; l--) {
-        const int tcur = 32 * r0 + l;
-        int sc = e - tcur;
-        if (sc < 0) sc += m;
-        const double* __restrict__ row = GT + (size_t)sc * m;
-        const double c = __shfl_sync(FULL, al[r0] - rho[r0] * u[r0], l);
-        if (lane == l) al[r0] = c;
-#pragma unroll
-        for (int r = 0; r < kGramR; r++) {
-          if (r <= r0) {
-            const int t = lane + 32 * r;
-            if (t < tcur) u[r] = fma(c, row[sl[r]], u[r]);
-          }
-        }
-      }
-    }
-  }
-  // ---- phase 6: d = d1 + sum_t c_t s_t
-#pragma unroll
-  for (int r = 0; r < kGramR; r++)
-    if (r < Rk && in[r]) coef_sm[lane + 32 * r] = al[r];
-  __syncwarp();
-  {
-    double pa[NPL], pb[NPL];
-#pragma unroll
-    for (int q = 0; q < NPL; q++) pa[q] = pb[q] = 0.0;
-    int sc = e;
-#pragma unroll 2
-    for (int t = 0; t + 1 < k; t += 2) {
-      int sc1 = sc - 1;
-      if (sc1 < 0) sc1 += m;
-      const double a0 = coef_sm[t], a1 = coef_sm[t + 1];
-#pragma unroll
-      for (int q = 0; q < NPL; q++) {
-        if (ok[q]) {
-          pa[q] = fma(a0, S[(size_t)sc * ld + lane + 32 * q], pa[q]);
-          pb[q] = fma(a1, S[(size_t)sc1 * ld + lane + 32 * q], pb[q]);
-        }
-      }
-      sc = sc1 - 1;
-      if (sc < 0) sc += m;
-    }
-    if (k & 1) {
-      const double a0 = coef_sm[k - 1];
-#pragma unroll
-      for (int q = 0; q < NPL; q++)
-        if (ok[q]) pa[q] = fma(a0, S[(size_t)sc * ld + lane + 32 * q], pa[q]);
-    }
-#pragma unroll
-    for (int q = 0; q < NPL; q++)
-      if (ok[q]) d_sm[lane + 32 * q] = d[q] + (pa[q] + pb[q]);
-  }
-  __syncwarp();
-}
-
-// ------------------------------------------------------------------------------------------------
 // the solver: persistent warps, each runs lbfgs_optimize (lbfgs.hpp:440-751) for one problem at a time.
 // Written as a state machine around ONE call site of eval_cost_grad (keeps the kernel inside the instruction cache):
 //   FETCH -> FIRST (evaluation at x0, lbfgs.hpp:524) -> LS (line-search trial, lbfgs.hpp:312-389) -> ... -> FETCH
@@ -2183,10 +1934,6 @@ __global__ void __launch_bounds__(32 * DFTPAV_MAX_WARPS, 1)
   double* alpha_sm = ws.stage;  // free outside the sweep; the host guarantees mem_size <= 2*12*kStageLd
   const int ld = hist.ld;
   const int npl = (n + 31) >> 5;
-  // Gram form of the two-loop recursion: needs its buffers (allocated by the host for mem_size <= 32 * kGramR) and n <= 96
-  const bool use_gram = !kStrict && DFTPAV_GRAM && hist.g != nullptr && npl <= 3 && m <= 32 * kGramR;
-  double* lm_st = use_gram ? hist.st + (size_t)slot * hist.mem * hist.ld : nullptr;
-  double* lm_yt = use_gram ? hist.yt + (size_t)slot * hist.mem * hist.ld : nullptr;
   const bool can_help = !kStrict && kMaxHelp > 0 && sh.helpable != 0 && nwarp > 1;
 
   int phase = PH_FETCH;
@@ -2472,11 +2219,9 @@ __global__ void __launch_bounds__(32 * DFTPAV_MAX_WARPS, 1)
         }
         if (!finish) {
           ++k;
-          // history update (lbfgs.hpp:676-687): the pair in entry-major form (classic recursion, direction updates) and, for
-          // the Gram form, component-major (lane <-> entry dot products); y also stays in shared memory for the Gram row
+          // history update (lbfgs.hpp:676-687)
           double* se = lm_s + (size_t)end * ld;
           double* ye = lm_y + (size_t)end * ld;
-          double* ynew_sm = ws.bt;  // free between two evaluations
           double r4[4] = {0.0, 0.0, 0.0, 0.0};  // ys, yy, ss, gg
 #pragma unroll 1
           for (int i = lane; i < n; i += 32) {
@@ -2484,11 +2229,6 @@ __global__ void __launch_bounds__(32 * DFTPAV_MAX_WARPS, 1)
             const double yv = ws.g[i] - ws.gp[i];
             se[i] = sv;
             ye[i] = yv;
-            if (use_gram) {
-              ynew_sm[i] = yv;
-              lm_st[(size_t)i * m + end] = sv;
-              lm_yt[(size_t)i * m + end] = yv;
-            }
             r4[0] += yv * sv;
             r4[1] += yv * yv;
             r4[2] += sv * sv;
@@ -2516,13 +2256,8 @@ __global__ void __launch_bounds__(32 * DFTPAV_MAX_WARPS, 1)
 #if DFTPAV_STRICT
             two_loop_generic(ws.d, alpha_sm, lm_s, lm_y, lm_ys, ld, m, end, bound, n, lane, ys, yy);
 #else
-            if (use_gram) {
-              // n <= 96, mem_size <= 256: Gram form (dot products off the dependent chain)
-              if (npl == 1) two_loop_gram<1>(ws.d, ynew_sm, alpha_sm, hist, slot, m, end, bound, n, lane, ys, yy);
-              else if (npl == 2) two_loop_gram<2>(ws.d, ynew_sm, alpha_sm, hist, slot, m, end, bound, n, lane, ys, yy);
-              else two_loop_gram<3>(ws.d, ynew_sm, alpha_sm, hist, slot, m, end, bound, n, lane, ys, yy);
-            } else if (npl <= 3 && !kClassicOff) {
-              // classic recursion with the direction in registers (mem_size > 256)
+            if (npl <= 3) {
+              // the direction in registers (n <= 96)
               if (npl == 1) two_loop<1>(ws.d, alpha_sm, lm_s, lm_y, lm_ys, ld, m, end, bound, n, lane, ys, yy);
               else if (npl == 2) two_loop<2>(ws.d, alpha_sm, lm_s, lm_y, lm_ys, ld, m, end, bound, n, lane, ys, yy);
               else two_loop<3>(ws.d, alpha_sm, lm_s, lm_y, lm_ys, ld, m, end, bound, n, lane, ys, yy);
@@ -2852,7 +2587,6 @@ int ws_doubles_host(int rows, int npad, int S, int has_obs) { return ws_doubles_
 int max_warps_host() { return DFTPAV_MAX_WARPS; }
 int virtual_ranks_host() { return kVR; }
 int strict_build_host() { return kStrict ? 1 : 0; }
-int gram_two_loop_host() { return (DFTPAV_GRAM && !kStrict) ? 32 * kGramR : 0; }  // largest mem_size of the Gram form
 
 cudaError_t set_phase_clock(unsigned long long* dev_ptr) {
   return cudaMemcpyToSymbol(g_phase_clock, &dev_ptr, sizeof(dev_ptr));

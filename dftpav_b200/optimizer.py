@@ -224,3 +224,54 @@ class BatchOptimizer:
         x0 = np.zeros((d.B, d.n_stride))
         self._check(self._lib.dftpav_initial_x(C.byref(self.params), C.byref(cb), x0.ctypes.data_as(capi.c_double_p)))
         return x0
+
+
+class MultiGpuOptimizer:
+    """dftpav_create_multi / dftpav_solve_multi: contiguous shards over several GPUs of one box, one host thread and handle
+    per device inside the library, NCCL all-reduce of the convergence flag (the C++ caller's multi-GPU entry point)."""
+
+    def __init__(self, params: Optional[capi.Params] = None, devices=(0,), variant: str = ""):
+        self._lib = capi.load_library(variant)
+        self.params = params if params is not None else capi.default_params()
+        self._m = C.c_void_p()
+        devs = np.ascontiguousarray(devices, dtype=np.int32)
+        rc = self._lib.dftpav_create_multi(C.byref(self.params), devs.ctypes.data_as(capi.c_int32_p), devs.shape[0],
+                                           C.byref(self._m))
+        if rc != capi.OK:
+            raise DftpavError(rc, "dftpav_create_multi failed")
+        self.n_dev = int(self._lib.dftpav_multi_devices(self._m))
+
+    def uses_nccl(self) -> bool:
+        return bool(self._lib.dftpav_multi_uses_nccl(self._m))
+
+    def solve(self, batch: TrajBatch, sol: Optional[Solution] = None):
+        """Returns (solution, all_accepted)."""
+        cb = batch.as_c()
+        if sol is None:
+            d = capi.Dims()
+            rc = self._lib.dftpav_batch_dims(C.byref(self.params), C.byref(cb), C.byref(d))
+            if rc != capi.OK:
+                raise DftpavError(rc, "invalid batch")
+            sol = Solution(d.B, d.n_stride, d.row_stride, d.seg_total)
+        res = sol.as_c()
+        flag = C.c_int32(0)
+        rc = self._lib.dftpav_solve_multi(self._m, C.byref(cb), C.byref(res), C.byref(flag))
+        if rc != capi.OK:
+            raise DftpavError(rc, self._lib.dftpav_multi_last_error(self._m).decode())
+        return sol, bool(flag.value)
+
+    def stats(self, dev_index: int) -> capi.Stats:
+        s = capi.Stats()
+        self._lib.dftpav_multi_stats(self._m, dev_index, C.byref(s))
+        return s
+
+    def close(self):
+        if self._m:
+            self._lib.dftpav_destroy_multi(self._m)
+            self._m = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass

@@ -287,6 +287,23 @@ int dftpav_sample_uniform(dftpav_handle* h, double dt, int32_t max_per_seg, doub
  * coef_x, coef_y: [6 * sum piece_num], duration: [sum piece_num]. */
 int dftpav_pack_polytraj(dftpav_handle* h, float* coef_x, float* coef_y, float* duration);
 
+/* ---- multi-GPU: the batch shards embarrassingly over the GPUs of one box ----
+ * dftpav_create_multi: one handle, host thread and stream per device of device_ids[0..n_dev) and - for n_dev > 1 - an NCCL
+ * communicator over them (libnccl.so.2 is loaded at run time; without it the flag below is reduced on the host and
+ * dftpav_multi_uses_nccl() returns 0).
+ * dftpav_solve_multi: problems are split into n_dev contiguous slices, every slice goes through dftpav_solve on its device
+ * concurrently, results are written into the caller's arrays (layout and strides of dftpav_batch_dims of the WHOLE batch;
+ * bit-identical to a single-device solve), and the path's single collective runs: an all-reduce (MIN) over the devices of
+ * "every problem of my slice ended with success == 1" -> *all_accepted (may be NULL).  No data-path collective exists. */
+typedef struct dftpav_multi dftpav_multi;
+int dftpav_create_multi(const dftpav_params* prm, const int32_t* device_ids, int32_t n_dev, dftpav_multi** out);
+int dftpav_destroy_multi(dftpav_multi* m);
+int dftpav_solve_multi(dftpav_multi* m, const dftpav_batch* batch, const dftpav_result* out, int32_t* all_accepted);
+int dftpav_multi_uses_nccl(const dftpav_multi* m);
+int dftpav_multi_devices(const dftpav_multi* m);
+int dftpav_multi_stats(const dftpav_multi* m, int32_t dev_index, dftpav_stats* stats);
+const char* dftpav_multi_last_error(const dftpav_multi* m);
+
 int dftpav_last_stats(const dftpav_handle* h, dftpav_stats* stats);
 const char* dftpav_last_error(const dftpav_handle* h);
 const char* dftpav_version(void);

@@ -139,8 +139,6 @@ __device__ __noinline__ void two_loop_h16(double* d_sm, double* alpha_sm, const 
   __syncwarp();
 }
 
-__device__ HistDev g_hist;  // Gram-form buffers (V == 6)
-
 template <int V>
 __global__ void __launch_bounds__(384, 1) bench_kernel(double* hist_s, double* hist_y, double* hist_ys, double* gram, int ld,
                                                        int m, int bound, int n, int reps, int smem_hist,
@@ -168,7 +166,6 @@ __global__ void __launch_bounds__(384, 1) bench_kernel(double* hist_s, double* h
     const int end = bound % m;
     if (V == 0) two_loop<2>(d_sm, alpha, lm_s, lm_y, lm_ys, ld, m, end, bound, n, lane, 1.0, 1.0);
     if (V == 2) two_loop_pd2(d_sm, alpha, lm_s, lm_y, lm_ys, ld, m, end, bound, n, lane, 1.0, 1.0);
-    if (V == 6) two_loop_gram<2>(d_sm, d_sm + 128, alpha + 64, g_hist, slot, m, end, bound, n, lane, 1.0, 1.0);
     if (V == 4) two_loop_h16(d_sm, alpha, lm_s, lm_y, lm_ys, ld, m, end, bound, n, lane, 1.0, 1.0);
     if (V == 5) two_loop_generic(d_sm, alpha, lm_s, lm_y, lm_ys, ld, m, end, bound, n, lane, 1.0, 1.0);
   }
@@ -192,17 +189,7 @@ int main() {
   cudaMemcpy(dy, hy.data(), hs.size() * 8, cudaMemcpyHostToDevice);
   cudaMemcpy(dys, hys.data(), hys.size() * 8, cudaMemcpyHostToDevice);
   cudaMemset(dg, 0, hys.size() * 32);
-  {  // Gram-form buffers: timing only (values arbitrary but finite)
-    HistDev hd;
-    hd.s = ds, hd.y = dy, hd.ys = dys, hd.ld = ld, hd.mem = m;
-    cudaMalloc(&hd.st, hs.size() * 8), cudaMalloc(&hd.yt, hs.size() * 8);
-    cudaMemcpy(hd.st, hs.data(), hs.size() * 8, cudaMemcpyHostToDevice);
-    cudaMemcpy(hd.yt, hy.data(), hs.size() * 8, cudaMemcpyHostToDevice);
-    cudaMalloc(&hd.g, (size_t)maxslots * m * m * 8), cudaMalloc(&hd.gt, (size_t)maxslots * m * m * 8);
-    cudaMemset(hd.g, 0, (size_t)maxslots * m * m * 8), cudaMemset(hd.gt, 0, (size_t)maxslots * m * m * 8);
-    cudaMemcpyToSymbol(g_hist, &hd, sizeof(hd));
-  }
-  const char* names[] = {"two_loop<2> (classic)", "", "prefetch distance 2", "", "16 lanes x 3", "generic (smem d)", "Gram form (product)"};
+  const char* names[] = {"two_loop<2> (classic)", "", "prefetch distance 2", "", "16 lanes x 3", "generic (smem d)"};
   auto run = [&](int V, int grid, int warps, int bound, int smem_hist) {
     const int reps = 20;
     size_t smem = (size_t)warps * 600 * 8 + (smem_hist ? (size_t)warps * (2 * smem_hist * ld + smem_hist) * 8 : 0);
@@ -215,7 +202,6 @@ int main() {
     };
     if (V == 0) launch(bench_kernel<0>);
     if (V == 2) launch(bench_kernel<2>);
-    if (V == 6) launch(bench_kernel<6>);
     if (V == 4) launch(bench_kernel<4>);
     if (V == 5) launch(bench_kernel<5>);
     cudaError_t e = cudaDeviceSynchronize();
@@ -225,10 +211,9 @@ int main() {
     printf("%-24s grid %3d warps %2d bound %3d %s: %7.1f cycles per history step%s\n", names[V], grid, warps, bound,
            smem_hist ? "smem-history" : "global      ", per_step, e == cudaSuccess ? "" : cudaGetErrorString(e));
   };
-  for (int V : {0, 6, 4}) {
+  for (int V : {0, 2, 4, 5}) {
     for (int bound : {16, 64, 128}) run(V, 1, 1, bound, 0);       // a lone warp on the GPU
-    if (V != 6) run(V, 1, 1, 16, 16);                             // chain only: history in shared memory
-    run(V, 1, 1, 32, 0);
+    run(V, 1, 1, 16, 16);                                         // chain only: history in shared memory
     run(V, 148, 12, 64, 0);                                       // every SM full of two-loops
     run(V, 148, 4, 64, 0);
   }
