@@ -21,6 +21,19 @@ namespace dftpav {
 
 #define FULL 0xffffffffu
 
+// Code that runs once per evaluation (or never, for a given shape) is kept OUT of line: an evaluation executes ~65 KB of
+// SASS against a 32 KB L1.5 instruction cache and `no_instruction` is the largest stall reason of the solver
+// (profiles/README.md); every inlined copy of a 1.3-1.6 KB warp reduction or of the 18 KB banded fallback widens the hot
+// instruction stream.  -DDFTPAV_COLD_INLINE=1 restores the inlined form (A/B).
+#ifndef DFTPAV_COLD_INLINE
+#define DFTPAV_COLD_INLINE 0
+#endif
+#if DFTPAV_COLD_INLINE
+#define DFTPAV_COLD __forceinline__
+#else
+#define DFTPAV_COLD __noinline__
+#endif
+
 // warps per CTA (one CTA per SM)
 #ifndef DFTPAV_MAX_WARPS
 #define DFTPAV_MAX_WARPS 12  // measured on B200, batch 4096: 8 warps 153 k, 10: 153 k, 12: 161 k, 14: 138 k, 16: 139 k solves/s (168 vs 128 registers: no spills)
@@ -34,6 +47,16 @@ __device__ __forceinline__ double warp_sum(double v) {
   for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(FULL, v, o);
   return v;
 }
+// once-per-evaluation reductions, out of line (see DFTPAV_COLD)
+__device__ DFTPAV_COLD double warp_sum_cold(double v) { return warp_sum(v); }
+__device__ DFTPAV_COLD void warp_sum2_cold(double& a, double& b) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    a += __shfl_xor_sync(FULL, a, o);
+    b += __shfl_xor_sync(FULL, b, o);
+  }
+}
+__device__ DFTPAV_COLD void sincos_cold(double th, double* sn, double* cs) { sincos(th, sn, cs); }
 // four sums at once: the butterflies are interleaved (the latency of one)
 __device__ __noinline__ void warp_sum4(double (&v)[4]) {
 #pragma unroll
@@ -392,11 +415,11 @@ __device__ __forceinline__ void band_pass(const double* C, double* b, int n, int
   }
 }
 
-__device__ __forceinline__ void banded_solve(const double* C, double* b, int n, int col, bool masks_ok) {
+__device__ DFTPAV_COLD void banded_solve(const double* C, double* b, int n, int col, bool masks_ok) {
   band_pass<PASS_FWD>(C, b, n, col, masks_ok);  // L y = b      (poly_traj_utils.hpp:808-815)
   band_pass<PASS_BWD>(C, b, n, col, masks_ok);  // U x = y      (poly_traj_utils.hpp:816-824)
 }
-__device__ __forceinline__ void banded_solve_adj(const double* C, double* b, int n, int col, bool masks_ok) {
+__device__ DFTPAV_COLD void banded_solve_adj(const double* C, double* b, int n, int col, bool masks_ok) {
   band_pass<PASS_ADJ_U>(C, b, n, col, masks_ok);  // U^T z = b  (poly_traj_utils.hpp:834-842)
   band_pass<PASS_ADJ_L>(C, b, n, col, masks_ok);  // L^T w = z  (poly_traj_utils.hpp:843-850)
 }
@@ -1246,12 +1269,7 @@ __device__ __forceinline__ void sweep_segment(const ShapeDev& sh, const ParamsDe
     // ---------------- stage F: leaving a virtual rank (or the end passes): its scalar sums, one interleaved butterfly
     if (!has_next || vr_next != vr) {
       double v4[4] = {acc_gdT, acc_p0, acc_p1, acc_p2};
-#pragma unroll
-      for (int o = 16; o > 0; o >>= 1) {
-#pragma unroll
-        for (int q = 0; q < 4; q++)
-          if (HAS_OBS || q != 2) v4[q] += __shfl_xor_sync(FULL, v4[q], o);
-      }
+      warp_sum4(v4);
       if (lane < 4) rsc[4 * vr + lane] = lane == 0 ? v4[0] : (lane == 1 ? v4[1] : (lane == 2 ? v4[2] : v4[3]));
       acc_gdT = acc_p0 = acc_p1 = acc_p2 = 0.0;
       __syncwarp();
@@ -1382,7 +1400,7 @@ __device__ __forceinline__ void eval_pre(const ShapeDev& sh, const ParamsDev& P,
     if (s > 0) {
       const double theta = x[ab + s - 1];
       double sn, cs;
-      sincos(theta, &sn, &cs);
+      sincos_cold(theta, &sn, &cs);
       sc.head[0] = x[gb + 2 * (s - 1)];
       sc.head[1] = x[gb + 2 * (s - 1) + 1];
       sc.head[2] = -P.non_sinv * cs;
@@ -1391,7 +1409,7 @@ __device__ __forceinline__ void eval_pre(const ShapeDev& sh, const ParamsDev& P,
     if (s < S - 1) {
       const double theta = x[ab + s];
       double sn, cs;
-      sincos(theta, &sn, &cs);
+      sincos_cold(theta, &sn, &cs);
       sc.tail[0] = x[gb + 2 * s];
       sc.tail[1] = x[gb + 2 * s + 1];
       sc.tail[2] = P.non_sinv * cs;
@@ -1498,8 +1516,7 @@ __device__ __forceinline__ void eval_pre(const ShapeDev& sh, const ParamsDev& P,
       gi[10] = 240.0 * c3x * t3 + 720.0 * c4x * t4 + 1440.0 * c5x * t5;
       gi[11] = 240.0 * c3y * t3 + 720.0 * c4y * t4 + 1440.0 * c5y * t5;
     }
-    energy = warp_sum(energy);
-    gdT = warp_sum(gdT);
+    warp_sum2_cold(energy, gdT);
     if (lane == 0) {
       ws.seg[s].jerk = energy;
       ws.seg[s].gdT = gdT;
@@ -1559,7 +1576,7 @@ __device__ __forceinline__ double eval_post(const ShapeDev& sh, const ParamsDev&
       }
       part += sacc;
     }
-    part = warp_sum(part);
+    part = warp_sum_cold(part);
     if (lane == 0) ws.seg[s].pad[0] = part;  // added to gdT after the boundary terms, like the reference
   }
   __syncwarp();
@@ -1611,7 +1628,7 @@ __device__ __forceinline__ double eval_post(const ShapeDev& sh, const ParamsDev&
     if (P.gear_opt) {
       const double theta = x[ab + j];
       double sn, cs;
-      sincos(theta, &sn, &cs);
+      sincos_cold(theta, &sn, &cs);
       {  // segment j: gradFin
         const int N = sh.N[j];
         const double* adj = ws.gd + 2 * sh.row0[j];

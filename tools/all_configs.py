@@ -19,4 +19,4 @@ for cfg, B in ((2, 1024), (3, 4096), (4, 8192), (5, 16384 // 8)):
                     alg_GBps=st.algorithmic_bytes / best / 1e6, status=dict(zip(*[a.tolist() for a in np.unique(sol.status, return_counts=True)])))
     print(cfg, json.dumps(out[cfg]))
     opt.close()
-json.dump(out, open("gpurun_out/all_configs_r1.json", "w"), indent=1)
+json.dump(out, open("gpurun_out/all_configs_latest.json", "w"), indent=1)
