@@ -58,7 +58,8 @@ class TrajBatch:
         self.fin_state = _f64(self.fin_state).reshape(-1, 6)
         self.init_T = _f64(self.init_T)
         self.inner_pts = _f64(self.inner_pts).reshape(-1)
-        self.planes = _f64(self.planes).reshape(-1, 4)
+        if self.planes is not None:  # None: the corridor is generated on the device (BatchOptimizer.corridor_rectangles(keep=True))
+            self.planes = _f64(self.planes).reshape(-1, 4)
         self.t_now = _f64(self.t_now)
         if self.plane_cnt is not None:
             self.plane_cnt = _i32(self.plane_cnt)

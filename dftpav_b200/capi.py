@@ -177,6 +177,25 @@ class Batch(C.Structure):
     ]
 
 
+class GridMap(C.Structure):
+    """struct dftpav_gridmap (mirror of common::GridMapND<uint8_t, 2>)."""
+
+    _fields_ = [("size_x", C.c_int32), ("size_y", C.c_int32), ("origin_x", C.c_double), ("origin_y", C.c_double),
+                ("resolution", C.c_double), ("data", C.POINTER(C.c_uint8)), ("occupied_value", C.c_uint8)]
+
+
+class CorridorParams(C.Structure):
+    _fields_ = [("veh_width", C.c_double), ("veh_length", C.c_double), ("veh_d_cr", C.c_double), ("limit_bound", C.c_double)]
+
+
+def default_corridor_params() -> "CorridorParams":
+    """The default common::VehicleParam getRectangleConst expands from (semantics.h:66-76) and its 10 m bound."""
+    return CorridorParams(1.90, 4.88, 1.015, 10.0)
+
+
+OCCUPIED = 80  # GridMap2D::OCCUPIED (semantics.h:354)
+
+
 class Dims(C.Structure):
     _fields_ = [
         ("B", C.c_int32),
@@ -234,6 +253,8 @@ EXPORTED_SYMBOLS = [
     "dftpav_sample",
     "dftpav_sample_uniform",
     "dftpav_pack_polytraj",
+    "dftpav_corridor_set_map",
+    "dftpav_corridor_rectangles",
     "dftpav_create_multi",
     "dftpav_destroy_multi",
     "dftpav_solve_multi",
@@ -285,6 +306,9 @@ def load_library(variant: str = "") -> C.CDLL:
     lib.dftpav_sample.argtypes = [H, C.c_int64, c_int32_p, c_double_p, C.c_int32, C.c_double, c_double_p]
     lib.dftpav_sample_uniform.argtypes = [H, C.c_double, C.c_int32, c_double_p, c_int32_p]
     lib.dftpav_pack_polytraj.argtypes = [H, C.POINTER(C.c_float), C.POINTER(C.c_float), C.POINTER(C.c_float)]
+    lib.dftpav_corridor_set_map.argtypes = [H, C.POINTER(GridMap)]
+    lib.dftpav_corridor_rectangles.argtypes = [H, C.POINTER(CorridorParams), C.c_int64, c_double_p, c_double_p, c_double_p,
+                                               C.c_int32]
     lib.dftpav_create_multi.argtypes = [C.POINTER(Params), c_int32_p, C.c_int32, C.POINTER(H)]
     lib.dftpav_destroy_multi.argtypes = [H]
     lib.dftpav_solve_multi.argtypes = [H, C.POINTER(Batch), C.POINTER(Result), c_int32_p]

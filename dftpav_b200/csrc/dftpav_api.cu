@@ -40,6 +40,8 @@ cudaError_t launch_sample(cudaStream_t st, const SampleDev& sd, long long nq, co
                           double wheel_base, double* out);
 cudaError_t launch_sample_uniform(cudaStream_t st, const SampleDev& sd, double dt, int max_per_seg, double* out, int* count);
 cudaError_t launch_pack_polytraj(cudaStream_t st, const SampleDev& sd, float* cx, float* cy, float* dur);
+cudaError_t launch_corridor(cudaStream_t st, const CorridorDev& cd, long long n, const double* states, const double* cos_sin,
+                            double* hpolys);
 int ws_doubles_host(int rows, int npad, int S, int has_obs);
 int max_warps_host();
 int virtual_ranks_host();
@@ -200,7 +202,7 @@ struct DevBuf {
 struct Group {
   ShapeDev sh;
   std::vector<int> probs;
-  DevBuf d_prob_id, d_planes, d_lu;
+  DevBuf d_prob_id, d_planes, d_lu, d_order;
   int warps = 0, grid = 0;
   size_t smem = 0;
 };
@@ -244,6 +246,13 @@ struct dftpav_handle {
   DevBuf hist_s, hist_y, hist_ys, trace, ready, laid;
   DevBuf seg_prob, seg_row0, seg_N, seg_piece0, q_seg, q_t, q_out, q_cnt;  // trajectory evaluator (dftpav_sample*)
   long long pieces_total = 0;
+  // corridor generator: device copy of the occupancy grid, ray-march offsets, and whether planes_raw holds generated polygons
+  DevBuf map_data, map_dl, cor_states, cor_cs;
+  dftpav_gridmap map_meta{};
+  int map_n_dl = 0;
+  std::vector<int> dbg_order;  // experiment hook (dftpav_debug_set_order): serve the work queue in this order of problem ids
+  bool planes_from_corridor = false;
+  long long corridor_n = -1;  // >= 0: planes_raw holds corridor_n generated rectangles (4 planes each)
   int trace_cap = 0;
   int hist_ld = 0, hist_slots = 0;
   int upload_launches = 0;
@@ -292,9 +301,11 @@ int validate(const dftpav_params* prm, const dftpav_batch* b, dftpav_dims* dims,
   if (!prm || !b) return bad(DFTPAV_ERR_INVALID_ARG, "null params or batch");
   if (prm->abi_version != DFTPAV_ABI_VERSION) return bad(DFTPAV_ERR_INVALID_ARG, "abi_version mismatch");
   if (b->B < 0) return bad(DFTPAV_ERR_INVALID_ARG, "B < 0");
-  if (b->B > 0 && (!b->seg_ptr || !b->piece_num || !b->singul || !b->ini_state || !b->fin_state || !b->init_T ||
-                   !b->inner_pts || !b->planes))
+  if (b->B > 0 && (!b->seg_ptr || !b->piece_num || !b->singul || !b->ini_state || !b->fin_state || !b->init_T || !b->inner_pts))
     return bad(DFTPAV_ERR_INVALID_ARG, "null array in batch");
+  // planes == NULL: the corridor comes from dftpav_corridor_rectangles (device-resident, 4 planes per sample)
+  if (b->B > 0 && !b->planes && (b->plane_cnt || b->uniform_H != 4))
+    return bad(DFTPAV_ERR_INVALID_ARG, "planes == NULL needs uniform_H == 4 and plane_cnt == NULL (generated corridor)");
   if (prm->traj_resolution < 1 || prm->des_traj_resolution < 1) return bad(DFTPAV_ERR_INVALID_ARG, "resolution < 1");
   if (prm->lbfgs_past > 8) return bad(DFTPAV_ERR_UNSUPPORTED, "lbfgs_past > 8");
   if (prm->lbfgs_mem_size > 2 * 12 * kStageLd)  // alpha array lives in the sweep staging buffer
@@ -420,6 +431,7 @@ void free_groups(dftpav_handle* h) {
     g->d_prob_id.release();
     g->d_planes.release();
     g->d_lu.release();
+    g->d_order.release();
     delete g;
   }
   h->group_pool.clear();
@@ -595,7 +607,7 @@ int dftpav_destroy(dftpav_handle* h) {
                     &h->obs_start, &h->obs_dur, &h->obs_piece_ptr, &h->obs_piece_dur, &h->obs_coeffs, &h->obs_uniform, &h->x0, &h->xin,
                     &h->fout, &h->gout, &h->o_x, &h->o_cost, &h->o_status, &h->o_success, &h->o_iters, &h->o_evals,
                     &h->o_coeffs, &h->o_dT, &h->counter, &h->hist_s, &h->hist_y, &h->hist_ys, &h->trace, &h->ready, &h->laid, &h->seg_prob, &h->seg_row0, &h->seg_N,
-                    &h->seg_piece0, &h->q_seg, &h->q_t, &h->q_out, &h->q_cnt};
+                    &h->seg_piece0, &h->q_seg, &h->q_t, &h->q_out, &h->q_cnt, &h->map_data, &h->map_dl, &h->cor_states, &h->cor_cs};
   for (DevBuf* b : bufs) b->release();
   for (auto& e : h->ev)
     if (e) cudaEventDestroy(e);
@@ -794,7 +806,14 @@ int upload_impl(dftpav_handle* h, const dftpav_batch* b, int n_chunks_wanted) {
     }
     CU_TRY(h, up(h->obs_uniform, uni.data(), sizeof(double) * U));
   }
-  CU_TRY(h, h->planes_raw.ensure(sizeof(double) * 4 * (size_t)h->total_planes));
+  h->planes_from_corridor = (b->planes == nullptr) && B > 0;
+  if (h->planes_from_corridor) {
+    if (h->corridor_n != Q)
+      return fail(h, DFTPAV_ERR_STATE, "planes == NULL but dftpav_corridor_rectangles(keep) has not produced one polygon per sample of this batch");
+  } else {
+    h->corridor_n = -1;  // the buffer is about to be overwritten by uploaded planes
+    CU_TRY(h, h->planes_raw.ensure(sizeof(double) * 4 * (size_t)h->total_planes));
+  }
   CU_TRY(h, h->ini.ensure(sizeof(double) * 6 * G));
   CU_TRY(h, h->fin.ensure(sizeof(double) * 6 * G));
   // outputs
@@ -1003,12 +1022,12 @@ int issue_plane_copies(dftpav_handle* h, const dftpav_batch* b, cudaStream_t cs)
     const long long q0 = h->h_samp_base[p0], q1 = h->h_samp_base[p1];
     const long long e0 = h->uniform_H < 0 ? h->h_plane_ptr[q0] : q0 * h->uniform_H;
     const long long e1 = h->uniform_H < 0 ? h->h_plane_ptr[q1] : q1 * h->uniform_H;
-    if (e1 > e0)
+    if (e1 > e0 && !h->planes_from_corridor)
       CU_TRY(h, cudaMemcpyAsync(h->planes_raw.as<double>() + 4 * e0, b->planes + 4 * e0, sizeof(double) * 4 * (size_t)(e1 - e0),
                                 cudaMemcpyHostToDevice, cs));
     CU_TRY(h, cudaMemcpyAsync(h->ready.as<int>() + c, h->h_epoch + c, sizeof(int), cudaMemcpyHostToDevice, cs));
   }
-  h->stats.h2d_bytes += (long long)sizeof(double) * 4 * h->total_planes;
+  if (!h->planes_from_corridor) h->stats.h2d_bytes += (long long)sizeof(double) * 4 * h->total_planes;
   return DFTPAV_OK;
 }
 
@@ -1054,6 +1073,18 @@ int launch_solve_kernels(dftpav_handle* h, int* launches_out) {
       gd.planes = grp->d_planes.as<double>();
       gd.lu = grp->d_lu.as<double>();
       gd.order = nullptr;
+      if (!h->dbg_order.empty()) {  // experiment hook: queue order supplied by the caller (no effect on results)
+        std::vector<int> local_of(h->dims.B, -1), ord;
+        for (int i = 0; i < (int)grp->probs.size(); i++) local_of[grp->probs[i]] = i;
+        for (int pid : h->dbg_order)
+          if (pid >= 0 && pid < h->dims.B && local_of[pid] >= 0) ord.push_back(local_of[pid]), local_of[pid] = -1;
+        for (int i = 0; i < (int)grp->probs.size(); i++)
+          if (local_of[grp->probs[i]] >= 0) ord.push_back(i);
+        CU_TRY(h, grp->d_order.ensure(sizeof(int) * ord.size()));
+        CU_TRY(h, cudaMemcpyAsync(grp->d_order.p, ord.data(), sizeof(int) * ord.size(), cudaMemcpyHostToDevice, st));
+        CU_TRY(h, cudaStreamSynchronize(st));
+        gd.order = grp->d_order.as<int>();
+      }
       CU_TRY(h, launch_solve(h->has_obs, grp->grid, 32 * grp->warps, grp->smem, st, grp->sh, h->pd, h->bd, gd, out, hist,
                              h->counter.as<int>() + gi));
       launches++;
@@ -1252,6 +1283,65 @@ int dftpav_success_count(dftpav_handle* h, int32_t* n_success) {
   return DFTPAV_OK;
 }
 
+int dftpav_corridor_set_map(dftpav_handle* h, const dftpav_gridmap* map) {
+  if (!h || !map || !map->data || map->size_x < 1 || map->size_y < 1 || !(map->resolution > 0.0)) return DFTPAV_ERR_INVALID_ARG;
+  CU_TRY(h, cudaSetDevice(h->device));
+  const size_t bytes = (size_t)map->size_x * map->size_y;
+  CU_TRY(h, h->map_data.ensure(bytes));
+  CU_TRY(h, cudaMemcpyAsync(h->map_data.p, map->data, bytes, cudaMemcpyHostToDevice, h->stream));
+  // ray-march offsets of CheckIfCollisionUsingLine: dl = 0; dl += resolution / 2 (sequential sums, like the reference's loop)
+  const double checkl = map->resolution / 2.0;
+  const double longest = 64.0 + 4.0 * map->resolution;  // > vehicle length + 2 * limit_bound for any sensible box
+  std::vector<double> dl;
+  for (double v = 0.0; v < longest && dl.size() < (1u << 16); v += checkl) dl.push_back(v);
+  CU_TRY(h, h->map_dl.ensure(sizeof(double) * dl.size()));
+  CU_TRY(h, cudaMemcpyAsync(h->map_dl.p, dl.data(), sizeof(double) * dl.size(), cudaMemcpyHostToDevice, h->stream));
+  CU_TRY(h, cudaStreamSynchronize(h->stream));
+  h->map_meta = *map;
+  h->map_meta.data = nullptr;
+  h->map_n_dl = (int)dl.size();
+  return DFTPAV_OK;
+}
+
+int dftpav_corridor_rectangles(dftpav_handle* h, const dftpav_corridor_params* cp, int64_t n, const double* states,
+                               const double* cos_sin, double* hpolys, int32_t keep) {
+  if (!h || !cp || n < 0 || (n > 0 && !states)) return DFTPAV_ERR_INVALID_ARG;
+  if (h->map_n_dl == 0) return fail(h, DFTPAV_ERR_STATE, "dftpav_corridor_rectangles before dftpav_corridor_set_map");
+  if (!(cp->limit_bound > 0.0) || (cp->veh_length + 2.0 * cp->limit_bound + 4.0 * h->map_meta.resolution) >= 64.0)
+    return fail(h, DFTPAV_ERR_UNSUPPORTED, "vehicle length + 2 * limit_bound must stay below 64 m");
+  CU_TRY(h, cudaSetDevice(h->device));
+  cudaStream_t st = h->stream;
+  h->corridor_n = -1;
+  if (n == 0) return DFTPAV_OK;
+  CU_TRY(h, h->cor_states.ensure(sizeof(double) * 3 * (size_t)n));
+  CU_TRY(h, cudaMemcpyAsync(h->cor_states.p, states, sizeof(double) * 3 * (size_t)n, cudaMemcpyHostToDevice, st));
+  if (cos_sin) {
+    CU_TRY(h, h->cor_cs.ensure(sizeof(double) * 2 * (size_t)n));
+    CU_TRY(h, cudaMemcpyAsync(h->cor_cs.p, cos_sin, sizeof(double) * 2 * (size_t)n, cudaMemcpyHostToDevice, st));
+  }
+  CU_TRY(h, h->planes_raw.ensure(sizeof(double) * 16 * (size_t)n));
+  CorridorDev cd;
+  cd.data = h->map_data.as<unsigned char>();
+  cd.dl = h->map_dl.as<double>();
+  cd.size_x = h->map_meta.size_x, cd.size_y = h->map_meta.size_y, cd.n_dl = h->map_n_dl;
+  cd.occupied = h->map_meta.occupied_value;
+  cd.origin_x = h->map_meta.origin_x, cd.origin_y = h->map_meta.origin_y, cd.resolution = h->map_meta.resolution;
+  cd.veh_width = cp->veh_width, cd.veh_length = cp->veh_length, cd.veh_d_cr = cp->veh_d_cr, cd.limit_bound = cp->limit_bound;
+  CU_TRY(h, cudaEventRecord(h->ev[0], st));
+  CU_TRY(h, launch_corridor(st, cd, n, h->cor_states.as<double>(), cos_sin ? h->cor_cs.as<double>() : nullptr,
+                            h->planes_raw.as<double>()));
+  CU_TRY(h, cudaEventRecord(h->ev[1], st));
+  if (hpolys)
+    CU_TRY(h, cudaMemcpyAsync(hpolys, h->planes_raw.p, sizeof(double) * 16 * (size_t)n, cudaMemcpyDeviceToHost, st));
+  CU_TRY(h, cudaStreamSynchronize(st));
+  float ms = 0.f;
+  cudaEventElapsedTime(&ms, h->ev[0], h->ev[1]);
+  h->stats.solve_ms = ms;
+  h->stats.kernel_launches = 1;
+  if (keep) h->corridor_n = n;
+  return DFTPAV_OK;
+}
+
 static SampleDev sample_view(const dftpav_handle* h) {
   SampleDev sd;
   sd.coeffs = h->o_coeffs.as<double>();
@@ -1341,6 +1431,13 @@ int dftpav_internal_set_min_strides(dftpav_handle* h, int n_stride, int row_stri
 int dftpav_debug_force_banded(dftpav_handle* h, int on) {
   if (!h) return DFTPAV_ERR_INVALID_ARG;
   h->force_banded = on != 0;
+  return DFTPAV_OK;
+}
+// Experiment hook (not part of the drop-in ABI): order in which the persistent warps take the problems (ids, longest-expected
+// first); NULL / n = 0 restores the input order.  Results do not depend on it.
+int dftpav_debug_set_order(dftpav_handle* h, const int32_t* order, int32_t n) {
+  if (!h) return DFTPAV_ERR_INVALID_ARG;
+  h->dbg_order.assign(order ? order : nullptr, order ? order + n : nullptr);
   return DFTPAV_OK;
 }
 // Build variant of the loaded library: bit 0 strict-order verification build; bits 8.. virtual ranks

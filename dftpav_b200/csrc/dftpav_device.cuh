@@ -126,6 +126,16 @@ struct SampleDev {
   int G, row_stride;
 };
 
+// Occupancy grid + vehicle box for the corridor generator (dftpav_corridor_*).
+struct CorridorDev {
+  const unsigned char* data;    // [size_y][size_x]
+  const double* dl;             // [n_dl] accumulated ray-march offsets: 0, r/2, r/2 + r/2, ... (sequential sums, built on the host)
+  int size_x, size_y, n_dl;
+  unsigned char occupied;
+  double origin_x, origin_y, resolution;
+  double veh_width, veh_length, veh_d_cr, limit_bound;
+};
+
 struct HistDev {
   double* s;        // [slots][mem][npad_max]
   double* y;

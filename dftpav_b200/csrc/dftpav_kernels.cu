@@ -21,19 +21,6 @@ namespace dftpav {
 
 #define FULL 0xffffffffu
 
-// Code that runs once per evaluation (or never, for a given shape) is kept OUT of line: an evaluation executes ~65 KB of
-// SASS against a 32 KB L1.5 instruction cache and `no_instruction` is the largest stall reason of the solver
-// (profiles/README.md); every inlined copy of a 1.3-1.6 KB warp reduction or of the 18 KB banded fallback widens the hot
-// instruction stream.  -DDFTPAV_COLD_INLINE=1 restores the inlined form (A/B).
-#ifndef DFTPAV_COLD_INLINE
-#define DFTPAV_COLD_INLINE 0
-#endif
-#if DFTPAV_COLD_INLINE
-#define DFTPAV_COLD __forceinline__
-#else
-#define DFTPAV_COLD __noinline__
-#endif
-
 // warps per CTA (one CTA per SM)
 #ifndef DFTPAV_MAX_WARPS
 #define DFTPAV_MAX_WARPS 12  // measured on B200, batch 4096: 8 warps 153 k, 10: 153 k, 12: 161 k, 14: 138 k, 16: 139 k solves/s (168 vs 128 registers: no spills)
@@ -47,16 +34,6 @@ __device__ __forceinline__ double warp_sum(double v) {
   for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(FULL, v, o);
   return v;
 }
-// once-per-evaluation reductions, out of line (see DFTPAV_COLD)
-__device__ DFTPAV_COLD double warp_sum_cold(double v) { return warp_sum(v); }
-__device__ DFTPAV_COLD void warp_sum2_cold(double& a, double& b) {
-#pragma unroll
-  for (int o = 16; o > 0; o >>= 1) {
-    a += __shfl_xor_sync(FULL, a, o);
-    b += __shfl_xor_sync(FULL, b, o);
-  }
-}
-__device__ DFTPAV_COLD void sincos_cold(double th, double* sn, double* cs) { sincos(th, sn, cs); }
 // four sums at once: the butterflies are interleaved (the latency of one)
 __device__ __noinline__ void warp_sum4(double (&v)[4]) {
 #pragma unroll
@@ -415,11 +392,11 @@ __device__ __forceinline__ void band_pass(const double* C, double* b, int n, int
   }
 }
 
-__device__ DFTPAV_COLD void banded_solve(const double* C, double* b, int n, int col, bool masks_ok) {
+__device__ __forceinline__ void banded_solve(const double* C, double* b, int n, int col, bool masks_ok) {
   band_pass<PASS_FWD>(C, b, n, col, masks_ok);  // L y = b      (poly_traj_utils.hpp:808-815)
   band_pass<PASS_BWD>(C, b, n, col, masks_ok);  // U x = y      (poly_traj_utils.hpp:816-824)
 }
-__device__ DFTPAV_COLD void banded_solve_adj(const double* C, double* b, int n, int col, bool masks_ok) {
+__device__ __forceinline__ void banded_solve_adj(const double* C, double* b, int n, int col, bool masks_ok) {
   band_pass<PASS_ADJ_U>(C, b, n, col, masks_ok);  // U^T z = b  (poly_traj_utils.hpp:834-842)
   band_pass<PASS_ADJ_L>(C, b, n, col, masks_ok);  // L^T w = z  (poly_traj_utils.hpp:843-850)
 }
@@ -1268,8 +1245,14 @@ __device__ __forceinline__ void sweep_segment(const ShapeDev& sh, const ParamsDe
     }
     // ---------------- stage F: leaving a virtual rank (or the end passes): its scalar sums, one interleaved butterfly
     if (!has_next || vr_next != vr) {
+      // (inline on purpose: a call inside the sweep loop costs more than the 4 KB of code; measured 172 k vs 188 k solves/s)
       double v4[4] = {acc_gdT, acc_p0, acc_p1, acc_p2};
-      warp_sum4(v4);
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) {
+#pragma unroll
+        for (int q = 0; q < 4; q++)
+          if (HAS_OBS || q != 2) v4[q] += __shfl_xor_sync(FULL, v4[q], o);
+      }
       if (lane < 4) rsc[4 * vr + lane] = lane == 0 ? v4[0] : (lane == 1 ? v4[1] : (lane == 2 ? v4[2] : v4[3]));
       acc_gdT = acc_p0 = acc_p1 = acc_p2 = 0.0;
       __syncwarp();
@@ -1400,7 +1383,7 @@ __device__ __forceinline__ void eval_pre(const ShapeDev& sh, const ParamsDev& P,
     if (s > 0) {
       const double theta = x[ab + s - 1];
       double sn, cs;
-      sincos_cold(theta, &sn, &cs);
+      sincos(theta, &sn, &cs);
       sc.head[0] = x[gb + 2 * (s - 1)];
       sc.head[1] = x[gb + 2 * (s - 1) + 1];
       sc.head[2] = -P.non_sinv * cs;
@@ -1409,7 +1392,7 @@ __device__ __forceinline__ void eval_pre(const ShapeDev& sh, const ParamsDev& P,
     if (s < S - 1) {
       const double theta = x[ab + s];
       double sn, cs;
-      sincos_cold(theta, &sn, &cs);
+      sincos(theta, &sn, &cs);
       sc.tail[0] = x[gb + 2 * s];
       sc.tail[1] = x[gb + 2 * s + 1];
       sc.tail[2] = P.non_sinv * cs;
@@ -1516,7 +1499,8 @@ __device__ __forceinline__ void eval_pre(const ShapeDev& sh, const ParamsDev& P,
       gi[10] = 240.0 * c3x * t3 + 720.0 * c4x * t4 + 1440.0 * c5x * t5;
       gi[11] = 240.0 * c3y * t3 + 720.0 * c4y * t4 + 1440.0 * c5y * t5;
     }
-    warp_sum2_cold(energy, gdT);
+    energy = warp_sum(energy);
+    gdT = warp_sum(gdT);
     if (lane == 0) {
       ws.seg[s].jerk = energy;
       ws.seg[s].gdT = gdT;
@@ -1576,7 +1560,7 @@ __device__ __forceinline__ double eval_post(const ShapeDev& sh, const ParamsDev&
       }
       part += sacc;
     }
-    part = warp_sum_cold(part);
+    part = warp_sum(part);
     if (lane == 0) ws.seg[s].pad[0] = part;  // added to gdT after the boundary terms, like the reference
   }
   __syncwarp();
@@ -1628,7 +1612,7 @@ __device__ __forceinline__ double eval_post(const ShapeDev& sh, const ParamsDev&
     if (P.gear_opt) {
       const double theta = x[ab + j];
       double sn, cs;
-      sincos_cold(theta, &sn, &cs);
+      sincos(theta, &sn, &cs);
       {  // segment j: gradFin
         const int N = sh.N[j];
         const double* adj = ws.gd + 2 * sh.row0[j];
@@ -2550,6 +2534,129 @@ __global__ void pack_polytraj_kernel(const SampleDev sd, float* __restrict__ coe
 }
 
 // ------------------------------------------------------------------------------------------------
+// Corridor generation: TrajPlanner::getRectangleConst (traj_manager.cpp:1211-1469) on the
+// occupancy grid, one WARP per sampled state.  The expansion state machine (round-robin over +dy, +dx, -dy, -dx, one cell
+// per step, three ray-marched segments per step) is warp-uniform; the ray march of a segment - the reference's loop
+// `for (dl = 0; dl < |p2-p1|; dl += res/2)` of CheckIfCollisionUsingLine (map_adapter.cpp:117-129) - is spread over the
+// lanes: the result of that loop is a boolean OR over its sample points (it returns at the first occupied one), so the
+// order does not matter.  Every coordinate is computed with explicitly rounded operations in the reference's
+// association; dl comes from a table of the sequentially accumulated sums (built on the host), so the sampled cells are
+// exactly the reference's.  Output: four half-planes (n_x, n_y, p_x, p_y) per state = the optimizer's raw plane layout.
+// HBM/L2-bound byte lookups; no tensor cores, no shared memory.
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ bool grid_occupied(const CorridorDev& cd, double px, double py) {
+  // GridMapND::GetCoordUsingGlobalPosition / CheckCoordInRange / CheckIfEqualUsingGlobalPosition (semantics.cc:169-288)
+  const double fx = round(__ddiv_rn(__dadd_rn(px, -cd.origin_x), cd.resolution));
+  const double fy = round(__ddiv_rn(__dadd_rn(py, -cd.origin_y), cd.resolution));
+  if (!(fx >= 0.0 && fx < (double)cd.size_x && fy >= 0.0 && fy < (double)cd.size_y)) return false;
+  return cd.data[(size_t)(int)fx + (size_t)(int)fy * cd.size_x] == cd.occupied;
+}
+// CheckIfCollisionUsingLine by one warp
+__device__ __forceinline__ bool line_blocked(const CorridorDev& cd, double p1x, double p1y, double p2x, double p2y, int lane) {
+  const double dx = __dadd_rn(p2x, -p1x), dy = __dadd_rn(p2y, -p1y);
+  const double nrm = sqrt(__dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy)));
+  bool hit = false;
+  for (int k0 = 0; k0 < cd.n_dl; k0 += 32) {
+    const int k = k0 + lane;
+    const double dl = k < cd.n_dl ? cd.dl[k] : 1.0e300;
+    const bool on = dl < nrm;
+    bool occ = false;
+    if (on) {
+      const double px = __dadd_rn(__ddiv_rn(__dmul_rn(dx, dl), nrm), p1x);
+      const double py = __dadd_rn(__ddiv_rn(__dmul_rn(dy, dl), nrm), p1y);
+      occ = grid_occupied(cd, px, py);
+    }
+    if (__any_sync(FULL, occ)) {
+      hit = true;
+      break;
+    }
+    if (!__all_sync(FULL, on)) break;  // dl is increasing: the segment ends inside this chunk
+  }
+  if (!hit) hit = grid_occupied(cd, p2x, p2y);  // the end point itself (map_adapter.cpp:127)
+  return hit;
+}
+
+__global__ void corridor_kernel(const CorridorDev cd, long long n, const double* __restrict__ states,
+                                const double* __restrict__ cos_sin, double* __restrict__ hpolys) {
+  const int lane = threadIdx.x & 31;
+  const long long warp0 = (blockIdx.x * (long long)blockDim.x + threadIdx.x) >> 5;
+  const long long nwarps = ((long long)gridDim.x * blockDim.x) >> 5;
+  const double step = cd.resolution, checkl = __ddiv_rn(cd.resolution, 2.0);
+  (void)checkl;  // the ray-march spacing lives in cd.dl (accumulated sums of resolution / 2)
+  for (long long q = warp0; q < n; q += nwarps) {
+    const double x = states[3 * q], y = states[3 * q + 1], yaw = states[3 * q + 2];
+    double c, s;
+    if (cos_sin) {
+      c = cos_sin[2 * q], s = cos_sin[2 * q + 1];
+    } else {
+      c = cos(yaw), s = sin(yaw);
+    }
+    const double ms = -s;
+    auto RX = [&](double a, double b) { return __dadd_rn(__dmul_rn(c, a), __dmul_rn(ms, b)); };
+    auto RY = [&](double a, double b) { return __dadd_rn(__dmul_rn(s, a), __dmul_rn(c, b)); };
+    double spx = x, spy = y;
+    double width = cd.veh_width, length = cd.veh_length;
+    const double dcr = cd.veh_d_cr;
+    int notfin = 0xf;
+    double ex0 = 0.0, ex1 = 0.0, ex2 = 0.0, ex3 = 0.0;
+    while (notfin) {
+      for (int i = 0; i < 4; i++) {
+        if (!((notfin >> i) & 1)) continue;
+        const double hl = __ddiv_rn(length, 2.0), hw = __ddiv_rn(width, 2.0);
+        double a1, b1, a2, b2, na1, nb1, na2, nb2;
+        if (i == 0) {  // +dy
+          a1 = __dadd_rn(hl, dcr), b1 = hw, a2 = __dadd_rn(-hl, dcr), b2 = hw;
+          na1 = a1, nb1 = __dadd_rn(hw, step), na2 = a2, nb2 = nb1;
+        } else if (i == 1) {  // +dx
+          a1 = __dadd_rn(hl, dcr), b1 = -hw, a2 = a1, b2 = hw;
+          na1 = __dadd_rn(__dadd_rn(step, hl), dcr), nb1 = -hw, na2 = na1, nb2 = hw;
+        } else if (i == 2) {  // -dy
+          a1 = __dadd_rn(-hl, dcr), b1 = -hw, a2 = __dadd_rn(hl, dcr), b2 = -hw;
+          na1 = a1, nb1 = __dadd_rn(-hw, -step), na2 = a2, nb2 = nb1;
+        } else {  // -dx
+          a1 = __dadd_rn(-hl, dcr), b1 = hw, a2 = a1, b2 = -hw;
+          na1 = __dadd_rn(a1, -step), nb1 = hw, na2 = na1, nb2 = -hw;
+        }
+        const double p1x = __dadd_rn(spx, RX(a1, b1)), p1y = __dadd_rn(spy, RY(a1, b1));
+        const double p2x = __dadd_rn(spx, RX(a2, b2)), p2y = __dadd_rn(spy, RY(a2, b2));
+        const double n1x = __dadd_rn(spx, RX(na1, nb1)), n1y = __dadd_rn(spy, RY(na1, nb1));
+        const double n2x = __dadd_rn(spx, RX(na2, nb2)), n2y = __dadd_rn(spy, RY(na2, nb2));
+        if (line_blocked(cd, p1x, p1y, n1x, n1y, lane) || line_blocked(cd, n1x, n1y, n2x, n2y, lane) ||
+            line_blocked(cd, n2x, n2y, p2x, p2y, lane)) {
+          notfin &= ~(1 << i);
+          continue;
+        }
+        double e = i == 0 ? ex0 : (i == 1 ? ex1 : (i == 2 ? ex2 : ex3));
+        e = __dadd_rn(e, step);
+        if (i == 0) ex0 = e; else if (i == 1) ex1 = e; else if (i == 2) ex2 = e; else ex3 = e;
+        if (e >= cd.limit_bound) {
+          notfin &= ~(1 << i);
+          continue;
+        }
+        const double h2 = __ddiv_rn(step, 2.0);
+        double ta, tb;
+        if (i == 0) ta = 0.0, tb = h2, width = __dadd_rn(width, step);
+        else if (i == 1) ta = h2, tb = 0.0, length = __dadd_rn(length, step);
+        else if (i == 2) ta = 0.0, tb = -h2, width = __dadd_rn(width, step);
+        else ta = -h2, tb = 0.0, length = __dadd_rn(length, step);
+        spx = __dadd_rn(spx, RX(ta, tb));
+        spy = __dadd_rn(spy, RY(ta, tb));
+      }
+    }
+    if (lane == 0) {
+      const double hl = __ddiv_rn(cd.veh_length, 2.0), hw = __ddiv_rn(cd.veh_width, 2.0);
+      const double fa = __dadd_rn(__dadd_rn(hl, dcr), ex1), ra = __dadd_rn(__dadd_rn(-hl, dcr), -ex3);
+      const double lb = __dadd_rn(hw, ex0), rb = __dadd_rn(-hw, -ex2);
+      double* h = hpolys + 16 * q;
+      h[0] = ms, h[1] = c, h[2] = __dadd_rn(x, RX(fa, lb)), h[3] = __dadd_rn(y, RY(fa, lb));
+      h[4] = c, h[5] = s, h[6] = __dadd_rn(x, RX(fa, rb)), h[7] = __dadd_rn(y, RY(fa, rb));
+      h[8] = s, h[9] = -c, h[10] = __dadd_rn(x, RX(ra, rb)), h[11] = __dadd_rn(y, RY(ra, rb));
+      h[12] = -c, h[13] = ms, h[14] = __dadd_rn(x, RX(ra, lb)), h[15] = __dadd_rn(y, RY(ra, lb));
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
 // host-callable launchers (used by dftpav_api.cu)
 // ------------------------------------------------------------------------------------------------
 cudaError_t launch_solve(bool has_obs, int grid, int block, size_t smem, cudaStream_t st, const ShapeDev& sh,
@@ -2597,6 +2704,13 @@ cudaError_t launch_sample_uniform(cudaStream_t st, const SampleDev& sd, double d
 }
 cudaError_t launch_pack_polytraj(cudaStream_t st, const SampleDev& sd, float* cx, float* cy, float* dur) {
   pack_polytraj_kernel<<<sd.G > 0 ? sd.G : 1, 64, 0, st>>>(sd, cx, cy, dur);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_corridor(cudaStream_t st, const CorridorDev& cd, long long n, const double* states, const double* cos_sin,
+                            double* hpolys) {
+  const long long blocks = std::min<long long>((n + 7) / 8, 148LL * 8);  // 8 warps per block, one warp per state
+  corridor_kernel<<<(int)std::max<long long>(1, blocks), 256, 0, st>>>(cd, n, states, cos_sin, hpolys);
   return cudaGetLastError();
 }
 

@@ -34,8 +34,11 @@ struct NcclApi {
   int (*GroupEnd)() = nullptr;
   const char* (*GetErrorString)(int) = nullptr;
   bool load() {
-    lib = dlopen("libnccl.so.2", RTLD_NOW | RTLD_GLOBAL);
-    if (!lib) lib = dlopen("libnccl.so", RTLD_NOW | RTLD_GLOBAL);
+    // a copy the process has already loaded (e.g. the one bundled with torch) first; otherwise a private one: RTLD_LOCAL keeps
+    // its symbols away from whatever loads another NCCL later
+    lib = dlopen("libnccl.so.2", RTLD_NOW | RTLD_NOLOAD);
+    if (!lib) lib = dlopen("libnccl.so.2", RTLD_NOW | RTLD_LOCAL);
+    if (!lib) lib = dlopen("libnccl.so", RTLD_NOW | RTLD_LOCAL);
     if (!lib) return false;
     CommInitAll = reinterpret_cast<decltype(CommInitAll)>(dlsym(lib, "ncclCommInitAll"));
     CommDestroy = reinterpret_cast<decltype(CommDestroy)>(dlsym(lib, "ncclCommDestroy"));

@@ -162,6 +162,15 @@ class BatchOptimizer:
         """Test hook: banded LU substitutions (the large-N fallback) even where the dense MINCO tables fit."""
         self._check(self._lib.dftpav_debug_force_banded(self._h, 1 if on else 0))
 
+    def set_order(self, order: Optional[np.ndarray]):
+        """Experiment hook: serve the work queue in this order of problem ids (None: input order)."""
+        self._lib.dftpav_debug_set_order.argtypes = [C.c_void_p, capi.c_int32_p, C.c_int32]
+        if order is None:
+            self._check(self._lib.dftpav_debug_set_order(self._h, None, 0))
+        else:
+            o = np.ascontiguousarray(order, dtype=np.int32)
+            self._check(self._lib.dftpav_debug_set_order(self._h, o.ctypes.data_as(capi.c_int32_p), o.shape[0]))
+
     def build_flags(self) -> int:
         return int(self._lib.dftpav_debug_build_flags())
 
@@ -204,6 +213,28 @@ class BatchOptimizer:
         fp = C.POINTER(C.c_float)
         self._check(self._lib.dftpav_pack_polytraj(self._h, cx.ctypes.data_as(fp), cy.ctypes.data_as(fp), du.ctypes.data_as(fp)))
         return cx, cy, du
+
+    # -- corridor generation (TrajPlanner::getRectangleConst on the device) ----------------------------------------------
+    def set_map(self, grid: np.ndarray, origin_xy, resolution: float, occupied: int = capi.OCCUPIED):
+        """grid: uint8 [size_y, size_x] (dimension 0 of the reference's GridMapND is the fastest-varying index)."""
+        grid = np.ascontiguousarray(grid, dtype=np.uint8)
+        m = capi.GridMap(grid.shape[1], grid.shape[0], float(origin_xy[0]), float(origin_xy[1]), float(resolution),
+                         grid.ctypes.data_as(C.POINTER(C.c_uint8)), occupied)
+        self._check(self._lib.dftpav_corridor_set_map(self._h, C.byref(m)))
+
+    def corridor_rectangles(self, states: np.ndarray, cos_sin: Optional[np.ndarray] = None, keep: bool = False,
+                            params: Optional[capi.CorridorParams] = None, want_host: bool = True):
+        """states [n, 3] = (x, y, yaw) -> half-planes [n, 4, 4] (n_x, n_y, p_x, p_y) (dftpav_corridor_rectangles)."""
+        states = np.ascontiguousarray(states, dtype=np.float64).reshape(-1, 3)
+        n = states.shape[0]
+        cp = params if params is not None else capi.default_corridor_params()
+        out = np.zeros((n, 4, 4)) if want_host else None
+        cs = None if cos_sin is None else np.ascontiguousarray(cos_sin, dtype=np.float64).reshape(n, 2)
+        dp = capi.c_double_p
+        self._check(self._lib.dftpav_corridor_rectangles(
+            self._h, C.byref(cp), n, states.ctypes.data_as(dp), cs.ctypes.data_as(dp) if cs is not None else None,
+            out.ctypes.data_as(dp) if out is not None else None, 1 if keep else 0))
+        return out
 
     # -- diagnostics (not part of the drop-in ABI) ---------------------------------------------
     def enable_trace(self, cap: int):

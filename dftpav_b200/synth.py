@@ -424,6 +424,57 @@ def make_custom(B: int, pieces, seed: int = 0) -> Tuple[TrajBatch, capi.Params]:
     return batch, prm
 
 
+def make_obstacle_map(batch: TrajBatch, prm: capi.Params, resolution: float = 0.2, clutter: int = 60, seed: int = 0):
+    """Occupancy grid (uint8 [size_y, size_x], OCCUPIED = 80) around the problems of a single-segment batch: random discs and
+    boxes that stay clear of every problem's front-end path (the piecewise-linear path through start, waypoints and goal,
+    with a margin that keeps the vehicle box free).  Returns (grid, origin_xy, resolution, states) where states [Q, 3] are
+    the per-sample poses (x, y, yaw) of the path - what traj_manager.cpp:576-600 feeds getRectangleConst - in the sample
+    order the optimizer expects (piece by piece, K_i + 1 samples each)."""
+    rng = np.random.default_rng(1000 + seed)
+    K, Kd = prm.traj_resolution, prm.des_traj_resolution
+    pts_all, states = [], []
+    for p in range(batch.B):
+        g = int(batch.seg_ptr[p])
+        N = int(batch.piece_num[g])
+        off = int(sum(2 * (int(batch.piece_num[q]) - 1) for q in range(g)))
+        inner = batch.inner_pts[off: off + 2 * (N - 1)].reshape(N - 1, 2)
+        pts = np.vstack([batch.ini_state[g, 0:2], inner, batch.fin_state[g, 0:2]])
+        pts_all.append(pts)
+        for i in range(N):
+            Ki = Kd if i in (0, N - 1) else K
+            a, b = pts[i], pts[i + 1]
+            yaw = np.arctan2(b[1] - a[1], b[0] - a[0])
+            for j in range(Ki + 1):
+                q = a + (b - a) * (j / Ki)
+                states.append((q[0], q[1], yaw))
+    states = np.array(states)
+    allp = np.vstack(pts_all)
+    lo = allp.min(axis=0) - 20.0
+    hi = allp.max(axis=0) + 20.0
+    size = np.ceil((hi - lo) / resolution).astype(int) + 1
+    grid = np.full((size[1], size[0]), 127, dtype=np.uint8)  # FREE
+    yy, xx = np.mgrid[0:size[1], 0:size[0]]
+    cx = lo[0] + xx * resolution
+    cy = lo[1] + yy * resolution
+    # distance of every cell to the nearest sampled pose (coarse: poses subsampled)
+    sub = states[:: max(1, len(states) // 4000), :2]
+    dmin = np.full(grid.shape, 1e9)
+    for k in range(0, len(sub), 256):
+        blk = sub[k:k + 256]
+        d = np.sqrt((cx[..., None] - blk[:, 0]) ** 2 + (cy[..., None] - blk[:, 1]) ** 2).min(axis=-1)
+        dmin = np.minimum(dmin, d)
+    for _ in range(clutter):
+        c = lo + rng.uniform(0, 1, 2) * (hi - lo)
+        if rng.uniform() < 0.5:
+            r = rng.uniform(0.5, 3.0)
+            mask = (cx - c[0]) ** 2 + (cy - c[1]) ** 2 <= r * r
+        else:
+            w, hgt = rng.uniform(0.5, 4.0, 2)
+            mask = (np.abs(cx - c[0]) <= w) & (np.abs(cy - c[1]) <= hgt)
+        grid[mask & (dmin > 4.5)] = capi.OCCUPIED  # the vehicle box (half diagonal ~3.6 m from the rear axle) stays free
+    return grid, (float(lo[0]), float(lo[1])), resolution, states
+
+
 def algorithmic_bytes_per_eval(batch: TrajBatch, prm: capi.Params, p: int = 0) -> int:
     """B_eval = 16 n + 32 sum_samples H_s + 96 S + 104 sum_obstacles P_o."""
     g0, g1 = int(batch.seg_ptr[p]), int(batch.seg_ptr[p + 1])

@@ -287,6 +287,38 @@ int dftpav_sample_uniform(dftpav_handle* h, double dt, int32_t max_per_seg, doub
  * coef_x, coef_y: [6 * sum piece_num], duration: [sum piece_num]. */
 int dftpav_pack_polytraj(dftpav_handle* h, float* coef_x, float* coef_y, float* duration);
 
+/* ---- corridor generation (the step immediately before the optimizer) ----
+ * Replaces TrajPlanner::getRectangleConst (src/traj_manager.cpp:1211-1469): for every sampled state (x, y, yaw) of the
+ * front-end path a safe rectangle is grown cell by cell on the occupancy grid - round-robin over +dy, +dx, -dy, -dx, each
+ * step ray-marching the three sides of the strip it would add at resolution/2 (TrajPlannerAdapter::CheckIfCollisionUsingLine,
+ * src/map_adapter.cpp:117-129) until blocked or limit_bound metres - and returned as four half-planes (n_x, n_y, p_x, p_y):
+ * exactly the per-sample polygon layout dftpav_batch.planes takes (uniform_H = 4).
+ * dftpav_gridmap mirrors common::GridMapND<uint8_t, 2> (Sim/core/common semantics.h:376-560): cell (cx, cy) of a position p is
+ * round((p - origin) / resolution) per axis (std::round), data index cx + cy * size_x (dimension 0 fastest), a cell is an
+ * obstacle iff data == occupied_value (OCCUPIED = 80); positions outside the map are free. */
+typedef struct dftpav_gridmap {
+  int32_t size_x, size_y;
+  double origin_x, origin_y, resolution;
+  const uint8_t* data;      /* [size_y][size_x] */
+  uint8_t occupied_value;   /* 80 */
+} dftpav_gridmap;
+
+typedef struct dftpav_corridor_params {
+  double veh_width, veh_length, veh_d_cr;  /* the default common::VehicleParam the reference expands from: 1.90, 4.88, 1.015 */
+  double limit_bound;                       /* 10.0 (traj_manager.cpp:1218) */
+} dftpav_corridor_params;
+
+/* Copies the occupancy grid to the device (replaces the GridMap2D copy of traj_manager.cpp:1213-1214). */
+int dftpav_corridor_set_map(dftpav_handle* h, const dftpav_gridmap* map);
+/* Rectangles for n states.  states: [n][3] = (x, y, yaw).  cos_sin (may be NULL): [n][2] = (cos yaw, sin yaw) computed by the
+ * caller - with it the result is bit-identical to a CPU evaluation that uses the same values (the CUDA and glibc sin / cos
+ * differ by an ulp now and then, which can move a ray-march sample across a cell border).  hpolys (may be NULL): [n][4][4]
+ * host output.  If keep != 0 the polygons also stay on the device as the corridor of the NEXT dftpav_upload_batch /
+ * dftpav_solve whose batch has planes == NULL and uniform_H == 4 (n must then equal the batch's sample total): the
+ * 56 KB-per-problem plane upload disappears from the planner cycle. */
+int dftpav_corridor_rectangles(dftpav_handle* h, const dftpav_corridor_params* cp, int64_t n, const double* states,
+                               const double* cos_sin, double* hpolys, int32_t keep);
+
 /* ---- multi-GPU: the batch shards embarrassingly over the GPUs of one box ----
  * dftpav_create_multi: one handle, host thread and stream per device of device_ids[0..n_dev) and - for n_dev > 1 - an NCCL
  * communicator over them (libnccl.so.2 is loaded at run time; without it the flag below is reduced on the host and

@@ -1,0 +1,143 @@
+// corridor_oracle.cpp — CPU restatement of the reference's per-sample safe-rectangle generation.
+//
+// TEST INFRASTRUCTURE ONLY (like everything under oracle/).  PARITY UNPINNED: the reference function is a member of
+// TrajPlanner (src/Plan/traj_planner/src/traj_manager.cpp:1211-1469) whose translation unit pulls in the whole ROS / OMPL /
+// semantic-map stack and cannot be compiled here; the restatement below follows its source statement by statement, and
+// the two leaf routines it calls - TrajPlannerAdapter::CheckIfCollisionUsingLine (src/map_adapter.cpp:117-129) and
+// GridMapND::CheckIfEqualUsingGlobalPosition / GetCoordUsingGlobalPosition (Sim/core/common/src/common/basics/
+// semantics.cc:169-179, 214-221, 264-288; OCCUPIED = 80, semantics.h:354) - likewise.  What pins it instead: geometric
+// invariants checked by tests/test_corridor_oracle.py (every returned rectangle contains the vehicle box, is collision-free
+// on its boundary at the sampled points, cannot grow by one more cell in any finished direction) and an independent numpy
+// implementation of the same procedure.
+//
+// Reference procedure (MGR.cpp = traj_manager.cpp):
+//   for each state (x, y, yaw):  sourcePt = (x, y), sourceVp = default VehicleParam (width 1.90, length 4.88, d_cr 1.015),
+//   expandLength = 0; round-robin over the four directions +dy, +dx, -dy, -dx while any is unfinished (MGR.cpp:1306-1432):
+//   the three segments  point1 -> newpoint1 -> newpoint2 -> point2  of the strip that one more `step` (= map resolution)
+//   would add are ray-marched at resolution/2 (CheckIfCollisionUsingLine); blocked -> the direction is finished; else
+//   expandLength[i] += step (finished when >= 10 m) and the source rectangle grows (centre shifts by step/2, width or length
+//   grows by step).  The polygon is then built from the RAW pose and the four expansion lengths (MGR.cpp:1433-1460):
+//   four columns (n_x, n_y, p_x, p_y) - the layout the optimizer's corridor takes.
+#include <cmath>
+#include <cstdint>
+
+#include "../include/dftpav_b200.h"
+
+namespace {
+
+struct Grid {
+  const dftpav_gridmap* g;
+  // GridMapND::CheckIfEqualUsingGlobalPosition(p, OCCUPIED): false outside the map
+  bool occupied(double px, double py) const {
+    const int cx = (int)std::round((px - g->origin_x) / g->resolution);
+    const int cy = (int)std::round((py - g->origin_y) / g->resolution);
+    if (cx < 0 || cx >= g->size_x || cy < 0 || cy >= g->size_y) return false;
+    return g->data[(size_t)cx + (size_t)cy * g->size_x] == g->occupied_value;
+  }
+  // TrajPlannerAdapter::CheckIfCollisionUsingLine (map_adapter.cpp:117-129)
+  bool line(double p1x, double p1y, double p2x, double p2y, double checkl) const {
+    const double dx = p2x - p1x, dy = p2y - p1y;
+    const double nrm = std::sqrt(dx * dx + dy * dy);
+    for (double dl = 0.0; dl < nrm; dl += checkl) {
+      const double px = dx * dl / nrm + p1x, py = dy * dl / nrm + p1y;
+      if (occupied(px, py)) return true;
+    }
+    return occupied(p2x, p2y);
+  }
+};
+
+struct Vp {
+  double width, length, d_cr;
+};
+
+}  // namespace
+
+extern "C" {
+
+// states [n][3] = (x, y, yaw); cs (optional) [n][2] = (cos yaw, sin yaw) to use instead of libm; hpolys [n][4][4]:
+// plane k = (n_x, n_y, p_x, p_y); expand (optional) [n][4] = the four expansion lengths (+dy, +dx, -dy, -dx).
+int oracle_corridor_rectangles(const dftpav_gridmap* map, const dftpav_corridor_params* cp, int64_t n, const double* states,
+                               const double* cs, double* hpolys, double* expand) {
+  if (!map || !cp || !states || !hpolys || n < 0) return DFTPAV_ERR_INVALID_ARG;
+  const Grid G{map};
+  const double resolution = map->resolution;
+  const double step = resolution * 1.0;  // MGR.cpp:1217
+  const double limitBound = cp->limit_bound;
+  for (int64_t q = 0; q < n; q++) {
+    const double x = states[3 * q], y = states[3 * q + 1], yaw = states[3 * q + 2];
+    const double c = cs ? cs[2 * q] : std::cos(yaw), s = cs ? cs[2 * q + 1] : std::sin(yaw);
+    auto R = [&](double a, double b, double& ox, double& oy) {  // egoR * (a, b)
+      ox = c * a + (-s) * b;
+      oy = s * a + c * b;
+    };
+    double spx = x, spy = y;  // sourcePt
+    Vp vp{cp->veh_width, cp->veh_length, cp->veh_d_cr};
+    const Vp raw = vp;
+    int notfin[4] = {1, 1, 1, 1};
+    double ex[4] = {0.0, 0.0, 0.0, 0.0};
+    while (notfin[0] || notfin[1] || notfin[2] || notfin[3]) {
+      for (int i = 0; i < 4; i++) {
+        if (!notfin[i]) continue;
+        double a1, b1, a2, b2, na1, nb1, na2, nb2;  // body-frame corners of the strip: point1, point2, newpoint1, newpoint2
+        const double hl = vp.length / 2.0, hw = vp.width / 2.0;
+        switch (i) {
+          case 0:  // +dy (MGR.cpp:1320-1349)
+            a1 = hl + vp.d_cr, b1 = hw, a2 = -hl + vp.d_cr, b2 = hw;
+            na1 = hl + vp.d_cr, nb1 = hw + step, na2 = -hl + vp.d_cr, nb2 = hw + step;
+            break;
+          case 1:  // +dx (1351-1380)
+            a1 = hl + vp.d_cr, b1 = -hw, a2 = hl + vp.d_cr, b2 = hw;
+            na1 = step + hl + vp.d_cr, nb1 = -hw, na2 = step + hl + vp.d_cr, nb2 = hw;
+            break;
+          case 2:  // -dy (1382-1411)
+            a1 = -hl + vp.d_cr, b1 = -hw, a2 = hl + vp.d_cr, b2 = -hw;
+            na1 = -hl + vp.d_cr, nb1 = -hw - step, na2 = hl + vp.d_cr, nb2 = -hw - step;
+            break;
+          default:  // -dx (1413-1429)
+            a1 = -hl + vp.d_cr, b1 = hw, a2 = -hl + vp.d_cr, b2 = -hw;
+            na1 = -hl + vp.d_cr - step, nb1 = hw, na2 = -hl + vp.d_cr - step, nb2 = -hw;
+            break;
+        }
+        double p1x, p1y, p2x, p2y, n1x, n1y, n2x, n2y, tx, ty;
+        R(a1, b1, tx, ty), p1x = spx + tx, p1y = spy + ty;
+        R(a2, b2, tx, ty), p2x = spx + tx, p2y = spy + ty;
+        R(na1, nb1, tx, ty), n1x = spx + tx, n1y = spy + ty;
+        R(na2, nb2, tx, ty), n2x = spx + tx, n2y = spy + ty;
+        if (G.line(p1x, p1y, n1x, n1y, resolution / 2.0) || G.line(n1x, n1y, n2x, n2y, resolution / 2.0) ||
+            G.line(n2x, n2y, p2x, p2y, resolution / 2.0)) {
+          notfin[i] = 0;
+          continue;
+        }
+        ex[i] += step;
+        if (ex[i] >= limitBound) {
+          notfin[i] = 0;
+          continue;
+        }
+        // the source rectangle grows by one step in direction i
+        switch (i) {
+          case 0: R(0.0, step / 2.0, tx, ty), vp.width = vp.width + step; break;
+          case 1: R(step / 2.0, 0.0, tx, ty), vp.length = vp.length + step; break;
+          case 2: R(0.0, -step / 2.0, tx, ty), vp.width = vp.width + step; break;
+          default: R(-step / 2.0, 0.0, tx, ty), vp.length = vp.length + step; break;
+        }
+        spx = spx + tx, spy = spy + ty;
+      }
+    }
+    // the polygon from the raw pose and the expansion lengths (MGR.cpp:1433-1460)
+    double* h = hpolys + 16 * q;
+    double tx, ty;
+    R(raw.length / 2.0 + raw.d_cr + ex[1], raw.width / 2.0 + ex[0], tx, ty);
+    h[0] = -s, h[1] = c, h[2] = x + tx, h[3] = y + ty;
+    R(raw.length / 2.0 + raw.d_cr + ex[1], -raw.width / 2.0 - ex[2], tx, ty);
+    h[4] = c, h[5] = s, h[6] = x + tx, h[7] = y + ty;
+    R(-raw.length / 2.0 + raw.d_cr - ex[3], -raw.width / 2.0 - ex[2], tx, ty);
+    h[8] = s, h[9] = -c, h[10] = x + tx, h[11] = y + ty;
+    R(-raw.length / 2.0 + raw.d_cr - ex[3], raw.width / 2.0 + ex[0], tx, ty);
+    h[12] = -c, h[13] = -s, h[14] = x + tx, h[15] = y + ty;
+    if (expand)
+      for (int k = 0; k < 4; k++) expand[4 * q + k] = ex[k];
+  }
+  return DFTPAV_OK;
+}
+
+}  // extern "C"

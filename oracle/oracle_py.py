@@ -27,8 +27,8 @@ _ref = None
 
 def build(force: bool = False) -> None:
     """Compiles the oracle (and oracle/_ref when /root/reference is present) with oracle/Makefile."""
-    if force or not os.path.exists(ORACLE_SO) or os.path.getmtime(ORACLE_SO) < os.path.getmtime(
-            os.path.join(HERE, "dftpav_oracle.cpp")):
+    if force or not os.path.exists(ORACLE_SO) or os.path.getmtime(ORACLE_SO) < max(
+            os.path.getmtime(os.path.join(HERE, f)) for f in ("dftpav_oracle.cpp", "corridor_oracle.cpp")):
         subprocess.check_call(["make", "-C", HERE, "libdftpav_oracle.so"])
     if os.path.exists("/root/reference/src/Plan/traj_planner/include/geo_utils2d/lbfgs.hpp") and (
             force or not os.path.exists(REF_SO)):
@@ -62,6 +62,7 @@ def lib() -> C.CDLL:
         L.oracle_problem_initial_x.restype = None
         L.oracle_problem_fg.restype = C.c_double
         L.oracle_num_threads.argtypes = []
+        L.oracle_corridor_rectangles.argtypes = [C.POINTER(capi.GridMap), C.POINTER(capi.CorridorParams), C.c_int64, dp, dp, dp, dp]
         L.oracle_traj_state.argtypes = [C.c_int, dp, C.c_double, C.c_int, C.c_double, C.c_int, C.c_double, dp, dp]
         _lib = L
     return _lib
@@ -152,6 +153,26 @@ def traj_state(c: np.ndarray, dT: float, singul: int, t: float, clamp: int = 0, 
                                      out.ctypes.data_as(dp), gs.ctypes.data_as(dp))
     assert rc == 0
     return out, gs
+
+
+def corridor_rectangles(grid: np.ndarray, origin_xy, resolution: float, states: np.ndarray, cos_sin=None, params=None,
+                        occupied: int = capi.OCCUPIED):
+    """CPU restatement of TrajPlanner::getRectangleConst (oracle/corridor_oracle.cpp): returns (hpolys [n,4,4], expand [n,4])."""
+    dp = capi.c_double_p
+    grid = np.ascontiguousarray(grid, dtype=np.uint8)
+    states = np.ascontiguousarray(states, dtype=np.float64).reshape(-1, 3)
+    n = states.shape[0]
+    m = capi.GridMap(grid.shape[1], grid.shape[0], float(origin_xy[0]), float(origin_xy[1]), float(resolution),
+                     grid.ctypes.data_as(C.POINTER(C.c_uint8)), occupied)
+    cp = params if params is not None else capi.default_corridor_params()
+    out = np.zeros((n, 4, 4))
+    ex = np.zeros((n, 4))
+    cs = None if cos_sin is None else np.ascontiguousarray(cos_sin, dtype=np.float64).reshape(n, 2)
+    rc = lib().oracle_corridor_rectangles(C.byref(m), C.byref(cp), n, states.ctypes.data_as(dp),
+                                          cs.ctypes.data_as(dp) if cs is not None else None, out.ctypes.data_as(dp),
+                                          ex.ctypes.data_as(dp))
+    assert rc == 0
+    return out, ex
 
 
 REF_OPT_SO = os.path.join(os.path.dirname(os.path.abspath(__file__)), "_ref", "libref_optimizer.so")

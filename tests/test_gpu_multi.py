@@ -6,6 +6,7 @@ import sys
 
 import numpy as np
 import pytest
+import torch  # noqa: F401  (before the library: it brings its own NCCL, which dftpav_create_multi then reuses)
 
 from dftpav_b200 import capi, synth
 
