@@ -471,24 +471,31 @@ __device__ __forceinline__ V2 piece_acc(const double* cm, double t) {
   return dd;
 }
 
-// log_sum_exp (traj_optimizer.cpp:1686-1707); v is overwritten with the exponentials (quirk Q7)
-template <int NV>
-__device__ __forceinline__ double lse(double alpha, double* v, double& exp_sum) {
+// log_sum_exp (traj_optimizer.cpp:1686-1707); v is overwritten with the exponentials (quirk Q7).
+// OUT OF LINE with rolled loops, and so is exp(): the moving-obstacle term calls this 17 times per colliding pair and the
+// inlined form (48 copies of the ~50-instruction exp sequence) made dyn_obstacles ~100 KB of SASS - every call streamed
+// through the 32 KB instruction cache (config 5: `no_instruction` was 60-90 % of all stall samples, profiles/README.md).
+__device__ __noinline__ double exp_ool(double x) { return exp(x); }
+__device__ __noinline__ double lse_n(double alpha, double* v, int nv, double& exp_sum) {
   double d0 = v[0];
   if (alpha > 0) {
-#pragma unroll
-    for (int j = 1; j < NV; j++) d0 = fmax(d0, v[j]);
+#pragma unroll 1
+    for (int j = 1; j < nv; j++) d0 = fmax(d0, v[j]);
   } else {
-#pragma unroll
-    for (int j = 1; j < NV; j++) d0 = fmin(d0, v[j]);
+#pragma unroll 1
+    for (int j = 1; j < nv; j++) d0 = fmin(d0, v[j]);
   }
   exp_sum = 0.0;
-#pragma unroll
-  for (int j = 0; j < NV; j++) {
-    v[j] = exp(alpha * (v[j] - d0));
+#pragma unroll 1
+  for (int j = 0; j < nv; j++) {
+    v[j] = exp_ool(alpha * (v[j] - d0));
     exp_sum += v[j];
   }
   return log(exp_sum) / alpha + d0;
+}
+template <int NV>
+__device__ __forceinline__ double lse(double alpha, double* v, double& exp_sum) {
+  return lse_n(alpha, v, NV, exp_sum);
 }
 
 // cold path (help_eps != 0, the header default of traj_optimizer.h:120): kept out of line to keep the sweep loop small.
@@ -710,45 +717,45 @@ __device__ __noinline__ void dyn_obstacles(const ParamsDev& P, const BatchDev& b
     //      pass the 1.5-car-length distance cull are still metres apart and leave here without a single exp/log.
     {
       double best = -1.0e300;
-#pragma unroll
+#pragma unroll 1
       for (int e = 0; e < 4; e++) {
         const V2 H_tilde = dnU_inv[e] * (Bh_mul(ego_R) * (vle[e + 1] - vle[e]));
         const V2 hr = rowmul(H_tilde, sur_R);
         double vmin = dot(hr, vle[0]);
-#pragma unroll
+#pragma unroll 1
         for (int o = 1; o < 4; o++) vmin = fmin(vmin, dot(hr, vle[o]));
         best = fmax(best, vmin + dot(H_tilde, (sp - sigma) - ego_R * vle[e]));
       }
-#pragma unroll
+#pragma unroll 1
       for (int o = 0; o < 4; o++) {
         const V2 H_tilde = dnU_inv[o] * (Bh_mul(sur_R) * (vle[o + 1] - vle[o]));
         const V2 hr = rowmul(H_tilde, ego_R);
         double vmin = dot(hr, vle[0]);
-#pragma unroll
+#pragma unroll 1
         for (int e = 1; e < 4; e++) vmin = fmin(vmin, dot(hr, vle[e]));
         best = fmax(best, vmin + dot(H_tilde, (sigma - sp) - sur_R * vle[o]));
       }
       if (d_min + 1.3862943611198906 / alpha - best < -1.0e-9) continue;
     }
     double d_test[8];
-#pragma unroll
+#pragma unroll 1
     for (int e = 0; e < 4; e++) {
       const V2 H_tilde = dnU_inv[e] * (Bh_mul(ego_R) * (vle[e + 1] - vle[e]));
       const double d_U_e_tilde = dot(H_tilde, (sp - sigma) - ego_R * vle[e]);
       const V2 hr = rowmul(H_tilde, sur_R);
       double v4[4];
-#pragma unroll
+#pragma unroll 1
       for (int o = 0; o < 4; o++) v4[o] = dot(hr, vle[o]);
       double es;
       d_test[e] = lse<4>(-alpha, v4, es) + d_U_e_tilde;
     }
-#pragma unroll
+#pragma unroll 1
     for (int o = 0; o < 4; o++) {
       const V2 H_tilde = dnU_inv[o] * (Bh_mul(sur_R) * (vle[o + 1] - vle[o]));
       const double d_E_o_tilde = dot(H_tilde, (sigma - sp) - sur_R * vle[o]);
       const V2 hr = rowmul(H_tilde, ego_R);
       double v4[4];
-#pragma unroll
+#pragma unroll 1
       for (int e = 0; e < 4; e++) v4[e] = dot(hr, vle[e]);
       double es;
       d_test[4 + o] = lse<4>(-alpha, v4, es) + d_E_o_tilde;
@@ -780,7 +787,7 @@ __device__ __noinline__ void dyn_obstacles(const ParamsDev& P, const BatchDev& b
       const V2 H_tilde = (1.0 / dnrm) * (Bh_mul(ego_R) * delta_le);
       const V2 hr = rowmul(H_tilde, sur_R);
       double ex[4], es;
-#pragma unroll
+#pragma unroll 1
       for (int o = 0; o < 4; o++) ex[o] = dot(hr, vle[o]);
       (void)lse<4>(-alpha, ex, es);  // ex <- exponentials, es <- their sum
       const double we = d_test[e] / exp_sum_d;
@@ -793,7 +800,7 @@ __device__ __noinline__ void dyn_obstacles(const ParamsDev& P, const BatchDev& b
       const M2 FdBt = mul_BhT(F_dle);
       double pdUt = dot(H_tilde, sv);
       const V2 nr = rowmul(H_tilde, Rud);
-#pragma unroll
+#pragma unroll 1
       for (int o = 0; o < 4; o++) {
         const V2 pd = (FdBt * (sur_R * vle[o])) / dnrm;
         pdU = pdU + (ex[o] / es) * pd;
@@ -810,7 +817,7 @@ __device__ __noinline__ void dyn_obstacles(const ParamsDev& P, const BatchDev& b
       const V2 H_tilde = (1.0 / dnrm) * (Bh_mul(sur_R) * delta_lo);
       const V2 hr = rowmul(H_tilde, ego_R);
       double ex[4], es;
-#pragma unroll
+#pragma unroll 1
       for (int e = 0; e < 4; e++) ex[e] = dot(hr, vle[e]);
       (void)lse<4>(-alpha, ex, es);
       const double wo = d_test[o + 4] / exp_sum_d;
@@ -819,7 +826,7 @@ __device__ __noinline__ void dyn_obstacles(const ParamsDev& P, const BatchDev& b
       const V2 r1 = (Bh_mul(Rud) * delta_lo) / dnrm;
       const V2 r2 = (Bh_mul(sur_R) * delta_lo) / dnrm;
       double pdEt = dot(r1, (sigma - sp) - sur_R * lo) + dot(r2, -sv - Rud * lo);
-#pragma unroll
+#pragma unroll 1
       for (int e = 0; e < 4; e++) {
         const M2 F_le = (temp0_reci * ((double)singul_ * transpose(l_Bl(vle[e])))) - (temp3 * outer(dsigma, ego_R * vle[e]));
         const V2 pd = ((mul_Bh(F_le) * sur_R) * delta_lo) / dnrm;
