@@ -287,7 +287,7 @@ def run_ours(args):
         opt.optimize()
         st = opt.stats()
         kernel_ms.append(st.solve_ms)
-        launches += int(st.n_shapes)  # one persistent solve kernel per problem shape
+        launches += int(st.kernel_launches - st.n_shapes)  # per shape: f(x0) pass + rank kernel (queue order) + the persistent solve kernel
         convergence_flag(int(opt.success_count() == args.batch))  # the real local flag (16 KB read-back), then MIN over ranks
     ev1.record(stream)
     sync_all()

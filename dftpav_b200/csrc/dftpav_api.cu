@@ -40,6 +40,7 @@ cudaError_t launch_sample(cudaStream_t st, const SampleDev& sd, long long nq, co
                           double wheel_base, double* out);
 cudaError_t launch_sample_uniform(cudaStream_t st, const SampleDev& sd, double dt, int max_per_seg, double* out, int* count);
 cudaError_t launch_pack_polytraj(cudaStream_t st, const SampleDev& sd, float* cx, float* cy, float* dur);
+cudaError_t launch_rank_order(cudaStream_t st, const double* f0, const int* prob_id, int count, int* order);
 cudaError_t launch_corridor(cudaStream_t st, const CorridorDev& cd, long long n, const double* states, const double* cos_sin,
                             double* hpolys);
 int ws_doubles_host(int rows, int npad, int S, int has_obs);
@@ -1032,7 +1033,7 @@ int issue_plane_copies(dftpav_handle* h, const dftpav_batch* b, cudaStream_t cs)
 }
 
 // launches the solver kernels of every shape group on the handle's stream (no synchronisation)
-int launch_solve_kernels(dftpav_handle* h, int* launches_out) {
+int launch_solve_kernels(dftpav_handle* h, int* launches_out, bool order_by_f0) {
   cudaStream_t st = h->stream;
   CU_TRY(h, cudaMemsetAsync(h->counter.p, 0, sizeof(int) * 64, st));
   OutDev out;
@@ -1060,6 +1061,27 @@ int launch_solve_kernels(dftpav_handle* h, int* launches_out) {
   hist.ld = h->hist_ld;
   hist.mem = h->prm.lbfgs_mem_size;
   int launches = 0, gi = 0;
+  // scheduling only: serve the queue in order of decreasing f(x0) (rank_order_kernel).  Needs one extra evaluation per
+  // problem with every plane on the device, so the overlapped dftpav_solve (planes still arriving) keeps the input order.
+  const bool lpt = order_by_f0 && !h->param_status && h->dbg_order.empty() && h->dims.B > 4 * h->num_sms;
+  if (lpt) {
+    const int B = h->dims.B;
+    CU_TRY(h, h->fout.ensure(sizeof(double) * B));
+    CU_TRY(h, h->gout.ensure(sizeof(double) * (size_t)B * h->dims.n_stride));
+    for (Group* grp : h->groups) {
+      GroupDev gd;
+      gd.prob_id = grp->d_prob_id.as<int>();
+      gd.count = (int)grp->probs.size();
+      gd.planes = grp->d_planes.as<double>();
+      gd.lu = grp->d_lu.as<double>();
+      gd.order = nullptr;
+      CU_TRY(h, launch_eval(h->has_obs, grp->grid, 32 * grp->warps, grp->smem, st, grp->sh, h->pd, h->bd, gd,
+                            h->x0.as<double>(), h->fout.as<double>(), h->gout.as<double>(), nullptr, nullptr));
+      CU_TRY(h, grp->d_order.ensure(sizeof(int) * gd.count));
+      CU_TRY(h, launch_rank_order(st, h->fout.as<double>(), gd.prob_id, gd.count, grp->d_order.as<int>()));
+      launches += 2;
+    }
+  }
   if (h->param_status) {
     // lbfgs_optimize returns before touching x (lbfgs.hpp:456-501): the decision vector stays the initial packing
     CU_TRY(h, cudaMemcpyAsync(h->o_x.p, h->x0.p, sizeof(double) * (size_t)h->dims.B * h->dims.n_stride,
@@ -1072,7 +1094,7 @@ int launch_solve_kernels(dftpav_handle* h, int* launches_out) {
       gd.count = (int)grp->probs.size();
       gd.planes = grp->d_planes.as<double>();
       gd.lu = grp->d_lu.as<double>();
-      gd.order = nullptr;
+      gd.order = lpt ? grp->d_order.as<int>() : nullptr;
       if (!h->dbg_order.empty()) {  // experiment hook: queue order supplied by the caller (no effect on results)
         std::vector<int> local_of(h->dims.B, -1), ord;
         for (int i = 0; i < (int)grp->probs.size(); i++) local_of[grp->probs[i]] = i;
@@ -1169,7 +1191,7 @@ int dftpav_optimize(dftpav_handle* h) {
   cudaStream_t st = h->stream;
   CU_TRY(h, cudaEventRecord(h->ev[0], st));
   int launches = 0;
-  int rc = launch_solve_kernels(h, &launches);
+  int rc = launch_solve_kernels(h, &launches, true);
   if (rc) return rc;
   CU_TRY(h, cudaEventRecord(h->ev[1], st));
   CU_TRY(h, cudaStreamSynchronize(st));
@@ -1244,7 +1266,7 @@ int dftpav_solve(dftpav_handle* h, const dftpav_batch* batch, const dftpav_resul
   CU_TRY(h, cudaEventRecord(h->ev_copy, st));
   CU_TRY(h, cudaStreamWaitEvent(h->copy_stream, h->ev_copy, 0));
   int launches = 0;
-  rc = launch_solve_kernels(h, &launches);
+  rc = launch_solve_kernels(h, &launches, false);
   if (rc) return rc;
   CU_TRY(h, cudaEventRecord(h->ev[5], st));
   // ... and is fed only now: the persistent kernels are already resident and polling

@@ -513,6 +513,7 @@ __device__ __noinline__ SpeedHelpers speed_helpers_eps(double v2, double eps) {
 }
 
 constexpr int kPlaneChunk = 4;
+constexpr int kObsRound = 16;  // obstacles per compaction round of the moving-obstacle term (pair list: 32 x 16 entries)
 // Plane storage of one problem is pass-major: [pass][chunk of 4 planes][16 components][32 lanes], so the 16 values a
 // lane needs for one chunk sit at compile-time offsets k*32 doubles from one base pointer (immediate-offset LDG.64,
 // each warp-wide load is one contiguous 256 B row).  The host pads the plane count to a multiple of 4 with null planes.
@@ -652,13 +653,18 @@ struct SampleAcc {
   double pen0, pen1, pen2;
 };
 
-// dynamicObsGradCostP (traj_optimizer.cpp:1311-1684) for one sample; `t` = time of the sample inside the segment.
-__device__ __noinline__ void dyn_obstacles(const ParamsDev& P, const BatchDev& bd, int prob, SampleAcc& acc, double omg,
-                                           double step, double t, double gama, int pieceid, int trajres, V2 sigma,
-                                           V2 dsigma, V2 ddsigma, M2 ego_R, int singul_, int trajid, int Nseg,
-                                           double trajtime, int o0, int o1) {
-  if (o1 <= o0) return;
-  const double alpha = P.lse_alpha, d_min = P.d_min, wei_surround = P.wei_surround;
+// dynamicObsGradCostP (traj_optimizer.cpp:1311-1684) for ONE (sample, obstacle) pair; `t` = time of the sample inside the
+// segment.  Returns false where the reference takes `continue` (distance cull, no penetration); otherwise the ingredients of
+// the pair's contributions, which the lane that owns the sample adds to its accumulators (apply_pair) - the pairs of a
+// sweep pass are compacted and evaluated one pair per lane (sweep_segment, stage D), so this 30 KB function runs with
+// (nearly) full warps instead of once per obstacle with the few lanes whose sample is near that obstacle.
+struct PairOut {
+  double pena, penaD, tbar, that;
+  V2 gs, gd;  // dG/dsigma, dG/dsigma'
+};
+__device__ __noinline__ bool dyn_pair(const ParamsDev& P, const BatchDev& bd, int prob, double t, V2 sigma, V2 dsigma,
+                                      V2 ddsigma, M2 ego_R, int singul_, double trajtime, int oi, PairOut& res) {
+  const double alpha = P.lse_alpha, d_min = P.d_min;
   const double temp0 = norm(dsigma);
   const double temp0_reci = (temp0 != 0.0) ? 1.0 / temp0 : 0.0;
   const double temp3 = temp0_reci * temp0_reci;
@@ -668,7 +674,7 @@ __device__ __noinline__ void dyn_obstacles(const ParamsDev& P, const BatchDev& b
   for (int k = 0; k < 4; k++) vle[k] = mk(P.le[k][0], P.le[k][1]);
   vle[4] = vle[0];
 
-  for (int oi = o0; oi < o1; oi++) {
+  {
     const int u = bd.obs_idx[oi];
     ObsView ob;
     ob.P = bd.obs_piece_ptr[u + 1] - bd.obs_piece_ptr[u];
@@ -698,7 +704,7 @@ __device__ __noinline__ void dyn_obstacles(const ParamsDev& P, const BatchDev& b
       h = mk(h.x * exceed, h.y * exceed);
       sp = piece_pos(ob.cf + 12 * i, tt) + exceed * vd + h;
     }
-    if (norm(sp - sigma) > P.cull_dist) continue;  // traj_optimizer.cpp:1393
+    if (norm(sp - sigma) > P.cull_dist) return false;  // traj_optimizer.cpp:1393
 
     // getR / getRdot at pt_time (quirk Q6: evaluated on the clamped last piece past the duration)
     double tr = pt_time;
@@ -735,7 +741,7 @@ __device__ __noinline__ void dyn_obstacles(const ParamsDev& P, const BatchDev& b
         for (int e = 1; e < 4; e++) vmin = fmin(vmin, dot(hr, vle[e]));
         best = fmax(best, vmin + dot(H_tilde, (sigma - sp) - sur_R * vle[o]));
       }
-      if (d_min + 1.3862943611198906 / alpha - best < -1.0e-9) continue;
+      if (d_min + 1.3862943611198906 / alpha - best < -1.0e-9) return false;
     }
     double d_test[8];
 #pragma unroll 1
@@ -762,10 +768,9 @@ __device__ __noinline__ void dyn_obstacles(const ParamsDev& P, const BatchDev& b
     }
     double exp_sum_d;
     const double costp = d_min - lse<8>(alpha, d_test, exp_sum_d);  // d_test now holds the exponentials (quirk Q7)
-    if (costp <= 0.0) continue;
+    if (costp <= 0.0) return false;
     double pena, penaD;
     smoothed_l1(P, costp, pena, penaD);
-    acc.pen1 += omg * step * wei_surround * pena;
 
     // ---- phase C: gradients (traj_optimizer.cpp:1510-1646); per-edge quantities are recomputed instead of stored
     V2 pG_sigma = mk(0.0, 0.0), pG_dsigma = mk(0.0, 0.0);
@@ -837,16 +842,26 @@ __device__ __noinline__ void dyn_obstacles(const ParamsDev& P, const BatchDev& b
       pG_dsigma = pG_dsigma - wo * pdE;
       pG_that -= wo * pdEt;
     }
-    const double pG_tbar = dot(pG_sigma, dsigma) + dot(pG_dsigma, ddsigma);
-
-    const double wc = omg * step * wei_surround * penaD;
-    acc.G0 = acc.G0 + wc * pG_sigma;
-    acc.G1 = acc.G1 + wc * pG_dsigma;
-    acc.gdT += omg * wei_surround * (pena / trajres + penaD * (gama * pG_tbar) * step);
-    acc.gdT += omg * step * wei_surround * pG_that * penaD * pieceid;
-    acc.gdT += omg * step * wei_surround * gama * pG_that * penaD;
-    for (int idx = 0; idx < trajid; idx++) acc.gdT += omg * step * wei_surround * pG_that * penaD * Nseg;  // quirk Q5
+    res.pena = pena, res.penaD = penaD;
+    res.tbar = dot(pG_sigma, dsigma) + dot(pG_dsigma, ddsigma);
+    res.that = pG_that;
+    res.gs = pG_sigma, res.gd = pG_dsigma;
   }
+  return true;
+}
+
+// the pair's contributions (traj_optimizer.cpp:1508, 1650-1676), added by the lane that owns the sample, in obstacle order
+__device__ __forceinline__ void apply_pair(const ParamsDev& P, SampleAcc& acc, const PairOut& r, double omg, double step,
+                                           double gama, int pieceid, int trajres, int trajid, int Nseg) {
+  const double wei_surround = P.wei_surround;
+  acc.pen1 += omg * step * wei_surround * r.pena;
+  const double wc = omg * step * wei_surround * r.penaD;
+  acc.G0 = acc.G0 + wc * r.gs;
+  acc.G1 = acc.G1 + wc * r.gd;
+  acc.gdT += omg * wei_surround * (r.pena / trajres + r.penaD * (gama * r.tbar) * step);
+  acc.gdT += omg * step * wei_surround * r.that * r.penaD * pieceid;
+  acc.gdT += omg * step * wei_surround * gama * r.that * r.penaD;
+  for (int idx = 0; idx < trajid; idx++) acc.gdT += omg * step * wei_surround * r.that * r.penaD * Nseg;  // quirk Q5
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -1091,60 +1106,125 @@ __device__ __forceinline__ void sweep_segment(const ShapeDev& sh, const ParamsDe
     //                  its consumers are most of a pass away)
     if (has_next) load_plane_chunk(pn, pl + (size_t)(pass_next * nchunk) * 512);
 
-    // ---------------- stage D: moving obstacles, velocity / acceleration / curvature limits, expansion
+    // ---------------- stage D1: moving obstacles (traj_optimizer.cpp:636-638)
+    if (HAS_OBS) {
+      // (a) light filter, lane <-> sample: obstacle position at the sample time and the distance cull of
+      //     traj_optimizer.cpp:1393 (same arithmetic as the reference up to that point) -> bit mask of surviving obstacles;
+      // (b) the surviving (sample, obstacle) pairs of the whole pass are compacted into a list (lane-major, obstacle order
+      //     inside a lane) and evaluated ONE PAIR PER LANE by dyn_pair, 32 at a time;
+      // (c) every lane adds the results of its own pairs to its accumulators in obstacle order - the order, and the
+      //     arithmetic, of the reference's loop over the obstacles.
+      const int ob0 = bd.obs_ptr[prob], ob1 = bd.obs_ptr[prob + 1];
+      const double t_samp = piece * dT + step * j;
+      const double t_now = bd.t_now[prob];
+#pragma unroll 1
+      for (int obase = ob0; obase < ob1; obase += kObsRound) {
+        const int nround = min(kObsRound, ob1 - obase);
+        unsigned omask = 0;
+        if (active) {
+#pragma unroll 1
+          for (int k = 0; k < nround; k++) {
+            const int oi = obase + k;
+            double o_start, o_dur, o_uni;
+            int oP, op0;
+            if (oi - ob0 < kObsCap) {
+              const double* m4 = ws.obs + 4 * (oi - ob0);
+              o_start = m4[0];
+              o_dur = m4[1];
+              o_uni = m4[2];
+              const long long pk = __double_as_longlong(m4[3]);
+              oP = (int)(pk >> 32);
+              op0 = (int)(pk & 0xffffffffLL);
+            } else {
+              const int u = bd.obs_idx[oi];
+              o_start = bd.obs_start[u];
+              o_dur = bd.obs_dur[u];
+              o_uni = bd.obs_uniform[u];
+              op0 = bd.obs_piece_ptr[u];
+              oP = bd.obs_piece_ptr[u + 1] - op0;
+            }
+            const double offsettime = t_now - o_start + trajtime;
+            const double pt_time = offsettime + t_samp;
+            const bool inside = pt_time < o_dur;
+            double tt = inside ? pt_time : o_dur;
+            // Trajectory::locatePieceIdx (poly_traj_utils.hpp:510-528): sequential subtraction of the piece durations;
+            // with bit-identical durations the loop needs no loads and stays exact
+            const int idx = locate_piece(o_uni, bd.obs_piece_dur + op0, oP, tt);
+            const double* cm = bd.obs_coeffs + 12L * (op0 + idx);
+            V2 sp = piece_pos(cm, tt);
+            if (!inside) {  // constant-acceleration extrapolation past the prediction (traj_optimizer.cpp:1379-1388)
+              const V2 sa = piece_acc(cm, tt);
+              const V2 vd = piece_vel(cm, tt);
+              const double exceed = pt_time - o_dur;
+              V2 h = 0.5 * sa;
+              h = mk(h.x * exceed, h.y * exceed);
+              h = mk(h.x * exceed, h.y * exceed);
+              sp = sp + exceed * vd + h;
+            }
+            if (!(norm(sp - sigma) > P.cull_dist)) omask |= 1u << k;
+          }
+        }
+        // compaction (all 32 lanes)
+        const int cnt = __popc(omask);
+        int incl = cnt;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+          const int v = __shfl_up_sync(FULL, incl, o);
+          if (lane >= o) incl += v;
+        }
+        const int pbase = incl - cnt;
+        const int total = __shfl_sync(FULL, incl, 31);
+        if (total == 0) continue;
+        unsigned short* plist = reinterpret_cast<unsigned short*>(stage0);  // [<= 32 * kObsRound] (lane << 8) | obstacle
+        double* pres = stage0 + (32 * kObsRound * 2 + 7) / 8;                // [32][8] results of the current chunk
+        {
+          unsigned mm = omask;
+          int q = pbase;
+          while (mm) {
+            const int k = __ffs(mm) - 1;
+            plist[q++] = (unsigned short)((lane << 8) | k);
+            mm &= mm - 1;
+          }
+        }
+        __syncwarp();
+#pragma unroll 1
+        for (int k0 = 0; k0 < total; k0 += 32) {
+          const int pi = k0 + lane;
+          const bool have = pi < total;
+          const int ent = have ? plist[pi] : 0;
+          const int src = ent >> 8;
+          // the sample of my pair lives in lane `src`
+          const V2 sig_s = mk(__shfl_sync(FULL, sigma.x, src), __shfl_sync(FULL, sigma.y, src));
+          const V2 ds_s = mk(__shfl_sync(FULL, dsigma.x, src), __shfl_sync(FULL, dsigma.y, src));
+          const V2 dds_s = mk(__shfl_sync(FULL, ddsigma.x, src), __shfl_sync(FULL, ddsigma.y, src));
+          const double ra = __shfl_sync(FULL, ego_R.a, src), rc = __shfl_sync(FULL, ego_R.c, src);
+          const double ts_s = __shfl_sync(FULL, t_samp, src);
+          PairOut r;
+          bool hit = false;
+          if (have) hit = dyn_pair(P, bd, prob, ts_s, sig_s, ds_s, dds_s, M2{ra, -rc, rc, ra}, singul_, trajtime, obase + (ent & 0xff), r);
+          double* mine = pres + 8 * lane;
+          mine[0] = hit ? r.pena : -1.0;
+          if (hit) mine[1] = r.penaD, mine[2] = r.tbar, mine[3] = r.that, mine[4] = r.gs.x, mine[5] = r.gs.y, mine[6] = r.gd.x, mine[7] = r.gd.y;
+          __syncwarp();
+          for (int q = max(pbase, k0); q < min(pbase + cnt, k0 + 32); q++) {
+            const double* rr = pres + 8 * (q - k0);
+            if (rr[0] >= 0.0) {
+              PairOut w;
+              w.pena = rr[0], w.penaD = rr[1], w.tbar = rr[2], w.that = rr[3];
+              w.gs = mk(rr[4], rr[5]), w.gd = mk(rr[6], rr[7]);
+              apply_pair(P, acc, w, omg, step, alpha, piece, Kp, s, N);
+            }
+          }
+          __syncwarp();
+        }
+      }
+    }
+
+    // ---------------- stage D2: velocity / acceleration / curvature limits, expansion
     double out[12];
 #pragma unroll
     for (int q = 0; q < 12; q++) out[q] = 0.0;
     if (active) {
-      if (HAS_OBS) {  // traj_optimizer.cpp:636-638
-        // Light filter per obstacle: obstacle position at the sample time and the distance cull of
-        // traj_optimizer.cpp:1393 (same arithmetic as the reference up to that point); only the few (sample,
-        // obstacle) pairs that survive run the full signed-distance term (out of line, dyn_obstacles).
-        const double t_samp = piece * dT + step * j;
-        const int ob0 = bd.obs_ptr[prob], ob1 = bd.obs_ptr[prob + 1];
-        const double t_now = bd.t_now[prob];
-        for (int oi = ob0; oi < ob1; oi++) {
-          double o_start, o_dur, o_uni;
-          int oP, op0;
-          if (oi - ob0 < kObsCap) {
-            const double* m4 = ws.obs + 4 * (oi - ob0);
-            o_start = m4[0];
-            o_dur = m4[1];
-            o_uni = m4[2];
-            const long long pk = __double_as_longlong(m4[3]);
-            oP = (int)(pk >> 32);
-            op0 = (int)(pk & 0xffffffffLL);
-          } else {
-            const int u = bd.obs_idx[oi];
-            o_start = bd.obs_start[u];
-            o_dur = bd.obs_dur[u];
-            o_uni = bd.obs_uniform[u];
-            op0 = bd.obs_piece_ptr[u];
-            oP = bd.obs_piece_ptr[u + 1] - op0;
-          }
-          const double offsettime = t_now - o_start + trajtime;
-          const double pt_time = offsettime + t_samp;
-          const bool inside = pt_time < o_dur;
-          double tt = inside ? pt_time : o_dur;
-          // Trajectory::locatePieceIdx (poly_traj_utils.hpp:510-528): sequential subtraction of the piece durations;
-          // with bit-identical durations the loop needs no loads and stays exact
-          const int idx = locate_piece(o_uni, bd.obs_piece_dur + op0, oP, tt);
-          const double* cm = bd.obs_coeffs + 12L * (op0 + idx);
-          V2 sp = piece_pos(cm, tt);
-          if (!inside) {  // constant-acceleration extrapolation past the prediction (traj_optimizer.cpp:1379-1388)
-            const V2 sa = piece_acc(cm, tt);
-            const V2 vd = piece_vel(cm, tt);
-            const double exceed = pt_time - o_dur;
-            V2 h = 0.5 * sa;
-            h = mk(h.x * exceed, h.y * exceed);
-            h = mk(h.x * exceed, h.y * exceed);
-            sp = sp + exceed * vd + h;
-          }
-          if (norm(sp - sigma) > P.cull_dist) continue;
-          dyn_obstacles(P, bd, prob, acc, omg, step, t_samp, alpha, piece, Kp, sigma, dsigma, ddsigma, ego_R, singul_, s, N,
-                        trajtime, oi, oi + 1);
-        }
-      }
       const double z_h4 = z_h1 * vel2_reci;
       const double violaVel = v2 - max_vel * max_vel;
       const double violaAcc = z_h1 * z_h1 * vel2_reci - max_acc * max_acc;
@@ -2664,6 +2744,30 @@ __global__ void corridor_kernel(const CorridorDev cd, long long n, const double*
 }
 
 // ------------------------------------------------------------------------------------------------
+// Queue order (scheduling only, no effect on results): the persistent warps take the problems in order of decreasing
+// f(x0).  The batch time is set by the longest solves, and the initial cost is the one cheap predictor of the solve length
+// (Spearman 0.39-0.46 with the evaluation / iteration counts at config 3): measured 20.3 ms against 21.9 ms in input order at
+// batch 4096 (perfect longest-first: 19.8 ms; tools/order_experiment.py).  Rank by counting: order[#{j: f_j > f_i}] = i, ties
+// by index, NaN first - O(count^2) comparisons, 16 M at batch 4096, on the device (the round-1 version sorted on the host
+// between two stream synchronisations).
+// ------------------------------------------------------------------------------------------------
+__global__ void rank_order_kernel(const double* __restrict__ f0, const int* __restrict__ prob_id, int count,
+                                  int* __restrict__ order) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= count) return;
+  const double fi = f0[prob_id[i]];
+  const bool ni = fi != fi;
+  int rank = 0;
+  for (int j = 0; j < count; j++) {
+    const double fj = f0[prob_id[j]];
+    const bool nj = fj != fj;
+    const bool before = (nj && !ni) || (nj == ni && (ni ? j < i : (fj > fi || (fj == fi && j < i))));
+    rank += before ? 1 : 0;
+  }
+  order[rank] = i;
+}
+
+// ------------------------------------------------------------------------------------------------
 // host-callable launchers (used by dftpav_api.cu)
 // ------------------------------------------------------------------------------------------------
 cudaError_t launch_solve(bool has_obs, int grid, int block, size_t smem, cudaStream_t st, const ShapeDev& sh,
@@ -2711,6 +2815,11 @@ cudaError_t launch_sample_uniform(cudaStream_t st, const SampleDev& sd, double d
 }
 cudaError_t launch_pack_polytraj(cudaStream_t st, const SampleDev& sd, float* cx, float* cy, float* dur) {
   pack_polytraj_kernel<<<sd.G > 0 ? sd.G : 1, 64, 0, st>>>(sd, cx, cy, dur);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_rank_order(cudaStream_t st, const double* f0, const int* prob_id, int count, int* order) {
+  rank_order_kernel<<<(count + 255) / 256, 256, 0, st>>>(f0, prob_id, count, order);
   return cudaGetLastError();
 }
 
