@@ -253,6 +253,8 @@ EXPORTED_SYMBOLS = [
     "dftpav_sample",
     "dftpav_sample_uniform",
     "dftpav_pack_polytraj",
+    "dftpav_minco_fit",
+    "dftpav_state_to_flat_output",
     "dftpav_corridor_set_map",
     "dftpav_corridor_rectangles",
     "dftpav_create_multi",
@@ -306,6 +308,9 @@ def load_library(variant: str = "") -> C.CDLL:
     lib.dftpav_sample.argtypes = [H, C.c_int64, c_int32_p, c_double_p, C.c_int32, C.c_double, c_double_p]
     lib.dftpav_sample_uniform.argtypes = [H, C.c_double, C.c_int32, c_double_p, c_int32_p]
     lib.dftpav_pack_polytraj.argtypes = [H, C.POINTER(C.c_float), C.POINTER(C.c_float), C.POINTER(C.c_float)]
+    lib.dftpav_minco_fit.argtypes = [H, C.c_int32, c_int32_p, c_double_p, c_double_p, c_double_p, c_double_p, c_double_p]
+    lib.dftpav_state_to_flat_output.argtypes = [c_double_p, c_double_p]
+    lib.dftpav_state_to_flat_output.restype = None
     lib.dftpav_corridor_set_map.argtypes = [H, C.POINTER(GridMap)]
     lib.dftpav_corridor_rectangles.argtypes = [H, C.POINTER(CorridorParams), C.c_int64, c_double_p, c_double_p, c_double_p,
                                                C.c_int32]

@@ -40,6 +40,9 @@ cudaError_t launch_sample(cudaStream_t st, const SampleDev& sd, long long nq, co
                           double wheel_base, double* out);
 cudaError_t launch_sample_uniform(cudaStream_t st, const SampleDev& sd, double dt, int max_per_seg, double* out, int* count);
 cudaError_t launch_pack_polytraj(cudaStream_t st, const SampleDev& sd, float* cx, float* cy, float* dur);
+cudaError_t launch_minco_fit(cudaStream_t st, int n_traj, const int* piece_ptr, const double* dT, const double* head,
+                             const double* tail, const double* inner_pts, const long long* inner_ptr, const double* lu_tables,
+                             const int* lu_off, double* scratch, double* coeffs);
 cudaError_t launch_rank_order(cudaStream_t st, const double* f0, const int* prob_id, int count, int* order);
 cudaError_t launch_corridor(cudaStream_t st, const CorridorDev& cd, long long n, const double* states, const double* cos_sin,
                             double* hpolys);
@@ -249,6 +252,7 @@ struct dftpav_handle {
   long long pieces_total = 0;
   // corridor generator: device copy of the occupancy grid, ray-march offsets, and whether planes_raw holds generated polygons
   DevBuf map_data, map_dl, cor_states, cor_cs;
+  DevBuf fit_pp, fit_dT, fit_head, fit_tail, fit_inner, fit_iptr, fit_lu, fit_luoff, fit_scratch, fit_coeffs;  // dftpav_minco_fit
   dftpav_gridmap map_meta{};
   int map_n_dl = 0;
   std::vector<int> dbg_order;  // experiment hook (dftpav_debug_set_order): serve the work queue in this order of problem ids
@@ -608,7 +612,8 @@ int dftpav_destroy(dftpav_handle* h) {
                     &h->obs_start, &h->obs_dur, &h->obs_piece_ptr, &h->obs_piece_dur, &h->obs_coeffs, &h->obs_uniform, &h->x0, &h->xin,
                     &h->fout, &h->gout, &h->o_x, &h->o_cost, &h->o_status, &h->o_success, &h->o_iters, &h->o_evals,
                     &h->o_coeffs, &h->o_dT, &h->counter, &h->hist_s, &h->hist_y, &h->hist_ys, &h->trace, &h->ready, &h->laid, &h->seg_prob, &h->seg_row0, &h->seg_N,
-                    &h->seg_piece0, &h->q_seg, &h->q_t, &h->q_out, &h->q_cnt, &h->map_data, &h->map_dl, &h->cor_states, &h->cor_cs};
+                    &h->seg_piece0, &h->q_seg, &h->q_t, &h->q_out, &h->q_cnt, &h->map_data, &h->map_dl, &h->cor_states, &h->cor_cs, &h->fit_pp, &h->fit_dT, &h->fit_head, &h->fit_tail,
+                    &h->fit_inner, &h->fit_iptr, &h->fit_lu, &h->fit_luoff, &h->fit_scratch, &h->fit_coeffs};
   for (DevBuf* b : bufs) b->release();
   for (auto& e : h->ev)
     if (e) cudaEventDestroy(e);
@@ -1302,6 +1307,70 @@ int dftpav_success_count(dftpav_handle* h, int32_t* n_success) {
   int n = 0;
   for (int v : ok) n += v != 0;
   *n_success = n;
+  return DFTPAV_OK;
+}
+
+void dftpav_state_to_flat_output(const double* state, double* flat) {
+  // TrajPlanner::state_to_flat_output (traj_manager.cpp:139-158); state = (x, y, angle, velocity, acceleration, curvature)
+  double vel = state[3];
+  const double angle = state[2], acc = state[4];
+  const double c = std::cos(angle), s = std::sin(angle);
+  if (vel == 0) vel = 1e-5;
+  flat[0] = state[0], flat[1] = state[1];
+  flat[2] = c * vel + (-s) * 0.0, flat[3] = s * vel + c * 0.0;
+  const double lat = state[5] * std::pow(vel, 2);
+  flat[4] = c * acc + (-s) * lat, flat[5] = s * acc + c * lat;
+}
+
+int dftpav_minco_fit(dftpav_handle* h, int32_t n_traj, const int32_t* piece_ptr, const double* dT, const double* head,
+                     const double* tail, const double* inner_pts, double* coeffs) {
+  if (!h || n_traj < 0 || (n_traj > 0 && (!piece_ptr || !dT || !head || !tail || !inner_pts || !coeffs))) return DFTPAV_ERR_INVALID_ARG;
+  if (n_traj == 0) return DFTPAV_OK;
+  if (piece_ptr[0] != 0) return fail(h, DFTPAV_ERR_INVALID_ARG, "piece_ptr[0] != 0");
+  // LU table per distinct piece count (MinJerkOpt::reset: the factor depends only on N), inner-point prefix
+  std::map<int, int> off_of_N;
+  std::vector<double> tables;
+  std::vector<int> lu_off(n_traj);
+  std::vector<long long> iptr(n_traj + 1, 0);
+  for (int k = 0; k < n_traj; k++) {
+    const int N = piece_ptr[k + 1] - piece_ptr[k];
+    if (N < 2) return fail(h, DFTPAV_ERR_INVALID_ARG, "a fit needs at least 2 pieces");
+    if (N > 4 * kMaxPieces) return fail(h, DFTPAV_ERR_UNSUPPORTED, "more than 256 pieces in one fit");
+    auto it = off_of_N.find(N);
+    if (it == off_of_N.end()) {
+      const int off = (int)tables.size();
+      tables.resize(tables.size() + (size_t)6 * N * kLuLd);
+      BandLU f(N);
+      f.pack(tables.data() + off);
+      it = off_of_N.emplace(N, off).first;
+    }
+    lu_off[k] = it->second;
+    iptr[k + 1] = iptr[k] + 2LL * (N - 1);
+  }
+  const long long NP = piece_ptr[n_traj];
+  CU_TRY(h, cudaSetDevice(h->device));
+  cudaStream_t st = h->stream;
+  auto up = [&](DevBuf& buf, const void* src, size_t bytes) -> cudaError_t {
+    cudaError_t e = buf.ensure(bytes);
+    if (e != cudaSuccess) return e;
+    return cudaMemcpyAsync(buf.p, src, bytes, cudaMemcpyHostToDevice, st);
+  };
+  CU_TRY(h, up(h->fit_pp, piece_ptr, sizeof(int) * (n_traj + 1)));
+  CU_TRY(h, up(h->fit_dT, dT, sizeof(double) * n_traj));
+  CU_TRY(h, up(h->fit_head, head, sizeof(double) * 6 * n_traj));
+  CU_TRY(h, up(h->fit_tail, tail, sizeof(double) * 6 * n_traj));
+  CU_TRY(h, up(h->fit_inner, inner_pts, sizeof(double) * (size_t)iptr[n_traj]));
+  CU_TRY(h, up(h->fit_iptr, iptr.data(), sizeof(long long) * (n_traj + 1)));
+  CU_TRY(h, up(h->fit_lu, tables.data(), sizeof(double) * tables.size()));
+  CU_TRY(h, up(h->fit_luoff, lu_off.data(), sizeof(int) * n_traj));
+  CU_TRY(h, h->fit_scratch.ensure(sizeof(double) * 12 * (size_t)NP));
+  CU_TRY(h, h->fit_coeffs.ensure(sizeof(double) * 12 * (size_t)NP));
+  CU_TRY(h, launch_minco_fit(st, n_traj, h->fit_pp.as<int>(), h->fit_dT.as<double>(), h->fit_head.as<double>(),
+                             h->fit_tail.as<double>(), h->fit_inner.as<double>(), h->fit_iptr.as<long long>(),
+                             h->fit_lu.as<double>(), h->fit_luoff.as<int>(), h->fit_scratch.as<double>(),
+                             h->fit_coeffs.as<double>()));
+  CU_TRY(h, cudaMemcpyAsync(coeffs, h->fit_coeffs.p, sizeof(double) * 12 * (size_t)NP, cudaMemcpyDeviceToHost, st));
+  CU_TRY(h, cudaStreamSynchronize(st));  // (also keeps the host staging vectors alive until the copies are done)
   return DFTPAV_OK;
 }
 

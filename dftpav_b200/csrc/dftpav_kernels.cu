@@ -416,6 +416,21 @@ struct ObsView {
 __device__ __forceinline__ int locate_piece(double uni, const double* __restrict__ dur, int P, double& t) {
   int idx = 0;
   if (uni == uni) {
+    // Power-of-two piece duration (the 1 s prediction step of the reference's obstacle trajectories): every subtraction
+    // t -= uni of the reference's loop is EXACT (the result lies on t's own floating-point grid and is smaller), so the loop
+    // has the closed form idx = ceil(t / uni) - 1, t -= idx * uni, bit for bit - without a dependent chain of 20-30
+    // subtractions per (sample, obstacle).
+    const long long ub = __double_as_longlong(uni);
+    if ((ub & 0x000fffffffffffffLL) == 0 && uni > 0.0 && t > uni && t < 4.0e15 * uni) {
+      const double k = fmin(ceil(t / uni) - 1.0, (double)P);  // steps the loop takes (it stops at idx == P)
+      idx = (int)k;
+      t -= k * uni;
+      if (idx == P) {
+        idx--;
+        t += uni;
+      }
+      return idx;
+    }
     while (idx < P && t > uni) {
       t -= uni;
       idx++;
@@ -2768,6 +2783,70 @@ __global__ void rank_order_kernel(const double* __restrict__ f0, const int* __re
 }
 
 // ------------------------------------------------------------------------------------------------
+// Batched MINCO fits: MinJerkOpt::reset + generate + getTraj (poly_traj_utils.hpp:880-997) for
+// many short trajectories at once - the fits of the predicted obstacle trajectories (TrajPlanner::ConverSurroundTrajFromPoints,
+// traj_manager.cpp:743-789) and of the initial guess (traj_manager.cpp:579-581).  One THREAD per trajectory runs the reference's
+// banded substitutions on the constant LU factor with explicitly rounded operations (no FMA contraction), so the coefficients
+// are BIT-IDENTICAL to the reference's; the work is tiny (a few thousand flops per fit), the batch supplies the parallelism.
+// Output: Piece::coeffMat per piece, 2x6 column-major, HIGHEST power first - the obstacle-pool format of dftpav_batch.
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ double fnma_rn(double a, double b, double c) { return __dadd_rn(c, -__dmul_rn(a, b)); }  // c - a*b, two roundings
+__global__ void minco_fit_kernel(int n_traj, const int* __restrict__ piece_ptr, const double* __restrict__ dT,
+                                 const double* __restrict__ head, const double* __restrict__ tail,
+                                 const double* __restrict__ inner_pts, const long long* __restrict__ inner_ptr,
+                                 const double* __restrict__ lu_tables, const int* __restrict__ lu_off,
+                                 double* __restrict__ scratch, double* __restrict__ coeffs) {
+  const int k = blockIdx.x * blockDim.x + threadIdx.x;
+  if (k >= n_traj) return;
+  const int p0 = piece_ptr[k], N = piece_ptr[k + 1] - p0, n = 6 * N;
+  const double* C = lu_tables + lu_off[k];  // packed LU columns of this N: A(i,j) = C[j*kLuLd + (i - j + 6)]
+  double* b = scratch + 12 * (size_t)p0;    // [6N][2]
+  const double t1 = dT[k], t2 = __dmul_rn(t1, t1), t3 = __dmul_rn(t2, t1), t4 = __dmul_rn(t2, t2), t5 = __dmul_rn(t4, t1);
+  const double tInv[6] = {1.0, __ddiv_rn(1.0, t1), __ddiv_rn(1.0, t2), __ddiv_rn(1.0, t3), __ddiv_rn(1.0, t4), __ddiv_rn(1.0, t5)};
+  // right-hand side (poly_traj_utils.hpp:968-977)
+  for (int i = 0; i < 2 * n; i++) b[i] = 0.0;
+  const double* P = inner_pts + inner_ptr[k];
+  for (int col = 0; col < 2; col++) {
+    b[0 + col] = head[6 * k + 0 + col];
+    b[2 + col] = __dmul_rn(head[6 * k + 2 + col], t1);
+    b[4 + col] = __dmul_rn(head[6 * k + 4 + col], t2);
+    for (int i = 0; i < N - 1; i++) b[2 * (6 * i + 5) + col] = P[2 * i + col];
+    b[2 * (n - 3) + col] = tail[6 * k + 0 + col];
+    b[2 * (n - 2) + col] = __dmul_rn(tail[6 * k + 2 + col], t1);
+    b[2 * (n - 1) + col] = __dmul_rn(tail[6 * k + 4 + col], t2);
+  }
+  // BandedSystem::solve (poly_traj_utils.hpp:805-826)
+  for (int j = 0; j <= n - 1; j++) {
+    const int iM = min(j + 6, n - 1);
+    for (int i = j + 1; i <= iM; i++) {
+      const double a = C[(size_t)j * kLuLd + (i - j + 6)];
+      if (a != 0.0) {
+        b[2 * i] = fnma_rn(a, b[2 * j], b[2 * i]);
+        b[2 * i + 1] = fnma_rn(a, b[2 * j + 1], b[2 * i + 1]);
+      }
+    }
+  }
+  for (int j = n - 1; j >= 0; j--) {
+    const double dj = C[(size_t)j * kLuLd + 6];
+    b[2 * j] = __ddiv_rn(b[2 * j], dj);
+    b[2 * j + 1] = __ddiv_rn(b[2 * j + 1], dj);
+    const int iM = max(0, j - 6);
+    for (int i = iM; i <= j - 1; i++) {
+      const double a = C[(size_t)j * kLuLd + (i - j + 6)];
+      if (a != 0.0) {
+        b[2 * i] = fnma_rn(a, b[2 * j], b[2 * i]);
+        b[2 * i + 1] = fnma_rn(a, b[2 * j + 1], b[2 * i + 1]);
+      }
+    }
+  }
+  // c = b / dT^k (981-984), then getTraj's column reversal (991): highest power first
+  for (int i = 0; i < N; i++)
+    for (int kk = 0; kk < 6; kk++)
+      for (int col = 0; col < 2; col++)
+        coeffs[12 * (size_t)(p0 + i) + 2 * (5 - kk) + col] = __dmul_rn(b[2 * (6 * i + kk) + col], tInv[kk]);
+}
+
+// ------------------------------------------------------------------------------------------------
 // host-callable launchers (used by dftpav_api.cu)
 // ------------------------------------------------------------------------------------------------
 cudaError_t launch_solve(bool has_obs, int grid, int block, size_t smem, cudaStream_t st, const ShapeDev& sh,
@@ -2815,6 +2894,14 @@ cudaError_t launch_sample_uniform(cudaStream_t st, const SampleDev& sd, double d
 }
 cudaError_t launch_pack_polytraj(cudaStream_t st, const SampleDev& sd, float* cx, float* cy, float* dur) {
   pack_polytraj_kernel<<<sd.G > 0 ? sd.G : 1, 64, 0, st>>>(sd, cx, cy, dur);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_minco_fit(cudaStream_t st, int n_traj, const int* piece_ptr, const double* dT, const double* head,
+                             const double* tail, const double* inner_pts, const long long* inner_ptr, const double* lu_tables,
+                             const int* lu_off, double* scratch, double* coeffs) {
+  minco_fit_kernel<<<(n_traj + 63) / 64, 64, 0, st>>>(n_traj, piece_ptr, dT, head, tail, inner_pts, inner_ptr, lu_tables, lu_off,
+                                                      scratch, coeffs);
   return cudaGetLastError();
 }
 

@@ -214,6 +214,22 @@ class BatchOptimizer:
         self._check(self._lib.dftpav_pack_polytraj(self._h, cx.ctypes.data_as(fp), cy.ctypes.data_as(fp), du.ctypes.data_as(fp)))
         return cx, cy, du
 
+    # -- batched MINCO fits (ConverSurroundTrajFromPoints / initial guess) ----------------------------------------------------
+    def minco_fit(self, piece_ptr: np.ndarray, dT: np.ndarray, head: np.ndarray, tail: np.ndarray, inner_pts: np.ndarray):
+        """coeffs [sum N, 12] (Piece::coeffMat, highest power first) of n fits (dftpav_minco_fit)."""
+        pp = np.ascontiguousarray(piece_ptr, dtype=np.int32)
+        n = pp.shape[0] - 1
+        dT = np.ascontiguousarray(dT, dtype=np.float64)
+        head = np.ascontiguousarray(head, dtype=np.float64).reshape(n, 6)
+        tail = np.ascontiguousarray(tail, dtype=np.float64).reshape(n, 6)
+        inner = np.ascontiguousarray(inner_pts, dtype=np.float64).reshape(-1)
+        out = np.zeros((int(pp[-1]), 12))
+        dp = capi.c_double_p
+        self._check(self._lib.dftpav_minco_fit(self._h, n, pp.ctypes.data_as(capi.c_int32_p), dT.ctypes.data_as(dp),
+                                               head.ctypes.data_as(dp), tail.ctypes.data_as(dp), inner.ctypes.data_as(dp),
+                                               out.ctypes.data_as(dp)))
+        return out
+
     # -- corridor generation (TrajPlanner::getRectangleConst on the device) ----------------------------------------------
     def set_map(self, grid: np.ndarray, origin_xy, resolution: float, occupied: int = capi.OCCUPIED):
         """grid: uint8 [size_y, size_x] (dimension 0 of the reference's GridMapND is the fastest-varying index)."""

@@ -287,6 +287,21 @@ int dftpav_sample_uniform(dftpav_handle* h, double dt, int32_t max_per_seg, doub
  * coef_x, coef_y: [6 * sum piece_num], duration: [sum piece_num]. */
 int dftpav_pack_polytraj(dftpav_handle* h, float* coef_x, float* coef_y, float* duration);
 
+/* ---- batched MINCO fits: predicted obstacle trajectories and initial guesses ----
+ * Replaces MinJerkOpt::reset + generate + getTraj (MINCO.hpp:880-997) as TrajPlanner::ConverSurroundTrajFromPoints runs them
+ * for every predicted obstacle trajectory (traj_manager.cpp:743-789: N = states - 1 pieces of the mean duration, inner points =
+ * the intermediate positions, head / tail = state_to_flat_output of the first / last state) and for the initial guess
+ * (traj_manager.cpp:579-581).  Trajectory k has piece_ptr[k+1] - piece_ptr[k] >= 2 pieces of duration dT[k], flat boundary
+ * states head[k][6] / tail[k][6] (2x3 column-major p v a) and 2*(N_k - 1) inner points (concatenated).  coeffs receives
+ * Piece::coeffMat for every piece: [sum N_k][12], 2x6 column-major, HIGHEST power first - directly usable as
+ * dftpav_batch.obs_coeffs (with obs_piece_dur = dT per piece, obs_duration = the SUM of the piece durations).
+ * Bit-identical to the reference's banded solve (explicitly rounded operations, no libm on the path). */
+int dftpav_minco_fit(dftpav_handle* h, int32_t n_traj, const int32_t* piece_ptr, const double* dT, const double* head,
+                     const double* tail, const double* inner_pts, double* coeffs);
+/* TrajPlanner::state_to_flat_output (traj_manager.cpp:139-158), host only (cos / sin / pow of the C library, like the
+ * reference): state = (x, y, angle, velocity, acceleration, curvature) -> flat[6] = 2x3 column-major (p, v, a). */
+void dftpav_state_to_flat_output(const double* state, double* flat);
+
 /* ---- corridor generation (the step immediately before the optimizer) ----
  * Replaces TrajPlanner::getRectangleConst (src/traj_manager.cpp:1211-1469): for every sampled state (x, y, yaw) of the
  * front-end path a safe rectangle is grown cell by cell on the occupancy grid - round-robin over +dy, +dx, -dy, -dx, each
