@@ -314,6 +314,8 @@ def run_ours(args):
     clocks = sampler.stop()  # sampled over both timed regions (value and e2e legs)
     st2 = opt.stats()
     e2e_launches = st2.kernel_launches
+    e2e_breakdown = {"small_arrays_and_state_kernel_ms": st2.upload_ms, "solver_kernels_incl_waiting_for_plane_chunks_ms": st2.solve_ms,
+                     "result_readback_ms": st2.download_ms}
 
     # max over ranks (device-timed); per-rank kernel times to name a straggler
     t = torch.tensor([dev_ms, e2e_ms], dtype=torch.float64, device="cuda")
@@ -347,7 +349,11 @@ def run_ours(args):
                        "lbfgs": "mem 256, past 3, delta 1e-4 (reference defaults)"},
             "clocks": clocks,
             "e2e": {"value": total_solves / (e2e_ms * 1e-3), "unit": UNIT, "h2d_bytes_per_step": int(batch.nbytes()),
-                    "d2h_bytes_per_step": int(sol.nbytes()), "ms_per_step": e2e_ms / args.steps},
+                    "d2h_bytes_per_step": int(sol.nbytes()), "ms_per_step": e2e_ms / args.steps,
+                    "last_step_breakdown_rank0": e2e_breakdown,
+                    "note": "one C-ABI call per step (dftpav_solve): the corridor planes are copied in 16 chunks on a second "
+                            "stream while the persistent solver kernel already runs (input queue order: the f(x0) ordering "
+                            "pass of the resident path needs every plane on the device first)"},
             "gpu_launches": int(launches),
             "gpu_launches_e2e_per_step": int(e2e_launches),
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,

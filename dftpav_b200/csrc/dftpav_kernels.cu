@@ -166,6 +166,7 @@ struct TeamCtl {
   int done;     // cumulative number of helper completions
   int alive;    // 1 until the warp finds the work queue empty
   int prob;     // problem of evaluation `go`
+  int iter;     // L-BFGS iteration of the owner's solve (helpers prefer long-running owners)
   unsigned long long planes;  // plane pointer of that problem
 };
 
@@ -2024,7 +2025,7 @@ __global__ void __launch_bounds__(32 * DFTPAV_MAX_WARPS, 1)
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarp = blockDim.x >> 5;
   if (threadIdx.x < DFTPAV_MAX_WARPS) {
     TeamCtl& c0 = ctl[threadIdx.x];
-    c0.go = go_word(0, 0), c0.h = 0, c0.nhelp = 0, c0.done = 0, c0.alive = threadIdx.x < nwarp ? 1 : 0, c0.prob = -1, c0.planes = 0ull;
+    c0.go = go_word(0, 0), c0.h = 0, c0.nhelp = 0, c0.done = 0, c0.alive = threadIdx.x < nwarp ? 1 : 0, c0.prob = -1, c0.iter = 0, c0.planes = 0ull;
   }
   tma_load_block(smem, grp.lu, (unsigned)(sh.lu_doubles * sizeof(double)), &mbar);  // (contains a __syncthreads)
   WarpWS ws = carve_ws(smem + sh.lu_doubles + warp * sh.ws_doubles, sh);
@@ -2097,6 +2098,7 @@ __global__ void __launch_bounds__(32 * DFTPAV_MAX_WARPS, 1)
         if (lane == 0) {
           hh = min(ld_flag(&ctl[warp].nhelp), kMaxHelp);
           ctl[warp].prob = prob;
+          ctl[warp].iter = k;
           ctl[warp].planes = reinterpret_cast<unsigned long long>(planes);
           __threadfence_block();  // coefficients, segment scalars, problem: visible before the go word
           st_flag(&ctl[warp].go, go_word(seq, hh));
@@ -2108,13 +2110,23 @@ __global__ void __launch_bounds__(32 * DFTPAV_MAX_WARPS, 1)
     } else {
       // ---------------- helper: find an owner of this CTA that is still solving, serve its evaluations
       if (own < 0) {
-        int alive_l = 0, nh_l = 0;
+        int alive_l = 0, nh_l = 0, it_l = 0;
         if (lane < nwarp && lane != warp) {
           alive_l = ld_flag(&ctl[lane].alive);
           nh_l = ld_flag(&ctl[lane].nhelp);
+          it_l = ld_flag(&ctl[lane].iter);
         }
         if (__ballot_sync(FULL, alive_l != 0) == 0u) break;  // nobody left to help
+#ifndef DFTPAV_HELP_PRIORITY
+#define DFTPAV_HELP_PRIORITY 0
+#endif
+#if DFTPAV_HELP_PRIORITY
+        // the owner furthest into its solve first (the problems that set the batch time are the long ones), then fewest helpers
+        int key = (alive_l && nh_l < kMaxHelp) ? ((0x3fff - min(it_l, 0x3fff)) << 12) | (nh_l << 6) | lane : 0x7fffffff;
+#else
         int key = (alive_l && nh_l < kMaxHelp) ? nh_l * 64 + lane : 0x7fffffff;  // fewest helpers first
+        (void)it_l;
+#endif
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) key = min(key, __shfl_xor_sync(FULL, key, o));
         if (key == 0x7fffffff) {
