@@ -1,12 +1,16 @@
 // dftpav_kernels.cu — sm_100a kernels of the batched MINCO / L-BFGS trajectory optimizer.
 //
 // Reference path restated here (file:line of ZJU-FAST-Lab/Dftpav):
-//   costFunctionCallback            src/Plan/traj_planner/src/traj_optimizer.cpp:206-350      -> eval_cost_grad()
-//   addPVAGradCost2CT               traj_optimizer.cpp:422-779                                -> sweep_segment()/sample_eval()
-//   dynamicObsGradCostP/log_sum_exp traj_optimizer.cpp:1311-1707                              -> dyn_obstacles()
-//   MinJerkOpt::generate/calGrads   include/plan_utils/poly_traj_utils.hpp:953-1066           -> minco_* ()
-//   BandedSystem::solve/solveAdj    poly_traj_utils.hpp:805-852                               -> banded_solve()/banded_solve_adj()
-//   lbfgs_optimize / lewisoverton   include/geo_utils2d/lbfgs.hpp:276-390, 440-751            -> lbfgs_solve()
+//   costFunctionCallback            src/Plan/traj_planner/src/traj_optimizer.cpp:206-350      -> eval_pre() / sweep_ranks() / eval_post()
+//   addPVAGradCost2CT               traj_optimizer.cpp:422-779                                -> sweep_segment()
+//   dynamicObsGradCostP/log_sum_exp traj_optimizer.cpp:1311-1707                              -> dyn_pair() / apply_pair() / lse_n()
+//   MinJerkOpt::generate/calGrads   include/plan_utils/poly_traj_utils.hpp:953-1066           -> eval_pre() / eval_post(), dense_forward() / dense_adjoint()
+//   BandedSystem::solve/solveAdj    poly_traj_utils.hpp:805-852                               -> banded_solve() / banded_solve_adj() (large shapes)
+//   lbfgs_optimize / lewisoverton   include/geo_utils2d/lbfgs.hpp:276-390, 440-751            -> solve_kernel() state machine, two_loop()
+//   plane normalisation + copy      traj_optimizer.cpp:15, 49-52                              -> layout_problem()
+//   Trajectory evaluators           poly_traj_utils.hpp:378-406, 554-645                      -> sample_kernel() ...
+//   getRectangleConst               src/traj_manager.cpp:1211-1469, src/map_adapter.cpp:117-129 -> corridor_kernel()
+//   ConverSurroundTrajFromPoints    src/traj_manager.cpp:743-789 (MinJerkOpt::generate)        -> minco_fit_kernel()
 // All arithmetic is IEEE fp64; no fast-math.  One warp per trajectory; nothing here touches tensor cores
 // (there is no dense contraction on this path).
 #include <cuda_runtime.h>
@@ -149,7 +153,7 @@ struct SegScratch {   // 38 doubles per segment
 // releases its helpers, which then look for another owner of the CTA or exit.
 // ------------------------------------------------------------------------------------------------
 #ifndef DFTPAV_VRANKS
-#define DFTPAV_VRANKS 4
+#define DFTPAV_VRANKS 4  // measured at config 3, batch 4096 (k solves/s): 2: 182, 3: 150, 4: 188-193, 6: 192, 8: 180
 #endif
 #ifndef DFTPAV_STRICT
 #define DFTPAV_STRICT 0
@@ -166,7 +170,6 @@ struct TeamCtl {
   int done;     // cumulative number of helper completions
   int alive;    // 1 until the warp finds the work queue empty
   int prob;     // problem of evaluation `go`
-  int iter;     // L-BFGS iteration of the owner's solve (helpers prefer long-running owners)
   unsigned long long planes;  // plane pointer of that problem
 };
 
@@ -2025,7 +2028,7 @@ __global__ void __launch_bounds__(32 * DFTPAV_MAX_WARPS, 1)
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarp = blockDim.x >> 5;
   if (threadIdx.x < DFTPAV_MAX_WARPS) {
     TeamCtl& c0 = ctl[threadIdx.x];
-    c0.go = go_word(0, 0), c0.h = 0, c0.nhelp = 0, c0.done = 0, c0.alive = threadIdx.x < nwarp ? 1 : 0, c0.prob = -1, c0.iter = 0, c0.planes = 0ull;
+    c0.go = go_word(0, 0), c0.h = 0, c0.nhelp = 0, c0.done = 0, c0.alive = threadIdx.x < nwarp ? 1 : 0, c0.prob = -1, c0.planes = 0ull;
   }
   tma_load_block(smem, grp.lu, (unsigned)(sh.lu_doubles * sizeof(double)), &mbar);  // (contains a __syncthreads)
   WarpWS ws = carve_ws(smem + sh.lu_doubles + warp * sh.ws_doubles, sh);
@@ -2098,7 +2101,6 @@ __global__ void __launch_bounds__(32 * DFTPAV_MAX_WARPS, 1)
         if (lane == 0) {
           hh = min(ld_flag(&ctl[warp].nhelp), kMaxHelp);
           ctl[warp].prob = prob;
-          ctl[warp].iter = k;
           ctl[warp].planes = reinterpret_cast<unsigned long long>(planes);
           __threadfence_block();  // coefficients, segment scalars, problem: visible before the go word
           st_flag(&ctl[warp].go, go_word(seq, hh));
@@ -2110,23 +2112,14 @@ __global__ void __launch_bounds__(32 * DFTPAV_MAX_WARPS, 1)
     } else {
       // ---------------- helper: find an owner of this CTA that is still solving, serve its evaluations
       if (own < 0) {
-        int alive_l = 0, nh_l = 0, it_l = 0;
+        int alive_l = 0, nh_l = 0;
         if (lane < nwarp && lane != warp) {
           alive_l = ld_flag(&ctl[lane].alive);
           nh_l = ld_flag(&ctl[lane].nhelp);
-          it_l = ld_flag(&ctl[lane].iter);
         }
         if (__ballot_sync(FULL, alive_l != 0) == 0u) break;  // nobody left to help
-#ifndef DFTPAV_HELP_PRIORITY
-#define DFTPAV_HELP_PRIORITY 0
-#endif
-#if DFTPAV_HELP_PRIORITY
-        // the owner furthest into its solve first (the problems that set the batch time are the long ones), then fewest helpers
-        int key = (alive_l && nh_l < kMaxHelp) ? ((0x3fff - min(it_l, 0x3fff)) << 12) | (nh_l << 6) | lane : 0x7fffffff;
-#else
-        int key = (alive_l && nh_l < kMaxHelp) ? nh_l * 64 + lane : 0x7fffffff;  // fewest helpers first
-        (void)it_l;
-#endif
+        // fewest helpers first (preferring the owner furthest into its solve instead was measured: no difference)
+        int key = (alive_l && nh_l < kMaxHelp) ? nh_l * 64 + lane : 0x7fffffff;
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) key = min(key, __shfl_xor_sync(FULL, key, o));
         if (key == 0x7fffffff) {
