@@ -1168,8 +1168,7 @@ int dftpav_eval(dftpav_handle* h, const double* x, double* f, double* g) {
     gd.lu = grp->d_lu.as<double>();
     gd.order = nullptr;
     CU_TRY(h, launch_eval(h->has_obs, grp->grid, 32 * grp->warps, grp->smem, st, grp->sh, h->pd, h->bd, gd,
-                          h->xin.as<double>(), h->fout.as<double>(), h->gout.as<double>(), h->o_coeffs.as<double>(),
-                          h->o_dT.as<double>()));
+                          h->xin.as<double>(), h->fout.as<double>(), h->gout.as<double>(), nullptr, nullptr));
     launches++;
   }
   CU_TRY(h, cudaEventRecord(h->ev[1], st));
@@ -1256,33 +1255,36 @@ int dftpav_download(dftpav_handle* h, const dftpav_result* out) {
   return DFTPAV_OK;
 }
 
-// One planner call: small arrays and state kernels first, then the solver kernels are launched, and only then the corridor
-// planes (95 % of the bytes) are copied in chunks on a second stream - the solve runs under the copy: a warp waits for
-// the arrival flag of its problem's chunk (layout_problem in dftpav_kernels.cu), the first problems start after the first
+// One planner call: small arrays and state kernels on the main stream, the corridor planes (95 % of the bytes) in chunks on a
+// second stream, and the solver kernels launched right behind them - the solve runs under the copy: a warp waits for the
+// arrival flag of its problem's chunk (layout_problem in dftpav_kernels.cu), the first problems start after the first
 // chunk.  Replaces the deep copy of hPoly_container at the top of OptimizeTrajectory (traj_optimizer.cpp:15).
 int dftpav_solve(dftpav_handle* h, const dftpav_batch* batch, const dftpav_result* out) {
   if (!h) return DFTPAV_ERR_INVALID_ARG;
   int rc = upload_impl(h, batch, kMaxChunks);
   if (rc) return rc;
   cudaStream_t st = h->stream;
-  CU_TRY(h, cudaEventRecord(h->ev[4], st));
-  // the copy stream starts after everything already queued on the main stream (previous results are read, the old plane
-  // buffer is free) ...
+  // The copy stream starts after everything already queued on the main stream (previous results are read, the old plane
+  // buffer is free).  The copies are queued BEFORE the solver kernels are launched: with pinned host buffers they return at
+  // once and run under the kernels; and whatever serialises the device work (a profiler, CUDA_LAUNCH_BLOCKING, pageable
+  // source buffers that the driver stages synchronously) only loses the overlap - the kernels can never be left polling
+  // for planes nobody has queued.
   CU_TRY(h, cudaEventRecord(h->ev_copy, st));
   CU_TRY(h, cudaStreamWaitEvent(h->copy_stream, h->ev_copy, 0));
-  int launches = 0;
-  rc = launch_solve_kernels(h, &launches, false);
-  if (rc) return rc;
-  CU_TRY(h, cudaEventRecord(h->ev[5], st));
-  // ... and is fed only now: the persistent kernels are already resident and polling
   rc = issue_plane_copies(h, batch, h->copy_stream);
-  if (rc) {  // release the polling kernels before reporting the failure
-    cudaMemcpyAsync(h->ready.p, h->h_epoch, sizeof(int) * kMaxChunks, cudaMemcpyHostToDevice, h->copy_stream);
+  if (rc) {
     cudaStreamSynchronize(h->copy_stream);
-    cudaStreamSynchronize(st);
-    h->solved = false;
+    h->uploaded = false;
     return rc;
   }
+  CU_TRY(h, cudaEventRecord(h->ev[4], st));
+  int launches = 0;
+  rc = launch_solve_kernels(h, &launches, false);
+  if (rc) {
+    cudaStreamSynchronize(h->copy_stream);
+    return rc;
+  }
+  CU_TRY(h, cudaEventRecord(h->ev[5], st));
   h->stats.kernel_launches = h->upload_launches + launches;
   h->solved = true;
   rc = dftpav_download(h, out);  // queued behind the kernels; synchronises the main stream

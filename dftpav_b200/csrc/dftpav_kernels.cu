@@ -2658,26 +2658,34 @@ __device__ __forceinline__ bool grid_occupied(const CorridorDev& cd, double px, 
   if (!(fx >= 0.0 && fx < (double)cd.size_x && fy >= 0.0 && fy < (double)cd.size_y)) return false;
   return cd.data[(size_t)(int)fx + (size_t)(int)fy * cd.size_x] == cd.occupied;
 }
-// CheckIfCollisionUsingLine by one warp
+// CheckIfCollisionUsingLine by one warp.  Four chunks of 32 sample points are in flight at a time: a chunk costs two fp64
+// divisions and one dependent byte load from L2 per lane, and the strip sides are up to 25 m (250 points) long - issuing the
+// chunks one after the other left the warp waiting ~700 cycles per chunk (4.5 ms for one wave of states).
 __device__ __forceinline__ bool line_blocked(const CorridorDev& cd, double p1x, double p1y, double p2x, double p2y, int lane) {
   const double dx = __dadd_rn(p2x, -p1x), dy = __dadd_rn(p2y, -p1y);
   const double nrm = sqrt(__dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy)));
+  constexpr int kFly = 4;
   bool hit = false;
-  for (int k0 = 0; k0 < cd.n_dl; k0 += 32) {
-    const int k = k0 + lane;
-    const double dl = k < cd.n_dl ? cd.dl[k] : 1.0e300;
-    const bool on = dl < nrm;
-    bool occ = false;
-    if (on) {
-      const double px = __dadd_rn(__ddiv_rn(__dmul_rn(dx, dl), nrm), p1x);
-      const double py = __dadd_rn(__ddiv_rn(__dmul_rn(dy, dl), nrm), p1y);
-      occ = grid_occupied(cd, px, py);
+  for (int k0 = 0; k0 < cd.n_dl && !hit; k0 += 32 * kFly) {
+    bool occ = false, all_on = true;
+    double dl[kFly];
+#pragma unroll
+    for (int u = 0; u < kFly; u++) {
+      const int k = k0 + 32 * u + lane;
+      dl[u] = k < cd.n_dl ? cd.dl[k] : 1.0e300;
     }
-    if (__any_sync(FULL, occ)) {
-      hit = true;
-      break;
+#pragma unroll
+    for (int u = 0; u < kFly; u++) {
+      const bool on = dl[u] < nrm;
+      all_on = all_on && on;
+      if (on) {
+        const double px = __dadd_rn(__ddiv_rn(__dmul_rn(dx, dl[u]), nrm), p1x);
+        const double py = __dadd_rn(__ddiv_rn(__dmul_rn(dy, dl[u]), nrm), p1y);
+        occ = occ || grid_occupied(cd, px, py);
+      }
     }
-    if (!__all_sync(FULL, on)) break;  // dl is increasing: the segment ends inside this chunk
+    if (__any_sync(FULL, occ)) hit = true;
+    if (!__all_sync(FULL, all_on)) break;  // dl is increasing: the segment ends inside these chunks
   }
   if (!hit) hit = grid_occupied(cd, p2x, p2y);  // the end point itself (map_adapter.cpp:127)
   return hit;
