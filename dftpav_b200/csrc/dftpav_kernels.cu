@@ -2779,20 +2779,29 @@ __global__ void corridor_kernel(const CorridorDev cd, long long n, const double*
 // by index, NaN first - O(count^2) comparisons, 16 M at batch 4096, on the device (the round-1 version sorted on the host
 // between two stream synchronisations).
 // ------------------------------------------------------------------------------------------------
-__global__ void rank_order_kernel(const double* __restrict__ f0, const int* __restrict__ prob_id, int count,
-                                  int* __restrict__ order) {
+__global__ void __launch_bounds__(256) rank_order_kernel(const double* __restrict__ f0, const int* __restrict__ prob_id, int count,
+                                                         int* __restrict__ order) {
+  __shared__ double tile[256];
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= count) return;
-  const double fi = f0[prob_id[i]];
+  const double fi = i < count ? f0[prob_id[i]] : 0.0;
   const bool ni = fi != fi;
   int rank = 0;
-  for (int j = 0; j < count; j++) {
-    const double fj = f0[prob_id[j]];
-    const bool nj = fj != fj;
-    const bool before = (nj && !ni) || (nj == ni && (ni ? j < i : (fj > fi || (fj == fi && j < i))));
-    rank += before ? 1 : 0;
+  for (int j0 = 0; j0 < count; j0 += 256) {  // keys staged through shared memory, 256 at a time (broadcast reads)
+    const int jj = j0 + threadIdx.x;
+    tile[threadIdx.x] = jj < count ? f0[prob_id[jj]] : 0.0;
+    __syncthreads();
+    const int nj_ = min(256, count - j0);
+#pragma unroll 8
+    for (int t = 0; t < nj_; t++) {
+      const double fj = tile[t];
+      const int j = j0 + t;
+      const bool nj = fj != fj;
+      const bool before = (nj && !ni) || (nj == ni && (ni ? j < i : (fj > fi || (fj == fi && j < i))));
+      rank += before ? 1 : 0;
+    }
+    __syncthreads();
   }
-  order[rank] = i;
+  if (i < count) order[rank] = i;
 }
 
 // ------------------------------------------------------------------------------------------------
