@@ -352,8 +352,8 @@ def run_ours(args):
                     "d2h_bytes_per_step": int(sol.nbytes()), "ms_per_step": e2e_ms / args.steps,
                     "last_step_breakdown_rank0": e2e_breakdown,
                     "note": "one C-ABI call per step (dftpav_solve): the corridor planes are copied in 16 chunks on a second "
-                            "stream while the persistent solver kernel already runs (input queue order: the f(x0) ordering "
-                            "pass of the resident path needs every plane on the device first)"},
+                            "stream while the persistent solver kernel already runs; the longest-predicted-first queue is "
+                            "keyed by the plane-free part of f(x0) and only hands out problems whose chunk has arrived"},
             "gpu_launches": int(launches),
             "gpu_launches_e2e_per_step": int(e2e_launches),
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,

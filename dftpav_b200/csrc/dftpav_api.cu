@@ -43,7 +43,8 @@ cudaError_t launch_pack_polytraj(cudaStream_t st, const SampleDev& sd, float* cx
 cudaError_t launch_minco_fit(cudaStream_t st, int n_traj, const int* piece_ptr, const double* dT, const double* head,
                              const double* tail, const double* inner_pts, const long long* inner_ptr, const double* lu_tables,
                              const int* lu_off, double* scratch, double* coeffs);
-cudaError_t launch_rank_order(cudaStream_t st, const double* f0, const int* prob_id, int count, int* order);
+cudaError_t launch_chunk_order(cudaStream_t st, const double* key, const int* prob_id, int count, int chunk, int n_chunks,
+                               int* clist, int* cbeg);
 cudaError_t launch_corridor(cudaStream_t st, const CorridorDev& cd, long long n, const double* states, const double* cos_sin,
                             double* hpolys);
 int ws_doubles_host(int rows, int npad, int S, int has_obs);
@@ -206,7 +207,7 @@ struct DevBuf {
 struct Group {
   ShapeDev sh;
   std::vector<int> probs;
-  DevBuf d_prob_id, d_planes, d_lu, d_order;
+  DevBuf d_prob_id, d_planes, d_lu, d_order, d_clist, d_cq;  // d_cq: cbeg[kMaxChunks+1] then chead[kMaxChunks]
   int warps = 0, grid = 0;
   size_t smem = 0;
 };
@@ -437,6 +438,8 @@ void free_groups(dftpav_handle* h) {
     g->d_planes.release();
     g->d_lu.release();
     g->d_order.release();
+    g->d_clist.release();
+    g->d_cq.release();
     delete g;
   }
   h->group_pool.clear();
@@ -1066,24 +1069,30 @@ int launch_solve_kernels(dftpav_handle* h, int* launches_out, bool order_by_f0) 
   hist.ld = h->hist_ld;
   hist.mem = h->prm.lbfgs_mem_size;
   int launches = 0, gi = 0;
-  // scheduling only: serve the queue in order of decreasing f(x0) (rank_order_kernel).  Needs one extra evaluation per
-  // problem with every plane on the device, so the overlapped dftpav_solve (planes still arriving) keeps the input order.
-  const bool lpt = order_by_f0 && !h->param_status && h->dbg_order.empty() && h->dims.B > 4 * h->num_sms;
+  // scheduling only: serve the queue longest-predicted-first (chunk_order_kernel, fetch_by_chunk).  The key is f(x0)
+  // WITHOUT the corridor term: one extra evaluation per problem that reads no plane, so it also runs in the overlapped
+  // dftpav_solve while the planes are still arriving; the queue only hands out problems of chunks that have arrived.
+  const bool lpt = order_by_f0 && !strict_build_host() && !h->param_status && h->dbg_order.empty() &&
+                   h->dims.B > 4 * h->num_sms;
   if (lpt) {
     const int B = h->dims.B;
     CU_TRY(h, h->fout.ensure(sizeof(double) * B));
     CU_TRY(h, h->gout.ensure(sizeof(double) * (size_t)B * h->dims.n_stride));
     for (Group* grp : h->groups) {
-      GroupDev gd;
+      GroupDev gd{};
       gd.prob_id = grp->d_prob_id.as<int>();
       gd.count = (int)grp->probs.size();
       gd.planes = grp->d_planes.as<double>();
       gd.lu = grp->d_lu.as<double>();
-      gd.order = nullptr;
-      CU_TRY(h, launch_eval(h->has_obs, grp->grid, 32 * grp->warps, grp->smem, st, grp->sh, h->pd, h->bd, gd,
+      ShapeDev sh0 = grp->sh;
+      sh0.H = 0;  // no corridor term, no plane read, no waiting for the upload
+      CU_TRY(h, launch_eval(h->has_obs, grp->grid, 32 * grp->warps, grp->smem, st, sh0, h->pd, h->bd, gd,
                             h->x0.as<double>(), h->fout.as<double>(), h->gout.as<double>(), nullptr, nullptr));
-      CU_TRY(h, grp->d_order.ensure(sizeof(int) * gd.count));
-      CU_TRY(h, launch_rank_order(st, h->fout.as<double>(), gd.prob_id, gd.count, grp->d_order.as<int>()));
+      CU_TRY(h, grp->d_clist.ensure(sizeof(int) * gd.count));
+      CU_TRY(h, grp->d_cq.ensure(sizeof(int) * (2 * kMaxChunks + 1)));
+      CU_TRY(h, cudaMemsetAsync(grp->d_cq.p, 0, sizeof(int) * (2 * kMaxChunks + 1), st));
+      CU_TRY(h, launch_chunk_order(st, h->fout.as<double>(), gd.prob_id, gd.count, h->chunk, h->n_chunks,
+                                   grp->d_clist.as<int>(), grp->d_cq.as<int>()));
       launches += 2;
     }
   }
@@ -1094,12 +1103,19 @@ int launch_solve_kernels(dftpav_handle* h, int* launches_out, bool order_by_f0) 
   } else {
     for (Group* grp : h->groups) {
       if (gi >= 64) return fail(h, DFTPAV_ERR_UNSUPPORTED, "more than 64 distinct shapes in one batch");
-      GroupDev gd;
+      GroupDev gd{};
       gd.prob_id = grp->d_prob_id.as<int>();
       gd.count = (int)grp->probs.size();
       gd.planes = grp->d_planes.as<double>();
       gd.lu = grp->d_lu.as<double>();
-      gd.order = lpt ? grp->d_order.as<int>() : nullptr;
+      gd.order = nullptr;
+      if (lpt) {
+        gd.clist = grp->d_clist.as<int>();
+        gd.cbeg = grp->d_cq.as<int>();
+        gd.chead = grp->d_cq.as<int>() + kMaxChunks + 1;
+        gd.key = h->fout.as<double>();
+        gd.n_chunks = h->n_chunks;
+      }
       if (!h->dbg_order.empty()) {  // experiment hook: queue order supplied by the caller (no effect on results)
         std::vector<int> local_of(h->dims.B, -1), ord;
         for (int i = 0; i < (int)grp->probs.size(); i++) local_of[grp->probs[i]] = i;
@@ -1161,7 +1177,7 @@ int dftpav_eval(dftpav_handle* h, const double* x, double* f, double* g) {
   CU_TRY(h, cudaEventRecord(h->ev[0], st));
   int launches = 0;
   for (Group* grp : h->groups) {
-    GroupDev gd;
+    GroupDev gd{};
     gd.prob_id = grp->d_prob_id.as<int>();
     gd.count = (int)grp->probs.size();
     gd.planes = grp->d_planes.as<double>();
@@ -1279,7 +1295,7 @@ int dftpav_solve(dftpav_handle* h, const dftpav_batch* batch, const dftpav_resul
   }
   CU_TRY(h, cudaEventRecord(h->ev[4], st));
   int launches = 0;
-  rc = launch_solve_kernels(h, &launches, false);
+  rc = launch_solve_kernels(h, &launches, true);
   if (rc) {
     cudaStreamSynchronize(h->copy_stream);
     return rc;
@@ -1558,9 +1574,12 @@ int dftpav_debug_phase_clock(dftpav_handle* h, int enable, unsigned long long* c
   static unsigned long long* d_clk = nullptr;
   CU_TRY(h, cudaSetDevice(h->device));
   CU_TRY(h, cudaStreamSynchronize(h->stream));
-  if (!d_clk) CU_TRY(h, cudaMalloc(&d_clk, 8 * sizeof(unsigned long long)));
-  if (cycles8) CU_TRY(h, cudaMemcpy(cycles8, d_clk, 8 * sizeof(unsigned long long), cudaMemcpyDeviceToHost));
-  CU_TRY(h, cudaMemset(d_clk, 0, 8 * sizeof(unsigned long long)));
+  if (!d_clk) CU_TRY(h, cudaMalloc(&d_clk, 16 * sizeof(unsigned long long)));
+  // slots 8..15 (filled by -DDFTPAV_PHASE_FINE=1 builds only) are returned when enable == 2 (cycles8 then holds 16 values)
+  if (cycles8)
+    CU_TRY(h, cudaMemcpy(cycles8, d_clk, (enable == 2 ? 16 : 8) * sizeof(unsigned long long), cudaMemcpyDeviceToHost));
+  if (enable == 2) return DFTPAV_OK;
+  CU_TRY(h, cudaMemset(d_clk, 0, 16 * sizeof(unsigned long long)));
   CU_TRY(h, set_phase_clock(enable ? d_clk : nullptr));
   return DFTPAV_OK;
 }

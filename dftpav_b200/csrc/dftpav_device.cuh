@@ -99,6 +99,14 @@ struct GroupDev {
   double* planes;               // tiled SoA: [count][H][4][Mpad], filled by the kernels on first use (layout_problem)
   const double* lu;             // packed LU block of this shape
   const int* order;             // work list: order[w] = local index served w-th, or nullptr (input order)
+  // longest-predicted-first queue that respects the arrival of the plane chunks (nullptr: the plain counter above).
+  // The problems of upload chunk c (global problem id / chunk size) are listed in clist[cbeg[c] .. cbeg[c+1]) by
+  // decreasing key; a fetching warp takes the best head among the chunks that have ARRIVED (BatchDev::ready).
+  const int* clist;             // [count] local indices
+  const int* cbeg;              // [n_chunks + 1]
+  int* chead;                   // [n_chunks] entries already taken per chunk (zeroed before the launch)
+  const double* key;            // [B] by global problem id: f(x0) without the corridor term (needs no plane)
+  int n_chunks;
 };
 
 struct OutDev {

@@ -1385,6 +1385,25 @@ __device__ __forceinline__ void sweep_ranks(const ShapeDev& sh, const ParamsDev&
 // ------------------------------------------------------------------------------------------------
 // diagnostic: when non-null, lane 0 of every warp adds the cycles spent in each phase of an evaluation
 __device__ unsigned long long* g_phase_clock = nullptr;
+// finer split of the L-BFGS part (slots 8..15), only in diagnostic builds (-DDFTPAV_PHASE_FINE=1, tools/lone_phases.py)
+#ifndef DFTPAV_TWO_LOOP_PD2
+#define DFTPAV_TWO_LOOP_PD2 0
+#endif
+#ifndef DFTPAV_PHASE_FINE
+#define DFTPAV_PHASE_FINE 0
+#endif
+#if DFTPAV_PHASE_FINE
+#define FINE_T0() long long t_f_ = clock64()
+#define FINE_ADD(slot)                                                                                      \
+  do {                                                                                                      \
+    const long long n_ = clock64();                                                                         \
+    if (g_phase_clock && lane == 0) atomicAdd(g_phase_clock + (slot), (unsigned long long)(n_ - t_f_));     \
+    t_f_ = n_;                                                                                              \
+  } while (0)
+#else
+#define FINE_T0()
+#define FINE_ADD(slot)
+#endif
 __device__ __noinline__ long long phase_mark(unsigned long long* pc, int idx, long long t_prev, int lane) {
   __syncwarp();
   const long long now = clock64();
@@ -1808,7 +1827,7 @@ __global__ void __launch_bounds__(32 * DFTPAV_MAX_WARPS, 1)
   for (int local = blockIdx.x * nwarp + warp; local < grp.count; local += gridDim.x * nwarp) {
     const int prob = grp.prob_id[local];
     double* planes = grp.planes + (size_t)local * sh.H * 4 * sh.Mpad;
-    layout_problem(sh, bd, prob, planes, lane);
+    if (sh.H > 0) layout_problem(sh, bd, prob, planes, lane);  // H == 0: the plane-free ordering pass (planes may still be in flight)
     long long t_prev = 0;
     for (int i = lane; i < sh.n; i += 32) ws.x[i] = xin[(size_t)prob * bd.n_stride + i];
     __syncwarp();
@@ -1964,6 +1983,92 @@ __device__ __noinline__ void two_loop(double* d_sm, double* alpha_sm, const doub
   __syncwarp();
 }
 
+// Prefetch distance 2: three register buffers, the loop unrolled by three (no register moves).
+template <int NPL>
+__device__ __noinline__ void two_loop_pd2(double* d_sm, double* alpha_sm, const double* __restrict__ lm_s,
+                                          const double* __restrict__ lm_y, const double* __restrict__ lm_ys, int ld, int m,
+                                          int end, int bound_in, int n, int lane, double ys, double yy) {
+  const int bound = __shfl_sync(FULL, bound_in, 0);
+  double d[NPL], s_[3][NPL], y_[3][NPL], r_[3];
+  bool ok[NPL];
+#pragma unroll
+  for (int e = 0; e < NPL; e++) {
+    ok[e] = lane + 32 * e < n;
+    d[e] = ok[e] ? d_sm[lane + 32 * e] : 0.0;
+  }
+  auto load = [&](int q, int j) {
+    const double* sj = lm_s + (size_t)j * ld + lane;
+    const double* yj = lm_y + (size_t)j * ld + lane;
+#pragma unroll
+    for (int e = 0; e < NPL; e++) {
+      s_[q][e] = ok[e] ? sj[32 * e] : 0.0;
+      y_[q][e] = ok[e] ? yj[32 * e] : 0.0;
+    }
+    r_[q] = lm_ys[j];
+  };
+  int j = end - 1;
+  if (j < 0) j += m;
+  int jf = j;
+  load(0, jf);
+  jf = jf == 0 ? m - 1 : jf - 1;
+  if (bound > 1) load(1, jf);
+  jf = jf == 0 ? m - 1 : jf - 1;
+#pragma unroll 1
+  for (int i = 0; i < bound; i += 3) {
+#pragma unroll
+    for (int q = 0; q < 3; q++) {
+      if (i + q < bound) {
+        if (i + q + 2 < bound) {
+          load((q + 2) % 3, jf);
+          jf = jf == 0 ? m - 1 : jf - 1;
+        }
+        double part = 0.0;
+#pragma unroll
+        for (int e = 0; e < NPL; e++) part += s_[q][e] * d[e];
+        const double a = DFTPAV_OVER_YS(warp_sum(part), r_[q]);
+        if (lane == 0) alpha_sm[j] = a;
+        const double na = -a;
+#pragma unroll
+        for (int e = 0; e < NPL; e++) d[e] += na * y_[q][e];
+        if (i + q + 1 < bound) j = j == 0 ? m - 1 : j - 1;
+      }
+    }
+  }
+  const double scl = ys / yy;
+#pragma unroll
+  for (int e = 0; e < NPL; e++) d[e] *= scl;
+  __syncwarp();
+  jf = j;
+  load(0, jf);
+  jf = jf + 1 == m ? 0 : jf + 1;
+  if (bound > 1) load(1, jf);
+  jf = jf + 1 == m ? 0 : jf + 1;
+#pragma unroll 1
+  for (int i = 0; i < bound; i += 3) {
+#pragma unroll
+    for (int q = 0; q < 3; q++) {
+      if (i + q < bound) {
+        if (i + q + 2 < bound) {
+          load((q + 2) % 3, jf);
+          jf = jf + 1 == m ? 0 : jf + 1;
+        }
+        double part = 0.0;
+#pragma unroll
+        for (int e = 0; e < NPL; e++) part += y_[q][e] * d[e];
+        const double beta = DFTPAV_OVER_YS(warp_sum(part), r_[q]);
+        const double a = alpha_sm[j] - beta;
+#pragma unroll
+        for (int e = 0; e < NPL; e++) d[e] += a * s_[q][e];
+        j = j + 1 == m ? 0 : j + 1;
+      }
+    }
+  }
+#pragma unroll
+  for (int e = 0; e < NPL; e++)
+    if (ok[e]) d_sm[lane + 32 * e] = d[e];
+  __syncwarp();
+}
+
 // Generic variant for any n (up to the 517 variables of 4 segments x 64 pieces): the direction stays in shared memory.
 // Also the form of the strict build: warp_dot is then the sequential sum of the reference (lbfgs.hpp:719-736).
 __device__ __noinline__ void two_loop_generic(double* d_sm, double* alpha_sm, const double* __restrict__ lm_s,
@@ -2018,6 +2123,55 @@ __device__ __forceinline__ int ld_flag(const int* p) { return *reinterpret_cast<
 __device__ __forceinline__ void st_flag(int* p, int v) { *reinterpret_cast<volatile int*>(p) = v; }
 __device__ __forceinline__ int go_word(int seq, int h) { return (seq << 4) | (h + 1); }  // h = -1: retired
 
+// Work fetch of the arrival-aware longest-first queue (GroupDev::clist): lane c looks at upload chunk c - is it on the
+// device, what is the key of its best remaining problem - the warp takes the largest key (NaN first, ties to the lower
+// chunk) with one atomicAdd on that chunk's head; a lost race (the head moved past the end) retries.  Returns the local
+// index, or -1 when every chunk is exhausted.  While only chunks that are still in flight have problems left, the warp
+// sleeps and looks again.  Scheduling only: no effect on any result.
+__device__ __noinline__ int fetch_by_chunk(const int* __restrict__ clist, const int* __restrict__ cbeg, int* chead,
+                                           const double* __restrict__ key, const int* __restrict__ prob_id, int n_chunks,
+                                           const int* ready, int epoch, int lane) {
+  while (true) {
+    double k = 0.0;
+    int state = 0;  // 0 exhausted, 1 available, 2 not yet arrived
+    if (lane < n_chunks) {
+      const int beg = cbeg[lane], endc = cbeg[lane + 1];
+      const int hd = *reinterpret_cast<const volatile int*>(chead + lane);
+      if (beg + hd < endc) {
+        if (*reinterpret_cast<const volatile int*>(ready + lane) == epoch) {
+          state = 1;
+          k = key[prob_id[clist[beg + hd]]];
+          if (k != k) k = __longlong_as_double(0x7ff0000000000000LL);  // NaN first
+        } else {
+          state = 2;
+        }
+      }
+    }
+    const unsigned avail = __ballot_sync(FULL, state == 1);
+    if (avail == 0u) {
+      if (__ballot_sync(FULL, state == 2) == 0u) return -1;
+      __nanosleep(500);
+      continue;
+    }
+    int best = state == 1 ? lane : 64;
+    if (state != 1) k = -__longlong_as_double(0x7ff0000000000000LL);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      const double ko = __shfl_xor_sync(FULL, k, o);
+      const int bo = __shfl_xor_sync(FULL, best, o);
+      if (ko > k || (ko == k && bo < best)) k = ko, best = bo;
+    }
+    int got = -1;
+    if (lane == 0) {
+      const int beg = cbeg[best], endc = cbeg[best + 1];
+      const int old = atomicAdd(chead + best, 1);
+      if (beg + old < endc) got = clist[beg + old];
+    }
+    got = __shfl_sync(FULL, got, 0);
+    if (got >= 0) return got;
+  }
+}
+
 template <bool HAS_OBS>
 __global__ void __launch_bounds__(32 * DFTPAV_MAX_WARPS, 1)
     solve_kernel(const __grid_constant__ ShapeDev sh, const __grid_constant__ ParamsDev P, const BatchDev bd,
@@ -2062,8 +2216,14 @@ __global__ void __launch_bounds__(32 * DFTPAV_MAX_WARPS, 1)
       // ---------------- owner: take a problem if needed, first part of the evaluation, publish it to the team
       if (phase == PH_FETCH) {
         int local = 0;
-        if (lane == 0) local = atomicAdd(work_counter, 1);
-        local = __shfl_sync(FULL, local, 0);
+        if (grp.clist) {
+          local = fetch_by_chunk(grp.clist, grp.cbeg, grp.chead, grp.key, grp.prob_id, grp.n_chunks, bd.ready, bd.epoch, lane);
+          if (local < 0) local = grp.count;
+        } else {
+          if (lane == 0) local = atomicAdd(work_counter, 1);
+          local = __shfl_sync(FULL, local, 0);
+          if (local < grp.count && grp.order) local = grp.order[local];
+        }
         if (local >= grp.count) {
           // the queue is empty: retire as an owner (releases my helpers), help the others or leave
           if (lane == 0) {
@@ -2076,7 +2236,6 @@ __global__ void __launch_bounds__(32 * DFTPAV_MAX_WARPS, 1)
           helper = true;
           continue;
         }
-        if (grp.order) local = grp.order[local];
         prob = grp.prob_id[local];
         planes = grp.planes + (size_t)local * sh.H * 4 * sh.Mpad;
         layout_problem(sh, bd, prob, grp.planes + (size_t)local * sh.H * 4 * sh.Mpad, lane);
@@ -2214,6 +2373,7 @@ __global__ void __launch_bounds__(32 * DFTPAV_MAX_WARPS, 1)
 #endif
     evals++;
     if (g_phase_clock) t_logic = clock64();
+    FINE_T0();
 
     bool start_ls = false;   // begin a new line search from the current (x, g, d, step)
     bool finish = false;     // problem done: write results
@@ -2288,11 +2448,13 @@ __global__ void __launch_bounds__(32 * DFTPAV_MAX_WARPS, 1)
           tr[2] = (double)ls;
         }
       }
+      FINE_ADD(8);  // line-search trial logic
       if (ls == 0) {
         // next trial point
 #pragma unroll 1
         for (int i = lane; i < n; i += 32) ws.x[i] = ws.xp[i] + step * ws.d[i];
         __syncwarp();
+        FINE_ADD(9);  // next trial point
         continue;
       }
       if (ls < 0) {
@@ -2325,6 +2487,7 @@ __global__ void __launch_bounds__(32 * DFTPAV_MAX_WARPS, 1)
           ret = DFTPAV_LBFGSERR_MAXIMUMITERATION;
           finish = true;
         }
+        FINE_ADD(10);  // end-of-iteration tests
         if (!finish) {
           ++k;
           // history update (lbfgs.hpp:676-687)
@@ -2357,6 +2520,7 @@ __global__ void __launch_bounds__(32 * DFTPAV_MAX_WARPS, 1)
           if (lane == 0) lm_ys[end] = DFTPAV_STORE_YS(ys);
           __syncwarp();
           const double cau = ss * sqrt(gg) * P.cautious_factor;
+          FINE_ADD(11);  // history update
           if (ys > cau) {
             ++bound;
             bound = m < bound ? m : bound;
@@ -2366,15 +2530,22 @@ __global__ void __launch_bounds__(32 * DFTPAV_MAX_WARPS, 1)
 #else
             if (npl <= 3) {
               // the direction in registers (n <= 96)
+#if DFTPAV_TWO_LOOP_PD2
+              if (npl == 1) two_loop_pd2<1>(ws.d, alpha_sm, lm_s, lm_y, lm_ys, ld, m, end, bound, n, lane, ys, yy);
+              else if (npl == 2) two_loop_pd2<2>(ws.d, alpha_sm, lm_s, lm_y, lm_ys, ld, m, end, bound, n, lane, ys, yy);
+              else two_loop_pd2<3>(ws.d, alpha_sm, lm_s, lm_y, lm_ys, ld, m, end, bound, n, lane, ys, yy);
+#else
               if (npl == 1) two_loop<1>(ws.d, alpha_sm, lm_s, lm_y, lm_ys, ld, m, end, bound, n, lane, ys, yy);
               else if (npl == 2) two_loop<2>(ws.d, alpha_sm, lm_s, lm_y, lm_ys, ld, m, end, bound, n, lane, ys, yy);
               else two_loop<3>(ws.d, alpha_sm, lm_s, lm_y, lm_ys, ld, m, end, bound, n, lane, ys, yy);
+#endif
             } else {
               // larger problems (up to 4 x 64 pieces, n = 517): the direction stays in shared memory
               two_loop_generic(ws.d, alpha_sm, lm_s, lm_y, lm_ys, ld, m, end, bound, n, lane, ys, yy);
             }
 #endif
           }
+          FINE_ADD(12);  // two-loop recursion
           step = 1.0;
           start_ls = true;
         }
@@ -2412,6 +2583,7 @@ __global__ void __launch_bounds__(32 * DFTPAV_MAX_WARPS, 1)
           phase = PH_LS;
         }
       }
+      FINE_ADD(13);  // line-search head
     }
 
     if (finish) {
@@ -2773,35 +2945,45 @@ __global__ void corridor_kernel(const CorridorDev cd, long long n, const double*
 
 // ------------------------------------------------------------------------------------------------
 // Queue order (scheduling only, no effect on results): the persistent warps take the problems in order of decreasing
-// f(x0).  The batch time is set by the longest solves, and the initial cost is the one cheap predictor of the solve length
-// (Spearman 0.39-0.46 with the evaluation / iteration counts at config 3): measured 20.3 ms against 21.9 ms in input order at
-// batch 4096 (perfect longest-first: 19.8 ms; tools/order_experiment.py).  Rank by counting: order[#{j: f_j > f_i}] = i, ties
-// by index, NaN first - O(count^2) comparisons, 16 M at batch 4096, on the device (the round-1 version sorted on the host
-// between two stream synchronisations).
+// predicted solve length.  The batch time is set by the longest solves, and the initial cost is the one cheap predictor of
+// the solve length (Spearman 0.38-0.46 with the evaluation count at config 3; the part of f(x0) that needs NO corridor
+// plane - jerk, time, feasibility penalties, moving obstacles - ranks as well as the whole: 0.376 vs 0.378, 768 problems
+// through the oracle), so the ordering pass runs while the planes are still being uploaded.  Measured at batch 4096: 20.3 ms
+// against 21.9 ms in input order (perfect longest-first: 19.8 ms; tools/order_experiment.py).
+// Rank by counting, per upload chunk: clist[#{j: chunk_j < chunk_i} + #{j in my chunk: key_j > key_i}] = i, ties by
+// index, NaN first - O(count^2) comparisons, 16 M at batch 4096, on the device; cbeg[c] = first list entry of chunk c.
 // ------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256) rank_order_kernel(const double* __restrict__ f0, const int* __restrict__ prob_id, int count,
-                                                         int* __restrict__ order) {
+__global__ void __launch_bounds__(256) chunk_order_kernel(const double* __restrict__ key, const int* __restrict__ prob_id,
+                                                          int count, int chunk, int n_chunks, int* __restrict__ clist,
+                                                          int* __restrict__ cbeg) {
   __shared__ double tile[256];
+  __shared__ int tchunk[256];
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  const double fi = i < count ? f0[prob_id[i]] : 0.0;
+  const double fi = i < count ? key[prob_id[i]] : 0.0;
+  const int ci = i < count ? prob_id[i] / chunk : 0;
   const bool ni = fi != fi;
-  int rank = 0;
+  int pos = 0;         // problems of my chunk that are served before me
+  int cnt_below = 0;   // (threads 0..n_chunks of block 0) problems in chunks below threadIdx.x
   for (int j0 = 0; j0 < count; j0 += 256) {  // keys staged through shared memory, 256 at a time (broadcast reads)
     const int jj = j0 + threadIdx.x;
-    tile[threadIdx.x] = jj < count ? f0[prob_id[jj]] : 0.0;
+    tile[threadIdx.x] = jj < count ? key[prob_id[jj]] : 0.0;
+    tchunk[threadIdx.x] = jj < count ? prob_id[jj] / chunk : 0x7fffffff;
     __syncthreads();
     const int nj_ = min(256, count - j0);
 #pragma unroll 8
     for (int t = 0; t < nj_; t++) {
       const double fj = tile[t];
+      const int cj = tchunk[t];
       const int j = j0 + t;
       const bool nj = fj != fj;
       const bool before = (nj && !ni) || (nj == ni && (ni ? j < i : (fj > fi || (fj == fi && j < i))));
-      rank += before ? 1 : 0;
+      pos += (cj < ci || (cj == ci && before)) ? 1 : 0;  // chunks are laid out one after the other
+      cnt_below += cj < (int)threadIdx.x ? 1 : 0;
     }
     __syncthreads();
   }
-  if (i < count) order[rank] = i;
+  if (i < count) clist[pos] = i;
+  if (blockIdx.x == 0 && (int)threadIdx.x <= n_chunks) cbeg[threadIdx.x] = cnt_below;
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -2927,8 +3109,9 @@ cudaError_t launch_minco_fit(cudaStream_t st, int n_traj, const int* piece_ptr, 
   return cudaGetLastError();
 }
 
-cudaError_t launch_rank_order(cudaStream_t st, const double* f0, const int* prob_id, int count, int* order) {
-  rank_order_kernel<<<(count + 255) / 256, 256, 0, st>>>(f0, prob_id, count, order);
+cudaError_t launch_chunk_order(cudaStream_t st, const double* key, const int* prob_id, int count, int chunk, int n_chunks,
+                               int* clist, int* cbeg) {
+  chunk_order_kernel<<<(count + 255) / 256, 256, 0, st>>>(key, prob_id, count, chunk, n_chunks, clist, cbeg);
   return cudaGetLastError();
 }
 
