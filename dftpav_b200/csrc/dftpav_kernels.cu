@@ -2953,37 +2953,45 @@ __global__ void corridor_kernel(const CorridorDev cd, long long n, const double*
 // Rank by counting, per upload chunk: clist[#{j: chunk_j < chunk_i} + #{j in my chunk: key_j > key_i}] = i, ties by
 // index, NaN first - O(count^2) comparisons, 16 M at batch 4096, on the device; cbeg[c] = first list entry of chunk c.
 // ------------------------------------------------------------------------------------------------
+constexpr int kOrderTile = 2048;  // keys per shared-memory tile
 __global__ void __launch_bounds__(256) chunk_order_kernel(const double* __restrict__ key, const int* __restrict__ prob_id,
                                                           int count, int chunk, int n_chunks, int* __restrict__ clist,
                                                           int* __restrict__ cbeg) {
-  __shared__ double tile[256];
-  __shared__ int tchunk[256];
-  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  // one WARP per problem i: the lanes split the comparisons (a thread per problem looped over all 4096 keys: 0.35 ms)
+  __shared__ double tkey[kOrderTile];
+  __shared__ int tchunk[kOrderTile];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int i = blockIdx.x * 8 + warp;
   const double fi = i < count ? key[prob_id[i]] : 0.0;
   const int ci = i < count ? prob_id[i] / chunk : 0;
   const bool ni = fi != fi;
-  int pos = 0;         // problems of my chunk that are served before me
-  int cnt_below = 0;   // (threads 0..n_chunks of block 0) problems in chunks below threadIdx.x
-  for (int j0 = 0; j0 < count; j0 += 256) {  // keys staged through shared memory, 256 at a time (broadcast reads)
-    const int jj = j0 + threadIdx.x;
-    tile[threadIdx.x] = jj < count ? key[prob_id[jj]] : 0.0;
-    tchunk[threadIdx.x] = jj < count ? prob_id[jj] / chunk : 0x7fffffff;
+  int pos = 0;  // problems served before i: those of lower chunks, and those of my chunk with a larger key
+  for (int j0 = 0; j0 < count; j0 += kOrderTile) {
+    const int nj_ = min(kOrderTile, count - j0);
+    for (int t = threadIdx.x; t < nj_; t += 256) {
+      const int pj = prob_id[j0 + t];
+      tkey[t] = key[pj];
+      tchunk[t] = pj / chunk;
+    }
     __syncthreads();
-    const int nj_ = min(256, count - j0);
-#pragma unroll 8
-    for (int t = 0; t < nj_; t++) {
-      const double fj = tile[t];
+    for (int t = lane; t < nj_; t += 32) {
+      const double fj = tkey[t];
       const int cj = tchunk[t];
       const int j = j0 + t;
       const bool nj = fj != fj;
       const bool before = (nj && !ni) || (nj == ni && (ni ? j < i : (fj > fi || (fj == fi && j < i))));
-      pos += (cj < ci || (cj == ci && before)) ? 1 : 0;  // chunks are laid out one after the other
-      cnt_below += cj < (int)threadIdx.x ? 1 : 0;
+      pos += (cj < ci || (cj == ci && before)) ? 1 : 0;
     }
     __syncthreads();
   }
-  if (i < count) clist[pos] = i;
-  if (blockIdx.x == 0 && (int)threadIdx.x <= n_chunks) cbeg[threadIdx.x] = cnt_below;
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) pos += __shfl_xor_sync(FULL, pos, o);
+  if (i < count && lane == 0) clist[pos] = i;
+  if (blockIdx.x == 0 && (int)threadIdx.x <= n_chunks) {  // first list entry of every chunk
+    int below = 0;
+    for (int j = 0; j < count; j++) below += prob_id[j] / chunk < (int)threadIdx.x ? 1 : 0;
+    cbeg[threadIdx.x] = below;
+  }
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -3111,7 +3119,7 @@ cudaError_t launch_minco_fit(cudaStream_t st, int n_traj, const int* piece_ptr, 
 
 cudaError_t launch_chunk_order(cudaStream_t st, const double* key, const int* prob_id, int count, int chunk, int n_chunks,
                                int* clist, int* cbeg) {
-  chunk_order_kernel<<<(count + 255) / 256, 256, 0, st>>>(key, prob_id, count, chunk, n_chunks, clist, cbeg);
+  chunk_order_kernel<<<(count + 7) / 8, 256, 0, st>>>(key, prob_id, count, chunk, n_chunks, clist, cbeg);
   return cudaGetLastError();
 }
 

@@ -283,6 +283,32 @@ def test_determinism_and_sharding(gpu_opt_factory):
     np.testing.assert_array_equal(full.iters[40:96], part.iters)
 
 
+@pytest.mark.parametrize("cfg,B", [(3, 1500), (2, 1031), (5, 700)])
+def test_queue_order_is_invisible(cfg, B, gpu_opt_factory):
+    """Batches above 4 problems per SM are served longest-predicted-first through per-chunk lists (chunk_order_kernel,
+    fetch_by_chunk): every problem must be solved exactly once and no result may depend on the order.  Compared: the
+    overlapped call (16 upload chunks), upload + optimize (one chunk), a caller-supplied reversed order (plain counter
+    queue), and the two halves solved as separate batches."""
+    batch, prm = synth.make_config(cfg, B=B, seed=9)
+    opt = gpu_opt_factory(prm)
+    a = opt.solve(batch)
+    b = opt.solve_stepwise(batch)
+    opt.set_order(np.arange(B - 1, -1, -1))
+    c = opt.solve_stepwise(batch)
+    opt.set_order(None)
+    assert np.all(a.evals >= 1)  # nobody was skipped
+    for other in (b, c):
+        np.testing.assert_array_equal(a.x, other.x)
+        np.testing.assert_array_equal(a.cost, other.cost)
+        np.testing.assert_array_equal(a.status, other.status)
+        np.testing.assert_array_equal(a.evals, other.evals)
+    h = B // 2
+    for lo, hi in ((0, h), (h, B)):
+        part = opt.solve(batch.slice(lo, hi, prm.traj_resolution, prm.des_traj_resolution))
+        np.testing.assert_array_equal(a.x[lo:hi], part.x)
+        np.testing.assert_array_equal(a.iters[lo:hi], part.iters)
+
+
 @pytest.mark.parametrize("cfg", [3, 4, 5])
 def test_helped_and_unhelped_solves_are_bit_identical(cfg, gpu_opt_factory):
     """Drain-phase helpers: which warps of the CTA swept which virtual ranks must not change a single
