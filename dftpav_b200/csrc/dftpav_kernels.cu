@@ -1386,9 +1386,6 @@ __device__ __forceinline__ void sweep_ranks(const ShapeDev& sh, const ParamsDev&
 // diagnostic: when non-null, lane 0 of every warp adds the cycles spent in each phase of an evaluation
 __device__ unsigned long long* g_phase_clock = nullptr;
 // finer split of the L-BFGS part (slots 8..15), only in diagnostic builds (-DDFTPAV_PHASE_FINE=1, tools/lone_phases.py)
-#ifndef DFTPAV_TWO_LOOP_PD2
-#define DFTPAV_TWO_LOOP_PD2 0
-#endif
 #ifndef DFTPAV_PHASE_FINE
 #define DFTPAV_PHASE_FINE 0
 #endif
@@ -1868,13 +1865,21 @@ __global__ void __launch_bounds__(32 * DFTPAV_MAX_WARPS, 1)
 
 // Register variant: the direction in registers (NPL elements per lane, n <= 32*NPL), the (s_j, y_j, 1/ys_j) stream
 // software-prefetched one entry ahead.  Measured on B200 (tools/microbench/two_loop_bench.cu, profiles/README.md): 300-313
-// cycles per history step for a lone warp, THE SAME with the history in shared memory - the step is bound by its dependent
-// chain (2 FMA, a 5-level shuffle butterfly, multiply, FMA), not by the L2 round trip.  Measured and rejected: prefetch
-// distance 2 (327), 16 lanes x 3 elements with a 4-level butterfly (297), four entries per step with a cached Gram band
-// (219 lone but 144 k vs 188 k solves/s in the solver: the extra loads are exposed), and a full Gram-matrix form with the
-// dot products lane <-> entry and the triangular recurrences on shuffle broadcasts (650-980: every recurrence step exposes
-// an L2 round trip for its Gram row; 62 k solves/s).  No integer modulo (wrap by compare); the trip
-// count is read through a shuffle so that the compiler treats the loop as warp-uniform and emits bare SHFL.
+// cycles per history step for a lone warp while the history fits the L1, THE SAME with the history in shared memory - the
+// step is bound by its dependent chain (2 FMA, a 5-level shuffle butterfly, multiply, FMA).  Inside the solver the L1 is
+// ~40 KB (185 KB of shared memory) and a 120-entry history is 90 KB: the step costs 446 cycles (tools/lone_phases.py with
+// a -DDFTPAV_PHASE_FINE=1 build: the two-loop is 44 % of a long problem's critical path), i.e. ~130 cycles of the L2 round
+// trip are exposed.  Every attempt to hide them lost more than it won (round 2, profiles/README.md):
+//   * prefetch distance 2..6 in registers: the noinline callee is held to ~60-80 registers by the caller's live state
+//     (whatever the caller re-materialises) and spills the ring - 185 / 161 / 142 / 136 / 114 k solves/s at distance
+//     1 / 2 / 3 / 4 / 6 against 198 k; inlined, the kernel's own spills grow from 0.5 to 2.4 KB;
+//   * staging ring in shared memory filled by cp.async: 632 cycles per step (~40 instructions on the in-order path), 160 k;
+//   * the same ring filled by one TMA bulk copy per entry (history rows interleaved): 691 cycles per step, 172 k.
+// Measured and rejected before: 16 lanes x 3 elements with a 4-level butterfly (297 lone), four entries per step with a
+// cached Gram band (219 lone but 144 k vs 188 k solves/s in the solver: the extra loads are exposed), and a full
+// Gram-matrix form with the dot products lane <-> entry and the triangular recurrences on shuffle broadcasts (650-980:
+// every recurrence step exposes an L2 round trip for its Gram row; 62 k solves/s).  No integer modulo (wrap by compare);
+// the trip count is read through a shuffle so that the compiler treats the loop as warp-uniform and emits bare SHFL.
 template <int NPL>
 __device__ __noinline__ void two_loop(double* d_sm, double* alpha_sm, const double* __restrict__ lm_s,
                                       const double* __restrict__ lm_y, const double* __restrict__ lm_ys, int ld, int m,
@@ -1980,92 +1985,6 @@ __device__ __noinline__ void two_loop(double* d_sm, double* alpha_sm, const doub
     const int i = lane + 32 * e;
     if (ok[e]) d_sm[i] = d[e];
   }
-  __syncwarp();
-}
-
-// Prefetch distance 2: three register buffers, the loop unrolled by three (no register moves).
-template <int NPL>
-__device__ __noinline__ void two_loop_pd2(double* d_sm, double* alpha_sm, const double* __restrict__ lm_s,
-                                          const double* __restrict__ lm_y, const double* __restrict__ lm_ys, int ld, int m,
-                                          int end, int bound_in, int n, int lane, double ys, double yy) {
-  const int bound = __shfl_sync(FULL, bound_in, 0);
-  double d[NPL], s_[3][NPL], y_[3][NPL], r_[3];
-  bool ok[NPL];
-#pragma unroll
-  for (int e = 0; e < NPL; e++) {
-    ok[e] = lane + 32 * e < n;
-    d[e] = ok[e] ? d_sm[lane + 32 * e] : 0.0;
-  }
-  auto load = [&](int q, int j) {
-    const double* sj = lm_s + (size_t)j * ld + lane;
-    const double* yj = lm_y + (size_t)j * ld + lane;
-#pragma unroll
-    for (int e = 0; e < NPL; e++) {
-      s_[q][e] = ok[e] ? sj[32 * e] : 0.0;
-      y_[q][e] = ok[e] ? yj[32 * e] : 0.0;
-    }
-    r_[q] = lm_ys[j];
-  };
-  int j = end - 1;
-  if (j < 0) j += m;
-  int jf = j;
-  load(0, jf);
-  jf = jf == 0 ? m - 1 : jf - 1;
-  if (bound > 1) load(1, jf);
-  jf = jf == 0 ? m - 1 : jf - 1;
-#pragma unroll 1
-  for (int i = 0; i < bound; i += 3) {
-#pragma unroll
-    for (int q = 0; q < 3; q++) {
-      if (i + q < bound) {
-        if (i + q + 2 < bound) {
-          load((q + 2) % 3, jf);
-          jf = jf == 0 ? m - 1 : jf - 1;
-        }
-        double part = 0.0;
-#pragma unroll
-        for (int e = 0; e < NPL; e++) part += s_[q][e] * d[e];
-        const double a = DFTPAV_OVER_YS(warp_sum(part), r_[q]);
-        if (lane == 0) alpha_sm[j] = a;
-        const double na = -a;
-#pragma unroll
-        for (int e = 0; e < NPL; e++) d[e] += na * y_[q][e];
-        if (i + q + 1 < bound) j = j == 0 ? m - 1 : j - 1;
-      }
-    }
-  }
-  const double scl = ys / yy;
-#pragma unroll
-  for (int e = 0; e < NPL; e++) d[e] *= scl;
-  __syncwarp();
-  jf = j;
-  load(0, jf);
-  jf = jf + 1 == m ? 0 : jf + 1;
-  if (bound > 1) load(1, jf);
-  jf = jf + 1 == m ? 0 : jf + 1;
-#pragma unroll 1
-  for (int i = 0; i < bound; i += 3) {
-#pragma unroll
-    for (int q = 0; q < 3; q++) {
-      if (i + q < bound) {
-        if (i + q + 2 < bound) {
-          load((q + 2) % 3, jf);
-          jf = jf + 1 == m ? 0 : jf + 1;
-        }
-        double part = 0.0;
-#pragma unroll
-        for (int e = 0; e < NPL; e++) part += y_[q][e] * d[e];
-        const double beta = DFTPAV_OVER_YS(warp_sum(part), r_[q]);
-        const double a = alpha_sm[j] - beta;
-#pragma unroll
-        for (int e = 0; e < NPL; e++) d[e] += a * s_[q][e];
-        j = j + 1 == m ? 0 : j + 1;
-      }
-    }
-  }
-#pragma unroll
-  for (int e = 0; e < NPL; e++)
-    if (ok[e]) d_sm[lane + 32 * e] = d[e];
   __syncwarp();
 }
 
@@ -2530,15 +2449,9 @@ __global__ void __launch_bounds__(32 * DFTPAV_MAX_WARPS, 1)
 #else
             if (npl <= 3) {
               // the direction in registers (n <= 96)
-#if DFTPAV_TWO_LOOP_PD2
-              if (npl == 1) two_loop_pd2<1>(ws.d, alpha_sm, lm_s, lm_y, lm_ys, ld, m, end, bound, n, lane, ys, yy);
-              else if (npl == 2) two_loop_pd2<2>(ws.d, alpha_sm, lm_s, lm_y, lm_ys, ld, m, end, bound, n, lane, ys, yy);
-              else two_loop_pd2<3>(ws.d, alpha_sm, lm_s, lm_y, lm_ys, ld, m, end, bound, n, lane, ys, yy);
-#else
               if (npl == 1) two_loop<1>(ws.d, alpha_sm, lm_s, lm_y, lm_ys, ld, m, end, bound, n, lane, ys, yy);
               else if (npl == 2) two_loop<2>(ws.d, alpha_sm, lm_s, lm_y, lm_ys, ld, m, end, bound, n, lane, ys, yy);
               else two_loop<3>(ws.d, alpha_sm, lm_s, lm_y, lm_ys, ld, m, end, bound, n, lane, ys, yy);
-#endif
             } else {
               // larger problems (up to 4 x 64 pieces, n = 517): the direction stays in shared memory
               two_loop_generic(ws.d, alpha_sm, lm_s, lm_y, lm_ys, ld, m, end, bound, n, lane, ys, yy);
