@@ -1874,7 +1874,9 @@ __global__ void __launch_bounds__(32 * DFTPAV_MAX_WARPS, 1)
 //     (whatever the caller re-materialises) and spills the ring - 185 / 161 / 142 / 136 / 114 k solves/s at distance
 //     1 / 2 / 3 / 4 / 6 against 198 k; inlined, the kernel's own spills grow from 0.5 to 2.4 KB;
 //   * staging ring in shared memory filled by cp.async: 632 cycles per step (~40 instructions on the in-order path), 160 k;
-//   * the same ring filled by one TMA bulk copy per entry (history rows interleaved): 691 cycles per step, 172 k.
+//   * the same ring filled by one TMA bulk copy per entry (history rows interleaved): 691 cycles per step, 172 k;
+//   * prefetch.global.L1 hints (CCTL.E.PF1) 2-4 entries ahead: the hint itself stalls the in-order warp - 398 cycles per
+//     step with the history IN the L1, 603-612 with the solver's carve-out (441 without the hints); 186-190 k vs 193 k.
 // Measured and rejected before: 16 lanes x 3 elements with a 4-level butterfly (297 lone), four entries per step with a
 // cached Gram band (219 lone but 144 k vs 188 k solves/s in the solver: the extra loads are exposed), and a full
 // Gram-matrix form with the dot products lane <-> entry and the triangular recurrences on shuffle broadcasts (650-980:

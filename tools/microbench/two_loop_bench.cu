@@ -189,10 +189,11 @@ int main() {
   cudaMemcpy(dy, hy.data(), hs.size() * 8, cudaMemcpyHostToDevice);
   cudaMemcpy(dys, hys.data(), hys.size() * 8, cudaMemcpyHostToDevice);
   cudaMemset(dg, 0, hys.size() * 32);
-  const char* names[] = {"two_loop<2> (classic)", "", "prefetch distance 2", "", "16 lanes x 3", "generic (smem d)"};
-  auto run = [&](int V, int grid, int warps, int bound, int smem_hist) {
+  const char* names[] = {"two_loop<2> (product)", "", "prefetch distance 2", "", "16 lanes x 3", "generic (smem d)"};
+  auto run = [&](int V, int grid, int warps, int bound, int smem_hist, bool small_l1 = false) {
     const int reps = 20;
     size_t smem = (size_t)warps * 600 * 8 + (smem_hist ? (size_t)warps * (2 * smem_hist * ld + smem_hist) * 8 : 0);
+    if (small_l1) smem = 185 * 1024;  // the solver's carve-out: ~40 KB of L1 left
     cudaMemset(cyc, 0, 8);
     auto launch = [&](auto kern) {
       cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
@@ -209,11 +210,13 @@ int main() {
     cudaMemcpy(&c, cyc, 8, cudaMemcpyDeviceToHost);
     const double per_step = (double)c / ((double)grid * warps * reps * 2.0 * bound);
     printf("%-24s grid %3d warps %2d bound %3d %s: %7.1f cycles per history step%s\n", names[V], grid, warps, bound,
-           smem_hist ? "smem-history" : "global      ", per_step, e == cudaSuccess ? "" : cudaGetErrorString(e));
+           smem_hist ? "smem-history" : (small_l1 ? "global,L1~40K" : "global       "), per_step, e == cudaSuccess ? "" : cudaGetErrorString(e));
   };
-  for (int V : {0, 2, 4, 5}) {
+  for (int V : {0, 2}) {
     for (int bound : {16, 64, 128}) run(V, 1, 1, bound, 0);       // a lone warp on the GPU
     run(V, 1, 1, 16, 16);                                         // chain only: history in shared memory
+    run(V, 1, 1, 128, 0, true);                                   // a lone warp, L1 as small as in the solver
+    run(V, 148, 12, 64, 0, true);
     run(V, 148, 12, 64, 0);                                       // every SM full of two-loops
     run(V, 148, 4, 64, 0);
   }
