@@ -257,6 +257,7 @@ EXPORTED_SYMBOLS = [
     "dftpav_state_to_flat_output",
     "dftpav_corridor_set_map",
     "dftpav_corridor_rectangles",
+    "dftpav_collision_check",
     "dftpav_create_multi",
     "dftpav_destroy_multi",
     "dftpav_solve_multi",
@@ -314,6 +315,7 @@ def load_library(variant: str = "") -> C.CDLL:
     lib.dftpav_corridor_set_map.argtypes = [H, C.POINTER(GridMap)]
     lib.dftpav_corridor_rectangles.argtypes = [H, C.POINTER(CorridorParams), C.c_int64, c_double_p, c_double_p, c_double_p,
                                                C.c_int32]
+    lib.dftpav_collision_check.argtypes = [H, C.POINTER(CorridorParams), C.c_double, C.c_double, C.c_int32, c_int32_p, c_int32_p]
     lib.dftpav_create_multi.argtypes = [C.POINTER(Params), c_int32_p, C.c_int32, C.POINTER(H)]
     lib.dftpav_destroy_multi.argtypes = [H]
     lib.dftpav_solve_multi.argtypes = [H, C.POINTER(Batch), C.POINTER(Result), c_int32_p]

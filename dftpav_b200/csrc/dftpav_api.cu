@@ -45,6 +45,8 @@ cudaError_t launch_minco_fit(cudaStream_t st, int n_traj, const int* piece_ptr, 
                              const int* lu_off, double* scratch, double* coeffs);
 cudaError_t launch_chunk_order(cudaStream_t st, const double* key, const int* prob_id, int count, int chunk, int n_chunks,
                                int* clist, int* cbeg);
+cudaError_t launch_collision(cudaStream_t st, const SampleDev& sd, const CorridorDev& cd, const double* t_tab, int n_tab,
+                             double dt, double spacing, const int* seg_prob, int* first_hit, int* collide);
 cudaError_t launch_corridor(cudaStream_t st, const CorridorDev& cd, long long n, const double* states, const double* cos_sin,
                             double* hpolys);
 int ws_doubles_host(int rows, int npad, int S, int has_obs);
@@ -1499,6 +1501,53 @@ int dftpav_sample_uniform(dftpav_handle* h, double dt, int32_t max_per_seg, doub
   CU_TRY(h, cudaMemcpyAsync(xyyaw, h->q_out.p, ob, cudaMemcpyDeviceToHost, st));
   CU_TRY(h, cudaMemcpyAsync(count, h->q_cnt.p, sizeof(int) * G, cudaMemcpyDeviceToHost, st));
   CU_TRY(h, cudaStreamSynchronize(st));
+  return DFTPAV_OK;
+}
+
+int dftpav_collision_check(dftpav_handle* h, const dftpav_corridor_params* vp, double dt, double vertex_spacing,
+                           int32_t max_samples, int32_t* collide, int32_t* first_hit) {
+  if (!h || !vp || !(dt > 0.0) || !(vertex_spacing > 0.0) || max_samples < 1 || !collide) return DFTPAV_ERR_INVALID_ARG;
+  if (!h->solved) return fail(h, DFTPAV_ERR_STATE, "dftpav_collision_check before dftpav_optimize");
+  if (!h->map_data.p) return fail(h, DFTPAV_ERR_STATE, "dftpav_collision_check before dftpav_corridor_set_map");
+  const int G = h->dims.seg_total, B = h->dims.B;
+  if (G == 0) return DFTPAV_OK;
+  CU_TRY(h, cudaSetDevice(h->device));
+  cudaStream_t st = h->stream;
+  // sample times of `for (t = 0; t < duration; t += dt)`: sequentially accumulated sums
+  std::vector<double> tt((size_t)max_samples);
+  double t = 0.0;
+  for (int k = 0; k < max_samples; k++, t += dt) tt[k] = t;
+  CU_TRY(h, h->q_t.ensure(sizeof(double) * tt.size()));
+  CU_TRY(h, cudaMemcpyAsync(h->q_t.p, tt.data(), sizeof(double) * tt.size(), cudaMemcpyHostToDevice, st));
+  CU_TRY(h, h->q_cnt.ensure(sizeof(int) * ((size_t)G + B)));
+  int* d_first = h->q_cnt.as<int>();
+  int* d_col = d_first + G;
+  CU_TRY(h, cudaMemsetAsync(d_col, 0, sizeof(int) * B, st));
+  CorridorDev cd;
+  cd.data = h->map_data.as<unsigned char>();
+  cd.dl = h->map_dl.as<double>();
+  cd.size_x = h->map_meta.size_x, cd.size_y = h->map_meta.size_y, cd.n_dl = h->map_n_dl;
+  cd.occupied = h->map_meta.occupied_value;
+  cd.origin_x = h->map_meta.origin_x, cd.origin_y = h->map_meta.origin_y, cd.resolution = h->map_meta.resolution;
+  cd.veh_width = vp->veh_width, cd.veh_length = vp->veh_length, cd.veh_d_cr = vp->veh_d_cr, cd.limit_bound = vp->limit_bound;
+  CU_TRY(h, cudaEventRecord(h->ev[0], st));
+  CU_TRY(h, launch_collision(st, sample_view(h), cd, h->q_t.as<double>(), max_samples, dt, vertex_spacing,
+                             h->seg_prob.as<int>(), d_first, d_col));
+  CU_TRY(h, cudaEventRecord(h->ev[1], st));
+  std::vector<int> fh((size_t)G);
+  CU_TRY(h, cudaMemcpyAsync(fh.data(), d_first, sizeof(int) * G, cudaMemcpyDeviceToHost, st));
+  CU_TRY(h, cudaMemcpyAsync(collide, d_col, sizeof(int) * B, cudaMemcpyDeviceToHost, st));
+  CU_TRY(h, cudaStreamSynchronize(st));
+  float ms = 0.f;
+  cudaEventElapsedTime(&ms, h->ev[0], h->ev[1]);
+  h->stats.solve_ms = ms;
+  h->stats.kernel_launches = 1;
+  bool truncated = false;
+  for (int g = 0; g < G; g++) {
+    truncated = truncated || fh[g] == -2;
+    if (first_hit) first_hit[g] = fh[g];
+  }
+  if (truncated) return fail(h, DFTPAV_ERR_INVALID_ARG, "dftpav_collision_check: max_samples * dt is shorter than a segment");
   return DFTPAV_OK;
 }
 

@@ -2976,6 +2976,80 @@ __global__ void minco_fit_kernel(int n_traj, const int* __restrict__ piece_ptr, 
 // ------------------------------------------------------------------------------------------------
 // host-callable launchers (used by dftpav_api.cu)
 // ------------------------------------------------------------------------------------------------
+// ------------------------------------------------------------------------------------------------
+// Collision re-check of the solved trajectories against the occupancy grid (the consumer loop of
+// traj_server_ros.cpp:385-397): sample k of a gear segment is t_k = 0 + dt + ... + dt (the reference's `t += 0.05`, taken
+// from a host-built table of the sequentially accumulated sums) while t_k < duration; the vehicle footprint at
+// (getPos(t), getAngle(t)) is the vertex set of SemanticMapManager::CheckCollisionUsingPosAndYaw (semantic_map_manager.cc:
+// 639-661): box centre = pos + d_cr (cos yaw, sin yaw), corners and edge points every `spacing` metres from
+// ShapeUtils::GetDenseVerticesOfOrientedBoundingBox (shapes.cc:110-149), each vertex one grid lookup.  The reference stops
+// at the first colliding sample; the result per segment is that sample's index (or -1).  One WARP per segment, lane <->
+// sample, every coordinate with explicitly rounded operations in the reference's association (yaw, cos and sin come from
+// the CUDA libm: they can differ from glibc by an ulp, which moves a vertex by ~1e-15 m).
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ bool edge_hits(const CorridorDev& cd, double ax, double ay, double bx, double by, double spacing) {
+  // for (dl = res; dl < |b - a|; dl += res) p = dl / |b - a| * (b - a) + a      (shapes.cc:128-143)
+  const double dx = __dadd_rn(bx, -ax), dy = __dadd_rn(by, -ay);
+  const double nrm = sqrt(__dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy)));
+  bool hit = false;
+  for (double dl = spacing; dl < nrm; dl = __dadd_rn(dl, spacing)) {
+    const double f = __ddiv_rn(dl, nrm);
+    hit = hit || grid_occupied(cd, __dadd_rn(__dmul_rn(f, dx), ax), __dadd_rn(__dmul_rn(f, dy), ay));
+  }
+  return hit;
+}
+
+__global__ void collision_kernel(const SampleDev sd, const CorridorDev cd, const double* __restrict__ t_tab, int n_tab,
+                                 double dt, double spacing, const int* __restrict__ seg_prob, int* __restrict__ first_hit,
+                                 int* __restrict__ collide) {
+  const int lane = threadIdx.x & 31;
+  const int g = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  if (g >= sd.G) return;
+  int first = 0x7fffffff;
+  bool truncated = false;
+  if (sd.seg_N[g] >= 1) {
+    const SegView v = seg_view(sd, g);
+    const double dur = seg_duration(v);
+    truncated = __dadd_rn(t_tab[n_tab - 1], dt) < dur;  // the caller's sample cap is too small for this segment
+    const double sg = (double)v.singul;
+    const double hl = __dmul_rn(0.5, cd.veh_length), hw = __dmul_rn(0.5, cd.veh_width);
+    for (int k0 = 0; k0 < n_tab; k0 += 32) {
+      const int k = k0 + lane;
+      const double t = k < n_tab ? t_tab[k] : dur;
+      const bool on = t < dur;
+      bool hit = false;
+      if (on) {
+        double tl = t;
+        const int idx = seg_locate(v, tl);
+        V2 p, d1, d2;
+        piece_eval(v.c + 12 * idx, tl, p, d1, d2);
+        const double yaw = atan2(__dmul_rn(sg, d1.y), __dmul_rn(sg, d1.x));
+        const double c = cos(yaw), s = sin(yaw);
+        const double ox = __dadd_rn(p.x, __dmul_rn(cd.veh_d_cr, c)), oy = __dadd_rn(p.y, __dmul_rn(cd.veh_d_cr, s));
+        const double lc = __dmul_rn(hl, c), ls = __dmul_rn(hl, s), wc = __dmul_rn(hw, c), ws = __dmul_rn(hw, s);
+        const double c1x = __dadd_rn(__dadd_rn(ox, lc), ws), c1y = __dadd_rn(__dadd_rn(oy, ls), -wc);
+        const double c2x = __dadd_rn(__dadd_rn(ox, lc), -ws), c2y = __dadd_rn(__dadd_rn(oy, ls), wc);
+        const double c3x = __dadd_rn(__dadd_rn(ox, -lc), -ws), c3y = __dadd_rn(__dadd_rn(oy, -ls), wc);
+        const double c4x = __dadd_rn(__dadd_rn(ox, -lc), ws), c4y = __dadd_rn(__dadd_rn(oy, -ls), -wc);
+        hit = edge_hits(cd, c1x, c1y, c2x, c2y, spacing) || edge_hits(cd, c2x, c2y, c3x, c3y, spacing) ||
+              edge_hits(cd, c3x, c3y, c4x, c4y, spacing) || edge_hits(cd, c4x, c4y, c1x, c1y, spacing) ||
+              grid_occupied(cd, c1x, c1y) || grid_occupied(cd, c2x, c2y) || grid_occupied(cd, c3x, c3y) ||
+              grid_occupied(cd, c4x, c4y);
+      }
+      const unsigned hits = __ballot_sync(FULL, hit);
+      if (hits) {
+        first = k0 + __ffs(hits) - 1;
+        break;
+      }
+      if (!__all_sync(FULL, on)) break;  // the table is increasing: the segment ends inside this chunk
+    }
+  }
+  if (lane == 0) {
+    first_hit[g] = first != 0x7fffffff ? first : (truncated ? -2 : -1);
+    if (first != 0x7fffffff) atomicOr(collide + seg_prob[g], 1);
+  }
+}
+
 cudaError_t launch_solve(bool has_obs, int grid, int block, size_t smem, cudaStream_t st, const ShapeDev& sh,
                          const ParamsDev& P, const BatchDev& bd, const GroupDev& grp, const OutDev& out,
                          const HistDev& hist, int* counter) {
@@ -3035,6 +3109,13 @@ cudaError_t launch_minco_fit(cudaStream_t st, int n_traj, const int* piece_ptr, 
 cudaError_t launch_chunk_order(cudaStream_t st, const double* key, const int* prob_id, int count, int chunk, int n_chunks,
                                int* clist, int* cbeg) {
   chunk_order_kernel<<<(count + 7) / 8, 256, 0, st>>>(key, prob_id, count, chunk, n_chunks, clist, cbeg);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_collision(cudaStream_t st, const SampleDev& sd, const CorridorDev& cd, const double* t_tab, int n_tab,
+                             double dt, double spacing, const int* seg_prob, int* first_hit, int* collide) {
+  const int warps = sd.G, blocks = (warps + 7) / 8;
+  collision_kernel<<<blocks > 0 ? blocks : 1, 256, 0, st>>>(sd, cd, t_tab, n_tab, dt, spacing, seg_prob, first_hit, collide);
   return cudaGetLastError();
 }
 

@@ -252,6 +252,17 @@ class BatchOptimizer:
             out.ctypes.data_as(dp) if out is not None else None, 1 if keep else 0))
         return out
 
+    def collision_check(self, dt: float = 0.05, vertex_spacing: float = 0.1, max_samples: int = 2048,
+                        params: Optional[capi.CorridorParams] = None):
+        """Collision re-check of the last solve's trajectories against the map of set_map (dftpav_collision_check):
+        returns (collide [B] int32, first_hit [seg_total] int32)."""
+        cp = params if params is not None else capi.default_corridor_params()
+        col = np.zeros(self._dims.B, dtype=np.int32)
+        first = np.zeros(self._dims.seg_total, dtype=np.int32)
+        self._check(self._lib.dftpav_collision_check(self._h, C.byref(cp), dt, vertex_spacing, max_samples,
+                                                     col.ctypes.data_as(capi.c_int32_p), first.ctypes.data_as(capi.c_int32_p)))
+        return col, first
+
     # -- diagnostics (not part of the drop-in ABI) ---------------------------------------------
     def enable_trace(self, cap: int):
         self._lib.dftpav_debug_set_trace.argtypes = [C.c_void_p, C.c_int]

@@ -334,6 +334,19 @@ int dftpav_corridor_set_map(dftpav_handle* h, const dftpav_gridmap* map);
 int dftpav_corridor_rectangles(dftpav_handle* h, const dftpav_corridor_params* cp, int64_t n, const double* states,
                                const double* cos_sin, double* hpolys, int32_t keep);
 
+/* Collision re-check of the trajectories of the last solve against the occupancy grid of dftpav_corridor_set_map - the loop the
+ * replanning server runs over the executing trajectory every cycle (src/traj_server_ros.cpp:385-397): every gear segment is
+ * sampled at t = 0, dt, dt + dt, ... while t < duration (dt = 0.05 there), the footprint at (getPos(t), getAngle(t)) is the
+ * vertex set of SemanticMapManager::CheckCollisionUsingPosAndYaw (Sim/core/semantic_map_manager/src/semantic_map_manager.cc:
+ * 639-661; box centre = pos + veh_d_cr (cos yaw, sin yaw); corners and edge points every vertex_spacing metres,
+ * ShapeUtils::GetDenseVerticesOfOrientedBoundingBox, Sim/core/common/src/common/basics/shapes.cc:110-149, default 0.1) and a
+ * sample collides if any vertex lies in an occupied cell.  collide[B]: 1 if any sample of any segment of the problem collides
+ * (the reference returns true at the first one).  first_hit (may be NULL) [seg_total]: index of the first colliding sample
+ * of the segment, -1 if none.  max_samples bounds the samples per segment; DFTPAV_ERR_INVALID_ARG if a segment is longer than
+ * max_samples * dt.  vp->limit_bound is not used. */
+int dftpav_collision_check(dftpav_handle* h, const dftpav_corridor_params* vp, double dt, double vertex_spacing,
+                           int32_t max_samples, int32_t* collide, int32_t* first_hit);
+
 /* ---- multi-GPU: the batch shards embarrassingly over the GPUs of one box ----
  * dftpav_create_multi: one handle, host thread and stream per device of device_ids[0..n_dev) and - for n_dev > 1 - an NCCL
  * communicator over them (libnccl.so.2 is loaded at run time; without it the flag below is reduced on the host and

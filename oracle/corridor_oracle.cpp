@@ -52,7 +52,54 @@ struct Vp {
 
 }  // namespace
 
+extern "C" int oracle_traj_state(int N, const double* c, double dT, int singul, double t, int clamp, double wheel_base,
+                                 double* out, double* gs);  // dftpav_oracle.cpp (pinned to the reference's evaluators)
+
 extern "C" {
+
+// Collision re-check of ONE gear segment (N pieces of duration dT, coefficients c = 6N x 2 row-major, lowest power first),
+// PARITY UNPINNED like the corridor: the loop of traj_server_ros.cpp:385-397
+//     for (t = 0; t < duration; t += 0.05) { pos = getPos(t); yaw = getAngle(t); CheckIfCollisionUsingPosAndYaw(vp, state) }
+// with SemanticMapManager::CheckCollisionUsingPosAndYaw (Sim/core/semantic_map_manager/src/semantic_map_manager.cc:639-661)
+// and ShapeUtils::GetDenseVerticesOfOrientedBoundingBox (Sim/core/common/src/common/basics/shapes.cc:110-149, res = 0.1 by
+// default, shapes.h:200-201) restated statement by statement; the trajectory evaluators are the pinned ones.
+// Returns the index of the first colliding sample, -1 if none, -2 if max_samples was reached before the end.
+int oracle_collision_check_segment(const dftpav_gridmap* map, const dftpav_corridor_params* vp, int N, const double* c,
+                                   double dT, int singul, double dt, double res, int max_samples) {
+  const Grid G{map};
+  double total = 0.0;  // Trajectory::getTotalDuration
+  for (int i = 0; i < N; i++) total += dT;
+  int k = 0;
+  for (double t = 0.0; t < total; t += dt, k++) {
+    if (k >= max_samples) return -2;
+    double st[12];
+    oracle_traj_state(N, c, dT, singul, t, 0, 2.85, st, nullptr);
+    const double sx = st[0], sy = st[1], yaw = st[6];
+    // obb_ego (semantic_map_manager.cc:645-649)
+    const double ox = sx + vp->veh_d_cr * std::cos(yaw), oy = sy + vp->veh_d_cr * std::sin(yaw);
+    const double W = vp->veh_width, L = vp->veh_length;
+    // shapes.cc:114-127
+    const double ct = std::cos(yaw), sn = std::sin(yaw);
+    const double c1x = ox + 0.5 * L * ct + 0.5 * W * sn, c1y = oy + 0.5 * L * sn - 0.5 * W * ct;
+    const double c2x = ox + 0.5 * L * ct - 0.5 * W * sn, c2y = oy + 0.5 * L * sn + 0.5 * W * ct;
+    const double c3x = ox - 0.5 * L * ct - 0.5 * W * sn, c3y = oy - 0.5 * L * sn + 0.5 * W * ct;
+    const double c4x = ox - 0.5 * L * ct + 0.5 * W * sn, c4y = oy - 0.5 * L * sn - 0.5 * W * ct;
+    auto edge = [&](double ax, double ay, double bx, double by) {  // shapes.cc:128-143
+      const double dx = bx - ax, dy = by - ay;
+      const double nrm = std::sqrt(dx * dx + dy * dy);
+      for (double dl = res; dl < nrm; dl += res) {
+        const double f = dl / nrm;
+        if (G.occupied(f * dx + ax, f * dy + ay)) return true;
+      }
+      return false;
+    };
+    // the vertex order of the reference (edges 12, 23, 34, 41, then the corners) does not matter: any hit returns true
+    if (edge(c1x, c1y, c2x, c2y) || edge(c2x, c2y, c3x, c3y) || edge(c3x, c3y, c4x, c4y) || edge(c4x, c4y, c1x, c1y) ||
+        G.occupied(c1x, c1y) || G.occupied(c2x, c2y) || G.occupied(c3x, c3y) || G.occupied(c4x, c4y))
+      return k;
+  }
+  return -1;
+}
 
 // states [n][3] = (x, y, yaw); cs (optional) [n][2] = (cos yaw, sin yaw) to use instead of libm; hpolys [n][4][4]:
 // plane k = (n_x, n_y, p_x, p_y); expand (optional) [n][4] = the four expansion lengths (+dy, +dx, -dy, -dx).

@@ -175,6 +175,25 @@ def corridor_rectangles(grid: np.ndarray, origin_xy, resolution: float, states: 
     return out, ex
 
 
+def collision_check_segment(grid: np.ndarray, origin_xy, resolution: float, c: np.ndarray, dT: float, singul: int,
+                            dt: float = 0.05, vertex_spacing: float = 0.1, max_samples: int = 2048, params=None,
+                            occupied: int = capi.OCCUPIED) -> int:
+    """CPU restatement of the collision re-check of one gear segment (oracle/corridor_oracle.cpp): index of the first
+    colliding sample, -1 if none.  c = [6N, 2] coefficients, lowest power first (the solver's output layout)."""
+    grid = np.ascontiguousarray(grid, dtype=np.uint8)
+    c = np.ascontiguousarray(c, dtype=np.float64)
+    N = c.shape[0] // 6
+    m = capi.GridMap(grid.shape[1], grid.shape[0], float(origin_xy[0]), float(origin_xy[1]), float(resolution),
+                     grid.ctypes.data_as(C.POINTER(C.c_uint8)), occupied)
+    cp = params if params is not None else capi.default_corridor_params()
+    fn = lib().oracle_collision_check_segment
+    fn.argtypes = [C.POINTER(capi.GridMap), C.POINTER(capi.CorridorParams), C.c_int, capi.c_double_p, C.c_double, C.c_int,
+                   C.c_double, C.c_double, C.c_int]
+    fn.restype = C.c_int
+    return int(fn(C.byref(m), C.byref(cp), N, c.ctypes.data_as(capi.c_double_p), float(dT), int(singul), float(dt),
+                  float(vertex_spacing), int(max_samples)))
+
+
 REF_OPT_SO = os.path.join(os.path.dirname(os.path.abspath(__file__)), "_ref", "libref_optimizer.so")
 _ref_opt = None
 
