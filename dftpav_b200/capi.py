@@ -184,6 +184,16 @@ class GridMap(C.Structure):
                 ("resolution", C.c_double), ("data", C.POINTER(C.c_uint8)), ("occupied_value", C.c_uint8)]
 
 
+class Frontend(C.Structure):
+    """struct dftpav_frontend: the searched paths of KinoAstar after getKinoNode (front-end resampling, row N3)."""
+
+    _fields_ = [("n_paths", C.c_int32), ("pt_ptr", C.POINTER(C.c_int32)), ("pts", C.POINTER(C.c_double)),
+                ("shot_ptr", C.POINTER(C.c_int32)), ("shot_index", C.POINTER(C.c_int32)), ("shot_time", C.POINTER(C.c_double)),
+                ("shot_length", C.POINTER(C.c_double)), ("shot_s", C.POINTER(C.c_int32)), ("start_vel", C.POINTER(C.c_double)),
+                ("end_vel", C.POINTER(C.c_double)), ("max_forward_vel", C.c_double), ("max_forward_acc", C.c_double),
+                ("max_backward_vel", C.c_double), ("max_backward_acc", C.c_double), ("non_siguav", C.c_double)]
+
+
 class CorridorParams(C.Structure):
     _fields_ = [("veh_width", C.c_double), ("veh_length", C.c_double), ("veh_d_cr", C.c_double), ("limit_bound", C.c_double)]
 
@@ -258,6 +268,9 @@ EXPORTED_SYMBOLS = [
     "dftpav_corridor_set_map",
     "dftpav_corridor_rectangles",
     "dftpav_collision_check",
+    "dftpav_frontend_evaluate_pos",
+    "dftpav_frontend_resample",
+    "dftpav_trapezoid_duration",
     "dftpav_create_multi",
     "dftpav_destroy_multi",
     "dftpav_solve_multi",
@@ -315,6 +328,11 @@ def load_library(variant: str = "") -> C.CDLL:
     lib.dftpav_corridor_set_map.argtypes = [H, C.POINTER(GridMap)]
     lib.dftpav_corridor_rectangles.argtypes = [H, C.POINTER(CorridorParams), C.c_int64, c_double_p, c_double_p, c_double_p,
                                                C.c_int32]
+    lib.dftpav_frontend_evaluate_pos.argtypes = [H, C.POINTER(Frontend), C.c_int64, c_int32_p, c_double_p, c_double_p]
+    lib.dftpav_frontend_resample.argtypes = [H, C.POINTER(Frontend), c_double_p, C.c_double, C.c_int32, C.c_int32, c_int32_p,
+                                             c_double_p, C.c_int64, c_double_p, c_double_p, C.POINTER(C.c_int64)]
+    lib.dftpav_trapezoid_duration.argtypes = [C.c_double] * 5
+    lib.dftpav_trapezoid_duration.restype = C.c_double
     lib.dftpav_collision_check.argtypes = [H, C.POINTER(CorridorParams), C.c_double, C.c_double, C.c_int32, c_int32_p, c_int32_p]
     lib.dftpav_create_multi.argtypes = [C.POINTER(Params), c_int32_p, C.c_int32, C.POINTER(H)]
     lib.dftpav_destroy_multi.argtypes = [H]

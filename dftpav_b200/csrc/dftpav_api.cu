@@ -45,6 +45,11 @@ cudaError_t launch_minco_fit(cudaStream_t st, int n_traj, const int* piece_ptr, 
                              const int* lu_off, double* scratch, double* coeffs);
 cudaError_t launch_chunk_order(cudaStream_t st, const double* key, const int* prob_id, int count, int chunk, int n_chunks,
                                int* clist, int* cbeg);
+cudaError_t launch_frontend_pos(cudaStream_t st, const FrontendDev& fe, long long nq, const int* path, const double* t,
+                                double* out);
+cudaError_t launch_frontend_resample(cudaStream_t st, const FrontendDev& fe, int n_seg, const int* seg_path, const int* seg_pn,
+                                     const double* seg_tpp, const double* seg_base, const long long* seg_st0,
+                                     const long long* seg_in0, int K, int Kd, double* states, double* inner);
 cudaError_t launch_collision(cudaStream_t st, const SampleDev& sd, const CorridorDev& cd, const double* t_tab, int n_tab,
                              double dt, double spacing, const int* seg_prob, int* first_hit, int* collide);
 cudaError_t launch_corridor(cudaStream_t st, const CorridorDev& cd, long long n, const double* states, const double* cos_sin,
@@ -256,6 +261,7 @@ struct dftpav_handle {
   // corridor generator: device copy of the occupancy grid, ray-march offsets, and whether planes_raw holds generated polygons
   DevBuf map_data, map_dl, cor_states, cor_cs;
   DevBuf fit_pp, fit_dT, fit_head, fit_tail, fit_inner, fit_iptr, fit_lu, fit_luoff, fit_scratch, fit_coeffs;  // dftpav_minco_fit
+  DevBuf fe_arena, fe_out;  // dftpav_frontend_*: all inputs in one upload, outputs
   dftpav_gridmap map_meta{};
   int map_n_dl = 0;
   std::vector<int> dbg_order;  // experiment hook (dftpav_debug_set_order): serve the work queue in this order of problem ids
@@ -618,7 +624,7 @@ int dftpav_destroy(dftpav_handle* h) {
                     &h->fout, &h->gout, &h->o_x, &h->o_cost, &h->o_status, &h->o_success, &h->o_iters, &h->o_evals,
                     &h->o_coeffs, &h->o_dT, &h->counter, &h->hist_s, &h->hist_y, &h->hist_ys, &h->trace, &h->ready, &h->laid, &h->seg_prob, &h->seg_row0, &h->seg_N,
                     &h->seg_piece0, &h->q_seg, &h->q_t, &h->q_out, &h->q_cnt, &h->map_data, &h->map_dl, &h->cor_states, &h->cor_cs, &h->fit_pp, &h->fit_dT, &h->fit_head, &h->fit_tail,
-                    &h->fit_inner, &h->fit_iptr, &h->fit_lu, &h->fit_luoff, &h->fit_scratch, &h->fit_coeffs};
+                    &h->fit_inner, &h->fit_iptr, &h->fit_lu, &h->fit_luoff, &h->fit_scratch, &h->fit_coeffs, &h->fe_arena, &h->fe_out};
   for (DevBuf* b : bufs) b->release();
   for (auto& e : h->ev)
     if (e) cudaEventDestroy(e);
@@ -1501,6 +1507,169 @@ int dftpav_sample_uniform(dftpav_handle* h, double dt, int32_t max_per_seg, doub
   CU_TRY(h, cudaMemcpyAsync(xyyaw, h->q_out.p, ob, cudaMemcpyDeviceToHost, st));
   CU_TRY(h, cudaMemcpyAsync(count, h->q_cnt.p, sizeof(int) * G, cudaMemcpyDeviceToHost, st));
   CU_TRY(h, cudaStreamSynchronize(st));
+  return DFTPAV_OK;
+}
+
+// ---- front-end resampling (row N3) ----
+namespace {
+
+// host-side packer: every array of one call goes into ONE staging vector (8-byte aligned slots) and one H2D copy
+struct Arena {
+  std::vector<unsigned char> host;
+  size_t put(const void* src, size_t bytes) {
+    const size_t off = (host.size() + 7) & ~(size_t)7;
+    host.resize(off + bytes);
+    if (bytes) std::memcpy(host.data() + off, src, bytes);
+    return off;
+  }
+};
+
+int check_frontend(dftpav_handle* h, const dftpav_frontend* fe) {
+  if (!fe || fe->n_paths < 0) return fail(h, DFTPAV_ERR_INVALID_ARG, "frontend: null or negative n_paths");
+  if (fe->n_paths == 0) return DFTPAV_OK;
+  if (!fe->pt_ptr || !fe->pts || !fe->shot_ptr || !fe->shot_index || !fe->shot_time || !fe->shot_length || !fe->shot_s ||
+      !fe->start_vel || !fe->end_vel)
+    return fail(h, DFTPAV_ERR_INVALID_ARG, "frontend: null array");
+  if (fe->pt_ptr[0] != 0 || fe->shot_ptr[0] != 0) return fail(h, DFTPAV_ERR_INVALID_ARG, "frontend: CSR pointers must start at 0");
+  for (int p = 0; p < fe->n_paths; p++) {
+    const int np = fe->pt_ptr[p + 1] - fe->pt_ptr[p], ns = fe->shot_ptr[p + 1] - fe->shot_ptr[p];
+    if (np < 2 || ns < 1) return fail(h, DFTPAV_ERR_INVALID_ARG, "frontend: a path needs two points and one gear segment");
+    const int32_t* si = fe->shot_index + fe->shot_ptr[p] + p;
+    for (int i = 0; i <= ns; i++)
+      if (si[i] < 0 || si[i] >= np || (i > 0 && si[i] < si[i - 1]))
+        return fail(h, DFTPAV_ERR_INVALID_ARG, "frontend: shot_index out of range or decreasing");
+  }
+  return DFTPAV_OK;
+}
+
+// packs the front end into the arena; returns the device view (pointers relative to `base`)
+FrontendDev pack_frontend(Arena& a, const dftpav_frontend* fe, size_t (&off)[9]) {
+  const int n = fe->n_paths, PT = fe->pt_ptr[n], SH = fe->shot_ptr[n];
+  off[0] = a.put(fe->pt_ptr, sizeof(int) * (n + 1));
+  off[1] = a.put(fe->pts, sizeof(double) * 3 * (size_t)PT);
+  off[2] = a.put(fe->shot_ptr, sizeof(int) * (n + 1));
+  off[3] = a.put(fe->shot_index, sizeof(int) * ((size_t)SH + n));
+  off[4] = a.put(fe->shot_time, sizeof(double) * SH);
+  off[5] = a.put(fe->shot_length, sizeof(double) * SH);
+  off[6] = a.put(fe->shot_s, sizeof(int) * SH);
+  off[7] = a.put(fe->start_vel, sizeof(double) * n);
+  off[8] = a.put(fe->end_vel, sizeof(double) * n);
+  FrontendDev d{};
+  d.n_paths = n;
+  d.max_forward_vel = fe->max_forward_vel, d.max_forward_acc = fe->max_forward_acc;
+  d.max_backward_vel = fe->max_backward_vel, d.max_backward_acc = fe->max_backward_acc, d.non_siguav = fe->non_siguav;
+  return d;
+}
+
+void bind_frontend(FrontendDev& d, const unsigned char* base, const size_t (&off)[9]) {
+  d.pt_ptr = reinterpret_cast<const int*>(base + off[0]);
+  d.pts = reinterpret_cast<const double*>(base + off[1]);
+  d.shot_ptr = reinterpret_cast<const int*>(base + off[2]);
+  d.shot_index = reinterpret_cast<const int*>(base + off[3]);
+  d.shot_time = reinterpret_cast<const double*>(base + off[4]);
+  d.shot_length = reinterpret_cast<const double*>(base + off[5]);
+  d.shot_s = reinterpret_cast<const int*>(base + off[6]);
+  d.start_vel = reinterpret_cast<const double*>(base + off[7]);
+  d.end_vel = reinterpret_cast<const double*>(base + off[8]);
+}
+
+}  // namespace
+
+double dftpav_trapezoid_duration(double length, double max_vel, double max_acc, double startV, double endV) {
+  // KinoAstar::evaluateDuration (kino_astar.cpp:744-762)
+  const double startv2 = startV * startV, endv2 = endV * endV, maxv2 = max_vel * max_vel;
+  const double critical_len = (maxv2 - startv2) / (2 * max_acc) + (maxv2 - endv2) / (2 * max_acc);
+  if (length >= critical_len) return (max_vel - startV) / max_acc + (max_vel - endV) / max_acc + (length - critical_len) / max_vel;
+  const double tmpv = std::sqrt(0.5 * (startv2 + endv2 + 2 * max_acc * length));
+  return (tmpv - startV) / max_acc + (tmpv - endV) / max_acc;
+}
+
+int dftpav_frontend_evaluate_pos(dftpav_handle* h, const dftpav_frontend* fe, int64_t nq, const int32_t* path, const double* t,
+                                 double* out) {
+  if (!h || nq < 0 || (nq > 0 && (!path || !t || !out))) return DFTPAV_ERR_INVALID_ARG;
+  int rc = check_frontend(h, fe);
+  if (rc || nq == 0) return rc;
+  for (int64_t q = 0; q < nq; q++)
+    if (path[q] < 0 || path[q] >= fe->n_paths) return fail(h, DFTPAV_ERR_INVALID_ARG, "frontend: query path out of range");
+  CU_TRY(h, cudaSetDevice(h->device));
+  cudaStream_t st = h->stream;
+  Arena a;
+  size_t off[9];
+  FrontendDev d = pack_frontend(a, fe, off);
+  const size_t o_path = a.put(path, sizeof(int) * (size_t)nq), o_t = a.put(t, sizeof(double) * (size_t)nq);
+  CU_TRY(h, h->fe_arena.ensure(a.host.size()));
+  CU_TRY(h, h->fe_out.ensure(sizeof(double) * 3 * (size_t)nq));
+  CU_TRY(h, cudaMemcpyAsync(h->fe_arena.p, a.host.data(), a.host.size(), cudaMemcpyHostToDevice, st));
+  const unsigned char* base = h->fe_arena.as<unsigned char>();
+  bind_frontend(d, base, off);
+  CU_TRY(h, launch_frontend_pos(st, d, nq, reinterpret_cast<const int*>(base + o_path),
+                                reinterpret_cast<const double*>(base + o_t), h->fe_out.as<double>()));
+  CU_TRY(h, cudaMemcpyAsync(out, h->fe_out.p, sizeof(double) * 3 * (size_t)nq, cudaMemcpyDeviceToHost, st));
+  CU_TRY(h, cudaStreamSynchronize(st));
+  return DFTPAV_OK;
+}
+
+int dftpav_frontend_resample(dftpav_handle* h, const dftpav_frontend* fe, const double* seg_duration,
+                             double traj_piece_duration, int32_t K, int32_t Kd, int32_t* piece_num, double* piece_dur,
+                             int64_t states_cap, double* states, double* inner, int64_t* n_states) {
+  if (!h || !seg_duration || !(traj_piece_duration > 0.0) || K < 1 || Kd < 1 || !piece_num || !piece_dur || !n_states)
+    return DFTPAV_ERR_INVALID_ARG;
+  int rc = check_frontend(h, fe);
+  if (rc) return rc;
+  const int n = fe->n_paths, SH = n ? fe->shot_ptr[n] : 0;
+  // per gear segment (host arithmetic of traj_manager.cpp:531-541, 566): piece count, piece duration, base time, offsets
+  std::vector<int> seg_path(SH), seg_pn(SH);
+  std::vector<double> seg_tpp(SH), seg_base(SH);
+  std::vector<long long> seg_st0(SH), seg_in0(SH);
+  long long ns = 0, ni = 0;
+  for (int p = 0; p < n; p++) {
+    double basetime = 0.0;
+    for (int g = fe->shot_ptr[p]; g < fe->shot_ptr[p + 1]; g++) {
+      const double D = seg_duration[g];
+      if (!(D > 0.0) || !(D / traj_piece_duration < 1.0e6)) return fail(h, DFTPAV_ERR_INVALID_ARG, "frontend: bad segment duration");
+      const int pn = std::max(int(D / traj_piece_duration + 0.5), 2);
+      seg_path[g] = p, seg_pn[g] = pn, seg_tpp[g] = D / pn, seg_base[g] = basetime;
+      seg_st0[g] = ns, seg_in0[g] = ni;
+      piece_num[g] = pn, piece_dur[g] = seg_tpp[g];
+      ns += 2LL * (Kd + 1) + (long long)(pn - 2) * (K + 1);
+      ni += pn - 1;
+      basetime += D;
+    }
+  }
+  *n_states = ns;
+  if (ns > states_cap) return fail(h, DFTPAV_ERR_INVALID_ARG, "frontend: states_cap is too small (see *n_states)");
+  if (SH == 0) return DFTPAV_OK;
+  if (!states || !inner) return DFTPAV_ERR_INVALID_ARG;
+  CU_TRY(h, cudaSetDevice(h->device));
+  cudaStream_t st = h->stream;
+  Arena a;
+  size_t off[9];
+  FrontendDev d = pack_frontend(a, fe, off);
+  const size_t o_path = a.put(seg_path.data(), sizeof(int) * SH), o_pn = a.put(seg_pn.data(), sizeof(int) * SH);
+  const size_t o_tpp = a.put(seg_tpp.data(), sizeof(double) * SH), o_base = a.put(seg_base.data(), sizeof(double) * SH);
+  const size_t o_st0 = a.put(seg_st0.data(), sizeof(long long) * SH), o_in0 = a.put(seg_in0.data(), sizeof(long long) * SH);
+  CU_TRY(h, h->fe_arena.ensure(a.host.size()));
+  const size_t sb = sizeof(double) * 3 * (size_t)ns, ib = sizeof(double) * 2 * (size_t)ni;
+  CU_TRY(h, h->fe_out.ensure(sb + ib));
+  CU_TRY(h, cudaMemcpyAsync(h->fe_arena.p, a.host.data(), a.host.size(), cudaMemcpyHostToDevice, st));
+  const unsigned char* base = h->fe_arena.as<unsigned char>();
+  bind_frontend(d, base, off);
+  double* d_states = h->fe_out.as<double>();
+  double* d_inner = d_states + 3 * (size_t)ns;
+  CU_TRY(h, cudaEventRecord(h->ev[0], st));
+  CU_TRY(h, launch_frontend_resample(st, d, SH, reinterpret_cast<const int*>(base + o_path),
+                                     reinterpret_cast<const int*>(base + o_pn), reinterpret_cast<const double*>(base + o_tpp),
+                                     reinterpret_cast<const double*>(base + o_base),
+                                     reinterpret_cast<const long long*>(base + o_st0),
+                                     reinterpret_cast<const long long*>(base + o_in0), K, Kd, d_states, d_inner));
+  CU_TRY(h, cudaEventRecord(h->ev[1], st));
+  CU_TRY(h, cudaMemcpyAsync(states, d_states, sb, cudaMemcpyDeviceToHost, st));
+  if (ib) CU_TRY(h, cudaMemcpyAsync(inner, d_inner, ib, cudaMemcpyDeviceToHost, st));
+  CU_TRY(h, cudaStreamSynchronize(st));
+  float ms = 0.f;
+  cudaEventElapsedTime(&ms, h->ev[0], h->ev[1]);
+  h->stats.solve_ms = ms;
+  h->stats.kernel_launches = 1;
   return DFTPAV_OK;
 }
 

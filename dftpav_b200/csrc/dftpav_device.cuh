@@ -144,6 +144,21 @@ struct CorridorDev {
   double veh_width, veh_length, veh_d_cr, limit_bound;
 };
 
+// Device view of dftpav_frontend (the searched paths of KinoAstar after getKinoNode) for the front-end resampling kernels.
+struct FrontendDev {
+  int n_paths;
+  const int* pt_ptr;
+  const double* pts;
+  const int* shot_ptr;
+  const int* shot_index;
+  const double* shot_time;
+  const double* shot_length;
+  const int* shot_s;
+  const double* start_vel;
+  const double* end_vel;
+  double max_forward_vel, max_forward_acc, max_backward_vel, max_backward_acc, non_siguav;
+};
+
 struct HistDev {
   double* s;        // [slots][mem][npad_max]
   double* y;

@@ -3050,6 +3050,136 @@ __global__ void collision_kernel(const SampleDev sd, const CorridorDev cd, const
   }
 }
 
+// ------------------------------------------------------------------------------------------------
+// Front-end resampling: KinoAstar::evaluatePos / evaluateLength (kino_astar.cpp:468-521,
+// 763-795) and the sampling loop of TrajPlanner::RunMINCOParking (traj_manager.cpp:531-567) that turns a searched path into
+// the optimizer's inputs (corridor states, inner waypoints, piece counts and durations).  One THREAD per query / state: the
+// work per pose is a short scan over the path's gear segments and samples; the batch supplies the parallelism.  Every
+// operation explicitly rounded in the reference's association (+ - * / sqrt only; pow(x, 2) is x * x): bit-identical to the
+// CPU restatement.
+// ------------------------------------------------------------------------------------------------
+__device__ double fe_length(double curt, double locallength, double max_vel, double max_acc, double startV, double endV) {
+  const double startv2 = __dmul_rn(startV, startV), endv2 = __dmul_rn(endV, endV), maxv2 = __dmul_rn(max_vel, max_vel);
+  const double two_a = __dmul_rn(2.0, max_acc), half_a = __dmul_rn(0.5, max_acc);
+  const double critical_len = __dadd_rn(__ddiv_rn(__dadd_rn(maxv2, -startv2), two_a), __ddiv_rn(__dadd_rn(maxv2, -endv2), two_a));
+  auto ramp = [&](double tq) {  // startV * t + 0.5 * max_acc * t^2
+    return __dadd_rn(__dmul_rn(startV, tq), __dmul_rn(half_a, __dmul_rn(tq, tq)));
+  };
+  if (locallength >= critical_len) {
+    const double t1 = __ddiv_rn(__dadd_rn(max_vel, -startV), max_acc);
+    const double t2 = __dadd_rn(t1, __ddiv_rn(__dadd_rn(locallength, -critical_len), max_vel));
+    if (curt <= t1) return ramp(curt);
+    if (curt <= t2) return __dadd_rn(ramp(t1), __dmul_rn(__dadd_rn(curt, -t1), max_vel));
+    const double u = __dadd_rn(curt, -t2);
+    return __dadd_rn(__dadd_rn(__dadd_rn(ramp(t1), __dmul_rn(__dadd_rn(t2, -t1), max_vel)), __dmul_rn(max_vel, u)),
+                     -__dmul_rn(half_a, __dmul_rn(u, u)));
+  }
+  const double tmpv = sqrt(__dmul_rn(0.5, __dadd_rn(__dadd_rn(startv2, endv2), __dmul_rn(two_a, locallength))));
+  const double tmpt = __ddiv_rn(__dadd_rn(tmpv, -startV), max_acc);
+  if (curt <= tmpt) return ramp(curt);
+  const double u = __dadd_rn(curt, -tmpt);
+  return __dadd_rn(__dadd_rn(ramp(tmpt), __dmul_rn(tmpv, u)), -__dmul_rn(half_a, __dmul_rn(u, u)));
+}
+
+__device__ void fe_evaluate_pos(const FrontendDev& fe, int p, double t, double* out) {
+  const int s0 = fe.shot_ptr[p], ns = fe.shot_ptr[p + 1] - s0;
+  const double* st = fe.shot_time + s0;
+  const int* si = fe.shot_index + s0 + p;
+  const double* pts = fe.pts + 3 * (size_t)fe.pt_ptr[p];
+  double total = 0.0;
+  for (int i = 0; i < ns; i++) total = __dadd_rn(total, st[i]);
+  t = 0.0 < t ? t : 0.0;      // std::max<double>(0, t)
+  t = total < t ? total : t;  // std::min<double>(., totalTrajTime)
+  int index = -1;
+  double tmpT = 0.0, cut = 0.0;
+  for (int i = 0; i < ns; i++) {
+    tmpT = __dadd_rn(tmpT, st[i]);
+    if (tmpT >= t) {
+      index = i;
+      cut = __dadd_rn(__dadd_rn(t, -tmpT), st[i]);
+      break;
+    }
+  }
+  if (index < 0) index = ns - 1;  // (NaN times only; the reference would index with -1)
+  const double initv = index == 0 ? fe.start_vel[p] : fe.non_siguav;
+  const double finv = index == ns - 1 ? fe.end_vel[p] : fe.non_siguav;
+  const double locallength = fe.shot_length[s0 + index];
+  const int front = si[index], back = si[index + 1];
+  const double* lt = pts + 3 * (size_t)front;
+  const int nl = back - front + 1;
+  const bool fwd = fe.shot_s[s0 + index] > 0;
+  const double arclength = fe_length(cut, locallength, fwd ? fe.max_forward_vel : fe.max_backward_vel,
+                                     fwd ? fe.max_forward_acc : fe.max_backward_acc, initv, finv);
+  double tmparc = 0.0;
+  for (int i = 0; i < nl - 1; i++) {
+    const double ax = lt[3 * i], ay = lt[3 * i + 1], ayaw = lt[3 * i + 2];
+    const double bx = lt[3 * i + 3], by = lt[3 * i + 4], byaw = lt[3 * i + 5];
+    const double dx = __dadd_rn(bx, -ax), dy = __dadd_rn(by, -ay);
+    const double l = sqrt(__dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy)));
+    tmparc = __dadd_rn(tmparc, l);
+    if (tmparc >= arclength) {
+      const double l1 = __dadd_rn(tmparc, -arclength), l2 = __dadd_rn(l, -l1);
+      const double w1 = __ddiv_rn(l1, l), w2 = __ddiv_rn(l2, l);
+      out[0] = __dadd_rn(__dmul_rn(w1, ax), __dmul_rn(w2, bx));
+      out[1] = __dadd_rn(__dmul_rn(w1, ay), __dmul_rn(w2, by));
+      double yaw = __dadd_rn(__dmul_rn(w1, ayaw), __dmul_rn(w2, byaw));
+      const double kPi = 3.14159265358979323846, k2Pi = 6.28318530717958647692;
+      if (fabs(__dadd_rn(byaw, -ayaw)) >= kPi) {
+        if (byaw <= 0.0) yaw = __dadd_rn(__dmul_rn(w1, ayaw), __dmul_rn(w2, __dadd_rn(byaw, k2Pi)));
+        else if (ayaw <= 0.0) yaw = __dadd_rn(__dmul_rn(w1, __dadd_rn(ayaw, k2Pi)), __dmul_rn(w2, byaw));
+      }
+      out[2] = yaw;
+      return;
+    }
+  }
+  out[0] = lt[3 * (nl - 1)], out[1] = lt[3 * (nl - 1) + 1], out[2] = lt[3 * (nl - 1) + 2];
+}
+
+__global__ void frontend_pos_kernel(const FrontendDev fe, long long nq, const int* __restrict__ path,
+                                    const double* __restrict__ t, double* __restrict__ out) {
+  const long long q = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  if (q >= nq) return;
+  double o[3];
+  fe_evaluate_pos(fe, path[q], t[q], o);
+  out[3 * q] = o[0], out[3 * q + 1] = o[1], out[3 * q + 2] = o[2];
+}
+
+// one block per gear segment; seg_path / seg_pn / seg_tpp / seg_base / seg_st0 / seg_in0 = path, piece count, piece
+// duration, base time (the durations of the path's earlier segments, summed in order), first state, first inner point
+__global__ void frontend_resample_kernel(const FrontendDev fe, int n_seg, const int* __restrict__ seg_path,
+                                         const int* __restrict__ seg_pn, const double* __restrict__ seg_tpp,
+                                         const double* __restrict__ seg_base, const long long* __restrict__ seg_st0,
+                                         const long long* __restrict__ seg_in0, int K, int Kd, double* __restrict__ states,
+                                         double* __restrict__ inner) {
+  const int g = blockIdx.x;
+  if (g >= n_seg) return;
+  const int pn = seg_pn[g], p = seg_path[g];
+  const double tpp = seg_tpp[g], base = seg_base[g];
+  const int n_states = 2 * (Kd + 1) + (pn - 2) * (K + 1);
+  for (int u = threadIdx.x; u < n_states; u += blockDim.x) {
+    int i, k;
+    if (u < Kd + 1) {
+      i = 0, k = u;
+    } else if (u - (Kd + 1) < (pn - 2) * (K + 1)) {
+      i = 1 + (u - (Kd + 1)) / (K + 1), k = (u - (Kd + 1)) % (K + 1);
+    } else {
+      i = pn - 1, k = u - (Kd + 1) - (pn - 2) * (K + 1);
+    }
+    const int resolution = (i == 0 || i == pn - 1) ? Kd : K;
+    double res_time = 0.0;  // res_time += ego_piece_dur_vec[i] after every piece
+    for (int q = 0; q < i; q++) res_time = __dadd_rn(res_time, tpp);
+    const double t = __dadd_rn(__dadd_rn(base, res_time), __dmul_rn(__ddiv_rn((double)k, (double)resolution), tpp));
+    double o[3];
+    fe_evaluate_pos(fe, p, t, o);
+    double* so = states + 3 * (seg_st0[g] + u);
+    so[0] = o[0], so[1] = o[1], so[2] = o[2];
+    if (k == resolution && i != pn - 1) {
+      double* io = inner + 2 * (seg_in0[g] + i);
+      io[0] = o[0], io[1] = o[1];
+    }
+  }
+}
+
 cudaError_t launch_solve(bool has_obs, int grid, int block, size_t smem, cudaStream_t st, const ShapeDev& sh,
                          const ParamsDev& P, const BatchDev& bd, const GroupDev& grp, const OutDev& out,
                          const HistDev& hist, int* counter) {
@@ -3116,6 +3246,19 @@ cudaError_t launch_collision(cudaStream_t st, const SampleDev& sd, const Corrido
                              double dt, double spacing, const int* seg_prob, int* first_hit, int* collide) {
   const int warps = sd.G, blocks = (warps + 7) / 8;
   collision_kernel<<<blocks > 0 ? blocks : 1, 256, 0, st>>>(sd, cd, t_tab, n_tab, dt, spacing, seg_prob, first_hit, collide);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_frontend_pos(cudaStream_t st, const FrontendDev& fe, long long nq, const int* path, const double* t,
+                                double* out) {
+  frontend_pos_kernel<<<(int)((nq + 127) / 128), 128, 0, st>>>(fe, nq, path, t, out);
+  return cudaGetLastError();
+}
+cudaError_t launch_frontend_resample(cudaStream_t st, const FrontendDev& fe, int n_seg, const int* seg_path, const int* seg_pn,
+                                     const double* seg_tpp, const double* seg_base, const long long* seg_st0,
+                                     const long long* seg_in0, int K, int Kd, double* states, double* inner) {
+  frontend_resample_kernel<<<n_seg, 128, 0, st>>>(fe, n_seg, seg_path, seg_pn, seg_tpp, seg_base, seg_st0, seg_in0, K, Kd,
+                                                  states, inner);
   return cudaGetLastError();
 }
 

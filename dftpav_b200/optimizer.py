@@ -252,6 +252,34 @@ class BatchOptimizer:
             out.ctypes.data_as(dp) if out is not None else None, 1 if keep else 0))
         return out
 
+    def frontend_evaluate_pos(self, fe, path: np.ndarray, t: np.ndarray) -> np.ndarray:
+        """KinoAstar::evaluatePos for queries (path index, time) on the front-end paths `fe` (synth.FrontendPaths)."""
+        path = np.ascontiguousarray(path, dtype=np.int32)
+        t = np.ascontiguousarray(t, dtype=np.float64)
+        out = np.zeros((len(t), 3))
+        c = fe.as_c()
+        self._check(self._lib.dftpav_frontend_evaluate_pos(self._h, C.byref(c), len(t), path.ctypes.data_as(capi.c_int32_p),
+                                                           t.ctypes.data_as(capi.c_double_p), out.ctypes.data_as(capi.c_double_p)))
+        return out
+
+    def frontend_resample(self, fe, seg_duration: np.ndarray, traj_piece_duration: float, K: int, Kd: int):
+        """The resampling loop of RunMINCOParking: returns (piece_num [shots], piece_dur [shots], states [n, 3], inner [m, 2])."""
+        seg_duration = np.ascontiguousarray(seg_duration, dtype=np.float64)
+        SH = len(seg_duration)
+        pn = np.zeros(SH, dtype=np.int32)
+        pd = np.zeros(SH)
+        pn_host = np.maximum((seg_duration / traj_piece_duration + 0.5).astype(np.int64), 2)
+        cap = int((2 * (Kd + 1) + (pn_host - 2) * (K + 1)).sum())
+        states = np.zeros((cap, 3))
+        inner = np.zeros((int((pn_host - 1).sum()), 2))
+        n = C.c_int64(0)
+        c = fe.as_c()
+        dp = capi.c_double_p
+        self._check(self._lib.dftpav_frontend_resample(self._h, C.byref(c), seg_duration.ctypes.data_as(dp), traj_piece_duration,
+                                                       K, Kd, pn.ctypes.data_as(capi.c_int32_p), pd.ctypes.data_as(dp), cap,
+                                                       states.ctypes.data_as(dp), inner.ctypes.data_as(dp), C.byref(n)))
+        return pn, pd, states[: n.value], inner
+
     def collision_check(self, dt: float = 0.05, vertex_spacing: float = 0.1, max_samples: int = 2048,
                         params: Optional[capi.CorridorParams] = None):
         """Collision re-check of the last solve's trajectories against the map of set_map (dftpav_collision_check):

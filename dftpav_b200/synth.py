@@ -491,3 +491,95 @@ def algorithmic_bytes_per_eval(batch: TrajBatch, prm: capi.Params, p: int = 0) -
             u = int(batch.obs_idx[k])
             obs += int(batch.obs_piece_ptr[u + 1] - batch.obs_piece_ptr[u])
     return 16 * n + 32 * planes + 96 * S + 104 * obs
+
+
+class FrontendPaths:
+    """Host arrays of a dftpav_frontend (kept alive by this object) - see include/dftpav_b200.h."""
+
+    def __init__(self, paths, shots, start_vel, end_vel, limits):
+        """paths: list of [n_i, 3] pose arrays; shots: per path a list of (first_pt, last_pt, time, length, sign)."""
+        self.pt_ptr = np.zeros(len(paths) + 1, dtype=np.int32)
+        self.shot_ptr = np.zeros(len(paths) + 1, dtype=np.int32)
+        for i, (pp, ss) in enumerate(zip(paths, shots)):
+            self.pt_ptr[i + 1] = self.pt_ptr[i] + len(pp)
+            self.shot_ptr[i + 1] = self.shot_ptr[i] + len(ss)
+        self.pts = np.ascontiguousarray(np.concatenate(paths), dtype=np.float64)
+        idx, tm, ln, sg = [], [], [], []
+        for ss in shots:
+            idx.append(ss[0][0])
+            for (a, b, t, l, s_) in ss:
+                idx.append(b)
+                tm.append(t), ln.append(l), sg.append(s_)
+        self.shot_index = np.array(idx, dtype=np.int32)
+        self.shot_time = np.array(tm, dtype=np.float64)
+        self.shot_length = np.array(ln, dtype=np.float64)
+        self.shot_s = np.array(sg, dtype=np.int32)
+        self.start_vel = np.ascontiguousarray(start_vel, dtype=np.float64)
+        self.end_vel = np.ascontiguousarray(end_vel, dtype=np.float64)
+        self.limits = tuple(float(v) for v in limits)  # max_forward_vel, max_forward_acc, max_backward_vel, max_backward_acc, non_siguav
+
+    @property
+    def n_paths(self):
+        return len(self.pt_ptr) - 1
+
+    def as_c(self) -> capi.Frontend:
+        import ctypes as C
+        ip, dp = C.POINTER(C.c_int32), C.POINTER(C.c_double)
+        return capi.Frontend(self.n_paths, self.pt_ptr.ctypes.data_as(ip), self.pts.ctypes.data_as(dp),
+                             self.shot_ptr.ctypes.data_as(ip), self.shot_index.ctypes.data_as(ip),
+                             self.shot_time.ctypes.data_as(dp), self.shot_length.ctypes.data_as(dp),
+                             self.shot_s.ctypes.data_as(ip), self.start_vel.ctypes.data_as(dp),
+                             self.end_vel.ctypes.data_as(dp), *self.limits)
+
+
+def make_frontend_paths(n_paths: int, seed: int = 0, trapezoid_duration=None, wrap_yaw: bool = True) -> FrontendPaths:
+    """Synthetic hybrid-A*-like paths: arcs and straights sampled every ~0.2 m, with gear changes (a cusp reverses the
+    direction of travel), divided into gear segments and timed exactly like KinoAstar::getKinoNode (kino_astar.cpp:617-668):
+    the direction sign of every step, the segment lengths, evaluateDuration per segment.  `trapezoid_duration` is the
+    evaluateDuration implementation to use (the library's host function or the oracle's)."""
+    rng = np.random.default_rng(2000 + seed)
+    vf, af, vb, ab, nsv = 3.0, 1.5, 1.5, 1.0, 0.05
+    paths, shots, v0s, v1s = [], [], [], []
+    for _ in range(n_paths):
+        x, y, yaw = rng.uniform(-5, 5), rng.uniform(-5, 5), rng.uniform(-np.pi, np.pi)
+        pts = [(x, y, yaw)]
+        direction = 1
+        for leg in range(int(rng.integers(1, 4))):
+            curv = rng.uniform(-0.25, 0.25)
+            for _ in range(int(rng.integers(20, 120))):
+                ds = 0.2 * direction
+                x += ds * np.cos(yaw)
+                y += ds * np.sin(yaw)
+                yaw += ds * curv
+                if wrap_yaw:
+                    yaw = (yaw + np.pi) % (2 * np.pi) - np.pi
+                pts.append((x, y, yaw))
+            direction = -direction
+        P = np.array(pts)
+        # getKinoNode: gear sign per step, shot division
+        d = P[1:, 0:2] - P[:-1, 0:2]
+        sgn = np.where(d[:, 0] * np.cos(P[:-1, 2]) + d[:, 1] * np.sin(P[:-1, 2]) >= 0, 1, -1)
+        lens = np.sqrt(d[:, 0] * d[:, 0] + d[:, 1] * d[:, 1])
+        shot_index, shot_s, shot_len = [0], [], []
+        tmpl, lastS = 0.0, int(sgn[0])
+        for i in range(len(P) - 1):
+            if sgn[i] * lastS >= 0:
+                tmpl += lens[i]
+            else:
+                shot_index.append(i), shot_s.append(lastS), shot_len.append(tmpl)
+                tmpl = lens[i]
+            lastS = int(sgn[i])
+        shot_s.append(lastS), shot_len.append(tmpl), shot_index.append(len(P) - 1)
+        v0, v1 = rng.uniform(0, 1.0), rng.uniform(0, 1.0)
+        ns = len(shot_s)
+        ss = []
+        for i in range(ns):
+            a, b = (nsv, nsv)
+            if i == 0:
+                a = v0
+            if i == ns - 1:
+                b = v1
+            mv, ma = (vf, af) if shot_s[i] > 0 else (vb, ab)
+            ss.append((shot_index[i], shot_index[i + 1], trapezoid_duration(shot_len[i], mv, ma, a, b), shot_len[i], shot_s[i]))
+        paths.append(P), shots.append(ss), v0s.append(v0), v1s.append(v1)
+    return FrontendPaths(paths, shots, v0s, v1s, (vf, af, vb, ab, nsv))

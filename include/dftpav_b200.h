@@ -334,6 +334,47 @@ int dftpav_corridor_set_map(dftpav_handle* h, const dftpav_gridmap* map);
 int dftpav_corridor_rectangles(dftpav_handle* h, const dftpav_corridor_params* cp, int64_t n, const double* states,
                                const double* cos_sin, double* hpolys, int32_t keep);
 
+/* ---- front-end path -> optimizer inputs (the resampling between the hybrid-A* search and the
+ * optimizer) ----
+ * dftpav_frontend mirrors what path_searching::KinoAstar keeps after getKinoNode (src/kino_astar.cpp:554-743) for every
+ * searched path p: SampleTraj = pts[pt_ptr[p] .. pt_ptr[p+1]) (x, y, yaw); its gear segments ("shots") shot_ptr[p] ..
+ * shot_ptr[p+1]: shot_time = shot_timeList, shot_length = shot_lengthList, shot_s = shot_SList (+1 forward, -1 backward),
+ * shot_index = shotindex (ns + 1 point indices per path, stored at shot_index[shot_ptr[p] + p ...]); start_vel / end_vel =
+ * fabs(start_state_[3]) / fabs(end_state_[3]); the limits are the search's max_forward_vel / _acc, max_backward_vel / _acc
+ * and non_siguav. */
+typedef struct dftpav_frontend {
+  int32_t n_paths;
+  const int32_t* pt_ptr;      /* [n_paths + 1] */
+  const double* pts;          /* [pt_total][3] */
+  const int32_t* shot_ptr;    /* [n_paths + 1] */
+  const int32_t* shot_index;  /* [shot_total + n_paths] */
+  const double* shot_time;    /* [shot_total] */
+  const double* shot_length;  /* [shot_total] */
+  const int32_t* shot_s;      /* [shot_total] */
+  const double* start_vel;    /* [n_paths] */
+  const double* end_vel;      /* [n_paths] */
+  double max_forward_vel, max_forward_acc, max_backward_vel, max_backward_acc, non_siguav;
+} dftpav_frontend;
+
+/* KinoAstar::evaluatePos (src/kino_astar.cpp:468-521) for nq queries: out[q] = (x, y, yaw) of path path[q] at time t[q]
+ * (clamped to [0, total time]): the shot that contains t, the arc length its trapezoidal speed profile has covered
+ * (evaluateLength, kino_astar.cpp:763-795), linear interpolation between the path samples around that arc length.
+ * Only + - * / sqrt on the path: bit-identical to the CPU restatement. */
+int dftpav_frontend_evaluate_pos(dftpav_handle* h, const dftpav_frontend* fe, int64_t nq, const int32_t* path, const double* t,
+                                 double* out);
+/* The resampling loop of TrajPlanner::RunMINCOParking (src/traj_manager.cpp:531-567) for every path: per gear segment g,
+ * piece_num[g] = max(int(seg_duration[g] / traj_piece_duration + 0.5), 2) pieces of piece_dur[g] = seg_duration[g] /
+ * piece_num[g] (seg_duration = the summed time steps of the segment's FlatTrajData), the states evaluatePos gives at
+ * K + 1 (inner pieces) or Kd + 1 (first / last piece) times per piece - [n_states][3], the statelist getRectangleConst
+ * consumes, directly usable by dftpav_corridor_rectangles - and the piece_num - 1 inner waypoints per segment (inner,
+ * [.][2], = dftpav_batch.inner_pts).  states_cap = capacity of states in states (inner needs sum (piece_num - 1) pairs);
+ * *n_states receives the number of states; DFTPAV_ERR_INVALID_ARG if states_cap is too small (*n_states is still set). */
+int dftpav_frontend_resample(dftpav_handle* h, const dftpav_frontend* fe, const double* seg_duration,
+                             double traj_piece_duration, int32_t K, int32_t Kd, int32_t* piece_num, double* piece_dur,
+                             int64_t states_cap, double* states, double* inner, int64_t* n_states);
+/* KinoAstar::evaluateDuration (src/kino_astar.cpp:744-762): duration of the trapezoidal speed profile over `length` (host). */
+double dftpav_trapezoid_duration(double length, double max_vel, double max_acc, double start_vel, double end_vel);
+
 /* Collision re-check of the trajectories of the last solve against the occupancy grid of dftpav_corridor_set_map - the loop the
  * replanning server runs over the executing trajectory every cycle (src/traj_server_ros.cpp:385-397): every gear segment is
  * sampled at t = 0, dt, dt + dt, ... while t < duration (dt = 0.05 there), the footprint at (getPos(t), getAngle(t)) is the

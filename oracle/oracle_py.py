@@ -194,6 +194,53 @@ def collision_check_segment(grid: np.ndarray, origin_xy, resolution: float, c: n
                   float(vertex_spacing), int(max_samples)))
 
 
+def trapezoid_duration(length, max_vel, max_acc, v0, v1) -> float:
+    fn = lib().oracle_trapezoid_duration
+    fn.argtypes = [C.c_double] * 5
+    fn.restype = C.c_double
+    return float(fn(length, max_vel, max_acc, v0, v1))
+
+
+def trapezoid_length(curt, locallength, max_vel, max_acc, v0, v1) -> float:
+    fn = lib().oracle_trapezoid_length
+    fn.argtypes = [C.c_double] * 6
+    fn.restype = C.c_double
+    return float(fn(curt, locallength, max_vel, max_acc, v0, v1))
+
+
+def frontend_evaluate_pos(fe, path: np.ndarray, t: np.ndarray) -> np.ndarray:
+    """CPU restatement of KinoAstar::evaluatePos (oracle/frontend_oracle.cpp)."""
+    path = np.ascontiguousarray(path, dtype=np.int32)
+    t = np.ascontiguousarray(t, dtype=np.float64)
+    out = np.zeros((len(t), 3))
+    c = fe.as_c()
+    fn = lib().oracle_frontend_evaluate_pos
+    fn.argtypes = [C.POINTER(capi.Frontend), C.c_int64, capi.c_int32_p, capi.c_double_p, capi.c_double_p]
+    assert fn(C.byref(c), len(t), path.ctypes.data_as(capi.c_int32_p), t.ctypes.data_as(capi.c_double_p),
+              out.ctypes.data_as(capi.c_double_p)) == 0
+    return out
+
+
+def frontend_resample(fe, seg_duration: np.ndarray, traj_piece_duration: float, K: int, Kd: int):
+    """CPU restatement of the resampling loop of TrajPlanner::RunMINCOParking: (piece_num, piece_dur, states, inner)."""
+    seg_duration = np.ascontiguousarray(seg_duration, dtype=np.float64)
+    SH = len(seg_duration)
+    c = fe.as_c()
+    fn = lib().oracle_frontend_resample
+    dp = capi.c_double_p
+    fn.argtypes = [C.POINTER(capi.Frontend), dp, C.c_double, C.c_int, C.c_int, capi.c_int32_p, dp, dp, dp]
+    fn.restype = C.c_int64
+    pn = np.zeros(SH, dtype=np.int32)
+    pd = np.zeros(SH)
+    n = fn(C.byref(c), seg_duration.ctypes.data_as(dp), traj_piece_duration, K, Kd, pn.ctypes.data_as(capi.c_int32_p),
+           pd.ctypes.data_as(dp), None, None)
+    states = np.zeros((n, 3))
+    inner = np.zeros((int((pn - 1).sum()), 2))
+    fn(C.byref(c), seg_duration.ctypes.data_as(dp), traj_piece_duration, K, Kd, pn.ctypes.data_as(capi.c_int32_p),
+       pd.ctypes.data_as(dp), states.ctypes.data_as(dp), inner.ctypes.data_as(dp))
+    return pn, pd, states, inner
+
+
 REF_OPT_SO = os.path.join(os.path.dirname(os.path.abspath(__file__)), "_ref", "libref_optimizer.so")
 _ref_opt = None
 
