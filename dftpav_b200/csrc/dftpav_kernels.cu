@@ -262,11 +262,7 @@ __device__ __forceinline__ void stage_problem(const ShapeDev& sh, const BatchDev
 // latency on every row of the dependent chain.
 __device__ __forceinline__ double lds_pure(unsigned addr) {
   double v;
-#ifdef DFTPAV_NO_PURE_LDS
-  asm volatile("ld.shared.f64 %0, [%1];" : "=d"(v) : "r"(addr) : "memory");
-#else
   asm("ld.shared.f64 %0, [%1];" : "=d"(v) : "r"(addr));
-#endif
   return v;
 }
 __device__ __forceinline__ unsigned smem_addr(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
@@ -1058,11 +1054,7 @@ __device__ __forceinline__ void sweep_segment(const ShapeDev& sh, const ParamsDe
       const double wobs = omg * step * P.wei_obs;
       for (int h0 = 0; h0 < H; h0 += kPlaneChunk) {
         if (h0 > 0) load_plane_chunk(pn, pl + (size_t)(pass * nchunk + h0 / kPlaneChunk) * 512);
-#ifndef DFTPAV_VTX_UNROLL
-#define DFTPAV_VTX_UNROLL 1
-#endif
-        constexpr int kVtxUnroll = DFTPAV_VTX_UNROLL;
-#pragma unroll kVtxUnroll
+#pragma unroll 1
         for (int v = 0; v < 4; v++) {  // rolled: measured 161 k solves/s vs 152 k with 2 vertices per trip (19 vs 22 KB loop)
           const V2 le = mk(P.le[v][0], P.le[v][1]);
           const V2 q = ego_R * le;
@@ -1078,17 +1070,6 @@ __device__ __forceinline__ void sweep_segment(const ShapeDev& sh, const ParamsDe
           if (viol[0] > 0.0 || viol[1] > 0.0 || viol[2] > 0.0 || viol[3] > 0.0) {
 #pragma unroll
             for (int hh = 0; hh < kPlaneChunk; hh++) {
-#ifdef DFTPAV_L1_BRANCHFREE
-              // branch-free positiveSmoothedL1 of max(viol, 0): f(0) = f'(0) = 0, so non-violated planes add nothing
-              const double xv = fmax(viol[hh], 0.0);
-              const double x2 = xv * xv;
-              const bool small = xv < P.smooth_eps;
-              const double pena = small ? (P.l1_f4c * xv + P.l1_f3c) * x2 * xv : xv - P.l1_half;
-              const double penaD = small ? (P.l1_d3c * xv + P.l1_d2c) * x2 : 1.0;
-              Bn.x += penaD * pn[hh][0];
-              Bn.y += penaD * pn[hh][1];
-              Sp += pena;
-#else
               if (viol[hh] > 0.0) {
                 double pena, penaD;
                 smoothed_l1(P, viol[hh], pena, penaD);
@@ -1096,7 +1077,6 @@ __device__ __forceinline__ void sweep_segment(const ShapeDev& sh, const ParamsDe
                 Bn.y += penaD * pn[hh][1];
                 Sp += pena;
               }
-#endif
             }
           }
           if (Sp > 0.0) {
