@@ -351,7 +351,7 @@ def run_ours(args):
             "e2e": {"value": total_solves / (e2e_ms * 1e-3), "unit": UNIT, "h2d_bytes_per_step": int(batch.nbytes()),
                     "d2h_bytes_per_step": int(sol.nbytes()), "ms_per_step": e2e_ms / args.steps,
                     "last_step_breakdown_rank0": e2e_breakdown,
-                    "note": "one C-ABI call per step (dftpav_solve): the corridor planes are copied in 16 chunks on a second "
+                    "note": "one C-ABI call per step (dftpav_solve): the corridor planes are copied in 32 chunks on a second "
                             "stream while the persistent solver kernel already runs; the longest-predicted-first queue is "
                             "keyed by the plane-free part of f(x0) and only hands out problems whose chunk has arrived"},
             "gpu_launches": int(launches),

@@ -221,7 +221,7 @@ struct Group {
 
 inline int samples_of(int N, int K, int Kd) { return (N - 2) * (K + 1) + 2 * (Kd + 1); }
 
-constexpr int kMaxChunks = 16;  // chunks of the plane upload that dftpav_solve overlaps with the solve
+constexpr int kMaxChunks = 32;  // chunks of the plane upload that dftpav_solve overlaps with the solve
 
 }  // namespace
 
@@ -657,7 +657,12 @@ namespace {
 // MINCO tables, small arrays, boundary-state / x0 kernel, launch configurations, history.  The planes follow through
 // issue_plane_copies() - before the solve for dftpav_upload_batch, AFTER the solve kernels have been launched for
 // dftpav_solve, so that the copy runs under the solve (the kernels wait per upload chunk, layout_problem()).
-int upload_impl(dftpav_handle* h, const dftpav_batch* b, int n_chunks_wanted) {
+int issue_plane_copies(dftpav_handle* h, const dftpav_batch* b, cudaStream_t cs);
+
+// early_copy_stream != nullptr (dftpav_solve): the plane copies are queued on that stream as soon as the plane prefixes are
+// known - BEFORE the host-side packing of x0, the MINCO tables and the small uploads (~0.4 ms of host work), which then run
+// under the copy
+int upload_impl(dftpav_handle* h, const dftpav_batch* b, int n_chunks_wanted, cudaStream_t early_copy_stream = nullptr) {
   std::string why;
   dftpav_dims dims;
   std::vector<unsigned char> rejected;
@@ -752,6 +757,38 @@ int upload_impl(dftpav_handle* h, const dftpav_batch* b, int n_chunks_wanted) {
   if (h->has_obs && strict_build_host())
     return fail(h, DFTPAV_ERR_UNSUPPORTED, "the strict verification build does not evaluate moving obstacles (exp/log)");
 
+  // ---- the corridor planes first: buffer, arrival flags, and - for the overlapped call - the copies themselves
+  h->planes_from_corridor = (b->planes == nullptr) && B > 0;
+  if (h->planes_from_corridor) {
+    if (h->corridor_n != Q)
+      return fail(h, DFTPAV_ERR_STATE, "planes == NULL but dftpav_corridor_rectangles(keep) has not produced one polygon per sample of this batch");
+  } else {
+    h->corridor_n = -1;  // the buffer is about to be overwritten by uploaded planes
+    CU_TRY(h, h->planes_raw.ensure(sizeof(double) * 4 * (size_t)h->total_planes));
+  }
+  // ---- arrival flags of the plane upload and per-problem layout flags (epoch-stamped: nothing to clear between uploads)
+  h->epoch += 1;
+  h->n_chunks = std::max(1, std::min(std::min(n_chunks_wanted, kMaxChunks), B / 64));
+  h->chunk = std::max(1, (B + h->n_chunks - 1) / h->n_chunks);
+  h->n_chunks = B > 0 ? (B + h->chunk - 1) / h->chunk : 1;
+  if (h->ready.cap < sizeof(int) * kMaxChunks) {
+    CU_TRY(h, h->ready.ensure(sizeof(int) * kMaxChunks));
+    CU_TRY(h, cudaMemsetAsync(h->ready.p, 0, sizeof(int) * kMaxChunks, st));
+  }
+  if (h->laid.cap < sizeof(int) * (size_t)std::max(1, B)) {
+    CU_TRY(h, h->laid.ensure(sizeof(int) * (size_t)std::max(1, B)));
+    CU_TRY(h, cudaMemsetAsync(h->laid.p, 0, h->laid.cap, st));
+  }
+  for (int c = 0; c < kMaxChunks; c++) h->h_epoch[c] = h->epoch;
+  if (early_copy_stream) {
+    // the copy stream starts after everything already queued on the main stream (previous results are read, the old plane
+    // buffer is free, the flag arrays are cleared)
+    CU_TRY(h, cudaEventRecord(h->ev_copy, st));
+    CU_TRY(h, cudaStreamWaitEvent(early_copy_stream, h->ev_copy, 0));
+    rc = issue_plane_copies(h, b, early_copy_stream);
+    if (rc) return rc;
+  }
+
   // ---- raw uploads (everything but the planes)
   auto up = [&](DevBuf& buf, const void* src, size_t bytes) -> cudaError_t {
     cudaError_t e = buf.ensure(bytes);
@@ -822,14 +859,6 @@ int upload_impl(dftpav_handle* h, const dftpav_batch* b, int n_chunks_wanted) {
       uni[u] = d0;
     }
     CU_TRY(h, up(h->obs_uniform, uni.data(), sizeof(double) * U));
-  }
-  h->planes_from_corridor = (b->planes == nullptr) && B > 0;
-  if (h->planes_from_corridor) {
-    if (h->corridor_n != Q)
-      return fail(h, DFTPAV_ERR_STATE, "planes == NULL but dftpav_corridor_rectangles(keep) has not produced one polygon per sample of this batch");
-  } else {
-    h->corridor_n = -1;  // the buffer is about to be overwritten by uploaded planes
-    CU_TRY(h, h->planes_raw.ensure(sizeof(double) * 4 * (size_t)h->total_planes));
   }
   CU_TRY(h, h->ini.ensure(sizeof(double) * 6 * G));
   CU_TRY(h, h->fin.ensure(sizeof(double) * 6 * G));
@@ -980,20 +1009,6 @@ int upload_impl(dftpav_handle* h, const dftpav_batch* b, int n_chunks_wanted) {
   CU_TRY(h, h->hist_y.ensure(hbytes));
   CU_TRY(h, h->hist_ys.ensure(sizeof(double) * (size_t)max_slots * mem));
 
-  // ---- arrival flags of the plane upload and per-problem layout flags (epoch-stamped: nothing to clear between uploads)
-  h->epoch += 1;
-  h->n_chunks = std::max(1, std::min(std::min(n_chunks_wanted, kMaxChunks), B / 64));
-  h->chunk = std::max(1, (B + h->n_chunks - 1) / h->n_chunks);
-  h->n_chunks = B > 0 ? (B + h->chunk - 1) / h->chunk : 1;
-  if (h->ready.cap < sizeof(int) * kMaxChunks) {
-    CU_TRY(h, h->ready.ensure(sizeof(int) * kMaxChunks));
-    CU_TRY(h, cudaMemsetAsync(h->ready.p, 0, sizeof(int) * kMaxChunks, st));
-  }
-  if (h->laid.cap < sizeof(int) * (size_t)std::max(1, B)) {
-    CU_TRY(h, h->laid.ensure(sizeof(int) * (size_t)std::max(1, B)));
-    CU_TRY(h, cudaMemsetAsync(h->laid.p, 0, h->laid.cap, st));
-  }
-  for (int c = 0; c < kMaxChunks; c++) h->h_epoch[c] = h->epoch;
 
   BatchDev& bd = h->bd;
   bd.seg_base = h->seg_base.as<int>();
@@ -1022,7 +1037,7 @@ int upload_impl(dftpav_handle* h, const dftpav_batch* b, int n_chunks_wanted) {
   bd.epoch = h->epoch;
 
   CU_TRY(h, cudaEventRecord(h->ev[1], st));
-  h->stats.h2d_bytes = h2d;
+  h->stats.h2d_bytes += h2d;  // (the early plane copies have already added theirs)
   h->upload_launches = launches;
   h->stats.kernel_launches = launches;
   h->stats.n_shapes = (int)h->groups.size();
@@ -1285,22 +1300,17 @@ int dftpav_download(dftpav_handle* h, const dftpav_result* out) {
 // chunk.  Replaces the deep copy of hPoly_container at the top of OptimizeTrajectory (traj_optimizer.cpp:15).
 int dftpav_solve(dftpav_handle* h, const dftpav_batch* batch, const dftpav_result* out) {
   if (!h) return DFTPAV_ERR_INVALID_ARG;
-  int rc = upload_impl(h, batch, kMaxChunks);
-  if (rc) return rc;
-  cudaStream_t st = h->stream;
-  // The copy stream starts after everything already queued on the main stream (previous results are read, the old plane
-  // buffer is free).  The copies are queued BEFORE the solver kernels are launched: with pinned host buffers they return at
-  // once and run under the kernels; and whatever serialises the device work (a profiler, CUDA_LAUNCH_BLOCKING, pageable
-  // source buffers that the driver stages synchronously) only loses the overlap - the kernels can never be left polling
-  // for planes nobody has queued.
-  CU_TRY(h, cudaEventRecord(h->ev_copy, st));
-  CU_TRY(h, cudaStreamWaitEvent(h->copy_stream, h->ev_copy, 0));
-  rc = issue_plane_copies(h, batch, h->copy_stream);
+  // The plane copies are queued on the copy stream from INSIDE upload_impl, as soon as the plane prefixes are known and before
+  // the solver kernels are launched: with pinned host buffers they return at once and run under the host-side packing and
+  // the kernels; and whatever serialises the device work (a profiler, CUDA_LAUNCH_BLOCKING, pageable source buffers that the
+  // driver stages synchronously) only loses the overlap - the kernels can never be left polling for planes nobody has queued.
+  int rc = upload_impl(h, batch, kMaxChunks, h->copy_stream);
   if (rc) {
     cudaStreamSynchronize(h->copy_stream);
     h->uploaded = false;
     return rc;
   }
+  cudaStream_t st = h->stream;
   CU_TRY(h, cudaEventRecord(h->ev[4], st));
   int launches = 0;
   rc = launch_solve_kernels(h, &launches, true);

@@ -287,7 +287,7 @@ def test_determinism_and_sharding(gpu_opt_factory):
 def test_queue_order_is_invisible(cfg, B, gpu_opt_factory):
     """Batches above 4 problems per SM are served longest-predicted-first through per-chunk lists (chunk_order_kernel,
     fetch_by_chunk): every problem must be solved exactly once and no result may depend on the order.  Compared: the
-    overlapped call (16 upload chunks), upload + optimize (one chunk), a caller-supplied reversed order (plain counter
+    overlapped call (32 upload chunks), upload + optimize (one chunk), a caller-supplied reversed order (plain counter
     queue), and the two halves solved as separate batches."""
     batch, prm = synth.make_config(cfg, B=B, seed=9)
     opt = gpu_opt_factory(prm)
