@@ -266,6 +266,7 @@ struct dftpav_handle {
   int map_n_dl = 0;
   std::vector<int> dbg_order;  // experiment hook (dftpav_debug_set_order): serve the work queue in this order of problem ids
   bool planes_from_corridor = false;
+  int dbg_order_key = 0;  // experiment hook: 0 = the caller's choice, 1 = plane-free key, 2 = the whole f(x0)
   long long corridor_n = -1;  // >= 0: planes_raw holds corridor_n generated rectangles (4 planes each)
   int trace_cap = 0;
   int hist_ld = 0, hist_slots = 0;
@@ -1064,7 +1065,10 @@ int issue_plane_copies(dftpav_handle* h, const dftpav_batch* b, cudaStream_t cs)
 }
 
 // launches the solver kernels of every shape group on the handle's stream (no synchronisation)
-int launch_solve_kernels(dftpav_handle* h, int* launches_out, bool order_by_f0) {
+// order_key: 0 = input order, 1 = longest-predicted-first keyed by f(x0) WITHOUT the corridor term (the overlapped call: no
+// plane needs to have arrived), 2 = keyed by the whole f(x0) (resident batches; measured equal at configs 2, 3, 5 and 1-4 %
+// better at config 4, where the corridor term separates the problems more)
+int launch_solve_kernels(dftpav_handle* h, int* launches_out, int order_key) {
   cudaStream_t st = h->stream;
   CU_TRY(h, cudaMemsetAsync(h->counter.p, 0, sizeof(int) * 64, st));
   OutDev out;
@@ -1095,8 +1099,9 @@ int launch_solve_kernels(dftpav_handle* h, int* launches_out, bool order_by_f0) 
   // scheduling only: serve the queue longest-predicted-first (chunk_order_kernel, fetch_by_chunk).  The key is f(x0)
   // WITHOUT the corridor term: one extra evaluation per problem that reads no plane, so it also runs in the overlapped
   // dftpav_solve while the planes are still arriving; the queue only hands out problems of chunks that have arrived.
-  const bool lpt = order_by_f0 && !strict_build_host() && !h->param_status && h->dbg_order.empty() &&
+  const bool lpt = order_key != 0 && !strict_build_host() && !h->param_status && h->dbg_order.empty() &&
                    h->dims.B > 4 * h->num_sms;
+  const bool full_key = h->dbg_order_key ? h->dbg_order_key == 2 : order_key == 2;
   if (lpt) {
     const int B = h->dims.B;
     CU_TRY(h, h->fout.ensure(sizeof(double) * B));
@@ -1108,7 +1113,7 @@ int launch_solve_kernels(dftpav_handle* h, int* launches_out, bool order_by_f0) 
       gd.planes = grp->d_planes.as<double>();
       gd.lu = grp->d_lu.as<double>();
       ShapeDev sh0 = grp->sh;
-      sh0.H = 0;  // no corridor term, no plane read, no waiting for the upload
+      if (!full_key) sh0.H = 0;  // no corridor term, no plane read, no waiting for the upload
       CU_TRY(h, launch_eval(h->has_obs, grp->grid, 32 * grp->warps, grp->smem, st, sh0, h->pd, h->bd, gd,
                             h->x0.as<double>(), h->fout.as<double>(), h->gout.as<double>(), nullptr, nullptr));
       CU_TRY(h, grp->d_clist.ensure(sizeof(int) * gd.count));
@@ -1234,7 +1239,7 @@ int dftpav_optimize(dftpav_handle* h) {
   cudaStream_t st = h->stream;
   CU_TRY(h, cudaEventRecord(h->ev[0], st));
   int launches = 0;
-  int rc = launch_solve_kernels(h, &launches, true);
+  int rc = launch_solve_kernels(h, &launches, 2);
   if (rc) return rc;
   CU_TRY(h, cudaEventRecord(h->ev[1], st));
   CU_TRY(h, cudaStreamSynchronize(st));
@@ -1313,7 +1318,7 @@ int dftpav_solve(dftpav_handle* h, const dftpav_batch* batch, const dftpav_resul
   cudaStream_t st = h->stream;
   CU_TRY(h, cudaEventRecord(h->ev[4], st));
   int launches = 0;
-  rc = launch_solve_kernels(h, &launches, true);
+  rc = launch_solve_kernels(h, &launches, 1);
   if (rc) {
     cudaStreamSynchronize(h->copy_stream);
     return rc;
@@ -1792,6 +1797,14 @@ int dftpav_debug_get_trace(dftpav_handle* h, double* out) {
   if (!h || !out || h->trace_cap <= 0 || !h->solved) return DFTPAV_ERR_STATE;
   CU_TRY(h, cudaSetDevice(h->device));
   CU_TRY(h, cudaMemcpy(out, h->trace.p, sizeof(double) * 3 * (size_t)h->trace_cap * h->dims.B, cudaMemcpyDeviceToHost));
+  return DFTPAV_OK;
+}
+
+// Experiment hook (scheduling only): key of the longest-first queue, 0 = default (the whole f(x0) for resident batches, f(x0)
+// without the corridor term for the overlapped dftpav_solve), 1 = always plane-free, 2 = always the whole f(x0).
+int dftpav_debug_set_order_key(dftpav_handle* h, int mode) {
+  if (!h) return DFTPAV_ERR_INVALID_ARG;
+  h->dbg_order_key = mode;
   return DFTPAV_OK;
 }
 
