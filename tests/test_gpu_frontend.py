@@ -82,3 +82,33 @@ def test_path_to_trajectory_pipeline(gpu_opt_factory):
     assert opt.stats().h2d_bytes < 2_000_000, "the corridor must not be uploaded"
     assert np.all(np.isfinite(sol.cost)) and (sol.status != capi.PROBLEM_REJECTED).all()
     assert sol.success.mean() > 0.5
+
+
+def test_malformed_front_end_is_refused(gpu_opt_factory):
+    import ctypes as C
+
+    fe = _paths(5, 2)
+    opt = gpu_opt_factory(capi.default_params())
+    lib = capi.load_library()
+    dp = capi.c_double_p
+    # a capacity that is too small: refused, but the needed number of states is reported
+    seg = fe.shot_time.copy()
+    pn = np.zeros(len(seg), dtype=np.int32)
+    pd = np.zeros(len(seg))
+    st = np.zeros((10, 3))
+    inn = np.zeros((1000, 2))
+    n = C.c_int64(0)
+    c = fe.as_c()
+    rc = lib.dftpav_frontend_resample(opt._h, C.byref(c), seg.ctypes.data_as(dp), 0.5, 8, 16, pn.ctypes.data_as(capi.c_int32_p),
+                                      pd.ctypes.data_as(dp), 10, st.ctypes.data_as(dp), inn.ctypes.data_as(dp), C.byref(n))
+    assert rc == capi.ERR_INVALID_ARG and n.value == int((2 * 17 + (np.maximum((seg / 0.5 + 0.5).astype(int), 2) - 2) * 9).sum())
+    # a decreasing shot index, a query on a path that does not exist, a non-positive segment duration
+    bad = _paths(5, 2)
+    bad.shot_index[1] = -3
+    with pytest.raises(Exception):
+        opt.frontend_evaluate_pos(bad, np.zeros(1, dtype=np.int32), np.zeros(1))
+    with pytest.raises(Exception):
+        opt.frontend_evaluate_pos(fe, np.array([99], dtype=np.int32), np.zeros(1))
+    seg[0] = 0.0
+    with pytest.raises(Exception):
+        opt.frontend_resample(fe, seg, 0.5, 8, 16)
