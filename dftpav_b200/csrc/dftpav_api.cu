@@ -696,11 +696,12 @@ int upload_impl(dftpav_handle* h, const dftpav_batch* b, int n_chunks_wanted, cu
   h->h_n.resize(B);
   h->h_status0.assign(B, 0);
   h->n_rejected = 0;
+  Group* last_grp = nullptr;  // batches are mostly runs of one shape: the map is consulted only when the shape changes
+  int last_g0 = 0, last_S = -1;
   for (int p = 0; p < B; p++) {
     const int g0 = b->seg_ptr[p], g1 = b->seg_ptr[p + 1];
     seg_base[p] = g0;
     samp_base[p] = samp;
-    std::vector<int> key(b->piece_num + g0, b->piece_num + g1);
     int n = 0;
     for (int g = g0; g < g1; g++) {
       samp += samples_of(b->piece_num[g], K, Kd);
@@ -715,6 +716,11 @@ int upload_impl(dftpav_handle* h, const dftpav_batch* b, int n_chunks_wanted, cu
       continue;
     }
     if (h->param_status) h->h_status0[p] = h->param_status;
+    if (last_grp && g1 - g0 == last_S && std::equal(b->piece_num + g0, b->piece_num + g1, b->piece_num + last_g0)) {
+      last_grp->probs.push_back(p);
+      continue;
+    }
+    std::vector<int> key(b->piece_num + g0, b->piece_num + g1);
     Group*& grp = by_shape[key];
     if (!grp) {
       if (!h->group_pool.empty()) {
@@ -726,6 +732,7 @@ int upload_impl(dftpav_handle* h, const dftpav_batch* b, int n_chunks_wanted, cu
       h->groups.push_back(grp);
     }
     grp->probs.push_back(p);
+    last_grp = grp, last_g0 = g0, last_S = g1 - g0;
   }
   samp_base[B] = samp;
   // plane prefix (only for ragged corridors)

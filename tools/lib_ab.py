@@ -20,7 +20,7 @@ from dftpav_b200.optimizer import BatchOptimizer
 cfg, B, old = int(sys.argv[1]), int(sys.argv[2]), sys.argv[3]
 batch, prm = synth.make_config(cfg, B=B, seed=0)
 for rep in range(2):
-    for name, variant in (("product", ""), ("old", old)):
+    for name, variant in (("product", ""), ("other", old)):
         opt = BatchOptimizer(prm, device=0, variant=variant)
         opt.upload(batch)
         ms = []
