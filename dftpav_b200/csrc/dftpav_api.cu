@@ -597,13 +597,19 @@ int dftpav_create(const dftpav_params* prm, int device, dftpav_handle** out) {
   h->device = device;
   h->num_sms = prop.multiProcessorCount;
   h->smem_optin = prop.sharedMemPerBlockOptin;
-  if (cudaSetDevice(device) != cudaSuccess || cudaStreamCreateWithFlags(&h->own_stream, cudaStreamNonBlocking) != cudaSuccess) {
+  // the solver stream outranks the plane-copy stream: where the hardware arbitrates by priority, the small uploads and the
+  // kernels of a call do not queue behind its own 233 MB of corridor planes
+  int prio_lo = 0, prio_hi = 0;
+  cudaSetDevice(device);
+  cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi);
+  if (cudaSetDevice(device) != cudaSuccess ||
+      cudaStreamCreateWithPriority(&h->own_stream, cudaStreamNonBlocking, prio_hi) != cudaSuccess) {
     delete h;
     return DFTPAV_ERR_CUDA;
   }
   h->stream = h->own_stream;
   for (auto& e : h->ev) cudaEventCreate(&e);
-  if (cudaStreamCreateWithFlags(&h->copy_stream, cudaStreamNonBlocking) != cudaSuccess ||
+  if (cudaStreamCreateWithPriority(&h->copy_stream, cudaStreamNonBlocking, prio_lo) != cudaSuccess ||
       cudaEventCreateWithFlags(&h->ev_copy, cudaEventDisableTiming) != cudaSuccess ||
       cudaMallocHost(&h->h_epoch, sizeof(int) * kMaxChunks) != cudaSuccess) {
     dftpav_destroy(h);
